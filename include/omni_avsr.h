@@ -1,0 +1,119 @@
+/*
+ * omni_avsr.h -- C ABI of the B200 (sm_100a) kernels behind the Omni-AVSR hot path.
+ *
+ * The reference (umbertocappellazzo/Omni-AVSR) has no FFI layer: its hot path is a chain of
+ * PyTorch library calls inside nn.Module.forward. Each entry point below replaces the op sequence
+ * at the cited reference lines (paths relative to the reference root). Host code (Python) keeps the
+ * reference's module/class API and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named h_*; tensors are row-major, bf16 unless noted;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises;
+ *   - functions never allocate or free caller memory, keep no mutable global state and are re-entrant;
+ *   - return 0 on success, <0 on error (OMNI_ERR_*); no exceptions cross the ABI.
+ */
+#ifndef OMNI_AVSR_H_
+#define OMNI_AVSR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMNI_ABI_VERSION 1
+
+#define OMNI_ACT_NONE 0
+#define OMNI_ACT_RELU 1
+#define OMNI_ACT_GELU 2
+
+#define OMNI_COMPRESS_AVG 0   /* nn.AvgPool1d(r)  : modeling_OmniAVSR.py:544-546 (audio), :469-471 (video) */
+#define OMNI_COMPRESS_STACK 1 /* frame stacking   : modeling_OmniAVSR.py:562-568 (audio), :487-493 (video) */
+
+/* ABI version + build info (no GPU needed). */
+int omni_abi_version(void);
+/* Returns the compute capability (major*10+minor) of the current device, or <0. */
+int omni_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 bf16 GEMM:  out = epi( alpha * (A . B^T  [+ K-extension blocks A2 . B2^T]) )
+ * Replaces: every nn.Linear on the path; with tile_group/ext_table it is the Omni-LoRA-adapted
+ * q/v projection (Llama_LoRA.py:246-259, Qwen_LoRA.py:557-570), the adapter picked per 128-token
+ * tile by task id.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct omni_gemm_args {
+  const void* A;   /* [M, K]  ld = lda */
+  const void* B;   /* [b_rows, K] ld = ldb ; row of B for an output tile = b_row_table ? table : n0 */
+  const void* A2;  /* [M, a2_cols] ld = lda2 (K-extension A operand, e.g. s*x.A_lora^T) */
+  const void* B2;  /* [b2_rows, b2_cols] ld = ldb2 (K-extension B operand, e.g. LoRA up weights) */
+  void* out;       /* [M, N] ld = ldo ; bf16, or fp32 if out_fp32 */
+  const void* bias;     /* [N] bf16 or NULL */
+  const void* residual; /* [M, N] ld = ldr, bf16 or NULL (added after activation) */
+  const int32_t* tile_group;  /* [ceil(M/128)] task id per M tile or NULL (=group 0) */
+  const int32_t* b_row_table; /* [groups * n_tiles] B row per (group, n_tile) or NULL */
+  const int32_t* ext_table;   /* [groups * n_tiles * n_ext][4] = {a2_col, b2_row, b2_col, 0}; b2_row<0: skip */
+  int64_t lda, ldb, lda2, ldb2, ldo, ldr;
+  int32_t M, N, K;
+  int32_t b_rows;          /* rows of B visible to the tensor map (>= N; more when grouped) */
+  int32_t a2_cols, b2_rows, b2_cols;
+  int32_t n_ext;           /* extension slots per (group, n_tile) */
+  int32_t block_n;         /* 0 = auto, else 64 / 128 / 256 (tables are indexed with this tile width) */
+  int32_t act;             /* OMNI_ACT_* */
+  int32_t out_fp32;
+  float alpha;
+} omni_gemm_args;
+
+int omni_gemm_bf16(const omni_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matryoshka compression of encoder features (truncate to n_tok, drop the remainder, pool/stack).
+ *   x   [B, t_stride_rows, D] (only the first n_tok rows of each clip are read; batch stride x_bs elements)
+ *   out [B, n_tok / rate, D]  (avg)   or   [B, n_tok / rate, rate*D]  (stack)
+ * avg: out = bf16( (sum_{i<rate} fp32(x[b, j*rate+i, :])) / rate ), sequential order -- bit-exact with
+ * transpose -> nn.AvgPool1d(rate) -> transpose  (modeling_OmniAVSR.py:537,544-546 / 469-471).
+ * ---------------------------------------------------------------------------------------------- */
+int omni_matryoshka_compress(const void* x, void* out, int32_t B, int32_t n_tok, int32_t D, int64_t x_bs,
+                             int32_t rate, int32_t mode, void* stream);
+/* backward of the avg mode: dx[b, j*rate+i, :] = bf16(fp32(dout[b,j,:]) / rate) for j < n_tok/rate, 0 for the
+ * dropped remainder rows (rows >= n_tok are not written). dx has batch stride dx_bs. */
+int omni_matryoshka_compress_bwd(const void* dout, void* dx, int32_t B, int32_t n_tok, int32_t D, int64_t dx_bs,
+                                 int32_t rate, int32_t mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prompt splice: builds the LLM input embeddings and labels of the ASR / VSR / AVSR sequences in one
+ * launch, straight into their final rows (modeling_OmniAVSR.py:270-299 + 337-395 train, :406-458 infer).
+ *   has_bos = 1 (Llama):  [X[0], A?, V?, P_t, X[1:]]       has_bos = 0 (Qwen): [A?, V?, P_t, X]
+ *   A = [e(<audio>), audio_tok[b], e(</audio>)], V likewise, P_t = prompt of task t, X = embed(tokens[b]).
+ *   labels_t = [lab[0], -100 x (P_t + media rows), lab[1:]]  (Qwen: [-100 x ..., lab]).
+ * task_mask bit0 = ASR, bit1 = VSR, bit2 = AVSR. Decode prefill = the same layout with L = 1 (Llama) / 0 (Qwen).
+ * out_t is [B, S_t, H]; S_t is implied by the lengths and returned through omni_splice_seq_len().
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct omni_splice_args {
+  const int64_t* tokens; /* [B, L] */
+  const int64_t* labels; /* [B, L] or NULL (no labels written) */
+  const void* embed;     /* [V, H] embedding table */
+  const void* audio_tok; /* [B, n_a, H] projected audio tokens or NULL */
+  const void* video_tok; /* [B, n_v, H] projected video tokens or NULL */
+  const void* prompt[3]; /* [P_t, H] per task (audio, video, audiovisual) */
+  void* out[3];          /* [B, S_t, H] per task or NULL */
+  int64_t* out_labels[3];/* [B, S_t] per task or NULL */
+  int32_t prompt_len[3];
+  int32_t B, L, H, n_a, n_v;
+  int32_t id_audio_sos, id_audio_eos, id_video_sos, id_video_eos;
+  int32_t has_bos;
+  int32_t task_mask;
+  int64_t vocab;         /* rows of embed (bounds check for token ids) */
+  int32_t* status;       /* optional device int: set to 1 when a token id is outside [0, vocab) (row zero-filled) */
+} omni_splice_args;
+
+int32_t omni_splice_seq_len(const omni_splice_args* args, int32_t task);
+int omni_splice_prompt(const omni_splice_args* args, void* stream);
+/* backward: accumulates d(audio_tok) / d(video_tok) = sum over the sequences that consumed them
+ * (own task + AVSR) from dout[3]; fp32 accumulation, bf16 result. */
+int omni_splice_prompt_bwd(const omni_splice_args* args, const void* const dout[3], void* d_audio_tok,
+                           void* d_video_tok, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNI_AVSR_H_ */

@@ -1,0 +1,101 @@
+"""ctypes binding of the C-ABI CUDA library (include/omni_avsr.h).
+
+There is no CPU fallback: if the library cannot be loaded the import raises, and every wrapper
+refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libomni_avsr.so"
+
+ERR = {-1: "bad argument", -2: "CUDA error", -3: "CUDA driver entry point unavailable", -4: "unsupported",
+       -5: "workspace too small"}
+
+
+class OmniKernelError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        from .build import build
+        build()
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m omni_avsr_b200.build` (needs nvcc)")
+    return C.CDLL(str(LIB_PATH))
+
+
+lib = _load()
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("A2", C.c_void_p), ("B2", C.c_void_p),
+        ("out", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("tile_group", C.c_void_p), ("b_row_table", C.c_void_p), ("ext_table", C.c_void_p),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("lda2", C.c_int64), ("ldb2", C.c_int64),
+        ("ldo", C.c_int64), ("ldr", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("b_rows", C.c_int32),
+        ("a2_cols", C.c_int32), ("b2_rows", C.c_int32), ("b2_cols", C.c_int32),
+        ("n_ext", C.c_int32), ("block_n", C.c_int32), ("act", C.c_int32), ("out_fp32", C.c_int32),
+        ("alpha", C.c_float),
+    ]
+
+
+class SpliceArgs(C.Structure):
+    _fields_ = [
+        ("tokens", C.c_void_p), ("labels", C.c_void_p), ("embed", C.c_void_p),
+        ("audio_tok", C.c_void_p), ("video_tok", C.c_void_p),
+        ("prompt", C.c_void_p * 3), ("out", C.c_void_p * 3), ("out_labels", C.c_void_p * 3),
+        ("prompt_len", C.c_int32 * 3),
+        ("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("n_a", C.c_int32), ("n_v", C.c_int32),
+        ("id_audio_sos", C.c_int32), ("id_audio_eos", C.c_int32),
+        ("id_video_sos", C.c_int32), ("id_video_eos", C.c_int32),
+        ("has_bos", C.c_int32), ("task_mask", C.c_int32),
+        ("vocab", C.c_int64), ("status", C.c_void_p),
+    ]
+
+
+def _sig(name, argtypes, restype=C.c_int):
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = restype
+    return fn
+
+
+_sig("omni_abi_version", [])
+_sig("omni_device_cc", [])
+_sig("omni_gemm_bf16", [C.POINTER(GemmArgs), C.c_void_p])
+_sig("omni_matryoshka_compress",
+     [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p])
+_sig("omni_matryoshka_compress_bwd",
+     [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p])
+_sig("omni_splice_seq_len", [C.POINTER(SpliceArgs), C.c_int32], C.c_int32)
+_sig("omni_splice_prompt", [C.POINTER(SpliceArgs), C.c_void_p])
+_sig("omni_splice_prompt_bwd", [C.POINTER(SpliceArgs), C.c_void_p * 3, C.c_void_p, C.c_void_p, C.c_void_p])
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise OmniKernelError(f"{what} failed: {ERR.get(rc, rc)}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise OmniKernelError("omni_avsr_b200 kernels are CUDA-only (sm_100a); got a CPU tensor — "
+                                  "there is no CPU fallback (the CPU restatement lives in oracle/ for tests only)")

@@ -1,0 +1,334 @@
+// bf16 GEMM on the sm_100a tensor cores: tcgen05.mma with TMEM accumulators, TMA-fed 128B-swizzled
+// shared-memory pipeline, warp-specialised (TMA producer / MMA issuer / 4 epilogue warps).
+//
+//   out[M,N] = epilogue( alpha * ( A[M,K] . B[rowsel(N),K]^T  +  sum_j A2[M, a2_col_j : +64] . B2[b2_row_j.., b2_col_j : +64]^T ) )
+//
+// * A, B, A2, B2 are row-major with the reduction dimension contiguous ("K-major"), i.e. exactly the
+//   nn.Linear layout (x [tokens, in], W [out, in]).
+// * tile_group[m_tile] (optional) is the task id of a 128-row tile of packed tokens; b_row_table /
+//   ext_table are indexed by (group, n_tile) and give the row of B (grouped weights) and the K-extension
+//   blocks (LoRA up-projection riding in the same TMEM accumulator) for that tile.
+//   This is how the Omni-LoRA adapter is "chosen per sample by task id"
+//   (reference semantics: Omni_AVSR/Llama_LoRA.py:246-259, Qwen_LoRA.py:557-570).
+// * epilogue: (+bias) -> round bf16 -> act -> (+residual) -> bf16 / fp32 store, mirroring the rounding
+//   points of the reference's unfused bf16 op sequence.
+#include "common.cuh"
+#include "../../include/omni_avsr.h"
+
+namespace omni {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue
+
+struct GemmKParams {
+  int M, N, K;
+  int num_k_blocks;
+  int n_tiles, m_tiles;
+  int n_ext;
+  const int* tile_group;
+  const int* b_row_table;
+  const int4* ext_table;  // {a2_col, b2_row, b2_col, unused}; b2_row < 0 => skip
+  const bf16* bias;
+  const bf16* residual;
+  void* out;
+  long long ldo, ldr;
+  int act;
+  int out_fp32;
+  float alpha;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                    const GemmKParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;
+  const int m_tile = blockIdx.y;
+  const int m0 = m_tile * BM;
+  const int n0 = n_tile * BN;
+
+  const int group = p.tile_group ? p.tile_group[m_tile] : 0;
+  const int tbl = group * p.n_tiles + n_tile;
+  const int b_row = p.b_row_table ? p.b_row_table[tbl] : n0;
+  const int4* ext = p.ext_table ? (p.ext_table + static_cast<long long>(tbl) * p.n_ext) : nullptr;
+  int n_ext_valid = 0;
+  if (ext) {
+    for (int j = 0; j < p.n_ext; ++j) n_ext_valid += (ext[j].y >= 0) ? 1 : 0;
+  }
+  const int total_iters = p.num_k_blocks + n_ext_valid;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (ext) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < p.num_k_blocks; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * S::STAGE_BYTES;
+        uint8_t* sB = sA + S::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+        tma_load_2d(&tmA, &full_bar[stage], sA, it * BK, m0);
+        tma_load_2d(&tmB, &full_bar[stage], sB, it * BK, b_row);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      for (int j = 0; j < p.n_ext; ++j) {
+        if (!ext) break;
+        const int4 e = ext[j];
+        if (e.y < 0) continue;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * S::STAGE_BYTES;
+        uint8_t* sB = sA + S::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+        tma_load_2d(&tmA2, &full_bar[stage], sA, e.x, m0);
+        tma_load_2d(&tmB2, &full_bar[stage], sB, e.z, e.y);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: lane 0 issues every tcgen05.mma and every commit =====
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < total_iters; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint32_t sB = sA + S::A_BYTES;
+        const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == total_iters - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+    const float alpha = p.alpha;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (!row_ok || col0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+      const bool full = (col0 + 32 <= p.N);
+      if (p.bias) {
+        if (full) {
+          const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 b = __ldg(bp + i);
+            float2 f;
+            f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+            f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+            f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+            f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
+        }
+      }
+      if (p.act != OMNI_ACT_NONE || p.residual) {
+        // reference rounding point: the linear's bf16 output feeds the activation / the residual add
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+        if (p.act == OMNI_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        } else if (p.act == OMNI_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_erf(v[i])));
+        }
+      }
+      if (p.residual) {
+        const bf16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
+        if (full) {
+          const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 b = ld_nc_u4(rp4 + i);
+            float2 f;
+            f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+            f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+            f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+            f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) v[i] += __bfloat162float(rp[i]);
+        }
+      }
+      if (p.out_fp32) {
+        float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) op[i] = v[i];
+        }
+      } else {
+        bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
+            o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
+            o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
+            o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(op + 8 * i) = o;
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) op[i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  int rc;
+  rc = omni_make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM, BK, 1);
+  if (rc) return rc;
+  rc = omni_make_tmap_2d_bf16(&tmB, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, BN, BK, 1);
+  if (rc) return rc;
+  if (a->ext_table) {
+    rc = omni_make_tmap_2d_bf16(&tmA2, a->A2, (uint64_t)a->M, (uint64_t)a->a2_cols, (uint64_t)a->lda2, BM, BK, 1);
+    if (rc) return rc;
+    rc = omni_make_tmap_2d_bf16(&tmB2, a->B2, (uint64_t)a->b2_rows, (uint64_t)a->b2_cols, (uint64_t)a->ldb2, BN, BK, 1);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+    tmB2 = tmB;
+  }
+  GemmKParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.num_k_blocks = ceil_div(a->K, BK);
+  p.n_tiles = ceil_div(a->N, BN);
+  p.m_tiles = ceil_div(a->M, BM);
+  p.n_ext = a->ext_table ? a->n_ext : 0;
+  p.tile_group = a->tile_group;
+  p.b_row_table = a->b_row_table;
+  p.ext_table = reinterpret_cast<const int4*>(a->ext_table);
+  p.bias = reinterpret_cast<const bf16*>(a->bias);
+  p.residual = reinterpret_cast<const bf16*>(a->residual);
+  p.out = a->out;
+  p.ldo = a->ldo; p.ldr = a->ldr;
+  p.act = a->act; p.out_fp32 = a->out_fp32; p.alpha = a->alpha;
+
+  auto kfn = gemm_bf16_tn_kernel<BN, STAGES>;
+  static bool attr_set = false;  // idempotent attribute; benign if set twice
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid(p.n_tiles, p.m_tiles, 1);
+  kfn<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+}  // namespace omni
+
+extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
+  using namespace omni;
+  OMNI_CHECK_ARG(a != nullptr);
+  OMNI_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0);
+  OMNI_CHECK_ARG(a->A && a->B && a->out);
+  OMNI_CHECK_ARG((a->lda % 8) == 0 && (a->ldb % 8) == 0 && (a->K % 8) == 0);
+  OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
+  OMNI_CHECK_ARG(a->ldo >= a->N);
+  OMNI_CHECK_ARG((a->ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0);
+  if (a->residual) OMNI_CHECK_ARG((a->ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
+  if (a->bias) OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
+  if (a->ext_table) {
+    OMNI_CHECK_ARG(a->A2 && a->B2 && a->n_ext > 0);
+    OMNI_CHECK_ARG((a->lda2 % 8) == 0 && (a->ldb2 % 8) == 0);
+  }
+  if (a->b_row_table || a->ext_table) OMNI_CHECK_ARG(a->block_n == 64 || a->block_n == 128 || a->block_n == 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int bn = a->block_n;
+  if (bn == 0) bn = (a->N <= 64) ? 64 : 128;
+  switch (bn) {
+    case 64: return launch_gemm<64, 8>(a, st);
+    case 128: return launch_gemm<128, 6>(a, st);
+    case 256: return launch_gemm<256, 4>(a, st);
+    default: return OMNI_ERR_BAD_ARG;
+  }
+}

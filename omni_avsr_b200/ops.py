@@ -1,0 +1,210 @@
+"""Raw (non-autograd) Python entry points over the C ABI.  Each function validates shapes/dtypes,
+allocates the output with torch (device memory plumbing only) and launches the sm_100a kernel on the
+current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, SpliceArgs, check, lib, ptr, require_cuda, stream_ptr
+
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+COMPRESS = {"avg-pooling": 0, "avg": 0, "stack": 1}
+
+# number of kernel launches issued through this module (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _bf16_2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"{name} must be bfloat16, got {t.dtype}")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D, got {tuple(t.shape)}")
+    if t.stride(1) != 1:
+        raise ValueError(f"{name} must have unit stride in the last dim")
+    return t
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+         residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
+         alpha: float = 1.0, n: Optional[int] = None, tile_group: Optional[torch.Tensor] = None,
+         b_row_table: Optional[torch.Tensor] = None, ext: Optional[tuple] = None, block_n: int = 0) -> torch.Tensor:
+    """out[M,N] = epi(alpha * (a[M,K] @ b[rows,K]^T (+ K-extension)))  -- tcgen05 kernel.
+
+    ext = (a2 [M, a2_cols], b2 [b2_rows, b2_cols], ext_table int32 [groups, n_tiles, n_ext, 4]).
+    """
+    require_cuda(a, b, bias, residual, out, tile_group, b_row_table)
+    a = _bf16_2d(a, "a")
+    b = _bf16_2d(b, "b")
+    M, K = a.shape
+    if b.shape[1] != K:
+        raise ValueError(f"K mismatch: a {tuple(a.shape)} vs b {tuple(b.shape)}")
+    N = int(n) if n is not None else b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    if out.dim() != 2 or out.shape[0] != M or out.shape[1] != N or out.stride(1) != 1:
+        raise ValueError("bad out tensor")
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("out must be bf16 or fp32")
+    g = GemmArgs()
+    g.A, g.B, g.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), out.stride(0)
+    g.M, g.N, g.K = M, N, K
+    g.b_rows = b.shape[0]
+    if bias is not None:
+        if bias.dtype != torch.bfloat16 or bias.numel() < N:
+            raise ValueError("bias must be bf16 [N]")
+        g.bias = bias.data_ptr()
+    if residual is not None:
+        residual = _bf16_2d(residual, "residual")
+        if residual.shape[0] != M or residual.shape[1] != N:
+            raise ValueError("residual shape mismatch")
+        g.residual, g.ldr = residual.data_ptr(), residual.stride(0)
+    if tile_group is not None:
+        if tile_group.dtype != torch.int32 or tile_group.numel() < (M + 127) // 128:
+            raise ValueError("tile_group must be int32 [ceil(M/128)]")
+        g.tile_group = tile_group.data_ptr()
+    if b_row_table is not None:
+        if b_row_table.dtype != torch.int32:
+            raise ValueError("b_row_table must be int32")
+        g.b_row_table = b_row_table.data_ptr()
+    if ext is not None:
+        a2, b2, table = ext
+        require_cuda(a2, b2, table)
+        a2 = _bf16_2d(a2, "a2")
+        b2 = _bf16_2d(b2, "b2")
+        if table.dtype != torch.int32 or table.shape[-1] != 4 or not table.is_contiguous():
+            raise ValueError("ext_table must be contiguous int32 [..., n_ext, 4]")
+        if a2.shape[0] != M:
+            raise ValueError("a2 rows must equal M")
+        g.A2, g.B2, g.ext_table = a2.data_ptr(), b2.data_ptr(), table.data_ptr()
+        g.lda2, g.ldb2 = a2.stride(0), b2.stride(0)
+        g.a2_cols, g.b2_rows, g.b2_cols = a2.shape[1], b2.shape[0], b2.shape[1]
+        g.n_ext = table.shape[-2]
+    g.block_n = block_n
+    g.act = ACT[act]
+    g.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    g.alpha = float(alpha)
+    check(lib.omni_gemm_bf16(C.byref(g), stream_ptr()), "omni_gemm_bf16")
+    _count()
+    return out
+
+
+def matryoshka_compress(x: torch.Tensor, n_tok: int, rate: int, mode: str = "avg-pooling") -> torch.Tensor:
+    """x [B, T>=n_tok, D] bf16 -> [B, n_tok//rate, D] (avg) / [B, n_tok//rate, rate*D] (stack)."""
+    require_cuda(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 3 or x.stride(2) != 1 or x.stride(1) != x.shape[2]:
+        raise ValueError("x must be bf16 [B, T, D] with contiguous rows")
+    B, T, D = x.shape
+    if n_tok > T:
+        raise ValueError("n_tok exceeds T")
+    m = COMPRESS[mode]
+    n_out = n_tok // rate
+    out = torch.empty((B, n_out, D if m == 0 else D * rate), device=x.device, dtype=torch.bfloat16)
+    if n_out > 0:
+        check(lib.omni_matryoshka_compress(x.data_ptr(), out.data_ptr(), B, n_tok, D, x.stride(0), rate, m,
+                                           stream_ptr()), "omni_matryoshka_compress")
+        _count()
+    return out
+
+
+def matryoshka_compress_bwd(dout: torch.Tensor, n_tok: int, t_full: int, rate: int, mode: str) -> torch.Tensor:
+    """Gradient wrt the [B, t_full, D] encoder output (rows >= n_tok get zero)."""
+    require_cuda(dout)
+    m = COMPRESS[mode]
+    B, n_out = dout.shape[0], dout.shape[1]
+    D = dout.shape[2] if m == 0 else dout.shape[2] // rate
+    dout = dout.contiguous()
+    dx = torch.empty((B, t_full, D), device=dout.device, dtype=torch.bfloat16)
+    if t_full > n_tok:
+        dx[:, n_tok:].zero_()
+    check(lib.omni_matryoshka_compress_bwd(dout.data_ptr(), dx.data_ptr(), B, n_tok, D, dx.stride(0), rate, m,
+                                           stream_ptr()), "omni_matryoshka_compress_bwd")
+    _count()
+    return dx
+
+
+class SpliceLayout:
+    """Host-side description of one splice call (mirrors omni_splice_args)."""
+
+    def __init__(self, *, tokens, labels, embed, audio_tok, video_tok, prompts: Sequence[torch.Tensor],
+                 marker_ids: Sequence[int], has_bos: bool, task_mask: int = 7):
+        require_cuda(tokens, labels, embed, audio_tok, video_tok, *prompts)
+        self.keep = (tokens, labels, embed, audio_tok, video_tok, tuple(prompts))
+        a = SpliceArgs()
+        B, L = tokens.shape
+        H = embed.shape[1]
+        if tokens.dtype != torch.int64 or not tokens.is_contiguous():
+            raise ValueError("tokens must be contiguous int64 [B, L]")
+        if labels is not None and (labels.dtype != torch.int64 or not labels.is_contiguous() or labels.shape != tokens.shape):
+            raise ValueError("labels must be contiguous int64 [B, L]")
+        if embed.dtype != torch.bfloat16 or not embed.is_contiguous():
+            raise ValueError("embed must be contiguous bf16 [V, H]")
+        for name, t in (("audio_tok", audio_tok), ("video_tok", video_tok)):
+            if t is not None and (t.dtype != torch.bfloat16 or not t.is_contiguous() or t.shape[0] != B or t.shape[2] != H):
+                raise ValueError(f"{name} must be contiguous bf16 [B, n, H]")
+        a.tokens, a.labels, a.embed = ptr(tokens) if L > 0 else None, ptr(labels) if L > 0 else None, ptr(embed)
+        a.audio_tok, a.video_tok = ptr(audio_tok), ptr(video_tok)
+        for t in range(3):
+            p = prompts[t]
+            if p is not None:
+                if p.dtype != torch.bfloat16 or not p.is_contiguous() or p.shape[-1] != H:
+                    raise ValueError("prompt must be contiguous bf16 [P, H]")
+                a.prompt[t] = p.data_ptr()
+                a.prompt_len[t] = p.shape[-2]
+        a.B, a.L, a.H = B, L, H
+        a.n_a = audio_tok.shape[1] if audio_tok is not None else 0
+        a.n_v = video_tok.shape[1] if video_tok is not None else 0
+        a.id_audio_sos, a.id_audio_eos, a.id_video_sos, a.id_video_eos = [int(i) for i in marker_ids]
+        a.has_bos = 1 if has_bos else 0
+        a.task_mask = task_mask
+        a.vocab = embed.shape[0]
+        self.args = a
+        self.B, self.H = B, H
+        self.seq_len = [int(lib.omni_splice_seq_len(C.byref(a), t)) if (task_mask >> t) & 1 else 0 for t in range(3)]
+
+
+def splice_prompt(layout: SpliceLayout, outs: Sequence[Optional[torch.Tensor]],
+                  out_labels: Sequence[Optional[torch.Tensor]], status: Optional[torch.Tensor] = None) -> None:
+    a = layout.args
+    for t in range(3):
+        o, l = outs[t], out_labels[t]
+        if o is not None:
+            require_cuda(o)
+            if o.dtype != torch.bfloat16 or not o.is_contiguous() or o.numel() != layout.B * layout.seq_len[t] * layout.H:
+                raise ValueError(f"out[{t}] must be contiguous bf16 [B, S_t, H]")
+        if l is not None:
+            require_cuda(l)
+            if l.dtype != torch.int64 or not l.is_contiguous() or l.numel() != layout.B * layout.seq_len[t]:
+                raise ValueError(f"out_labels[{t}] must be contiguous int64 [B, S_t]")
+        a.out[t] = ptr(o)
+        a.out_labels[t] = ptr(l)
+    a.status = ptr(status)
+    check(lib.omni_splice_prompt(C.byref(a), stream_ptr()), "omni_splice_prompt")
+    _count()
+
+
+def splice_prompt_bwd(layout: SpliceLayout, douts: Sequence[Optional[torch.Tensor]], want_audio: bool,
+                      want_video: bool):
+    a = layout.args
+    d = (C.c_void_p * 3)()
+    for t in range(3):
+        if douts[t] is not None:
+            require_cuda(douts[t])
+            if not douts[t].is_contiguous() or douts[t].dtype != torch.bfloat16:
+                raise ValueError("dout must be contiguous bf16")
+            d[t] = douts[t].data_ptr()
+    dev = layout.keep[2].device
+    da = torch.empty((layout.B, a.n_a, layout.H), device=dev, dtype=torch.bfloat16) if want_audio else None
+    dv = torch.empty((layout.B, a.n_v, layout.H), device=dev, dtype=torch.bfloat16) if want_video else None
+    check(lib.omni_splice_prompt_bwd(C.byref(a), d, ptr(da), ptr(dv), stream_ptr()), "omni_splice_prompt_bwd")
+    _count()
+    return da, dv

@@ -1,0 +1,108 @@
+"""Micro-benchmarks of the individual kernels (CUDA events, L2 flushed between iterations).
+Usage: python tools/bench_kernels.py [gemm] [compress] [splice]   -> JSON lines on stdout."""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, __file__.rsplit("/tools/", 1)[0])
+from omni_avsr_b200 import ops  # noqa: E402
+
+PEAKS = {"hbm_gbs": 6543.7, "bf16_tflops": 1675.7}
+try:
+    PEAKS.update(json.load(open(__file__.rsplit("/tools/", 1)[0] + "/MEASURED_PEAKS.json")))
+except Exception:
+    pass
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def timeit(fn, iters=20, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_gemm():
+    shapes = [(4096, 3072, 2048), (4096, 2048, 2048), (4096, 16384, 2048), (4096, 2048, 8192), (8192, 8192, 8192),
+              (15616, 3072, 2048), (2304, 128256, 2048), (64, 3072, 2048)]
+    for M, N, K in shapes:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        b = torch.randn(N, K, device="cuda").bfloat16()
+        for bn in (128, 256):
+            med, best = timeit(lambda: ops.gemm(a, b, block_n=bn))
+            tf = 2.0 * M * N * K / (med * 1e-3) / 1e12
+            print(json.dumps({"kernel": "gemm_tcgen05", "M": M, "N": N, "K": K, "block_n": bn, "ms": round(med, 4),
+                              "ms_best": round(best, 4), "tflops": round(tf, 1),
+                              "frac_of_measured_peak": round(tf / PEAKS["bf16_tflops"], 3)}), flush=True)
+        med, best = timeit(lambda: torch.matmul(a, b.t()))
+        tf = 2.0 * M * N * K / (med * 1e-3) / 1e12
+        print(json.dumps({"kernel": "torch.matmul(cuBLAS)", "M": M, "N": N, "K": K, "ms": round(med, 4),
+                          "tflops": round(tf, 1)}), flush=True)
+
+
+def bench_compress():
+    for B, T, n_tok, D, rate in [(64, 1500, 800, 1024, 4), (64, 1500, 800, 1024, 16), (64, 400, 400, 1024, 2),
+                                 (64, 400, 400, 1024, 5)]:
+        x = torch.randn(B, T, D, device="cuda").bfloat16()
+        for mode in ("avg-pooling", "stack"):
+            med, best = timeit(lambda: ops.matryoshka_compress(x, n_tok, rate, mode))
+            n_out = n_tok // rate
+            byts = B * n_out * rate * D * 2 + B * n_out * (D if mode != "stack" else D * rate) * 2
+            gbs = byts / (med * 1e-3) / 1e9
+            print(json.dumps({"kernel": "matryoshka_compress", "mode": mode, "B": B, "n_tok": n_tok, "rate": rate,
+                              "ms": round(med, 4), "GBs": round(gbs, 1),
+                              "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3)}), flush=True)
+
+
+def bench_splice():
+    H, V, L = 2048, 128261, 48
+    for B, n_a, n_v in [(64, 200, 200), (64, 50, 80), (16, 200, 200)]:
+        embed = torch.randn(V, H, device="cuda").bfloat16()
+        tokens = torch.randint(0, V, (B, L), device="cuda")
+        a = torch.randn(B, n_a, H, device="cuda").bfloat16()
+        v = torch.randn(B, n_v, H, device="cuda").bfloat16()
+        prompts = [torch.randn(p, H, device="cuda").bfloat16() for p in (6, 6, 8)]
+        lay = ops.SpliceLayout(tokens=tokens, labels=tokens, embed=embed, audio_tok=a, video_tok=v, prompts=prompts,
+                               marker_ids=(V - 4, V - 3, V - 2, V - 1), has_bos=True)
+        outs = [torch.empty(B, s, H, device="cuda", dtype=torch.bfloat16) for s in lay.seq_len]
+        outl = [torch.empty(B, s, device="cuda", dtype=torch.int64) for s in lay.seq_len]
+        med, best = timeit(lambda: ops.splice_prompt(lay, outs, outl))
+        rows = B * sum(lay.seq_len)
+        # algorithmic bytes: every destination row written once (H*2) + its source row read once, media rows
+        # are read once but written twice (own task + AVSR)  => reads = unique source rows
+        uniq = B * (n_a + n_v) + B * (L + 4 + 4) + 20
+        byts = rows * H * 2 + rows * 8 + (B * (n_a + n_v) + rows - 2 * B * (n_a + n_v)) * H * 2
+        gbs = byts / (med * 1e-3) / 1e9
+        print(json.dumps({"kernel": "splice_prompt", "B": B, "n_a": n_a, "n_v": n_v, "rows": rows,
+                          "ms": round(med, 4), "GBs": round(gbs, 1),
+                          "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3)}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "compress", "splice"]
+    if "compress" in which:
+        bench_compress()
+    if "splice" in which:
+        bench_splice()
+    if "gemm" in which:
+        bench_gemm()
