@@ -108,6 +108,9 @@ def matryoshka_compress(x: torch.Tensor, n_tok: int, rate: int, mode: str = "avg
         raise ValueError("n_tok exceeds T")
     m = COMPRESS[mode]
     n_out = n_tok // rate
+    if m == 0 and n_out == 0:
+        # same failure as nn.AvgPool1d in the reference (modeling_OmniAVSR.py:545)
+        raise RuntimeError(f"Given input size: ({D}x1x{n_tok}). Calculated output size: ({D}x1x0). Output size is too small")
     out = torch.empty((B, n_out, D if m == 0 else D * rate), device=x.device, dtype=torch.bfloat16)
     if n_out > 0:
         check(lib.omni_matryoshka_compress(x.data_ptr(), out.data_ptr(), B, n_tok, D, x.stride(0), rate, m,
