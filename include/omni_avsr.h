@@ -113,6 +113,56 @@ int omni_splice_prompt(const omni_splice_args* args, void* stream);
 int omni_splice_prompt_bwd(const omni_splice_args* args, const void* const dout[3], void* d_audio_tok,
                            void* d_video_tok, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row kernels of the decoder / encoder blocks (all bf16 in/out, fp32 statistics).
+ * Replace the transformers==4.43.1 ops reached from Llama_LoRA.py:624,643-644 (RMSNorm), :277 (RoPE),
+ * LlamaMLP (SwiGLU), and the fairseq LayerNorm/GELU of the AV-HuBERT blocks
+ * (av_hubert/fairseq/fairseq/models/wav2vec/wav2vec2.py:979-1006).
+ * ---------------------------------------------------------------------------------------------- */
+/* y = w * bf16(x * rsqrt(mean(x^2)+eps)); rstd [rows] fp32 is optional (needed by the backward). */
+int omni_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int32_t H, int64_t ldx,
+                     int64_t ldy, float eps, void* stream);
+/* dx = rstd*(dy*w - xhat*mean(dy*w*xhat)) (+ dx_add if given); x, dy, dx contiguous [rows, H]. */
+int omni_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, const void* dx_add,
+                     int64_t rows, int32_t H, void* stream);
+int omni_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t rows,
+                       int32_t H, int64_t ldx, int64_t ldy, float eps, void* stream);
+int omni_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                       const void* dx_add, int64_t rows, int32_t H, void* stream);
+/* In-place rotary embedding of the first n_heads_total heads of every row of a packed [rows, ld] q|k|v buffer;
+ * cos/sin are bf16 tables [max_pos, head_dim], pos [rows] int32. inverse=1 applies the transposed rotation. */
+int omni_rope(void* qkv, const void* cos_t, const void* sin_t, const int32_t* pos, int64_t rows, int64_t ld,
+              int32_t n_heads_total, int32_t head_dim, int32_t inverse, void* stream);
+/* gu [rows, 2I] = [gate | up] -> act [rows, I] = bf16(bf16(silu(gate)) * up), and its backward. */
+int omni_swiglu_fwd(const void* gu, void* act, int64_t rows, int32_t I, void* stream);
+int omni_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, void* stream);
+int omni_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
+int omni_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
+/* out[i,:] = table[idx[i],:] (embed_tokens of the decode step, label-row selection); status as in the splice. */
+int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
+                     int64_t table_rows, int32_t* status, void* stream);
+/* out[idx[i],:] = src[i,:] for unique idx. */
+int omni_scatter_rows(const void* src, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss / decode head / optimizer.
+ * omni_ce_*: `logits.float()` + CrossEntropyLoss (Llama_LoRA.py:373-386) on the label rows only:
+ *   loss[r] = logsumexp(logits[r]) - logits[r, target[r]]  (0 for ignore_index); the backward overwrites the
+ *   logits with bf16((softmax - onehot) * scale[r]).
+ * omni_argmax: greedy token choice of HF generate (modeling_OmniAVSR.py:313-322 with num_beams=1).
+ * omni_sumsq + omni_adamw: gradient_clip_val (train_OmniAVSR.py:53) + AdamW (lightning_OmniAVSR.py:153) fused
+ *   over the flat trainable buffer: grad scaled by grad_scale*min(1, max_norm/(grad_scale*sqrt(*sumsq)+1e-6)).
+ * ---------------------------------------------------------------------------------------------- */
+int omni_ce_fwd(const void* logits, const int64_t* targets, float* loss, float* lse, int64_t rows, int32_t V,
+                int64_t ld, int64_t ignore_index, void* stream);
+int omni_ce_bwd(void* logits, const int64_t* targets, const float* lse, const float* scale, int64_t rows, int32_t V,
+                int64_t ld, int64_t ignore_index, void* stream);
+int omni_argmax(const void* logits, int64_t* out, int64_t rows, int32_t V, int64_t ld, void* stream);
+int omni_sumsq(const void* g, int64_t n, float* acc, void* stream);
+int omni_adamw(void* p, const void* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int32_t step, float grad_scale, float max_norm, const float* sumsq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,34 @@ _sig("omni_splice_prompt", [C.POINTER(SpliceArgs), C.c_void_p])
 _sig("omni_splice_prompt_bwd", [C.POINTER(SpliceArgs), C.c_void_p * 3, C.c_void_p, C.c_void_p, C.c_void_p])
 
 
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_sig("omni_rmsnorm_fwd", [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _F, _P])
+_sig("omni_rmsnorm_bwd", [_P, _P, _P, _P, _P, _P, _I64, _I32, _P])
+_sig("omni_layernorm_fwd", [_P, _P, _P, _P, _P, _P, _I64, _I32, _I64, _I64, _F, _P])
+_sig("omni_layernorm_bwd", [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P])
+_sig("omni_rope", [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P])
+_sig("omni_swiglu_fwd", [_P, _P, _I64, _I32, _P])
+_sig("omni_swiglu_bwd", [_P, _P, _P, _I64, _I32, _P])
+_sig("omni_gelu_fwd", [_P, _P, _I64, _P])
+_sig("omni_gelu_bwd", [_P, _P, _P, _I64, _P])
+_sig("omni_gather_rows", [_P, _P, _P, _I64, _I32, _I64, _I64, _P, _P])
+_sig("omni_scatter_rows", [_P, _P, _P, _I64, _I32, _I64, _P])
+_sig("omni_ce_fwd", [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P])
+_sig("omni_ce_bwd", [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P])
+_sig("omni_argmax", [_P, _P, _I64, _I32, _I64, _P])
+_sig("omni_sumsq", [_P, _I64, _P, _P])
+_sig("omni_adamw", [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _F, _P, _P])
+
+# every symbol include/omni_avsr.h declares (tests/test_abi.py checks the header against this list and the .so)
+EXPORTS = [
+    "omni_abi_version", "omni_device_cc", "omni_gemm_bf16", "omni_matryoshka_compress",
+    "omni_matryoshka_compress_bwd", "omni_splice_seq_len", "omni_splice_prompt", "omni_splice_prompt_bwd",
+    "omni_rmsnorm_fwd", "omni_rmsnorm_bwd", "omni_layernorm_fwd", "omni_layernorm_bwd", "omni_rope",
+    "omni_swiglu_fwd", "omni_swiglu_bwd", "omni_gelu_fwd", "omni_gelu_bwd", "omni_gather_rows", "omni_scatter_rows",
+    "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw",
+]
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise OmniKernelError(f"{what} failed: {ERR.get(rc, rc)}")

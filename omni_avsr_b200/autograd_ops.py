@@ -1,0 +1,212 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (forward AND backward run our kernels; torch only
+owns the device buffers and the autograd tape).  All tensors are 2-D [rows, features] bf16 on CUDA."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class FrozenLinearFn(torch.autograd.Function):
+    """y = x @ W^T (+bias) (+residual) with a FROZEN weight; backward dx = dy @ W via the pre-transposed copy WT."""
+
+    @staticmethod
+    def forward(ctx, x, W, WT, bias, residual, block_n):
+        ctx.WT = WT
+        ctx.block_n = block_n
+        ctx.has_res = residual is not None
+        return ops.gemm(x, W, bias=bias, residual=residual, block_n=block_n)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = ops.gemm(dy, ctx.WT, block_n=ctx.block_n) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, (dy if ctx.has_res else None), None
+
+
+def frozen_linear(x, W, WT, bias=None, residual=None, block_n=0):
+    if not (x.requires_grad or (residual is not None and residual.requires_grad)):
+        return ops.gemm(x, W, bias=bias, residual=residual, block_n=block_n)
+    return FrozenLinearFn.apply(x, W, WT, bias, residual, block_n)
+
+
+class TrainableLinearFn(torch.autograd.Function):
+    """Projector linear: y = act(x @ W^T + b); W, b trainable.  dx via our GEMM on W^T (transposed per call, the
+    weight changes every step); dW = dy^T x is a reduction over tokens (small) -- library GEMM for now."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        y = ops.gemm(x, W, bias=b, act=act)
+        ctx.save_for_backward(x, W, y if act == "relu" else None)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.act == "relu":
+            dy = dy * (y > 0)
+        dx = ops.gemm(dy, W.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dW = torch.matmul(dy.t(), x)          # TODO(round 2): MN-major tcgen05 wgrad kernel
+        db = dy.sum(0, dtype=torch.float32).to(dy.dtype)
+        return dx, dW, db, None
+
+
+class RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        y, rstd = ops.rmsnorm_fwd(x, w, eps, want_rstd=True)
+        ctx.save_for_backward(x, w, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, rstd = ctx.saved_tensors
+        return ops.rmsnorm_bwd(dy, x, w, rstd), None, None
+
+
+def rmsnorm(x, w, eps):
+    if not x.requires_grad:
+        return ops.rmsnorm_fwd(x, w, eps)
+    return RMSNormFn.apply(x, w, eps)
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, eps, want_stats=True)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        return ops.layernorm_bwd(dy, x, w, mean, rstd), None, None, None
+
+
+def layernorm(x, w, b, eps):
+    if not x.requires_grad:
+        return ops.layernorm_fwd(x, w, b, eps)
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+class RopeFn(torch.autograd.Function):
+    """RoPE applied in place on the q|k heads of the packed qkv buffer (the input buffer is consumed)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos_t, sin_t, pos, n_heads_total, head_dim):
+        ctx.save_for_backward(cos_t, sin_t, pos)
+        ctx.meta = (n_heads_total, head_dim)
+        ctx.mark_dirty(qkv)
+        ops.rope_(qkv, cos_t, sin_t, pos, n_heads_total, head_dim)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, d):
+        cos_t, sin_t, pos = ctx.saved_tensors
+        d = d.clone(memory_format=torch.contiguous_format)
+        ops.rope_(d, cos_t, sin_t, pos, ctx.meta[0], ctx.meta[1], inverse=True)
+        return d, None, None, None, None, None
+
+
+class SwigluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gu):
+        ctx.save_for_backward(gu)
+        return ops.swiglu_fwd(gu)
+
+    @staticmethod
+    def backward(ctx, dact):
+        (gu,) = ctx.saved_tensors
+        return ops.swiglu_bwd(dact, gu)
+
+
+def swiglu(gu):
+    return SwigluFn.apply(gu) if gu.requires_grad else ops.swiglu_fwd(gu)
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.gelu_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_bwd(dy, x)
+
+
+def gelu(x):
+    return GeluFn.apply(x) if x.requires_grad else ops.gelu_fwd(x)
+
+
+class LoraLinearFn(torch.autograd.Function):
+    """Omni-LoRA adapted fused projection (q|k|v of the LLM, or q|k|v of an AV-HuBERT block):
+
+        T   = s * h @ down[sel(task)]^T                   (phase 1, grouped tcgen05 GEMM, N = n_active*2*rp)
+        out = h @ W^T (+bias) + T_q @ up_q[sel]^T (Q cols) + T_v @ up_v[sel]^T (V cols)   (phase 2: K-extension)
+
+    Reference math: Llama_LoRA.py:246-259 / Qwen_LoRA.py:557-570 / multihead_attention.py:485-494.
+    `plan` carries the static tables (see LoraPlan)."""
+
+    @staticmethod
+    def forward(ctx, h, W, WT, bias, down, up, rows, plan):
+        tile_group = rows.tile_group
+        T = ops.gemm(h, down, n=plan.t_cols, alpha=plan.scaling, tile_group=tile_group, b_row_table=plan.brow_fwd,
+                     block_n=64)
+        out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd), block_n=plan.block_n)
+        ctx.save_for_backward(h, T, down, up)
+        ctx.WT, ctx.plan, ctx.rows = WT, plan, rows
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, T, down, up = ctx.saved_tensors
+        plan, tile_group = ctx.plan, ctx.rows.tile_group
+        dout = dout.contiguous()
+        M = h.shape[0]
+        # dT' = s * dOut_{q|v} @ up[sel]   (two grouped GEMMs on the transposed up-projections)
+        upT_q, upT_v = plan.transposed_up(up)
+        dT = torch.empty((M, plan.t_cols), device=h.device, dtype=torch.bfloat16)
+        half = plan.t_cols // 2
+        ops.gemm(dout[:, : plan.q_cols], upT_q, out=dT[:, :half], n=half, alpha=plan.scaling, tile_group=tile_group,
+                 b_row_table=plan.brow_bwd, block_n=64)
+        v0 = plan.v_col0
+        ops.gemm(dout[:, v0: v0 + plan.v_cols], upT_v, out=dT[:, half:], n=half, alpha=plan.scaling,
+                 tile_group=tile_group, b_row_table=plan.brow_bwd, block_n=64)
+        # dh = dOut @ W + dT' @ down[sel]   (K-extension again)
+        dh = None
+        if ctx.needs_input_grad[0]:
+            downT = down.t().contiguous()
+            dh = ops.gemm(dout, ctx.WT, tile_group=tile_group, ext=(dT, downT, plan.ext_bwd), block_n=plan.block_n_bwd)
+        # weight gradients: reductions over the tokens of each task (TODO(round 2): MN-major tcgen05 wgrad)
+        d_down = torch.zeros_like(down)
+        d_up = torch.zeros_like(up)
+        plan.accumulate_wgrads(d_down, d_up, h, T, dT, dout, ctx.rows.runs)
+        return dh, None, None, None, d_down, d_up, None, None
+
+
+class LmHeadCEFn(torch.autograd.Function):
+    """lm_head + fp32 cross-entropy evaluated ONLY on the rows whose shifted label is not ignore_index
+    (identical loss to Llama_LoRA.py:372-386: ignored rows contribute nothing to the mean)."""
+
+    @staticmethod
+    def forward(ctx, hrows, W, WT, targets, row_scale):
+        # logits of the label rows, bf16 (as lm_head produces them before `.float()`)
+        logits = ops.gemm(hrows, W, block_n=256 if W.shape[0] >= 256 else 0)
+        loss_rows, lse = ops.ce_fwd(logits, targets)
+        ctx.save_for_backward(logits, targets, lse, row_scale)
+        ctx.WT = WT
+        return (loss_rows * row_scale).sum()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, targets, lse, row_scale = ctx.saved_tensors
+        scale = (row_scale * dloss.float()).contiguous()
+        ops.ce_bwd_(logits, targets, lse, scale)        # in place: logits -> dlogits
+        dh = ops.gemm(logits, ctx.WT, block_n=256)
+        return dh, None, None, None, None

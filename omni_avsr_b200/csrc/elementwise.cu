@@ -1,0 +1,483 @@
+// HBM-bound row kernels of the LLM / encoder blocks: RMSNorm, LayerNorm, RoPE, SwiGLU, GELU, row gather.
+// One warp owns one row (16-byte vector accesses, lanes interleaved over 16-byte chunks), reductions by
+// shuffles; every kernel mirrors the bf16 rounding points of the reference's unfused torch op sequence.
+//
+// Reference semantics (third-party transformers==4.43.1 classes used by Omni_AVSR/Llama_LoRA.py:12, Qwen_LoRA.py:7):
+//   LlamaRMSNorm / Qwen2RMSNorm, apply_rotary_pos_emb (Llama_LoRA.py:277), LlamaMLP (SwiGLU),
+//   fairseq LayerNorm + gelu (av_hubert/fairseq/fairseq/modules/{layer_norm,gelu}.py), WhisperEncoderLayer LN/GELU.
+#include "common.cuh"
+#include "../../include/omni_avsr.h"
+
+namespace omni {
+
+constexpr int EW_THREADS = 256;
+constexpr int EW_WARPS = EW_THREADS / 32;
+
+static int rows_grid(long long rows) {
+  long long blocks = ceil_div_ll(rows, EW_WARPS);
+  const long long cap = static_cast<long long>(kNumSMs) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = bf2_to_f2(u.x); f[0] = t.x; f[1] = t.y;
+  t = bf2_to_f2(u.y); f[2] = t.x; f[3] = t.y;
+  t = bf2_to_f2(u.z); f[4] = t.x; f[5] = t.y;
+  t = bf2_to_f2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = f2_to_bf2(f[0], f[1]); o.y = f2_to_bf2(f[2], f[3]);
+  o.z = f2_to_bf2(f[4], f[5]); o.w = f2_to_bf2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm:  y = w * bf16(x * rsqrt(mean(x^2) + eps))     (fp32 statistics)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                   float* __restrict__ rstd_out, long long rows, int H8, long long ldx, long long ldy, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = wg; r < rows; r += nw) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
+    float ss = 0.f;
+    for (int c = lane; c < H8; c += 32) {
+      float f[8];
+      unpack8(__ldg(xr + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(H8 * 8) + eps);
+    if (lane == 0 && rstd_out) rstd_out[r] = rstd;
+    uint4* yr = reinterpret_cast<uint4*>(y + r * ldy);
+    for (int c = lane; c < H8; c += 32) {
+      float f[8], g[8];
+      unpack8(__ldg(xr + c), f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = g[i] * rbf(f[i] * rstd);
+      yr[c] = pack8(f);
+    }
+  }
+}
+
+// dx = rstd * (g - xhat * mean(g * xhat)),  g = dy * w, xhat = x * rstd   (weights are frozen: no dw)
+__global__ void __launch_bounds__(EW_THREADS)
+rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                   const float* __restrict__ rstd_in, bf16* __restrict__ dx, const bf16* __restrict__ dx_add,
+                   long long rows, int H8) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float invH = 1.0f / static_cast<float>(H8 * 8);
+  for (long long r = wg; r < rows; r += nw) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x) + r * H8;
+    const uint4* dr = reinterpret_cast<const uint4*>(dy) + r * H8;
+    const float rstd = rstd_in[r];
+    float dot = 0.f;
+    for (int c = lane; c < H8; c += 32) {
+      float f[8], d[8], g[8];
+      unpack8(__ldg(xr + c), f);
+      unpack8(__ldg(dr + c), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot += d[i] * g[i] * f[i] * rstd;
+    }
+    dot = warp_sum(dot) * invH;
+    uint4* outr = reinterpret_cast<uint4*>(dx) + r * H8;
+    for (int c = lane; c < H8; c += 32) {
+      float f[8], d[8], g[8], a[8];
+      unpack8(__ldg(xr + c), f);
+      unpack8(__ldg(dr + c), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+      if (dx_add) unpack8(__ldg(reinterpret_cast<const uint4*>(dx_add) + r * H8 + c), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = rstd * (d[i] * g[i] - f[i] * rstd * dot);
+        if (dx_add) v += a[i];
+        f[i] = v;
+      }
+      outr[c] = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (fp32 statistics, eps inside sqrt), affine w/b:  y = bf16( (x-mean)*rstd * w + b )
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     long long rows, int H8, long long ldx, long long ldy, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float invH = 1.0f / static_cast<float>(H8 * 8);
+  for (long long r = wg; r < rows; r += nw) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
+    float s = 0.f;
+    for (int c = lane; c < H8; c += 32) {
+      float f[8];
+      unpack8(__ldg(xr + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[i];
+    }
+    const float mean = warp_sum(s) * invH;
+    float v = 0.f;
+    for (int c = lane; c < H8; c += 32) {
+      float f[8];
+      unpack8(__ldg(xr + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[i] - mean; v += d * d; }
+    }
+    const float rstd = rsqrtf(warp_sum(v) * invH + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+    uint4* yr = reinterpret_cast<uint4*>(y + r * ldy);
+    for (int c = lane; c < H8; c += 32) {
+      float f[8], g[8], bb[8];
+      unpack8(__ldg(xr + c), f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(b) + c), bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * g[i] + bb[i];
+      yr[c] = pack8(f);
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*w   (frozen affine: no dw/db)
+__global__ void __launch_bounds__(EW_THREADS)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dx,
+                     const bf16* __restrict__ dx_add, long long rows, int H8) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float invH = 1.0f / static_cast<float>(H8 * 8);
+  for (long long r = wg; r < rows; r += nw) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x) + r * H8;
+    const uint4* dr = reinterpret_cast<const uint4*>(dy) + r * H8;
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < H8; c += 32) {
+      float f[8], d[8], g[8];
+      unpack8(__ldg(xr + c), f);
+      unpack8(__ldg(dr + c), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gi = d[i] * g[i];
+        s1 += gi;
+        s2 += gi * (f[i] - mean) * rstd;
+      }
+    }
+    s1 = warp_sum(s1) * invH;
+    s2 = warp_sum(s2) * invH;
+    uint4* outr = reinterpret_cast<uint4*>(dx) + r * H8;
+    for (int c = lane; c < H8; c += 32) {
+      float f[8], d[8], g[8], a[8];
+      unpack8(__ldg(xr + c), f);
+      unpack8(__ldg(dr + c), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
+      if (dx_add) unpack8(__ldg(reinterpret_cast<const uint4*>(dx_add) + r * H8 + c), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = rstd * (d[i] * g[i] - s1 - (f[i] - mean) * rstd * s2);
+        if (dx_add) v += a[i];
+        f[i] = v;
+      }
+      outr[c] = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE on the q and k parts of a packed [rows, ld] qkv buffer, in place.
+//   out = bf16( bf16(x*cos) + bf16(rotate_half(x)*sin) ),  cos/sin bf16 tables [max_pos, head_dim]
+// inverse = 1 applies the transposed rotation (backward).
+// one thread = 8 consecutive dims of the first half of one head (and their partners in the second half)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+            const int* __restrict__ pos, long long rows, long long ld, int n_heads_total, int head_dim, int inverse,
+            long long total) {
+  const int half8 = head_dim / 16;  // 16-byte chunks in half a head
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % half8);
+    const long long t = idx / half8;
+    const int h = static_cast<int>(t % n_heads_total);
+    const long long r = t / n_heads_total;
+    const int p = pos[r];
+    bf16* base = qkv + r * ld + static_cast<long long>(h) * head_dim;
+    uint4* p1 = reinterpret_cast<uint4*>(base) + c;
+    uint4* p2 = reinterpret_cast<uint4*>(base + head_dim / 2) + c;
+    float x1[8], x2[8], cs[8], sn[8];
+    unpack8(*p1, x1);
+    unpack8(*p2, x2);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(cos_t + static_cast<long long>(p) * head_dim) + c), cs);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(sin_t + static_cast<long long>(p) * head_dim) + c), sn);
+    float o1[8], o2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!inverse) {
+        o1[i] = rbf(x1[i] * cs[i]) + rbf(-x2[i] * sn[i]);
+        o2[i] = rbf(x2[i] * cs[i]) + rbf(x1[i] * sn[i]);
+      } else {
+        o1[i] = x1[i] * cs[i] + x2[i] * sn[i];
+        o2[i] = x2[i] * cs[i] - x1[i] * sn[i];
+      }
+    }
+    *p1 = pack8(o1);
+    *p2 = pack8(o2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SwiGLU: gu [rows, 2I] = [gate | up]  ->  act [rows, I] = bf16( bf16(silu(g)) * u )
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, long long rows, int I8, long long total) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % I8);
+    const long long r = idx / I8;
+    const uint4* g4 = reinterpret_cast<const uint4*>(gu) + r * (2LL * I8);
+    float g[8], u[8];
+    unpack8(ld_nc_u4(g4 + c), g);
+    unpack8(ld_nc_u4(g4 + I8 + c), u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = rbf(silu(g[i])) * u[i];
+    st_na_u4(reinterpret_cast<uint4*>(act) + idx, pack8(g));
+  }
+}
+
+// d_gu [rows, 2I] from d_act [rows, I] and the saved gu
+__global__ void __launch_bounds__(EW_THREADS)
+swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf16* __restrict__ dgu, long long rows,
+                  int I8, long long total) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % I8);
+    const long long r = idx / I8;
+    const uint4* g4 = reinterpret_cast<const uint4*>(gu) + r * (2LL * I8);
+    uint4* o4 = reinterpret_cast<uint4*>(dgu) + r * (2LL * I8);
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8(ld_nc_u4(g4 + c), g);
+    unpack8(ld_nc_u4(g4 + I8 + c), u);
+    unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(dact) + idx), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float sg = 1.0f / (1.0f + __expf(-g[i]));
+      const float s = g[i] * sg;
+      du[i] = d[i] * s;
+      dg[i] = d[i] * u[i] * (sg * (1.0f + g[i] * (1.0f - sg)));
+    }
+    st_na_u4(o4 + c, pack8(dg));
+    st_na_u4(o4 + I8 + c, pack8(du));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GELU (erf):  y = bf16(gelu(fp32(x)))   and its backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long total8) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[8];
+    unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(x) + idx), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
+    st_na_u4(reinterpret_cast<uint4*>(y) + idx, pack8(f));
+  }
+}
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, long long total8) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[8], d[8];
+    unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(x) + idx), f);
+    unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(dy) + idx), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float cdf = 0.5f * (1.0f + erff(f[i] * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * __expf(-0.5f * f[i] * f[i]);
+      f[i] = d[i] * (cdf + f[i] * pdf);
+    }
+    st_na_u4(reinterpret_cast<uint4*>(dx) + idx, pack8(f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row gather: out[i, :] = table[idx[i], :]   (embedding lookup of the decode step / label-row selection)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+gather_rows_kernel(const bf16* __restrict__ table, const int64_t* __restrict__ idx, bf16* __restrict__ out,
+                   long long n, int H8, long long ld_table, long long table_rows, int* status) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = wg; r < n; r += nw) {
+    const long long src = idx[r];
+    uint4* o = reinterpret_cast<uint4*>(out) + r * H8;
+    if (src < 0 || src >= table_rows) {
+      if (status && lane == 0) *status = 1;
+      for (int c = lane; c < H8; c += 32) o[c] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    const uint4* s = reinterpret_cast<const uint4*>(table + src * ld_table);
+    for (int c = lane; c < H8; c += 32) st_na_u4(o + c, ld_nc_u4(s + c));
+  }
+}
+
+// out[idx[i], :] += src[i, :]  with unique idx (scatter-add of row gradients back to a packed buffer); zero elsewhere is
+// the caller's job.
+__global__ void __launch_bounds__(EW_THREADS)
+scatter_rows_kernel(const bf16* __restrict__ src, const int64_t* __restrict__ idx, bf16* __restrict__ out, long long n,
+                    int H8, long long ld_out) {
+  const int lane = threadIdx.x & 31;
+  const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = wg; r < n; r += nw) {
+    const long long dst = idx[r];
+    const uint4* s = reinterpret_cast<const uint4*>(src) + r * H8;
+    uint4* o = reinterpret_cast<uint4*>(out + dst * ld_out);
+    for (int c = lane; c < H8; c += 32) st_na_u4(o + c, ld_nc_u4(s + c));
+  }
+}
+
+}  // namespace omni
+
+using namespace omni;
+
+extern "C" int omni_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int32_t H, int64_t ldx,
+                                int64_t ldy, float eps, void* stream) {
+  OMNI_CHECK_ARG(x && w && y && rows >= 0 && H > 0 && (H % 8) == 0 && (ldx % 8) == 0 && (ldy % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  rmsnorm_fwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H / 8, ldx, ldy, eps);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                                const void* dx_add, int64_t rows, int32_t H, void* stream) {
+  OMNI_CHECK_ARG(dy && x && w && rstd && dx && rows >= 0 && H > 0 && (H % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  rmsnorm_bwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (bf16*)dx, (const bf16*)dx_add, rows, H / 8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd,
+                                  int64_t rows, int32_t H, int64_t ldx, int64_t ldy, float eps, void* stream) {
+  OMNI_CHECK_ARG(x && w && b && y && rows >= 0 && H > 0 && (H % 8) == 0 && (ldx % 8) == 0 && (ldy % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  layernorm_fwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, mean, rstd, rows, H / 8, ldx, ldy, eps);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                                  void* dx, const void* dx_add, int64_t rows, int32_t H, void* stream) {
+  OMNI_CHECK_ARG(dy && x && w && mean && rstd && dx && rows >= 0 && H > 0 && (H % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  layernorm_bwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, (const bf16*)dx_add, rows, H / 8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_rope(void* qkv, const void* cos_t, const void* sin_t, const int32_t* pos, int64_t rows, int64_t ld,
+                         int32_t n_heads_total, int32_t head_dim, int32_t inverse, void* stream) {
+  OMNI_CHECK_ARG(qkv && cos_t && sin_t && pos && rows >= 0 && n_heads_total > 0);
+  OMNI_CHECK_ARG(head_dim > 0 && (head_dim % 16) == 0 && (ld % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  const long long total = rows * n_heads_total * (head_dim / 16);
+  long long blocks = ceil_div_ll(total, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  rope_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((bf16*)qkv, (const bf16*)cos_t, (const bf16*)sin_t,
+                                                                     pos, rows, ld, n_heads_total, head_dim, inverse,
+                                                                     total);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_swiglu_fwd(const void* gu, void* act, int64_t rows, int32_t I, void* stream) {
+  OMNI_CHECK_ARG(gu && act && rows >= 0 && I > 0 && (I % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  const long long total = rows * (I / 8);
+  long long blocks = ceil_div_ll(total, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  swiglu_fwd_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)gu, (bf16*)act, rows, I / 8,
+                                                                           total);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, void* stream) {
+  OMNI_CHECK_ARG(dact && gu && dgu && rows >= 0 && I > 0 && (I % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  const long long total = rows * (I / 8);
+  long long blocks = ceil_div_ll(total, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  swiglu_bwd_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)dact, (const bf16*)gu,
+                                                                           (bf16*)dgu, rows, I / 8, total);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_gelu_fwd(const void* x, void* y, int64_t n, void* stream) {
+  OMNI_CHECK_ARG(x && y && n >= 0 && (n % 8) == 0);
+  if (n == 0) return OMNI_OK;
+  long long blocks = ceil_div_ll(n / 8, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  gelu_fwd_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n / 8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream) {
+  OMNI_CHECK_ARG(dy && x && dx && n >= 0 && (n % 8) == 0);
+  if (n == 0) return OMNI_OK;
+  long long blocks = ceil_div_ll(n / 8, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  gelu_bwd_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)x, (bf16*)dx,
+                                                                         n / 8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
+                                int64_t table_rows, int32_t* status, void* stream) {
+  OMNI_CHECK_ARG(table && idx && out && n >= 0 && H > 0 && (H % 8) == 0 && (ld_table % 8) == 0);
+  if (n == 0) return OMNI_OK;
+  gather_rows_kernel<<<rows_grid(n), EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)table, idx, (bf16*)out, n,
+                                                                             H / 8, ld_table, table_rows, status);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_scatter_rows(const void* src, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_out,
+                                 void* stream) {
+  OMNI_CHECK_ARG(src && idx && out && n >= 0 && H > 0 && (H % 8) == 0 && (ld_out % 8) == 0);
+  if (n == 0) return OMNI_OK;
+  scatter_rows_kernel<<<rows_grid(n), EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)src, idx, (bf16*)out, n,
+                                                                              H / 8, ld_out);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}

@@ -311,7 +311,7 @@ extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
   OMNI_CHECK_ARG(a != nullptr);
   OMNI_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0);
   OMNI_CHECK_ARG(a->A && a->B && a->out);
-  OMNI_CHECK_ARG((a->lda % 8) == 0 && (a->ldb % 8) == 0 && (a->K % 8) == 0);
+  OMNI_CHECK_ARG((a->lda % 8) == 0 && (a->ldb % 8) == 0);
   OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
   OMNI_CHECK_ARG(a->ldo >= a->N);
   OMNI_CHECK_ARG((a->ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0);

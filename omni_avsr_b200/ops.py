@@ -211,3 +211,178 @@ def splice_prompt_bwd(layout: SpliceLayout, douts: Sequence[Optional[torch.Tenso
     check(lib.omni_splice_prompt_bwd(C.byref(a), d, ptr(da), ptr(dv), stream_ptr()), "omni_splice_prompt_bwd")
     _count()
     return da, dv
+
+
+# ---------------------------------------------------------------------------------------------------
+# row kernels
+# ---------------------------------------------------------------------------------------------------
+def _rows2d(x: torch.Tensor, name: str) -> torch.Tensor:
+    require_cuda(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError(f"{name} must be bf16 [rows, H] with unit inner stride")
+    return x
+
+
+def rmsnorm_fwd(x, w, eps: float, want_rstd: bool = False):
+    x = _rows2d(x, "x")
+    rows, H = x.shape
+    y = torch.empty((rows, H), device=x.device, dtype=torch.bfloat16)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_rstd else None
+    check(lib.omni_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), ptr(rstd), rows, H, x.stride(0), H, eps,
+                               stream_ptr()), "omni_rmsnorm_fwd")
+    _count()
+    return (y, rstd) if want_rstd else y
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dx_add=None):
+    dy, x = dy.contiguous(), x.contiguous()
+    rows, H = x.shape
+    dx = torch.empty_like(x)
+    if dx_add is not None:
+        dx_add = dx_add.contiguous()
+    check(lib.omni_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), dx.data_ptr(), ptr(dx_add),
+                               rows, H, stream_ptr()), "omni_rmsnorm_bwd")
+    _count()
+    return dx
+
+
+def layernorm_fwd(x, w, b, eps: float, want_stats: bool = False):
+    x = _rows2d(x, "x")
+    rows, H = x.shape
+    y = torch.empty((rows, H), device=x.device, dtype=torch.bfloat16)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    check(lib.omni_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), ptr(mean), ptr(rstd), rows, H,
+                                 x.stride(0), H, eps, stream_ptr()), "omni_layernorm_fwd")
+    _count()
+    return (y, mean, rstd) if want_stats else y
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx_add=None):
+    dy, x = dy.contiguous(), x.contiguous()
+    rows, H = x.shape
+    dx = torch.empty_like(x)
+    if dx_add is not None:
+        dx_add = dx_add.contiguous()
+    check(lib.omni_layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                 dx.data_ptr(), ptr(dx_add), rows, H, stream_ptr()), "omni_layernorm_bwd")
+    _count()
+    return dx
+
+
+def rope_(qkv, cos_t, sin_t, pos, n_heads_total: int, head_dim: int, inverse: bool = False):
+    """In-place RoPE on the first n_heads_total heads of each row of the packed [rows, ld] buffer."""
+    qkv = _rows2d(qkv, "qkv")
+    require_cuda(cos_t, sin_t, pos)
+    if pos.dtype != torch.int32 or pos.numel() < qkv.shape[0]:
+        raise ValueError("pos must be int32 [rows]")
+    if cos_t.dtype != torch.bfloat16 or cos_t.shape[-1] != head_dim or not cos_t.is_contiguous():
+        raise ValueError("cos/sin tables must be contiguous bf16 [max_pos, head_dim]")
+    check(lib.omni_rope(qkv.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), pos.data_ptr(), qkv.shape[0],
+                        qkv.stride(0), n_heads_total, head_dim, 1 if inverse else 0, stream_ptr()), "omni_rope")
+    _count()
+    return qkv
+
+
+def swiglu_fwd(gu):
+    gu = _rows2d(gu, "gu")
+    if not gu.is_contiguous():
+        raise ValueError("gu must be contiguous")
+    rows, I2 = gu.shape
+    act = torch.empty((rows, I2 // 2), device=gu.device, dtype=torch.bfloat16)
+    check(lib.omni_swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, I2 // 2, stream_ptr()), "omni_swiglu_fwd")
+    _count()
+    return act
+
+
+def swiglu_bwd(dact, gu):
+    dact = dact.contiguous()
+    rows, I2 = gu.shape
+    dgu = torch.empty_like(gu)
+    check(lib.omni_swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, I2 // 2, stream_ptr()),
+          "omni_swiglu_bwd")
+    _count()
+    return dgu
+
+
+def gelu_fwd(x):
+    require_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib.omni_gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), stream_ptr()), "omni_gelu_fwd")
+    _count()
+    return y
+
+
+def gelu_bwd(dy, x):
+    dy, x = dy.contiguous(), x.contiguous()
+    dx = torch.empty_like(x)
+    check(lib.omni_gelu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), stream_ptr()), "omni_gelu_bwd")
+    _count()
+    return dx
+
+
+def gather_rows(table, idx, status=None):
+    require_cuda(table, idx)
+    if table.dtype != torch.bfloat16 or table.dim() != 2 or table.stride(1) != 1:
+        raise ValueError("table must be bf16 [rows, H]")
+    idx = idx.reshape(-1)
+    if idx.dtype != torch.int64 or not idx.is_contiguous():
+        raise ValueError("idx must be contiguous int64")
+    out = torch.empty((idx.numel(), table.shape[1]), device=table.device, dtype=torch.bfloat16)
+    check(lib.omni_gather_rows(table.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), table.shape[1],
+                               table.stride(0), table.shape[0], ptr(status), stream_ptr()), "omni_gather_rows")
+    _count()
+    return out
+
+
+def scatter_rows(src, idx, out):
+    """out[idx[i]] = src[i] (unique idx)."""
+    require_cuda(src, idx, out)
+    src = src.contiguous()
+    check(lib.omni_scatter_rows(src.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), src.shape[1],
+                                out.stride(0), stream_ptr()), "omni_scatter_rows")
+    _count()
+    return out
+
+
+def ce_fwd(logits, targets, ignore_index: int = -100):
+    """logits bf16 [R, V] (row stride may exceed V), targets int64 [R] -> (loss_rows fp32 [R], lse fp32 [R])."""
+    require_cuda(logits, targets)
+    R, V = logits.shape
+    loss = torch.empty(R, device=logits.device, dtype=torch.float32)
+    lse = torch.empty(R, device=logits.device, dtype=torch.float32)
+    check(lib.omni_ce_fwd(logits.data_ptr(), targets.data_ptr(), loss.data_ptr(), lse.data_ptr(), R, V,
+                          logits.stride(0), ignore_index, stream_ptr()), "omni_ce_fwd")
+    _count()
+    return loss, lse
+
+
+def ce_bwd_(logits, targets, lse, scale, ignore_index: int = -100):
+    """Overwrites logits with d(loss)/d(logits) * scale[r]."""
+    R, V = logits.shape
+    check(lib.omni_ce_bwd(logits.data_ptr(), targets.data_ptr(), lse.data_ptr(), scale.data_ptr(), R, V,
+                          logits.stride(0), ignore_index, stream_ptr()), "omni_ce_bwd")
+    _count()
+    return logits
+
+
+def argmax_rows(logits):
+    require_cuda(logits)
+    R, V = logits.shape
+    out = torch.empty(R, device=logits.device, dtype=torch.int64)
+    check(lib.omni_argmax(logits.data_ptr(), out.data_ptr(), R, V, logits.stride(0), stream_ptr()), "omni_argmax")
+    _count()
+    return out
+
+
+def sumsq_(g, acc):
+    check(lib.omni_sumsq(g.data_ptr(), g.numel(), acc.data_ptr(), stream_ptr()), "omni_sumsq")
+    _count()
+
+
+def adamw_(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, sumsq=None):
+    require_cuda(p, g, m, v)
+    check(lib.omni_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                         weight_decay, step, grad_scale, max_norm, ptr(sumsq), stream_ptr()), "omni_adamw")
+    _count()

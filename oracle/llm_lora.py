@@ -344,7 +344,7 @@ class ForCausalLM_lora(nn.Module):  # Llama_LoRA.py:318-444 / Qwen_LoRA.py:105-2
 
     @torch.no_grad()
     def generate(self, inputs_embeds, max_new_tokens, eos_token_id, pad_token_id, modality=None, num_beams=1,
-                 bos_token_id=None):
+                 bos_token_id=None, return_margins=False):
         """Greedy branch of HF GenerationMixin.generate as used at modeling_OmniAVSR.py:313-322:
         inputs_embeds only => returns only the new tokens; step 0 consumes the embeddings, later steps embed the
         previous token (Llama_LoRA.py:429-432); finished rows are padded with pad_token_id; stops when all rows are
@@ -354,17 +354,21 @@ class ForCausalLM_lora(nn.Module):  # Llama_LoRA.py:318-444 / Qwen_LoRA.py:105-2
         B = inputs_embeds.shape[0]
         past = [None] * self.config.num_hidden_layers
         unfinished = torch.ones(B, dtype=torch.long)
-        out = []
+        out, margins = [], []
         cur = dict(inputs_embeds=inputs_embeds)
         for _ in range(max_new_tokens):
             logits = self.forward(past_kv=past, modality=modality, **cur).logits[:, -1, :]
             nxt = torch.argmax(logits.float(), dim=-1)
+            top2 = logits.float().topk(2, dim=-1).values
+            margins.append((top2[:, 0] - top2[:, 1]) / logits.float().abs().max(dim=-1).values)
             nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
             out.append(nxt)
             unfinished = unfinished * (nxt != eos_token_id).long()
             if unfinished.max() == 0:
                 break
             cur = dict(input_ids=nxt[:, None])
+        if return_margins:
+            return torch.stack(out, dim=1), torch.stack(margins, dim=1)
         return torch.stack(out, dim=1)
 
 

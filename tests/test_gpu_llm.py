@@ -1,0 +1,159 @@
+"""GPU parity of the Omni-LoRA LLM mirror (packed rows, grouped LoRA GEMMs, label-row CE, greedy decode) against
+the CPU oracle (oracle/llm_lora.py) on the same weights.
+
+Tolerances: logits  max|a-b| <= 1e-2 * max|b|  (north_star's bf16 tolerance); losses |a-b| <= 2e-2 (bf16 logits,
+~1000-way softmax); LoRA gradients max|a-b| <= 5e-2 * max|b| (bf16 backward chain on both sides);
+greedy tokens identical except where the oracle's own top-1/top-2 margin is below the logits tolerance."""
+import pytest
+import torch
+
+from oracle import llm_lora as ol
+
+pytestmark = pytest.mark.gpu
+
+TASKS = ("audio", "video", "audiovisual")
+
+
+def _build(family, task_specific, shared, layers=2):
+    from omni_avsr_b200 import Llama_LoRA as pl
+    from omni_avsr_b200 import Qwen_LoRA as pq
+    torch.manual_seed(0)
+    if family == "llama":
+        arch = pl.LLMArch("llama", 256, 512, layers, 4, 1, 1005, 1e-5, 500000.0, 64,
+                          dict(factor=32.0, low_freq_factor=1.0, high_freq_factor=4.0,
+                               original_max_position_embeddings=8192), False, True, inv_freq_dtype="bf16")
+        lc = pl.LoRA_config(4, 2, True, False, task_specific, shared)
+        olc = ol.LoRA_config(4, 2, True, False, task_specific, shared)
+        model = pl.LlamaForCausalLM_lora(arch, lc)
+    else:
+        arch = pl.LLMArch("qwen2", 512, 1024, layers, 8, 1, 1003, 1e-6, 1000000.0, 64, None, True, True,
+                          max_position_embeddings=32768, inv_freq_dtype="fp32")
+        lc = pq.QwenLoRA_config(8, 4, IS_QWEN25_3B=True, IS_TASK_SPECIFIC=task_specific, SHARED_LORA=shared)
+        olc = ol.QwenLoRA_config(8, 4, IS_QWEN25_3B=True, IS_TASK_SPECIFIC=task_specific, SHARED_LORA=shared)
+        model = pq.Qwen2ForCausalLM_lora(arch, lc)
+    for layer in model.model.layers:
+        layer.self_attn.reset_lora_parameters(down_std=0.05)
+        if layer.self_attn.qkv_bias is not None:
+            layer.self_attn.qkv_bias.normal_(0, 0.05)
+    ocfg = ol.LLMConfig(arch.family, arch.hidden_size, arch.intermediate_size, arch.num_hidden_layers,
+                        arch.num_attention_heads, arch.num_key_value_heads, arch.vocab_size, arch.rms_norm_eps,
+                        arch.rope_theta, arch.head_dim, arch.rope_scaling, arch.attention_bias, True,
+                        inv_freq_dtype=arch.inv_freq_dtype)
+    oracle = ol.ForCausalLM_lora(ocfg, olc).bfloat16()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    missing, unexpected = oracle.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not missing, missing
+    return model, oracle, arch
+
+
+def _rel(a, b):
+    return (a.float().cpu() - b.float()).abs().max().item() / max(b.float().abs().max().item(), 1e-9)
+
+
+@pytest.mark.parametrize("family,ts,sh", [("llama", False, False), ("llama", True, False), ("llama", True, True),
+                                          ("qwen2", True, True)])
+def test_forward_logits_and_loss(family, ts, sh):
+    model, oracle, arch = _build(family, ts, sh)
+    g = torch.Generator().manual_seed(1)
+    B, S = 3, 37
+    x = (torch.randn(B, S, arch.hidden_size, generator=g) * 0.5).bfloat16()
+    labels = torch.randint(0, arch.vocab_size, (B, S), generator=g)
+    labels[:, :20] = -100
+    for t in TASKS if ts else ("audio",):
+        with torch.no_grad():
+            want = oracle(inputs_embeds=x, labels=labels, modality=t)
+            got = model(inputs_embeds=x.cuda(), modality=t)
+            got_loss = model(inputs_embeds=x.cuda(), labels=labels.cuda(), modality=t).loss
+        assert _rel(got.logits, want.logits) <= 1e-2, (t, _rel(got.logits, want.logits))
+        assert abs(got_loss.item() - want.loss.item()) <= 2e-2, (t, got_loss.item(), want.loss.item())
+
+
+def test_task_specific_requires_modality():
+    model, oracle, arch = _build("llama", True, True)
+    with pytest.raises(KeyError):
+        model(inputs_embeds=torch.zeros(1, 4, arch.hidden_size, device="cuda", dtype=torch.bfloat16))
+
+
+def test_cpu_tensor_is_refused():
+    from omni_avsr_b200._lib import OmniKernelError
+    model, oracle, arch = _build("llama", False, False)
+    with pytest.raises(OmniKernelError):
+        model(inputs_embeds=torch.zeros(1, 4, arch.hidden_size, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("family,ts,sh", [("llama", True, True), ("llama", False, False), ("qwen2", True, False)])
+def test_packed_three_task_step_grads(family, ts, sh):
+    """One packed pass over ASR+VSR+AVSR segments == three separate oracle passes (losses and LoRA grads)."""
+    from omni_avsr_b200 import Llama_LoRA as pl
+    model, oracle, arch = _build(family, ts, sh)
+    g = torch.Generator().manual_seed(2)
+    B, H = 2, arch.hidden_size
+    lens = (45, 70, 130)
+    xs = [(torch.randn(B, S, H, generator=g) * 0.5).bfloat16() for S in lens]
+    labs = []
+    for S in lens:
+        lab = torch.randint(0, arch.vocab_size, (B, S), generator=g)
+        lab[:, : S - 12] = -100
+        labs.append(lab)
+    w = (1.0, 1.5, 1.0)
+    # oracle
+    oracle.zero_grad()
+    o_losses = []
+    for t, x, lab, wt in zip(TASKS, xs, labs, w):
+        o_losses.append(oracle(inputs_embeds=x, labels=lab, modality=t).loss * wt)
+    (sum(o_losses) / 3).backward()
+    # product: one packed pass
+    rows = pl.PackedRows.get([(i, B, S) for i, S in enumerate(lens)], "cuda")
+    xg = [x.cuda().requires_grad_(True) for x in xs]
+    xp = pl.pack_segments(xg, rows)
+    hid = model.model.forward_packed(xp, rows)
+    segs = [(B, S, off) for (_, B, S, off) in rows.segments]
+    losses = model.loss_from_hidden(hid, segs, [l.cuda() for l in labs], list(w))
+    model.flat.grad.zero_()
+    (sum(losses) / 3).backward()
+    for a, b in zip(losses, o_losses):
+        assert abs(a.item() - b.item()) <= 3e-2, (a.item(), b.item())
+    # LoRA grads through the reference-named views
+    checked = 0
+    for li, layer in enumerate(model.model.layers):
+        att = layer.self_attn
+        oatt = oracle.model.layers[li].self_attn
+        r = round(arch.hidden_size / att.rank)
+        p = att.plan
+        for slot in range(p.n_slots):
+            dq = att.lora_down.grad[slot * p.rp: slot * p.rp + r]
+            uq = att.lora_up.grad[slot * p.q_cols: (slot + 1) * p.q_cols, :r]
+            if ts:
+                if slot < 3:
+                    odq, ouq = oatt.lora_down_Q[TASKS[slot]].weight.grad, oatt.lora_up_Q[TASKS[slot]].weight.grad
+                else:
+                    odq, ouq = oatt.lora_down_Q_shared.weight.grad, oatt.lora_up_Q_shared.weight.grad
+            else:
+                odq, ouq = oatt.lora_down_Q.weight.grad, oatt.lora_up_Q.weight.grad
+            assert _rel(dq, odq) <= 5e-2, (li, slot, "down_Q", _rel(dq, odq))
+            assert _rel(uq, ouq) <= 5e-2, (li, slot, "up_Q", _rel(uq, ouq))
+            checked += 1
+    assert checked >= 2
+    # input gradient of the first segment
+    assert xg[0].grad is not None
+
+
+def test_greedy_decode_tokens():
+    model, oracle, arch = _build("llama", True, True)
+    g = torch.Generator().manual_seed(5)
+    B, S0 = 4, 23
+    x = (torch.randn(B, S0, arch.hidden_size, generator=g) * 0.5).bfloat16()
+    eos, pad = 7, 1004
+    want, margins = oracle.generate(x, 12, eos, pad, modality="audiovisual", return_margins=True)
+    got = model.generate(inputs_embeds=x.cuda(), max_new_tokens=12, num_beams=1, eos_token_id=eos, pad_token_id=pad,
+                         modality="audiovisual").cpu()
+    n = min(got.shape[1], want.shape[1])
+    exact = 0
+    for b in range(B):
+        for i in range(n):
+            if got[b, i] != want[b, i]:
+                assert margins[b, i] <= 2e-2, f"row {b} step {i}: token mismatch with oracle margin {margins[b, i]}"
+                break
+            exact += 1
+    assert exact >= B * n // 2

@@ -1,0 +1,178 @@
+"""GPU parity of the row kernels (norms, RoPE, SwiGLU, GELU, CE, argmax, AdamW) against plain torch references that
+restate the reference's op sequence (transformers LlamaRMSNorm / apply_rotary_pos_emb / LlamaMLP, fairseq LayerNorm +
+gelu, CrossEntropyLoss on fp32 logits, torch.optim.AdamW + clip_grad_norm_)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import llm_lora as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from omni_avsr_b200 import ops
+    return ops
+
+
+def _bits(t):
+    return t.detach().cpu().view(torch.int16)
+
+
+@pytest.mark.parametrize("rows,H", [(5, 64), (300, 2048), (129, 4096)])
+def test_rmsnorm_fwd_bit_exact_and_bwd(rows, H):
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, H, generator=g).bfloat16()
+    w = (1 + 0.1 * torch.randn(H, generator=g)).bfloat16()
+    norm = ol.RMSNorm(H, 1e-5)
+    norm.weight.data = w.clone()
+    xr = x.clone().requires_grad_(True)
+    want = norm(xr)
+    got, rstd = ops.rmsnorm_fwd(x.cuda(), w.cuda(), 1e-5, want_rstd=True)
+    # rsqrt may differ by an ulp between CPU and GPU: allow <= 1 bf16 ulp on a handful of elements
+    diff = (got.cpu().float() - want.float()).abs()
+    assert diff.max().item() <= 2 ** -6 * want.float().abs().max().item()
+    assert (diff > 0).float().mean().item() < 0.01
+    dy = torch.randn(rows, H, generator=g).bfloat16()
+    want.backward(dy)
+    dx = ops.rmsnorm_bwd(dy.cuda(), x.cuda(), w.cuda(), rstd)
+    err = (dx.cpu().float() - xr.grad.float()).abs().max().item()
+    assert err <= 3e-2 * xr.grad.float().abs().max().item()
+
+
+@pytest.mark.parametrize("rows,H", [(7, 1024), (400, 2048)])
+def test_layernorm_fwd_bwd(rows, H):
+    ops = _ops()
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(rows, H, generator=g).bfloat16()
+    w = (1 + 0.1 * torch.randn(H, generator=g)).bfloat16()
+    b = (0.1 * torch.randn(H, generator=g)).bfloat16()
+    xr = x.clone().requires_grad_(True)
+    want = F.layer_norm(xr, (H,), w, b, 1e-5)
+    got, mean, rstd = ops.layernorm_fwd(x.cuda(), w.cuda(), b.cuda(), 1e-5, want_stats=True)
+    assert (got.cpu().float() - want.float()).abs().max().item() <= 2 ** -6 * want.float().abs().max().item()
+    dy = torch.randn(rows, H, generator=g).bfloat16()
+    want.backward(dy)
+    dx = ops.layernorm_bwd(dy.cuda(), x.cuda(), w.cuda(), mean, rstd)
+    assert (dx.cpu().float() - xr.grad.float()).abs().max().item() <= 3e-2 * xr.grad.float().abs().max().item()
+
+
+@pytest.mark.parametrize("hd,nh,nkv", [(64, 32, 8), (128, 16, 2)])
+def test_rope_bit_exact(hd, nh, nkv):
+    ops = _ops()
+    from omni_avsr_b200.Llama_LoRA import LLMArch, rope_tables
+    g = torch.Generator().manual_seed(hd)
+    B, S = 2, 50
+    rs = dict(factor=32.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=8192)
+    arch = LLMArch("llama", nh * hd, 4 * nh * hd, 1, nh, nkv, 100, 1e-5, 500000.0, hd, rs, inv_freq_dtype="bf16")
+    cfg = ol.LLMConfig("llama", nh * hd, 4 * nh * hd, 1, nh, nkv, 100, 1e-5, 500000.0, hd, rs, inv_freq_dtype="bf16")
+    qkv = torch.randn(B * S, (nh + 2 * nkv) * hd, generator=g).bfloat16()
+    pos = torch.arange(S).repeat(B)
+    cos, sin = ol.rope_cos_sin(cfg, torch.arange(S).unsqueeze(0), torch.bfloat16)
+    q = qkv[:, : nh * hd].view(B, S, nh, hd).transpose(1, 2)
+    k = qkv[:, nh * hd: (nh + nkv) * hd].view(B, S, nkv, hd).transpose(1, 2)
+    qo, ko = ol.apply_rotary_pos_emb(q, k, cos, sin)
+    cos_t, sin_t = rope_tables(arch, 64, "cuda")
+    assert torch.equal(_bits(cos_t[:S]), _bits(cos[0]))
+    buf = qkv.cuda().clone()
+    ops.rope_(buf, cos_t, sin_t, pos.int().cuda(), nh + nkv, hd)
+    out = buf.cpu()
+    assert torch.equal(_bits(out[:, : nh * hd].view(B, S, nh, hd).transpose(1, 2)), _bits(qo))
+    assert torch.equal(_bits(out[:, nh * hd: (nh + nkv) * hd].view(B, S, nkv, hd).transpose(1, 2)), _bits(ko))
+    assert torch.equal(_bits(out[:, (nh + nkv) * hd:]), _bits(qkv[:, (nh + nkv) * hd:]))   # v untouched
+    # inverse rotation == autograd of the forward
+    qr = q.clone().float().requires_grad_(True)
+    o, _ = ol.apply_rotary_pos_emb(qr, k.float(), cos.float(), sin.float())
+    dy = torch.randn(o.shape, generator=g)
+    o.backward(dy)
+    dbuf = torch.zeros_like(qkv)
+    dbuf[:, : nh * hd] = dy.transpose(1, 2).reshape(B * S, nh * hd).bfloat16()
+    d = dbuf.cuda()
+    ops.rope_(d, cos_t, sin_t, pos.int().cuda(), nh + nkv, hd, inverse=True)
+    got = d.cpu()[:, : nh * hd].view(B, S, nh, hd).transpose(1, 2).float()
+    assert (got - qr.grad).abs().max().item() <= 2e-2 * qr.grad.abs().max().item()
+
+
+def test_swiglu_and_gelu():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    rows, I = 37, 512
+    gu = torch.randn(rows, 2 * I, generator=g).bfloat16()
+    gr = gu.clone().requires_grad_(True)
+    want = F.silu(gr[:, :I]) * gr[:, I:]
+    got = ops.swiglu_fwd(gu.cuda())
+    assert (got.cpu().float() - want.float()).abs().max().item() <= 2 ** -7 * want.float().abs().max().item()
+    d = torch.randn(rows, I, generator=g).bfloat16()
+    want.backward(d)
+    dgu = ops.swiglu_bwd(d.cuda(), gu.cuda())
+    assert (dgu.cpu().float() - gr.grad.float()).abs().max().item() <= 3e-2 * gr.grad.float().abs().max().item()
+    x = torch.randn(rows, I, generator=g).bfloat16()
+    xr = x.clone().requires_grad_(True)
+    wy = F.gelu(xr.float()).type_as(xr)          # fairseq gelu: fp32 then cast (modules/gelu.py)
+    gy = ops.gelu_fwd(x.cuda())
+    assert (gy.cpu().float() - wy.float()).abs().max().item() <= 2 ** -7 * wy.float().abs().max().item()
+    wy.backward(d)
+    gdx = ops.gelu_bwd(d.cuda(), x.cuda())
+    assert (gdx.cpu().float() - xr.grad.float()).abs().max().item() <= 2e-2 * xr.grad.float().abs().max().item()
+
+
+@pytest.mark.parametrize("R,V", [(9, 1005), (33, 128261)])
+def test_cross_entropy_and_argmax(R, V):
+    ops = _ops()
+    g = torch.Generator().manual_seed(V)
+    Vp = (V + 7) // 8 * 8
+    buf = torch.zeros(R, Vp).bfloat16()
+    buf[:, :V] = (torch.randn(R, V, generator=g) * 3).bfloat16()
+    tgt = torch.randint(0, V, (R,), generator=g)
+    tgt[1] = -100
+    lr = buf[:, :V].float().requires_grad_(True)
+    want = F.cross_entropy(lr, tgt, reduction="none", ignore_index=-100)
+    d_logits = buf.cuda()[:, :V]
+    loss, lse = ops.ce_fwd(d_logits, tgt.cuda())
+    assert torch.allclose(loss.cpu(), want.detach(), atol=2e-4, rtol=1e-5)
+    assert torch.equal(ops.argmax_rows(d_logits).cpu(), buf[:, :V].float().argmax(-1))
+    scale = torch.rand(R, generator=g)
+    (want * scale).sum().backward()
+    ops.ce_bwd_(d_logits, tgt.cuda(), lse, scale.cuda())
+    err = (d_logits.cpu().float() - lr.grad).abs().max().item()
+    assert err <= 1e-2 * lr.grad.abs().max().item()
+    assert d_logits[1].abs().max().item() == 0
+
+
+def test_gather_scatter_rows():
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    table = torch.randn(50, 128, generator=g).bfloat16()
+    idx = torch.randperm(50, generator=g)[:17]
+    got = ops.gather_rows(table.cuda(), idx.cuda())
+    assert torch.equal(_bits(got), _bits(table[idx]))
+    out = torch.zeros(50, 128, device="cuda", dtype=torch.bfloat16)
+    ops.scatter_rows(got, idx.cuda(), out)
+    want = torch.zeros(50, 128).bfloat16()
+    want[idx] = table[idx]
+    assert torch.equal(_bits(out), _bits(want))
+
+
+def test_fused_clip_adamw_matches_torch():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    n = 10007
+    p0 = torch.randn(n, generator=g).bfloat16()
+    ref = torch.nn.Parameter(p0.float().clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=0.1, betas=(0.9, 0.98))
+    p = p0.cuda().clone()
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        grad = (torch.randn(n, generator=g) * (30.0 if step == 2 else 0.01)).bfloat16()
+        ref.grad = grad.float().clone()
+        torch.nn.utils.clip_grad_norm_([ref], 10.0)
+        opt.step()
+        acc = torch.zeros(1, device="cuda")
+        ops.sumsq_(grad.cuda(), acc)
+        assert abs(acc.item() - grad.float().pow(2).sum().item()) <= 1e-3 * grad.float().pow(2).sum().item()
+        ops.adamw_(p, grad.cuda(), m, v, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-8, weight_decay=0.1, step=step,
+                   max_norm=10.0, sumsq=acc)
+        # the product keeps bf16 params: compare against the fp32 reference rounded, 1 bf16 ulp slack per step
+        assert (p.cpu().float() - ref.data).abs().max().item() <= step * 2 ** -7 * ref.data.abs().max().item()
