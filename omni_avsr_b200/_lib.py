@@ -22,9 +22,12 @@ class OmniKernelError(RuntimeError):
 
 
 def _load() -> C.CDLL:
-    if not LIB_PATH.exists():
+    try:    # (re)build when the sources changed since the last build (no-op when the stamp matches)
         from .build import build
         build()
+    except Exception:
+        if not LIB_PATH.exists():
+            raise
     if not LIB_PATH.exists():
         raise ImportError(f"{LIB_PATH} is missing: run `python -m omni_avsr_b200.build` (needs nvcc)")
     return C.CDLL(str(LIB_PATH))

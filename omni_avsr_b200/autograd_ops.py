@@ -197,7 +197,10 @@ class LmHeadCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hrows, W, WT, targets, row_scale):
         # logits of the label rows, bf16 (as lm_head produces them before `.float()`)
-        logits = ops.gemm(hrows, W, block_n=256 if W.shape[0] >= 256 else 0)
+        V = W.shape[0]
+        Vp = (V + 7) // 8 * 8     # row stride must be a multiple of 16 bytes (vector stores, TMA in the backward)
+        buf = torch.empty((hrows.shape[0], Vp), device=hrows.device, dtype=torch.bfloat16)
+        logits = ops.gemm(hrows, W, out=buf[:, :V], block_n=256 if V >= 256 else 0)
         loss_rows, lse = ops.ce_fwd(logits, targets)
         ctx.save_for_backward(logits, targets, lse, row_scale)
         ctx.WT = WT
