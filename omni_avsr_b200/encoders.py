@@ -1,0 +1,446 @@
+"""Frozen encoders of the Omni-AVSR path on the sm_100a kernels.
+
+* `LogMel` + `WhisperEncoder`  -- replaces WhisperFeatureExtractor (host CPU in the reference, with a D2H/H2D
+  round trip every step: Omni_AVSR/modeling_OmniAVSR.py:531-534) and transformers' WhisperEncoder
+  (state-dict names kept: conv1, conv2, embed_positions, layers.{i}.self_attn.{q,k,v,out}_proj, ..., layer_norm).
+* `AVHubertVideoEncoder` -- AVHubertModel.extract_finetune(source={'video': v, 'audio': None}) of
+  av_hubert/avhubert/hubert.py:695-755 (ResEncoder resnet.py:131-169, SubModel hubert.py:318-333,
+  TransformerEncoder wav2vec2.py:818-905, layer :977-1006, MultiheadAttention.forward_lora
+  multihead_attention.py:485-662), fairseq state-dict names kept, LoRA r = round(1024/16), scale 2
+  (modeling_OmniAVSR.py:127-142).
+
+Linear layers, LayerNorm, GELU and the LoRA-fused q|k|v projection run on our kernels (tcgen05 GEMM with bias /
+GELU / residual epilogues).  Still on library kernels in this round (TODO round 2): the STFT (cuFFT),
+the convolutions (cuDNN: Whisper stem, ResNet-18 front-end, grouped positional conv) and the attention core (SDPA).
+Encoders run in eval mode (no dropout / layerdrop, BatchNorm running statistics): SURVEY §5.8 / §7.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import autograd_ops as ag
+from . import ops
+from .Llama_LoRA import FlatParams, LoraPlan, _LinearView
+
+SAMPLE_RATE, N_FFT, HOP, N_MELS, N_SAMPLES = 16000, 400, 160, 80, 480000
+
+
+# ------------------------------------------------------------------------------------------------
+# log-mel (on device)
+# ------------------------------------------------------------------------------------------------
+def _slaney_mel_filters(n_freq=201, n_mels=80, sr=16000, fmin=0.0, fmax=8000.0) -> torch.Tensor:
+    def hz2mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-10) / 1000.0) * (27.0 / np.log(6.4)), 3.0 * f / 200.0)
+
+    def mel2hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), 200.0 * m / 3.0)
+
+    fft_freqs = np.linspace(0, sr // 2, n_freq)
+    pts = mel2hz(np.linspace(hz2mel(fmin), hz2mel(fmax), n_mels + 2))
+    fdiff = np.diff(pts)
+    slopes = pts[None, :] - fft_freqs[:, None]
+    fb = np.maximum(0, np.minimum(-slopes[:, :-2] / fdiff[:-1], slopes[:, 2:] / fdiff[1:]))
+    fb = fb * (2.0 / (pts[2: n_mels + 2] - pts[:n_mels]))[None, :]
+    return torch.from_numpy(fb).to(torch.float32)
+
+
+class LogMel(nn.Module):
+    """[B, T] (bf16/fp32 waveform) -> [B, 80, 3000] bf16 Whisper input features, entirely on the GPU."""
+
+    def __init__(self, device="cuda"):
+        super().__init__()
+        self.register_buffer("window", torch.hann_window(N_FFT, device=device), persistent=False)
+        self.register_buffer("filters", _slaney_mel_filters().to(device).t().contiguous(), persistent=False)
+
+    @torch.no_grad()
+    def forward(self, audio: torch.Tensor) -> torch.Tensor:
+        ops.require_cuda(audio)
+        B, T = audio.shape
+        wav = torch.zeros(B, N_SAMPLES, device=audio.device, dtype=torch.float32)
+        n = min(T, N_SAMPLES)
+        wav[:, :n] = audio[:, :n].float()
+        stft = torch.stft(wav, N_FFT, HOP, window=self.window, return_complex=True)   # TODO(round 2): own DFT kernel
+        mag = stft[..., :-1].abs() ** 2
+        mel = self.filters @ mag
+        log_spec = torch.clamp(mel, min=1e-10).log10()
+        log_spec = torch.maximum(log_spec, log_spec.amax(dim=(1, 2), keepdim=True) - 8.0)
+        return ((log_spec + 4.0) / 4.0).to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------
+# Whisper encoder (frozen, inference only)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class WhisperArch:
+    d_model: int = 1024
+    encoder_layers: int = 24
+    encoder_attention_heads: int = 16
+    encoder_ffn_dim: int = 4096
+    num_mel_bins: int = 80
+    max_source_positions: int = 1500
+
+    @property
+    def hidden_size(self):
+        return self.d_model
+
+
+WHISPER_ARCHS = {
+    "openai/whisper-medium.en": WhisperArch(), "openai/whisper-medium": WhisperArch(),
+    "openai/whisper-small.en": WhisperArch(768, 12, 12, 3072), "openai/whisper-small": WhisperArch(768, 12, 12, 3072),
+    "openai/whisper-base.en": WhisperArch(512, 6, 8, 2048), "openai/whisper-tiny.en": WhisperArch(384, 4, 6, 1536),
+    "openai/whisper-large-v3": WhisperArch(1280, 32, 20, 5120, 128),
+}
+
+
+def _w(out_f, in_f, device, std=0.02):
+    return (torch.randn(out_f, in_f, device=device) * std).to(torch.bfloat16)
+
+
+def _b(n, device, std=0.0):
+    return (torch.randn(n, device=device) * std).to(torch.bfloat16) if std else torch.zeros(n, device=device, dtype=torch.bfloat16)
+
+
+class _LN(nn.Module):
+    def __init__(self, d, device, eps=1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d, device=device, dtype=torch.bfloat16), requires_grad=False)
+        self.bias = nn.Parameter(torch.zeros(d, device=device, dtype=torch.bfloat16), requires_grad=False)
+        self.eps = eps
+
+    def forward(self, x):
+        return ag.layernorm(x, self.weight.data, self.bias.data, self.eps)
+
+
+class _PackedSelfAttention(nn.Module):
+    """q|k|v packed into one [3D, D] weight (+[3D] bias); reference-named views q_proj/k_proj/v_proj/out_proj."""
+
+    def __init__(self, d, heads, device, k_bias=True):
+        super().__init__()
+        self.d, self.h, self.hd = d, heads, d // heads
+        self.qkv_weight = _w(3 * d, d, device)
+        self.qkv_bias = _b(3 * d, device)
+        self.q_proj = _LinearView(self.qkv_weight[:d], self.qkv_bias[:d])
+        self.k_proj = _LinearView(self.qkv_weight[d:2 * d], self.qkv_bias[d:2 * d] if k_bias else None)
+        self.v_proj = _LinearView(self.qkv_weight[2 * d:], self.qkv_bias[2 * d:])
+        self.out_proj = _LinearView(_w(d, d, device), _b(d, device))
+        self._wt = None
+
+    def transposed(self):
+        if self._wt is None:
+            self._wt = (self.qkv_weight.t().contiguous(), self.out_proj.weight.data.t().contiguous())
+        return self._wt
+
+    def sdpa(self, qkv, B, T):
+        d, h, hd = self.d, self.h, self.hd
+        q = qkv[:, :d].view(B, T, h, hd).transpose(1, 2)
+        k = qkv[:, d:2 * d].view(B, T, h, hd).transpose(1, 2)
+        v = qkv[:, 2 * d:].view(B, T, h, hd).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v)           # TODO(round 2): tcgen05 flash kernel
+        return o.transpose(1, 2).reshape(B * T, d)
+
+
+class WhisperEncoderLayer(nn.Module):
+    def __init__(self, a: WhisperArch, device):
+        super().__init__()
+        d = a.d_model
+        self.self_attn = _PackedSelfAttention(d, a.encoder_attention_heads, device, k_bias=False)
+        self.self_attn_layer_norm = _LN(d, device)
+        self.fc1 = _LinearView(_w(a.encoder_ffn_dim, d, device), _b(a.encoder_ffn_dim, device))
+        self.fc2 = _LinearView(_w(d, a.encoder_ffn_dim, device), _b(d, device))
+        self.final_layer_norm = _LN(d, device)
+
+    def forward(self, x, B, T):
+        att = self.self_attn
+        h = self.self_attn_layer_norm(x)
+        qkv = ops.gemm(h, att.qkv_weight, bias=att.qkv_bias, block_n=256)
+        o = att.sdpa(qkv, B, T)
+        x = ops.gemm(o, att.out_proj.weight.data, bias=att.out_proj.bias.data, residual=x, block_n=256)
+        h = self.final_layer_norm(x)
+        f = ops.gemm(h, self.fc1.weight.data, bias=self.fc1.bias.data, act="gelu", block_n=256)
+        return ops.gemm(f, self.fc2.weight.data, bias=self.fc2.bias.data, residual=x, block_n=256)
+
+
+@dataclass
+class _EncOut:
+    last_hidden_state: torch.Tensor
+
+
+class WhisperEncoder(nn.Module):
+    def __init__(self, a: WhisperArch, device="cuda"):
+        super().__init__()
+        self.config = a
+        d = a.d_model
+        self.conv1 = nn.Conv1d(a.num_mel_bins, d, 3, padding=1, device=device, dtype=torch.bfloat16)
+        self.conv2 = nn.Conv1d(d, d, 3, stride=2, padding=1, device=device, dtype=torch.bfloat16)
+        half = d // 2
+        inv = torch.exp(-(math.log(10000.0) / (half - 1)) * torch.arange(half))
+        t = torch.arange(a.max_source_positions).view(-1, 1) * inv.view(1, -1)
+        pos = torch.cat([t.sin(), t.cos()], dim=1)
+        self.embed_positions = nn.Embedding(a.max_source_positions, d, device=device, dtype=torch.bfloat16)
+        self.embed_positions.weight.data.copy_(pos)
+        self.layers = nn.ModuleList([WhisperEncoderLayer(a, device) for _ in range(a.encoder_layers)])
+        self.layer_norm = _LN(d, device)
+        self.requires_grad_(False)
+
+    @classmethod
+    def from_pretrained(cls, name: str, device="cuda"):
+        if name not in WHISPER_ARCHS:
+            raise KeyError(f"unknown audio encoder {name!r}")
+        return cls(WHISPER_ARCHS[name], device)
+
+    @torch.no_grad()
+    def forward(self, input_features: torch.Tensor) -> _EncOut:
+        ops.require_cuda(input_features)
+        x = F.gelu(self.conv1(input_features.to(torch.bfloat16)))        # TODO(round 2): conv stem as TMA-strided GEMM
+        x = F.gelu(self.conv2(x))
+        B, d, T = x.shape
+        x = (x.permute(0, 2, 1) + self.embed_positions.weight).reshape(B * T, d).contiguous()
+        for layer in self.layers:
+            x = layer(x, B, T)
+        x = self.layer_norm(x)
+        return _EncOut(x.view(B, T, d))
+
+
+# ------------------------------------------------------------------------------------------------
+# AV-HuBERT (video-only), LoRA on q/v of every block
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class AVHubertArch:
+    encoder_embed_dim: int = 1024
+    encoder_ffn_embed_dim: int = 4096
+    encoder_layers: int = 24
+    encoder_attention_heads: int = 16
+    conv_pos: int = 128
+    conv_pos_groups: int = 16
+    resnet_widths: tuple = (64, 128, 256, 512)
+
+
+AVHUBERT_ARCHS = {"large": AVHubertArch(), "base": AVHubertArch(768, 3072, 12, 12)}
+
+
+class _BasicBlock(nn.Module):
+    def __init__(self, inp, planes, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inp, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu1 = nn.PReLU(planes)
+        self.relu2 = nn.PReLU(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.relu1(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        res = x if self.downsample is None else self.downsample(x)
+        return self.relu2(out + res)
+
+
+class _Trunk(nn.Module):
+    def __init__(self, widths):
+        super().__init__()
+        inp = widths[0]
+        for i, (w, s) in enumerate(zip(widths, (1, 2, 2, 2)), start=1):
+            ds = None
+            if s != 1 or inp != w:
+                ds = nn.Sequential(nn.Conv2d(inp, w, 1, s, bias=False), nn.BatchNorm2d(w))
+            setattr(self, f"layer{i}", nn.Sequential(_BasicBlock(inp, w, s, ds), _BasicBlock(w, w, 1, None)))
+            inp = w
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data.normal_(0, math.sqrt(2.0 / (m.kernel_size[0] * m.kernel_size[1] * m.out_channels)))
+
+    def forward(self, x):
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.avgpool(x).flatten(1)
+
+
+class _ResEncoder(nn.Module):
+    """Conv3d front-end + ResNet-18 trunk (library convolutions, channels-last, eval-mode BatchNorm)."""
+
+    def __init__(self, widths):
+        super().__init__()
+        self.frontend3D = nn.Sequential(
+            nn.Conv3d(1, widths[0], (5, 7, 7), (1, 2, 2), (2, 3, 3), bias=False), nn.BatchNorm3d(widths[0]),
+            nn.PReLU(widths[0]), nn.MaxPool3d((1, 3, 3), (1, 2, 2), (0, 1, 1)))
+        self.trunk = _Trunk(widths)
+
+    def forward(self, x):                       # [B, 1, T, 88, 88] -> [B*T, C]
+        B = x.shape[0]
+        x = self.frontend3D(x)
+        T = x.shape[2]
+        x = x.transpose(1, 2).reshape(B * T, *x.shape[1:2], *x.shape[3:])
+        return self.trunk(x.contiguous(memory_format=torch.channels_last))
+
+
+class _VideoFeatureExtractor(nn.Module):
+    def __init__(self, a: AVHubertArch, device):
+        super().__init__()
+        self.resnet = _ResEncoder(a.resnet_widths).to(device=device, dtype=torch.bfloat16)
+        self.proj = _LinearView(_w(a.encoder_embed_dim, a.resnet_widths[-1], device), _b(a.encoder_embed_dim, device))
+
+
+class _Rows:
+    """Minimal row-layout object for the LoRA kernels when there is a single adapter group."""
+
+    def __init__(self, M):
+        self.tile_group = None
+        self.runs = [(0, 0, M)]
+
+
+class AVHAttention_lora(_PackedSelfAttention):
+    def __init__(self, a: AVHubertArch, device, flat: Optional[FlatParams], use_lora: bool, layer_idx: int):
+        d = a.encoder_embed_dim
+        super().__init__(d, a.encoder_attention_heads, device)
+        self.use_lora = use_lora
+        if use_lora:
+            self.rank = 16                                   # modeling_OmniAVSR.py:131
+            self.scaling_lora = 2                            # :132
+            r = round(d / self.rank)
+            self.plan = LoraPlan(d, d, d, d, r, self.scaling_lora, False, False, device)
+            p = self.plan
+            if flat is None:
+                flat = FlatParams(device, p.down_rows * d + p.up_rows * p.rp + 64)
+            self.lora_down = flat.alloc((p.down_rows, d), f"avh.{layer_idx}.lora_down")
+            self.lora_up = flat.alloc((p.up_rows, p.rp), f"avh.{layer_idx}.lora_up")
+            self.lora_down_Q = _LinearView(self.lora_down.data[:r])
+            self.lora_down_V = _LinearView(self.lora_down.data[p.rp: p.rp + r])
+            self.lora_up_Q = _LinearView(self.lora_up.data[:d, :r])
+            self.lora_up_V = _LinearView(self.lora_up.data[d:, :r])
+            bound = 1.0 / math.sqrt(r)
+            with torch.no_grad():
+                self.lora_up_Q.weight.uniform_(-bound, bound)    # kaiming_uniform_(a=sqrt(5)) (:141-142); down stays 0
+                self.lora_up_V.weight.uniform_(-bound, bound)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        sd = super().state_dict(*args, destination=destination, prefix=prefix, keep_vars=keep_vars)
+        for k in (prefix + "lora_down", prefix + "lora_up"):
+            sd.pop(k, None)
+        return sd
+
+
+class AVHLayer(nn.Module):
+    def __init__(self, a: AVHubertArch, device, flat, use_lora, idx):
+        super().__init__()
+        d = a.encoder_embed_dim
+        self.apply_lora = use_lora
+        self.self_attn = AVHAttention_lora(a, device, flat, use_lora, idx)
+        self.self_attn_layer_norm = _LN(d, device)
+        self.fc1 = _LinearView(_w(a.encoder_ffn_embed_dim, d, device), _b(a.encoder_ffn_embed_dim, device))
+        self.fc2 = _LinearView(_w(d, a.encoder_ffn_embed_dim, device), _b(d, device))
+        self.final_layer_norm = _LN(d, device)
+        self._wt = None
+
+    def transposed(self):
+        if self._wt is None:
+            self._wt = (self.fc1.weight.data.t().contiguous(), self.fc2.weight.data.t().contiguous())
+        return self._wt
+
+    def forward(self, x, B, T, rows, first: bool):
+        att = self.self_attn
+        wt_qkv, wt_o = att.transposed()
+        wt1, wt2 = self.transposed()
+        h = self.self_attn_layer_norm(x)
+        if att.use_lora and (torch.is_grad_enabled() and att.lora_down.requires_grad):
+            qkv = ag.LoraLinearFn.apply(h, att.qkv_weight, wt_qkv, att.qkv_bias, att.lora_down, att.lora_up, rows, att.plan)
+        elif att.use_lora:
+            Tm = ops.gemm(h, att.lora_down.data, n=att.plan.t_cols, alpha=att.plan.scaling, b_row_table=att.plan.brow_fwd,
+                          block_n=64)
+            qkv = ops.gemm(h, att.qkv_weight, bias=att.qkv_bias, ext=(Tm, att.lora_up.data, att.plan.ext_fwd),
+                           block_n=att.plan.block_n)
+        else:
+            qkv = ops.gemm(h, att.qkv_weight, bias=att.qkv_bias, block_n=256)
+        o = att.sdpa(qkv, B, T)       # q * head_dim^-0.5 (:511) is SDPA's default scale (exact: power of two)
+        x = ag.frozen_linear(o, att.out_proj.weight.data, wt_o, bias=att.out_proj.bias.data, residual=x, block_n=256)
+        h = self.final_layer_norm(x)
+        if h.requires_grad:
+            f = ag.frozen_linear(h, self.fc1.weight.data, wt1, bias=self.fc1.bias.data, block_n=256)
+            f = ag.gelu(f)
+        else:
+            f = ops.gemm(h, self.fc1.weight.data, bias=self.fc1.bias.data, act="gelu", block_n=256)
+        return ag.frozen_linear(f, self.fc2.weight.data, wt2, bias=self.fc2.bias.data, residual=x, block_n=256)
+
+
+class _AVHTransformerEncoder(nn.Module):
+    def __init__(self, a: AVHubertArch, device, flat, use_lora):
+        super().__init__()
+        d = a.encoder_embed_dim
+        conv = nn.Conv1d(d, d, a.conv_pos, padding=a.conv_pos // 2, groups=a.conv_pos_groups)
+        nn.init.normal_(conv.weight, 0, math.sqrt(4.0 / (a.conv_pos * d)))
+        nn.init.constant_(conv.bias, 0)
+        conv = nn.utils.weight_norm(conv, name="weight", dim=2)      # keys pos_conv.0.{bias,weight_g,weight_v}
+        self.pos_conv = nn.Sequential(conv.to(device=device, dtype=torch.bfloat16))
+        self.remove = 1 if a.conv_pos % 2 == 0 else 0
+        self.layers = nn.ModuleList([AVHLayer(a, device, flat, use_lora, i) for i in range(a.encoder_layers)])
+        self.layer_norm = _LN(d, device)
+
+    def forward(self, x, B, T):                  # x [B*T, C]
+        d = x.shape[1]
+        with torch.no_grad():
+            xc = self.pos_conv(x.view(B, T, d).transpose(1, 2))      # TODO(round 2): grouped conv as GEMM
+            if self.remove:
+                xc = xc[:, :, : -self.remove]
+            x = (x.view(B, T, d) + F.gelu(xc).transpose(1, 2)).reshape(B * T, d).contiguous()
+        rows = _Rows(B * T)
+        for i, layer in enumerate(self.layers):
+            x = layer(x, B, T, rows, i == 0)
+        return self.layer_norm(x)
+
+
+class AVHubertVideoEncoder(nn.Module):
+    """`video_encoder` of AVSR_LLMs: .extract_finetune(source) -> (features [B, T, C], None, layer_outputs)."""
+
+    def __init__(self, a: AVHubertArch = AVHubertArch(), device="cuda", flat: Optional[FlatParams] = None,
+                 use_lora: bool = True):
+        super().__init__()
+        self.arch = a
+        d = a.encoder_embed_dim
+        self.encoder_embed_dim = d
+        self.feature_extractor_video = _VideoFeatureExtractor(a, device)
+        self.layer_norm = _LN(2 * d, device)
+        self.post_extract_proj = _LinearView(_w(d, 2 * d, device), _b(d, device))
+        self.encoder = _AVHTransformerEncoder(a, device, flat, use_lora)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.eval()
+
+    def lora_parameters(self):
+        for layer in self.encoder.layers:
+            if layer.self_attn.use_lora:
+                yield layer.self_attn.lora_down
+                yield layer.self_attn.lora_up
+
+    @staticmethod
+    def lora_param_count(a: AVHubertArch) -> int:
+        d = a.encoder_embed_dim
+        r = round(d / 16)
+        rp = (r + 63) // 64 * 64
+        return a.encoder_layers * (2 * rp * d + 2 * d * rp + 32)
+
+    def extract_finetune(self, source, padding_mask=None, mask=False, ret_conv=False, output_layer=None):
+        video = source["video"]
+        if source.get("audio") is not None:
+            raise NotImplementedError("the Omni-AVSR path feeds AV-HuBERT with video only (modeling_OmniAVSR.py:463)")
+        ops.require_cuda(video)
+        B, _, T = video.shape[:3]
+        d = self.encoder_embed_dim
+        fe = self.feature_extractor_video
+        with torch.no_grad():
+            f = fe.resnet(video.to(torch.bfloat16))                                   # [B*T, 512]
+            f = ops.gemm(f.contiguous(), fe.proj.weight.data, bias=fe.proj.bias.data)  # SubModel.proj
+            cat = torch.zeros((B * T, 2 * d), device=video.device, dtype=torch.bfloat16)
+            cat[:, d:] = f                                                            # audio half = zeros (hubert.py:709)
+            x = ops.layernorm_fwd(cat, self.layer_norm.weight.data, self.layer_norm.bias.data, self.layer_norm.eps)
+            x = ops.gemm(x, self.post_extract_proj.weight.data, bias=self.post_extract_proj.bias.data)
+        x = self.encoder(x, B, T)
+        return x.view(B, T, d), None, []

@@ -1,0 +1,385 @@
+"""Drop-in mirror of the reference's Omni_AVSR/modeling_OmniAVSR.py (class AVSR_LLMs) on the sm_100a kernels.
+
+Same constructor / forward / prepare_inputs / encode_audio / encode_video signatures and return values as the
+reference (file:line in /root/reference/Omni_AVSR/modeling_OmniAVSR.py):
+  __init__ :28-231, _unfreeze_PETF :234-260, forward :263-323, prepare_inputs :326-458,
+  encode_video :461-526, encode_audio :528-606.
+
+Hot-path differences (same results, different execution):
+  * log-mel on the GPU (no .cpu().numpy() round trip, :531-534);
+  * compression straight from the [B, T, D] encoder output, truncation folded into the kernel (:537-588);
+  * projector MLP on the tcgen05 GEMM (bias+ReLU / bias epilogues);
+  * ONE splice launch writes the three task sequences and their labels into a packed, 128-row-aligned buffer;
+  * ONE LLM pass over the packed rows, adapter chosen per tile by task id, lm_head + CE on label rows only.
+"""
+from __future__ import annotations
+
+import random
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import autograd_ops as ag
+from . import ops
+from .encoders import AVHUBERT_ARCHS, AVHubertVideoEncoder, LogMel, WhisperEncoder
+from .Llama_LoRA import (FlatParams, LlamaForCausalLM_lora, PackedRows, TASKS, arch_from_name)
+from .Qwen_LoRA import Qwen2ForCausalLM_lora
+
+IGNORE_INDEX = -100
+
+
+class _TrainLinear(nn.Module):
+    def __init__(self, in_f, out_f, flat: FlatParams, name: str, bias=True):
+        super().__init__()
+        self.weight = flat.alloc((out_f, in_f), name + ".weight")
+        self.bias = flat.alloc((out_f,), name + ".bias") if bias else None
+        with torch.no_grad():   # nn.Linear default init
+            bound = 1.0 / (in_f ** 0.5)
+            self.weight.uniform_(-bound, bound)
+            if self.bias is not None:
+                self.bias.uniform_(-bound, bound)
+
+
+class _TrainLayerNorm(nn.Module):
+    def __init__(self, d, flat: FlatParams, name: str):
+        super().__init__()
+        self.weight = flat.alloc((d,), name + ".weight")
+        self.bias = flat.alloc((d,), name + ".bias")
+        self.d = d
+        with torch.no_grad():
+            self.weight.fill_(1.0)
+            self.bias.zero_()
+
+
+class Projector(nn.Sequential):
+    """nn.Sequential(Linear, ReLU, Linear[, LayerNorm]) with the reference's child names 0, 1, 2[, 3]
+    (state-dict keys audio_proj.{k}.{0,2}.{weight,bias}); forward runs the tcgen05 GEMMs with fused bias(+ReLU)."""
+
+    def __init__(self, in_dim, intermediate, hidden, layernorm, flat, name):
+        mods = [_TrainLinear(in_dim, intermediate, flat, name + ".0"), nn.ReLU(),
+                _TrainLinear(intermediate, hidden, flat, name + ".2")]
+        if layernorm:
+            mods.append(_TrainLayerNorm(hidden, flat, name + ".3"))
+        super().__init__(*mods)
+
+    def forward(self, x):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        h = ag.TrainableLinearFn.apply(x2, self[0].weight, self[0].bias, "relu")
+        y = ag.TrainableLinearFn.apply(h, self[2].weight, self[2].bias, None)
+        if len(self) == 4:   # single-projector mode only (:102,:186); trainable affine -> library LN for now
+            y = torch.nn.functional.layer_norm(y, (self[3].d,), self[3].weight, self[3].bias, 1e-5)
+        return y.view(*shape[:-1], y.shape[-1])
+
+    @staticmethod
+    def param_count(in_dim, intermediate, hidden, layernorm):
+        return in_dim * intermediate + intermediate + intermediate * hidden + hidden + (2 * hidden if layernorm else 0) + 64
+
+
+class CompressFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc, n_tok, rate, mode):
+        ctx.meta = (n_tok, enc.shape[1], rate, mode)
+        return ops.matryoshka_compress(enc, n_tok, rate, mode)
+
+    @staticmethod
+    def backward(ctx, d):
+        n_tok, t_full, rate, mode = ctx.meta
+        return ops.matryoshka_compress_bwd(d.contiguous(), n_tok, t_full, rate, mode), None, None, None
+
+
+def compress(enc, n_tok, rate, mode):
+    enc = enc.contiguous()
+    if enc.requires_grad:
+        return CompressFn.apply(enc, n_tok, rate, mode)
+    return ops.matryoshka_compress(enc, n_tok, rate, mode)
+
+
+class SpliceFn(torch.autograd.Function):
+    """One launch: media tokens + marker/prompt/text embedding rows -> packed LLM input rows + labels."""
+
+    @staticmethod
+    def forward(ctx, audio_tok, video_tok, layout, rows, want_labels):
+        H = layout.H
+        xp = torch.zeros((rows.M, H), device=layout.keep[2].device, dtype=torch.bfloat16) \
+            if rows.valid_rows != rows.M else torch.empty((rows.M, H), device=layout.keep[2].device, dtype=torch.bfloat16)
+        outs, labs, lab_t = [None] * 3, [None] * 3, []
+        seg_of = {task: (B, S, off) for (task, B, S, off) in rows.segments}
+        for t in range(3):
+            if t in seg_of:
+                B, S, off = seg_of[t]
+                outs[t] = xp[off: off + B * S]
+                if want_labels:
+                    labs[t] = torch.empty((B, S), device=xp.device, dtype=torch.int64)
+        ops.splice_prompt(layout, outs, labs)
+        ctx.layout, ctx.seg_of = layout, seg_of
+        ctx.mark_non_differentiable(*[l for l in labs if l is not None])
+        return (xp, *[l if l is not None else torch.empty(0, device=xp.device, dtype=torch.int64) for l in labs])
+
+    @staticmethod
+    def backward(ctx, dxp, *_):
+        dxp = dxp.contiguous()
+        douts = [None] * 3
+        for t, (B, S, off) in ctx.seg_of.items():
+            douts[t] = dxp[off: off + B * S]
+        da, dv = ops.splice_prompt_bwd(ctx.layout, douts, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return da, dv, None, None, None
+
+
+class AVSR_LLMs(nn.Module):
+    def __init__(self, modality, pretrain_avhubert_enc_video, use_lora_avhubert, llm_model, hidden_size,
+                 intermediate_size, tokenizer, prompt_audio, prompt_video, prompt_audiovisual, pad_id,
+                 downsample_ratio_audio, downsample_ratio_video, audio_encoder_name, compression_mode,
+                 unfrozen_modules, max_dec_tokens, num_beams, PETF_LLM_name=None, peft_config_llm=None,
+                 remove_layernorm_from_projector=False, matry_weights=None,
+                 is_task_specific=None, is_matryoshka=False, is_single_matry_projector=False,
+                 device="cuda", llm_overrides: Optional[dict] = None, audio_arch=None, video_arch=None):
+        super().__init__()
+        self.modality = modality
+        self.pretrain_avhubert_enc_video = pretrain_avhubert_enc_video
+        self.max_dec_tokens = max_dec_tokens
+        self.num_beams = num_beams
+        self.downsample_ratio_audio = downsample_ratio_audio
+        self.downsample_ratio_video = downsample_ratio_video
+        self.audio_encoder_name = audio_encoder_name
+        self.llm_model = llm_model
+        self.peft_config_llm = peft_config_llm
+        self.PETF_LLM_name = PETF_LLM_name
+        self.compression_mode = compression_mode
+        self.hidden_size = hidden_size
+        self.remove_layernorm_from_projector = remove_layernorm_from_projector
+        self.matry_weights = matry_weights
+        self.is_task_specific = is_task_specific
+        self.is_matryoshka = is_matryoshka
+        self.is_single_matry_projector = is_single_matry_projector
+        self.device_ = torch.device(device)
+        if compression_mode not in ("stack", "avg-pooling"):
+            raise ValueError(compression_mode)
+        if PETF_LLM_name != "lora":
+            raise NotImplementedError("the Omni-AVSR hot path is the LoRA-adapted LLM (PETF_LLM_name='lora')")
+
+        has_a = modality in ("audio", "audiovisual")
+        has_v = modality in ("video", "audiovisual")
+        rates_a = list(downsample_ratio_audio) if is_matryoshka else [downsample_ratio_audio]
+        rates_v = list(downsample_ratio_video) if is_matryoshka else [downsample_ratio_video]
+
+        # ---- one flat store for everything trainable (LLM LoRA, AV-HuBERT LoRA, projectors) ----------------
+        larch = arch_from_name(llm_model, **(llm_overrides or {}))
+        if hidden_size != larch.hidden_size:
+            raise ValueError(f"hidden_size {hidden_size} != {llm_model} hidden {larch.hidden_size}")
+        v_arch = video_arch or AVHUBERT_ARCHS["large" if (pretrain_avhubert_enc_video and "large" in
+                                                          str(pretrain_avhubert_enc_video)) else "base"]
+        audio_dim = (audio_arch.d_model if audio_arch else None)
+        cap = LlamaForCausalLM_lora.lora_param_count(larch, peft_config_llm) + 4096
+        if has_v:
+            cap += AVHubertVideoEncoder.lora_param_count(v_arch)
+        stack = compression_mode == "stack"
+
+        # encoders first (the projector input widths come from them)
+        if has_a:
+            self.audio_encoder = (WhisperEncoder(audio_arch, device) if audio_arch is not None
+                                  else WhisperEncoder.from_pretrained(audio_encoder_name, device))
+            self.audio_frontend = LogMel(device)
+            audio_dim = self.audio_encoder.config.hidden_size
+        video_dim = v_arch.encoder_embed_dim
+        for present, dim, rates in ((has_a, audio_dim, rates_a), (has_v, video_dim, rates_v)):
+            if present:
+                for r in rates:   # generous: one projector per rate, stack width
+                    cap += Projector.param_count(dim * (r if stack else 1), intermediate_size, hidden_size, True)
+        self.flat = FlatParams(device, cap)
+
+        if has_v:
+            self.video_encoder = AVHubertVideoEncoder(v_arch, device, self.flat, use_lora=bool(use_lora_avhubert))
+
+        # ---- projectors (:65-111 audio, :152-196 video) ----------------------------------------------------
+        if has_a:
+            self.audio_proj, self.matry_map_audio = self._make_projectors("audio_proj", audio_dim, rates_a, intermediate_size,
+                                                                         hidden_size, is_audio=True)
+        if has_v:
+            self.video_proj, self.matry_map_video = self._make_projectors("video_proj", video_dim, rates_v, intermediate_size,
+                                                                         hidden_size, is_audio=False)
+
+        # ---- LLM (:198-216) ---------------------------------------------------------------------------------
+        cls = Qwen2ForCausalLM_lora if "Qwen" in llm_model else LlamaForCausalLM_lora
+        self.llm = cls(larch, peft_config_llm, device=device, flat=self.flat)
+        self.tokenizer = tokenizer
+        if "llama" in llm_model:
+            self.llm.config.pad_token_id = pad_id
+        self.llm.resize_token_embeddings(len(self.tokenizer))
+        for p in self.llm.parameters():
+            p.requires_grad_(False)
+
+        start = 0 if "Qwen" in self.llm_model else 1                       # :218
+        emb = self.llm.model.embed_tokens
+        for name, prompt in (("prompt_audio", prompt_audio), ("prompt_video", prompt_video),
+                             ("prompt_audiovisual", prompt_audiovisual)):
+            ids = self.tokenizer(prompt, return_tensors="pt").input_ids[:, start:-1].to(device)
+            self.register_buffer(name, emb(ids).detach().clone())        # [1, P, H] buffers (:219-221)
+        self.prompt_audio_len = self.prompt_audio.shape[1]
+        self.prompt_video_len = self.prompt_video.shape[1]
+        self.prompt_audiovisual_len = self.prompt_audiovisual.shape[1]
+        v = self.tokenizer.vocab
+        self._marker_ids = (v["<audio>"], v["</audio>"], v["<video>"], v["</video>"])
+        self._has_bos = "Qwen" not in self.llm_model
+        self._unfreeze_PETF(unfrozen_modules)
+
+    # ------------------------------------------------------------------------------------------------
+    def _make_projectors(self, name, dim, rates, inter, hidden, is_audio):
+        stack = self.compression_mode == "stack"
+        mm = {el: i for i, el in enumerate(rates)} if self.is_matryoshka else None
+        rm = self.remove_layernorm_from_projector
+        if self.is_matryoshka:
+            if stack:
+                # audio :74-77 (condition inverted in the reference: LN only when remove_layernorm is True);
+                # video :159-162 (LayerNorm passed as Linear's bias argument => never a LayerNorm)
+                ln = rm if is_audio else False
+                proj = nn.ModuleList([Projector(dim * r, inter, hidden, ln, self.flat, f"{name}.{i}")
+                                      for i, r in enumerate(rates)])
+            elif self.is_single_matry_projector:
+                proj = Projector(dim, inter, hidden, not rm, self.flat, name)                      # :96-97,:101-102
+            else:
+                proj = nn.ModuleList([Projector(dim, inter, hidden, False, self.flat, f"{name}.{i}")  # :99,:104 (no LN)
+                                      for i, _ in enumerate(rates)])
+        else:
+            r = rates[0]
+            ln = (not rm)
+            proj = Projector(dim * r if stack else dim, inter, hidden, ln, self.flat, name)        # :81-85,:107-111
+        return proj, mm
+
+    def _unfreeze_PETF(self, unfrozen_modules):
+        """:234-260.  Projectors are always trainable (never frozen in the reference)."""
+        if unfrozen_modules is None or None in unfrozen_modules:
+            unfrozen_modules = []
+        llm_on = "peft_llm" in unfrozen_modules
+        for layer in self.llm.model.layers:
+            layer.self_attn.lora_down.requires_grad_(llm_on)
+            layer.self_attn.lora_up.requires_grad_(llm_on)
+        if hasattr(self, "video_encoder"):
+            avh_on = "lora_avhubert" in unfrozen_modules
+            for p in self.video_encoder.lora_parameters():
+                p.requires_grad_(avh_on)
+
+    def trainable_parameter_count(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    # ------------------------------------------------------------------------------------------------
+    def _project(self, feats, which, rate):
+        proj = self.audio_proj if which == "audio" else self.video_proj
+        mm = self.matry_map_audio if which == "audio" else self.matry_map_video
+        if isinstance(proj, nn.ModuleList):
+            proj = proj[mm[rate]]                      # KeyError for an unknown rate, as in the reference (:353,:366)
+        return proj(feats)
+
+    def _layout(self, inputs, audio_tok, video_tok, task_mask, with_labels):
+        tokens = inputs["tokens"]
+        labels = inputs.get("labels") if with_labels else None
+        return ops.SpliceLayout(tokens=tokens.contiguous(), labels=None if labels is None else labels.contiguous(),
+                                embed=self.llm.model.embed_tokens.weight.data, audio_tok=audio_tok, video_tok=video_tok,
+                                prompts=[self.prompt_audio[0], self.prompt_video[0], self.prompt_audiovisual[0]],
+                                marker_ids=self._marker_ids, has_bos=self._has_bos, task_mask=task_mask)
+
+    def forward(self, inputs, is_trainval=True, modality=None, test_ratio_matry_audio=None, test_ratio_matry_video=None):
+        if is_trainval:
+            out = self.prepare_inputs(inputs, is_trainval, test_ratio_matry_audio=test_ratio_matry_audio,
+                                      test_ratio_matry_video=test_ratio_matry_video)
+            xp, rows, labels = out["packed"], out["rows"], out["labels"]
+            hid = self.llm.model.forward_packed(xp, rows)
+            w = self.matry_weights if self.matry_weights else (1.0, 1.0, 1.0)
+            segs = [(B, S, off) for (_, B, S, off) in rows.segments]
+            losses = self.llm.loss_from_hidden(hid, segs, labels, [float(x) for x in w])
+            return losses[0], losses[1], losses[2]                          # :302-306
+        embeddings = self.prepare_inputs(inputs, is_trainval, test_ratio_matry_audio=test_ratio_matry_audio,
+                                         test_ratio_matry_video=test_ratio_matry_video)
+        vocab = self.tokenizer.vocab
+        if "Qwen" in self.llm_model:                                        # :318-322
+            return self.llm.generate(inputs_embeds=embeddings, max_new_tokens=self.max_dec_tokens, num_beams=self.num_beams,
+                                     eos_token_id=vocab["<|endoftext|>"], pad_token_id=vocab["<|endoftext|>"],
+                                     modality=modality)
+        return self.llm.generate(inputs_embeds=embeddings, max_new_tokens=self.max_dec_tokens, num_beams=self.num_beams,
+                                 eos_token_id=vocab["<|end_of_text|>"], bos_token_id=vocab["<|begin_of_text|>"],
+                                 pad_token_id=vocab["<pad>"], modality=modality)   # :313-317
+
+    def prepare_inputs(self, inputs, is_trainval, test_ratio_matry_audio=None, test_ratio_matry_video=None):
+        if is_trainval:
+            if self.is_matryoshka:
+                audio_features, ra = self.encode_audio(inputs["audio"], max(inputs["lengths"]), is_trainval=is_trainval,
+                                                       test_ratio_matry_audio=test_ratio_matry_audio)
+                video_features, rv = self.encode_video(inputs["video"], is_trainval=is_trainval,
+                                                       test_ratio_matry_video=test_ratio_matry_video)
+            else:
+                audio_features, ra = self.encode_audio(inputs["audio"], max(inputs["lengths"])), self.downsample_ratio_audio
+                video_features, rv = self.encode_video(inputs["video"]), self.downsample_ratio_video
+            audio_tok = self._project(audio_features, "audio", ra).contiguous()
+            video_tok = self._project(video_features, "video", rv).contiguous()
+            layout = self._layout(inputs, audio_tok, video_tok, 7, True)
+            B = inputs["tokens"].shape[0]
+            rows = PackedRows.get([(t, B, layout.seq_len[t]) for t in range(3)], audio_tok.device)
+            xp, la, lv, lav = SpliceFn.apply(audio_tok, video_tok, layout, rows, True)
+            return {"packed": xp, "rows": rows, "labels": [la, lv, lav], "labels_audio": la, "labels_video": lv,
+                    "labels_audiovisual": lav, "selected_rates": (ra, rv)}
+        # ---- inference (:397-458): [bos, A?, V?, prompt_t] ------------------------------------------------------
+        use_a = self.modality in ("audio", "audiovisual")
+        use_v = self.modality in ("video", "audiovisual")
+        audio_tok = video_tok = None
+        if use_a:
+            if self.is_matryoshka:
+                af = self.encode_audio(inputs["audio"], max(inputs["lengths"]), is_trainval=is_trainval,
+                                       test_ratio_matry_audio=test_ratio_matry_audio)
+                ra = test_ratio_matry_audio
+            else:
+                af, ra = self.encode_audio(inputs["audio"], max(inputs["lengths"])), self.downsample_ratio_audio
+            audio_tok = self._project(af, "audio", ra).contiguous()
+        if use_v:
+            if self.is_matryoshka:
+                vf = self.encode_video(inputs["video"], is_trainval=is_trainval, test_ratio_matry_video=test_ratio_matry_video)
+                rv = test_ratio_matry_video
+            else:
+                vf, rv = self.encode_video(inputs["video"]), self.downsample_ratio_video
+            video_tok = self._project(vf, "video", rv).contiguous()
+        t = TASKS.index(self.modality)
+        tokens = inputs["tokens"]
+        tok1 = tokens[:, :1] if self._has_bos else tokens[:, :0]          # only e(BOS) is used (:419)
+        layout = self._layout({"tokens": tok1.contiguous()}, audio_tok, video_tok, 1 << t, False)
+        B = tokens.shape[0]
+        out = [None] * 3
+        out[t] = torch.empty((B, layout.seq_len[t], self.hidden_size), device=tokens.device, dtype=torch.bfloat16)
+        ops.splice_prompt(layout, out, [None] * 3)
+        return out[t]
+
+    # ------------------------------------------------------------------------------------------------
+    def _pick_rate(self, rates, test_ratio, is_trainval):
+        if is_trainval and not test_ratio:
+            return random.choice(rates)                                     # :474,:549 (python RNG)
+        return test_ratio
+
+    def encode_video(self, videos, is_trainval=None, test_ratio_matry_video=None):
+        B = videos.shape[0]
+        src = torch.reshape(videos, (-1, videos.shape[2], videos.shape[1], videos.shape[3], videos.shape[-1]))  # :463
+        video_enc, _, _ = self.video_encoder.extract_finetune(source={"video": src, "audio": None})
+        n_tok = video_enc.shape[1]
+        if self.is_matryoshka:
+            rate = self._pick_rate(self.downsample_ratio_video, test_ratio_matry_video, is_trainval)
+            if rate not in self.matry_map_video:
+                raise KeyError(rate)
+            out = compress(video_enc, n_tok, rate, self.compression_mode)
+            return (out, rate) if is_trainval else out
+        if self.downsample_ratio_video != 1:
+            return compress(video_enc, n_tok, self.downsample_ratio_video, self.compression_mode)
+        return video_enc
+
+    def encode_audio(self, audio, max_len, is_trainval=None, test_ratio_matry_audio=None):
+        feats = self.audio_frontend(audio.squeeze(-1))                                  # :531-533 on the GPU
+        audio_enc = self.audio_encoder(feats).last_hidden_state                         # :534
+        ml = max_len if torch.is_tensor(max_len) else torch.tensor(max_len)
+        n_tok = max(int(ml.detach().cpu().to(torch.int64) / 16000 * 50), 25)            # :537 (float32 tensor arithmetic)
+        n_tok = min(n_tok, audio_enc.shape[1])
+        if self.is_matryoshka:
+            rate = self._pick_rate(self.downsample_ratio_audio, test_ratio_matry_audio, is_trainval)
+            if rate not in self.matry_map_audio:
+                raise KeyError(rate)
+            out = compress(audio_enc, n_tok, rate, self.compression_mode)
+            return (out, rate) if is_trainval else out
+        if self.downsample_ratio_audio != 1:
+            return compress(audio_enc, n_tok, self.downsample_ratio_audio, self.compression_mode)
+        return audio_enc[:, :n_tok].contiguous()

@@ -1,0 +1,147 @@
+"""GPU parity of the whole Omni-AVSR hot path (drop-in AVSR_LLMs / ModelModule_LLM) against the CPU oracle on a small
+configuration with identical weights: encoder features, the three task losses at every rate pair, trainable
+gradients, greedy transcripts, and an optimisation sanity check.
+
+Tolerances (bf16 end to end on both sides): features / logits max|a-b| <= 2e-2*max|b|; losses |a-b| <= 5e-2;
+gradients max|a-b| <= 1e-1*max|b| (two long bf16 backward chains); greedy tokens equal unless the oracle's own
+top-1/top-2 margin is below 2e-2 of its logit scale."""
+import pytest
+import torch
+
+from tests._small import small_module
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return (a.float().cpu() - b.float()).abs().max().item() / max(b.float().abs().max().item(), 1e-9)
+
+
+def _batch(mod, B=2, seconds=2.0, L=12, seed=7):
+    from omni_avsr_b200.synthetic import synthetic_batch, to_device
+    cpu = synthetic_batch(B, mod.tokenizer, seconds=seconds, text_len=L, seed=seed)
+    return cpu, to_device(cpu, "cuda")
+
+
+@pytest.fixture(scope="module")
+def pair():
+    from oracle.pairing import oracle_from_product
+    mod = small_module()
+    return mod, oracle_from_product(mod)
+
+
+def test_state_dict_uses_reference_key_names(pair):
+    mod, oracle = pair
+    keys = set(mod.model.state_dict().keys())
+    for k in ["audio_encoder.layers.0.self_attn.q_proj.weight", "audio_encoder.conv1.weight",
+              "video_encoder.encoder.layers.0.self_attn.lora_down_Q.weight",
+              "video_encoder.encoder.pos_conv.0.weight_g",
+              "video_encoder.feature_extractor_video.resnet.frontend3D.0.weight",
+              "audio_proj.0.0.weight", "audio_proj.1.2.bias", "video_proj.0.2.weight",
+              "llm.model.layers.0.self_attn.lora_down_Q.audio.weight",
+              "llm.model.layers.1.self_attn.lora_up_V_shared.weight", "llm.model.embed_tokens.weight",
+              "prompt_audio", "prompt_video", "prompt_audiovisual"]:
+        assert k in keys, k
+    assert mod.model.prompt_audio.shape[1] == 6 and mod.model.prompt_audiovisual.shape[1] == 8
+    # round trip through load_state_dict keeps the packed tensors in sync
+    sd = {k: v.clone() for k, v in mod.model.state_dict().items()}
+    mod.model.load_state_dict(sd)
+
+
+def test_encoder_features(pair):
+    mod, oracle = pair
+    cpu, gpu = _batch(mod)
+    m = mod.model
+    with torch.no_grad():
+        fa = m.audio_encoder(m.audio_frontend(gpu["audio"].squeeze(-1))).last_hidden_state
+        from oracle import encoders as oe
+        wa = oracle.audio_encoder(oe.log_mel(cpu["audio"].float().squeeze(-1)).bfloat16())
+        assert _rel(fa, wa) <= 2e-2, _rel(fa, wa)
+        src = torch.reshape(gpu["video"], (-1, 1, gpu["video"].shape[1], 88, 88))
+        fv, _, _ = m.video_encoder.extract_finetune({"video": src, "audio": None})
+        wv = oracle.video_encoder(torch.reshape(cpu["video"], (-1, 1, cpu["video"].shape[1], 88, 88)))
+        assert _rel(fv, wv) <= 3e-2, _rel(fv, wv)
+
+
+@pytest.mark.parametrize("ra,rv", [(4, 2), (16, 5)])
+def test_three_task_losses_and_grads(pair, ra, rv):
+    mod, oracle = pair
+    cpu, gpu = _batch(mod)
+    oracle.zero_grad()
+    o_loss, o_parts = __import__("oracle.modeling", fromlist=["training_step"]).training_step(oracle, cpu, ra, rv)
+    o_loss.backward()
+    mod.zero_grad_flat()
+    loss = mod.training_step(gpu, 0, rates=(ra, rv))
+    loss.backward()
+    for a, b in zip(mod.last_losses, o_parts):
+        assert abs(a.item() - b.item()) <= 5e-2, (a.item(), b.item())
+    assert abs(loss.item() - o_loss.item()) <= 5e-2
+    m = mod.model
+    ia, iv = m.matry_map_audio[ra], m.matry_map_video[rv]
+    checks = [
+        (m.audio_proj[ia][0].weight.grad, oracle.audio_proj[ia][0].weight.grad, "audio_proj.0"),
+        (m.audio_proj[ia][2].weight.grad, oracle.audio_proj[ia][2].weight.grad, "audio_proj.2"),
+        (m.video_proj[iv][2].bias.grad, oracle.video_proj[iv][2].bias.grad, "video_proj.2.bias"),
+    ]
+    att = m.llm.model.layers[0].self_attn
+    oatt = oracle.llm.model.layers[0].self_attn
+    p = att.plan
+    r = round(m.llm.config.hidden_size / att.rank)
+    checks.append((att.lora_down.grad[3 * p.rp: 3 * p.rp + r], oatt.lora_down_Q_shared.weight.grad, "llm.lora_down_Q_shared"))
+    checks.append((att.lora_up.grad[2 * p.q_cols: 3 * p.q_cols, :r], oatt.lora_up_Q["audiovisual"].weight.grad, "llm.lora_up_Q.av"))
+    vatt = m.video_encoder.encoder.layers[1].self_attn
+    ovatt = oracle.video_encoder.encoder.layers[1].self_attn
+    rv_ = round(128 / 16)
+    checks.append((vatt.lora_up.grad[:128, :rv_], ovatt.lora_up_Q.weight.grad, "avh.lora_up_Q"))
+    checks.append((vatt.lora_down.grad[:rv_], ovatt.lora_down_Q.weight.grad, "avh.lora_down_Q"))
+    for got, want, name in checks:
+        assert want is not None, name
+        assert _rel(got, want) <= 1e-1, (name, _rel(got, want))
+    # projectors of the rates that were NOT selected get no gradient (why the reference needs find_unused_parameters)
+    other = 1 - ia
+    assert m.audio_proj[other][0].weight.grad.abs().max().item() == 0
+
+
+@pytest.mark.parametrize("task,ra,rv", [("audio", 4, None), ("video", None, 5), ("audiovisual", 16, 2)])
+def test_greedy_transcripts(pair, task, ra, rv):
+    mod, oracle = pair
+    cpu, gpu = _batch(mod, B=3)
+    infer_cpu = dict(cpu, tokens=cpu["tokens"][:, :1])
+    infer_gpu = dict(gpu, tokens=gpu["tokens"][:, :1].contiguous())
+    want, margins = oracle.decode(infer_cpu, task, ra, rv, return_margins=True)
+    mod.args.modality = task
+    mod.args.downsample_ratio_test_matry_audio, mod.args.downsample_ratio_test_matry_video = ra, rv
+    mod.on_test_epoch_start()
+    got = mod.test_step(infer_gpu).cpu()
+    n = min(got.shape[1], want.shape[1])
+    same = 0
+    for b in range(got.shape[0]):
+        for i in range(n):
+            if got[b, i] != want[b, i]:
+                assert margins[b, i] <= 2e-2, f"{task} row {b} step {i}: mismatch, oracle margin {margins[b, i]}"
+                break
+            same += 1
+    assert same >= got.shape[0] * n // 2
+
+
+def test_train_steps_reduce_loss():
+    mod = small_module(seed=1)
+    _, gpu = _batch(mod, seed=3)
+    mod.configure_optimizers()
+    before = mod.model.flat.data[: mod.model.flat.used].clone()
+    losses = [mod.train_step(gpu, rates=(4, 2), lr=2e-3).item() for _ in range(6)]
+    assert (mod.model.flat.data[: mod.model.flat.used] != before).any()
+    assert losses[-1] < losses[0], losses
+    assert all(torch.isfinite(torch.tensor(losses)))
+
+
+def test_qwen_stack_mode_step():
+    from oracle.pairing import oracle_from_product
+    from oracle.modeling import training_step
+    mod = small_module(llm="Qwen/Qwen2.5-3B", task_specific=True, shared=False, compression="stack")
+    oracle = oracle_from_product(mod)
+    cpu, gpu = _batch(mod)
+    o_loss, o_parts = training_step(oracle, cpu, 4, 5)
+    loss = mod.training_step(gpu, 0, rates=(4, 5))
+    for a, b in zip(mod.last_losses, o_parts):
+        assert abs(a.item() - b.item()) <= 5e-2, (a.item(), b.item())
