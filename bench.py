@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Omni-AVSR hot-path benchmark (BASELINE.json metric: utterances/sec, train step, 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--mode train|decode] [--impl ours|reference]
+
+Workload (config.workload): BASELINE config 2 -- AVSR train step, Whisper-medium + AV-HuBERT-Large + Llama-3.2-1B,
+hybrid (task-specific + shared) Omni-LoRA, audio rates {4,16} x video rates {2,5}, bf16, synthetic 16 s clips,
+random-init weights.  One "step" = forward of the three task sequences (ASR, VSR, AVSR) of B utterances + backward +
+gradient all-reduce (N>1) + global-norm clip + AdamW; step k uses rate pair k mod 4 so K steps sweep the grid.
+Data parallel over utterances: weak scaling (per-GPU batch fixed), one NCCL all-reduce of the flat trainable-gradient
+buffer per step.
+
+`value`  : utterances/s with the batch already resident in HBM.
+`e2e`    : the same step through the public API (ModelModule_LLM.train_step) with the batch copied from pinned host
+           memory inside the timed region and the loss read back to the host every step.
+`--impl reference`: the reference's own PyTorch CPU path (the oracle restatement, since the reference cannot be
+           imported here -- see DESIGN.md) on the host cores, bounded sample (batch 1 per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+RATE_GRID = [(4, 2), (4, 5), (16, 2), (16, 5)]
+WORKLOAD = ("Omni-AVSR AVSR train step: Whisper-medium + AV-HuBERT-Large + Llama-3.2-1B, audio rates {4,16} x video "
+            "rates {2,5} (step k uses pair k mod 4), hybrid Omni-LoRA (task-specific + shared, r=64), bf16, 3 tasks/utterance")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_module(args, device):
+    from omni_avsr_b200 import lightning_OmniAVSR as L
+    margs = L.make_args(num_beams=1, max_dec_tokens=32)
+    torch.manual_seed(0)
+    mod = L.ModelModule_LLM(margs, device=device)
+    with torch.no_grad():   # non-degenerate adapters (LoRA down AND up ~ N(0, 0.02))
+        for layer in mod.model.llm.model.layers:
+            layer.self_attn.reset_lora_parameters(down_std=0.02)
+        for layer in mod.model.video_encoder.encoder.layers:
+            layer.self_attn.lora_down_Q.weight.normal_(0, 0.02)
+            layer.self_attn.lora_down_V.weight.normal_(0, 0.02)
+    mod.configure_optimizers()
+    return mod
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from omni_avsr_b200 import ops
+    from omni_avsr_b200.synthetic import host_bytes, synthetic_batch, to_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    mod = build_module(args, device)
+    B = args.batch
+    host = synthetic_batch(B, mod.tokenizer, seconds=16.0, text_len=48, seed=1234 + rank, pin=True)
+    resident = to_device(host, device)
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(k):
+        return mod.train_step(resident, rates=RATE_GRID[k % 4], lr=1e-4)
+
+    def step_e2e(k):
+        dev = to_device(host, device)                       # H2D from pinned memory, inside the timed region
+        loss = mod.train_step(dev, rates=RATE_GRID[k % 4], lr=1e-4)
+        return float(loss.item())                           # D2H read of the step's result
+
+    def timed(fn, K):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.LAUNCHES
+        s.record()
+        for k in range(K):
+            l2_flush.zero_()                                 # flush L2 between timed iterations
+            fn(k)
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)         # max over ranks
+        return t.item(), ops.LAUNCHES - l0
+
+    for k in range(args.warmup):
+        step_resident(k)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for k in range(min(args.warmup, 2)):
+        step_e2e(k)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): one instrumented step, CUDA events per launch ---------
+    roof = None
+    if rank == 0:
+        recs = []
+        orig = ops.gemm
+
+        def traced(a, b, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = orig(a, b, **kw)
+            e.record()
+            n = kw.get("n") or b.shape[0]
+            k_ext = 0
+            if kw.get("ext") is not None:
+                k_ext = kw["ext"][2].shape[-2] * 64
+            recs.append((s, e, 2.0 * a.shape[0] * n * (a.shape[1] + k_ext)))
+            return out
+        ops.gemm = traced
+        import omni_avsr_b200.autograd_ops as ag
+        try:
+            step_resident(0)
+            torch.cuda.synchronize()
+        finally:
+            ops.gemm = orig
+        tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        tot_fl = sum(f for _, _, f in recs)
+        peaks = load_peaks()
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "omni::gemm_bf16_tn_kernel (tcgen05)", "achieved": round(ach, 1),
+                "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["_source"] + " (sustained: timed inside a long step)",
+                "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 3), "traffic": None,
+                "launches": len(recs), "gemm_ms_per_step": round(tot_ms, 2),
+                "how": "algorithmic 2*M*N*(K+K_ext) per launch / CUDA-event duration per launch, summed over one step"}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    utt = B * world * args.steps
+    value = utt / (ms_total * 1e-3)
+    e2e = utt / (ms_e2e * 1e-3)
+    line = {
+        "metric": "utterances/sec (train step)", "value": round(value, 3), "unit": "utterances/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": 16,
+                   "text_tokens": 48, "parallelism": f"dp{world}", "l2": "256 MiB buffer written between timed steps",
+                   "optimizer": "fused all-reduce + clip(10) + AdamW", "random_init": True},
+        "e2e": {"value": round(e2e, 3), "unit": "utterances/s", "h2d_bytes_per_step": host_bytes(host),
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(steps=1, warmup=0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def build_oracle():
+    """The reference's CPU path = the oracle restatement at the benchmark's architecture (random init)."""
+    from oracle import encoders as oe
+    from oracle import llm_lora as ol
+    from oracle import modeling as omod
+    torch.manual_seed(0)
+    cfg = ol.llama_3_2_1b()
+    lc = ol.LoRA_config(32, 4, True, False, True, True)
+    prompts = {k: torch.randint(0, 1000, (1, n)) for k, n in (("audio", 6), ("video", 6), ("audiovisual", 8))}
+    m = omod.AVSR_LLMs(cfg, lc, oe.WHISPER["openai/whisper-medium.en"], oe.AVHubertCfg(), 2048, [4, 16], [2, 5],
+                       "avg-pooling", prompts, (128257, 128258, 128259, 128260), False, [1.0, 1.5, 1.0], True,
+                       eos_id=128001, pad_id=128256).bfloat16().eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    for n, p in m.named_parameters():
+        if "lora_" in n or n.startswith("audio_proj") or n.startswith("video_proj"):
+            p.requires_grad_(True)
+    return m, omod
+
+
+def cpu_baseline(steps=1, warmup=0, B=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m, omod = build_oracle()
+    g = torch.Generator().manual_seed(1234)
+    batch = {"tokens": torch.randint(0, 128000, (B, 48), generator=g),
+             "audio": torch.nn.functional.layer_norm(torch.randn(B, 256000, generator=g), (256000,)).unsqueeze(-1).bfloat16(),
+             "lengths": torch.full((B,), 256000, dtype=torch.int64),
+             "video": ((torch.rand(B, 400, 1, 88, 88, generator=g) - 0.421) / 0.165).bfloat16()}
+    batch["tokens"][:, 0], batch["tokens"][:, -1] = 128000, 128001
+    batch["labels"] = batch["tokens"].clone()
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.1, betas=(0.9, 0.98))
+    times = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _ = omod.training_step(m, batch, *RATE_GRID[k % 4])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in m.parameters() if p.requires_grad], 10.0)
+        opt.step()
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    return {"value": round(B * len(times) / tot, 4), "unit": "utterances/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} train step(s) of batch {B} (16 s clip, same architecture/config, bf16, "
+                      f"torch {torch.__version__} CPU, {cores} threads) after {warmup} warm-up",
+            "ms_per_step": round(1e3 * tot / len(times), 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=args.steps, warmup=args.warmup, B=1)
+    line = {"impl": "reference", "metric": "utterances/sec (train step)", "value": cb["value"], "unit": "utterances/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": 1, "note": "reference CPU path (oracle port; the reference "
+                       "itself cannot be imported in this image, see DESIGN.md), bounded sample: batch 1 per step"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=16, help="utterances per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -328,6 +328,18 @@ class AVHAttention_lora(_PackedSelfAttention):
             sd.pop(k, None)
         return sd
 
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        injected = []
+        if self.use_lora:
+            for k in ("lora_down", "lora_up"):      # packed tensors are filled through the aliased views
+                if prefix + k not in state_dict:
+                    state_dict[prefix + k] = getattr(self, k).data
+                    injected.append(prefix + k)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        for k in injected:
+            state_dict.pop(k, None)
+        self._wt = None
+
 
 class AVHLayer(nn.Module):
     def __init__(self, a: AVHubertArch, device, flat, use_lora, idx):

@@ -260,6 +260,17 @@ class AVSR_LLMs(nn.Module):
             for p in self.video_encoder.lora_parameters():
                 p.requires_grad_(avh_on)
 
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """Accepts the reference's bare AVSR_LLMs state dict (lightning_OmniAVSR.py:148-150); the packed / transposed
+        copies used by the kernels are rebuilt lazily afterwards."""
+        out = super().load_state_dict(state_dict, strict=strict)
+        for mod in self.modules():
+            if hasattr(mod, "_wt"):
+                mod._wt = None
+            if hasattr(mod, "_head_t"):
+                mod._head_t = None
+        return out
+
     def trainable_parameter_count(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
 
