@@ -17,7 +17,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import dp, ops
 from .Llama_LoRA import LoRA_config
 from .modeling_OmniAVSR import AVSR_LLMs
 from .Qwen_LoRA import QwenLoRA_config
@@ -207,9 +207,7 @@ class ModelModule_LLM(torch.nn.Module):
             self.configure_optimizers()
         o, flat = self._opt, self.model.flat
         p, g = flat.flat()
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        if world > 1:
-            dist.all_reduce(g)                     # the single NCCL all-reduce of the step (sum; averaged below)
+        grad_scale = dp.allreduce_flat_grad(g)     # the single NCCL all-reduce of the step (sum; 1/W applied below)
         o["step"] += 1
         o["sumsq"].zero_()
         ops.sumsq_(g, o["sumsq"])
@@ -217,7 +215,7 @@ class ModelModule_LLM(torch.nn.Module):
             self.scheduler.step()
             lr = self.scheduler.lr()
         ops.adamw_(p, g, o["m"], o["v"], lr=lr, beta1=0.9, beta2=0.98, eps=1e-8, weight_decay=self.args.weight_decay,
-                   step=o["step"], grad_scale=1.0 / world, max_norm=float(getattr(self.args, "gradient_clip_val", 10.0)),
+                   step=o["step"], grad_scale=grad_scale, max_norm=float(getattr(self.args, "gradient_clip_val", 10.0)),
                    sumsq=o["sumsq"])
         self.global_step += 1
 
@@ -230,15 +228,7 @@ class ModelModule_LLM(torch.nn.Module):
         self.last_losses = (audio_loss.detach(), video_loss.detach(), audiovisual_loss.detach())
         # :171-173: loss *= W / sum(batch sizes); equal per-rank batch sizes => 1/B
         batch_size = batch["tokens"].shape[0]
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            sizes = torch.tensor([batch_size], device=train_loss.device, dtype=torch.int64)
-            gathered = [torch.zeros_like(sizes) for _ in range(dist.get_world_size())]
-            dist.all_gather(gathered, sizes)
-            tot = torch.cat(gathered).sum()
-            train_loss = train_loss * (len(gathered) / tot)
-        else:
-            train_loss = train_loss * (1.0 / batch_size)
-        return train_loss
+        return train_loss * dp.loss_scale(batch_size, device=train_loss.device)
 
     def train_step(self, batch, rates=None, lr=None):
         """zero_grad -> training_step -> backward -> all-reduce + clip + AdamW.  Returns the (detached) loss."""
