@@ -12,6 +12,7 @@
 //   (reference semantics: Omni_AVSR/Llama_LoRA.py:246-259, Qwen_LoRA.py:557-570).
 // * epilogue: (+bias) -> round bf16 -> act -> (+residual) -> bf16 / fp32 store, mirroring the rounding
 //   points of the reference's unfused bf16 op sequence.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/omni_avsr.h"
 
@@ -47,6 +48,85 @@ struct GemmSmem {
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
 };
+
+// Epilogue of 32 accumulator columns of one row: alpha, bias, rounding point, activation, residual, store.
+__device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&v)[32], int row, int col0) {
+  const bool full = (col0 + 32 <= p.N);
+  if (p.bias) {
+    if (full) {
+      const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 b = __ldg(bp + i);
+        float2 f;
+        f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+        f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+        f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+        f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
+    }
+  }
+  if (p.act != OMNI_ACT_NONE || p.residual) {
+    // reference rounding point: the linear's bf16 output feeds the activation / the residual add
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    if (p.act == OMNI_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (p.act == OMNI_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_erf(v[i])));
+    }
+  }
+  if (p.residual) {
+    const bf16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
+    if (full) {
+      const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 b = ld_nc_u4(rp4 + i);
+        float2 f;
+        f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+        f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+        f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+        f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __bfloat162float(rp[i]);
+    }
+  }
+  if (p.out_fp32) {
+    float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) op[i] = v[i];
+    }
+  } else {
+    bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
+        o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
+        o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
+        o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(op + 8 * i) = o;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) op[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -173,81 +253,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-      const bool full = (col0 + 32 <= p.N);
-      if (p.bias) {
-        if (full) {
-          const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 b = __ldg(bp + i);
-            float2 f;
-            f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-            f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-            f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-            f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
-          }
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
-        }
-      }
-      if (p.act != OMNI_ACT_NONE || p.residual) {
-        // reference rounding point: the linear's bf16 output feeds the activation / the residual add
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-        if (p.act == OMNI_ACT_RELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-        } else if (p.act == OMNI_ACT_GELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_erf(v[i])));
-        }
-      }
-      if (p.residual) {
-        const bf16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
-        if (full) {
-          const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 b = ld_nc_u4(rp4 + i);
-            float2 f;
-            f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-            f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-            f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-            f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
-          }
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) v[i] += __bfloat162float(rp[i]);
-        }
-      }
-      if (p.out_fp32) {
-        float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) op[i] = v[i];
-        }
-      } else {
-        bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
-            o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
-            o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
-            o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
-            *reinterpret_cast<uint4*>(op + 8 * i) = o;
-          }
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) op[i] = __float2bfloat16_rn(v[i]);
-        }
-      }
+      epilogue_store_32(p, v, row, col0);
     }
   }
 
@@ -256,6 +262,209 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     tmem_dealloc(tmem_base, BN);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over output tiles; the TMEM accumulator is double-buffered
+// (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1, and the TMA pipeline
+// never drains between tiles.
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmemP {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int m_fast, int& m_tile, int& n_tile) {
+  if (m_fast) {
+    n_tile = t / m_tiles;
+    m_tile = t - n_tile * m_tiles;
+  } else {
+    m_tile = t / n_tiles;
+    n_tile = t - m_tile * n_tiles;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                        const GemmKParams p, const int m_fast) {
+  using S = GemmSmemP<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.ext_table) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], 1);
+        mbar_init(&tmem_empty_bar[s], 4);   // one arrive per epilogue warp
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_tile, n_tile;
+        tile_coords(t, p.m_tiles, p.n_tiles, m_fast, m_tile, n_tile);
+        const int m0 = m_tile * BM;
+        const int group = p.tile_group ? p.tile_group[m_tile] : 0;
+        const int tbl = group * p.n_tiles + n_tile;
+        const int b_row = p.b_row_table ? p.b_row_table[tbl] : n_tile * BN;
+        for (int it = 0; it < p.num_k_blocks; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * S::STAGE_BYTES;
+          uint8_t* sB = sA + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_2d(&tmA, &full_bar[stage], sA, it * BK, m0);
+          tma_load_2d(&tmB, &full_bar[stage], sB, it * BK, b_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (p.ext_table) {
+          const int4* ext = p.ext_table + static_cast<long long>(tbl) * p.n_ext;
+          for (int j = 0; j < p.n_ext; ++j) {
+            const int4 e = ext[j];
+            if (e.y < 0) continue;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * S::STAGE_BYTES;
+            uint8_t* sB = sA + S::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            tma_load_2d(&tmA2, &full_bar[stage], sA, e.x, m0);
+            tma_load_2d(&tmB2, &full_bar[stage], sB, e.z, e.y);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_tile, n_tile;
+      tile_coords(t, p.m_tiles, p.n_tiles, m_fast, m_tile, n_tile);
+      int total_iters = p.num_k_blocks;
+      if (p.ext_table) {
+        const int group = p.tile_group ? p.tile_group[m_tile] : 0;
+        const int4* ext = p.ext_table + static_cast<long long>(group * p.n_tiles + n_tile) * p.n_ext;
+        for (int j = 0; j < p.n_ext; ++j) total_iters += (ext[j].y >= 0) ? 1 : 0;
+      }
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int it = 0; it < total_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sB = sA + S::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (it == total_iters - 1) umma_commit(&tmem_full_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else {
+    // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    const float alpha = p.alpha;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_tile, n_tile;
+      tile_coords(t, p.m_tiles, p.n_tiles, m_fast, m_tile, n_tile);
+      const int row = m_tile * BM + q * 32 + lane;
+      const int n0 = n_tile * BN;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // all TMEM reads of this warp for this tile are done: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+        epilogue_store_32(p, v, row, col0);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+static int omni_sm_count() {
+  static int n = 0;   // immutable once resolved
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return kNumSMs;
+    n = v;
+  }
+  return n;
 }
 
 template <int BN, int STAGES>
@@ -291,6 +500,26 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
   p.ldo = a->ldo; p.ldr = a->ldr;
   p.act = a->act; p.out_fp32 = a->out_fp32; p.alpha = a->alpha;
 
+  static const bool use_v1 = (getenv("OMNI_GEMM_V1") != nullptr);   // debugging switch: one tile per CTA
+  if (!use_v1) {
+    using SP = GemmSmemP<BN, STAGES>;
+    auto kp = gemm_bf16_tn_persistent<BN, STAGES>;
+    static bool attr_set_p = false;
+    if (!attr_set_p) {
+      if (cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL) != cudaSuccess)
+        return OMNI_ERR_CUDA;
+      attr_set_p = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int sms = omni_sm_count();
+    // raster: walk M fastest when the A panel is small enough to live in L2 and there are more N tiles than M tiles
+    // (lm_head-like shapes: the big B operand is then streamed from HBM exactly once)
+    const long long a_bytes = static_cast<long long>(a->M) * a->K * 2;
+    const int m_fast = (!a->b_row_table && !a->ext_table && p.m_tiles < p.n_tiles && a_bytes <= (40ll << 20)) ? 1 : 0;
+    kp<<<tiles < sms ? tiles : sms, GEMM_THREADS, SP::TOTAL, stream>>>(tmA, tmB, tmA2, tmB2, p, m_fast);
+    OMNI_LAUNCH_CHECK();
+    return OMNI_OK;
+  }
   auto kfn = gemm_bf16_tn_kernel<BN, STAGES>;
   static bool attr_set = false;  // idempotent attribute; benign if set twice
   if (!attr_set) {
