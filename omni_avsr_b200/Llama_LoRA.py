@@ -485,8 +485,6 @@ class LlamaSdpaAttention_lora(nn.Module):
 def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
     """Causal GQA attention per segment of the packed rows.
     TODO(round 2): replace the library SDPA call with the tcgen05 flash kernel (csrc/attention.cu)."""
-    out = torch.zeros((rows.M, a.q_dim), device=qkv.device, dtype=torch.bfloat16) if rows.valid_rows != rows.M else \
-        torch.empty((rows.M, a.q_dim), device=qkv.device, dtype=torch.bfloat16)
     outs = []
     for (task, B, S, off) in rows.segments:
         blk = qkv[off: off + B * S]
@@ -501,13 +499,14 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
     if len(outs) == 1 and outs[0][1] == rows.M:
         return outs[0][2]
     pieces, cur = [], 0
+    zeros = lambda n: torch.zeros((n, a.q_dim), device=qkv.device, dtype=torch.bfloat16)   # only the pad rows
     for off, n, o in outs:
         if off > cur:
-            pieces.append(out[cur:off])
+            pieces.append(zeros(off - cur))
         pieces.append(o)
         cur = off + n
     if cur < rows.M:
-        pieces.append(out[cur:])
+        pieces.append(zeros(rows.M - cur))
     return torch.cat(pieces, dim=0)
 
 
@@ -740,16 +739,20 @@ class LlamaForCausalLM_lora(nn.Module):
         weighted mean loss of each segment."""
         W = self.lm_head.weight.data
         WT = self.head_transposed()
-        out = []
+        idxs, tgts, scales = [], [], []
         for (B, S, off), lab, w in zip(segs, labels_list, weights):
             tgt = lab[:, 1:]
             mask = tgt != IGNORE_INDEX
             b_idx, s_idx = mask.nonzero(as_tuple=True)
-            idx = (off + b_idx * S + s_idx).contiguous()
-            targets = tgt[mask].contiguous()
-            scale = (w / mask.sum().clamp(min=1).float()).expand(idx.numel()).contiguous()
-            hrows = GatherRowsFn.apply(hid, idx)
-            out.append(ag.LmHeadCEFn.apply(hrows, W, WT, targets, scale))
+            idxs.append(off + b_idx * S + s_idx)
+            tgts.append(tgt[mask].contiguous())
+            scales.append((w / mask.sum().clamp(min=1).float()).expand(b_idx.numel()).contiguous())
+        hrows = GatherRowsFn.apply(hid, torch.cat(idxs).contiguous())      # one gather / one scatter for all tasks
+        out, start = [], 0
+        for tg, sc in zip(tgts, scales):
+            n = tg.numel()
+            out.append(ag.LmHeadCEFn.apply(hrows[start: start + n], W, WT, tg, sc))
+            start += n
         return out
 
     @torch.no_grad()
@@ -758,7 +761,8 @@ class LlamaForCausalLM_lora(nn.Module):
         from .decode import greedy_generate
         if num_beams != 1:
             raise NotImplementedError("beam search is SURVEY §8f rank 1 (next); greedy (num_beams=1) is implemented")
-        return greedy_generate(self, inputs_embeds, max_new_tokens, eos_token_id, pad_token_id, modality)
+        return greedy_generate(self, inputs_embeds, max_new_tokens, eos_token_id, pad_token_id, modality,
+                               trim=kw.get("trim", True))
 
 
 class GatherRowsFn(torch.autograd.Function):

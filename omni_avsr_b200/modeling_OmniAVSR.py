@@ -102,10 +102,16 @@ class SpliceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, audio_tok, video_tok, layout, rows, want_labels):
         H = layout.H
-        xp = torch.zeros((rows.M, H), device=layout.keep[2].device, dtype=torch.bfloat16) \
-            if rows.valid_rows != rows.M else torch.empty((rows.M, H), device=layout.keep[2].device, dtype=torch.bfloat16)
+        xp = torch.empty((rows.M, H), device=layout.keep[2].device, dtype=torch.bfloat16)
         outs, labs, lab_t = [None] * 3, [None] * 3, []
         seg_of = {task: (B, S, off) for (task, B, S, off) in rows.segments}
+        cur = 0
+        for (task, B, S, off) in rows.segments:       # zero only the pad rows between the 128-aligned segments
+            if off > cur:
+                xp[cur:off].zero_()
+            cur = off + B * S
+        if cur < rows.M:
+            xp[cur:].zero_()
         for t in range(3):
             if t in seg_of:
                 B, S, off = seg_of[t]
@@ -306,10 +312,11 @@ class AVSR_LLMs(nn.Module):
         if "Qwen" in self.llm_model:                                        # :318-322
             return self.llm.generate(inputs_embeds=embeddings, max_new_tokens=self.max_dec_tokens, num_beams=self.num_beams,
                                      eos_token_id=vocab["<|endoftext|>"], pad_token_id=vocab["<|endoftext|>"],
-                                     modality=modality)
+                                     modality=modality, trim=not getattr(self, "decode_no_trim", False))
         return self.llm.generate(inputs_embeds=embeddings, max_new_tokens=self.max_dec_tokens, num_beams=self.num_beams,
                                  eos_token_id=vocab["<|end_of_text|>"], bos_token_id=vocab["<|begin_of_text|>"],
-                                 pad_token_id=vocab["<pad>"], modality=modality)   # :313-317
+                                 pad_token_id=vocab["<pad>"], modality=modality,                # :313-317
+                                 trim=not getattr(self, "decode_no_trim", False))
 
     def prepare_inputs(self, inputs, is_trainval, test_ratio_matry_audio=None, test_ratio_matry_video=None):
         if is_trainval:
