@@ -491,10 +491,11 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
         q = blk[:, : a.q_dim].view(B, S, a.num_attention_heads, a.head_dim).transpose(1, 2)
         k = blk[:, a.q_dim: a.q_dim + a.kv_dim].view(B, S, a.num_key_value_heads, a.head_dim).transpose(1, 2)
         v = blk[:, a.q_dim + a.kv_dim:].view(B, S, a.num_key_value_heads, a.head_dim).transpose(1, 2)
+        mask = None
         if kv_cache is not None:
-            k, v = kv_cache.update(layer_idx, k, v)
-        causal = S > 1
-        o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and (k.shape[2] == S), enable_gqa=True)
+            k, v, mask = kv_cache.update(layer_idx, k, v)
+        causal = S > 1 and k.shape[2] == S and mask is None
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal, enable_gqa=True)
         outs.append((off, B * S, o.transpose(1, 2).reshape(B * S, a.q_dim)))
     if len(outs) == 1 and outs[0][1] == rows.M:
         return outs[0][2]
@@ -511,22 +512,41 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
 
 
 class KVCache:
-    """Static per-layer KV cache [B, kv_heads, max_len, head_dim] for decode."""
+    """Static per-layer KV cache [layers, B, kv_heads, max_len, head_dim].
+
+    Two write modes: eager (prefill / ungraphed steps: python-int offset `len`) and `graph_mode` (decode step captured
+    in a CUDA graph: the write index, the key mask and the RoPE positions live in device tensors that the graph itself
+    advances, and attention always spans max_len under the mask so every shape is static)."""
 
     def __init__(self, a: LLMArch, B: int, max_len: int, device):
         shape = (a.num_hidden_layers, B, a.num_key_value_heads, max_len, a.head_dim)
-        self.k = torch.empty(shape, device=device, dtype=torch.bfloat16)
-        self.v = torch.empty(shape, device=device, dtype=torch.bfloat16)
+        self.k = torch.zeros(shape, device=device, dtype=torch.bfloat16)
+        self.v = torch.zeros(shape, device=device, dtype=torch.bfloat16)
         self.len = 0
+        self.max_len = max_len
+        self.graph_mode = False
+        self.len_idx = torch.zeros(1, device=device, dtype=torch.int64)            # device copy of `len`
+        self.mask = torch.zeros((B, 1, 1, max_len), device=device, dtype=torch.bool)
 
     def update(self, layer, k, v):
+        """Returns (k_all, v_all, attn_mask or None)."""
         S = k.shape[2]
+        if self.graph_mode:
+            self.k[layer].index_copy_(2, self.len_idx, k)
+            self.v[layer].index_copy_(2, self.len_idx, v)
+            return self.k[layer], self.v[layer], self.mask
         self.k[layer][:, :, self.len: self.len + S] = k
         self.v[layer][:, :, self.len: self.len + S] = v
-        return self.k[layer][:, :, : self.len + S], self.v[layer][:, :, : self.len + S]
+        return self.k[layer][:, :, : self.len + S], self.v[layer][:, :, : self.len + S], None
 
     def advance(self, S):
         self.len += S
+
+    def sync_device_state(self):
+        """After the eager prefill: publish `len` to the device-side state used by the graphed decode step."""
+        self.len_idx.fill_(self.len)
+        self.mask.zero_()
+        self.mask[..., : self.len] = True
 
 
 class LlamaMLP(nn.Module):

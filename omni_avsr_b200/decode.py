@@ -1,5 +1,5 @@
-"""Greedy decode with a static KV cache (the `eval_OmniAVSR.py` path: modeling_OmniAVSR.py:308-323 ->
-HF GenerationMixin.generate with inputs_embeds, reproduced per SURVEY A.5):
+"""Greedy decode with a static KV cache and a CUDA-graph-captured decode step (the `eval_OmniAVSR.py` path:
+modeling_OmniAVSR.py:308-323 -> HF GenerationMixin.generate with inputs_embeds, reproduced per SURVEY A.5):
 
   * only `inputs_embeds` is given, so the returned ids contain ONLY the new tokens;
   * step 0 consumes the embeddings, later steps embed the previously chosen id (Llama_LoRA.py:429-432);
@@ -7,51 +7,156 @@ HF GenerationMixin.generate with inputs_embeds, reproduced per SURVEY A.5):
   * greedy = argmax(fp32(logits[:, -1])); a row that emitted EOS is padded with pad_token_id afterwards;
   * generation stops when every row is finished or after max_new_tokens.
 
-All max_new_tokens steps are enqueued without a host sync; the "all rows finished" cut is applied once at the end,
-which yields the same ids as HF's per-step check.
+Execution: the prefill runs eagerly; the per-token step (embed gather -> N decoder layers -> lm_head -> argmax ->
+finished-row bookkeeping -> KV/mask/position advance) is captured ONCE per (batch, max_len) in a CUDA graph and
+replayed, so a step costs one graph launch instead of ~250 kernel launches from Python.  Everything the step needs to
+advance (cache write index, key mask, RoPE positions, output slot) lives in device tensors updated inside the graph; the
+"all rows finished" cut is applied once at the end (same ids as HF's per-step check, one host sync per decode).
 """
 from __future__ import annotations
 
 import torch
 
 from . import ops
-from .Llama_LoRA import KVCache, PackedRows, pack_segments
+from .Llama_LoRA import TILE, KVCache, PackedRows, pack_segments
+
+
+class _StepRows:
+    """PackedRows-like layout of the single-token step (B rows padded to one 128-row tile, static device tensors)."""
+
+    def __init__(self, B, device, max_pos):
+        self.M = (B + TILE - 1) // TILE * TILE
+        self.segments = [(0, B, 1, 0)]
+        self.valid_rows = B
+        self.max_pos = max_pos
+        self.runs = [(0, 0, self.M)]
+        self.tile_group = torch.zeros(self.M // TILE, dtype=torch.int32, device=device)
+        self.pos = torch.zeros(self.M, dtype=torch.int32, device=device)
+
+
+class GraphedGreedyStep:
+    """One decode step captured in a CUDA graph (static buffers; see module docstring)."""
+
+    def __init__(self, llm, B, max_len, max_new, device):
+        a = llm.config
+        self.llm, self.B, self.max_len, self.max_new = llm, B, max_len, max_new
+        self.cache = KVCache(a, B, max_len, device)
+        self.rows = _StepRows(B, device, max_len)
+        self.tok = torch.zeros(B, dtype=torch.int64, device=device)
+        self.unfinished = torch.ones(B, dtype=torch.int64, device=device)
+        self.out = torch.zeros((max_new, B), dtype=torch.int64, device=device)
+        self.alive = torch.zeros(max_new, dtype=torch.int64, device=device)
+        self.step_idx = torch.zeros(1, dtype=torch.int64, device=device)
+        self.eos = torch.zeros(1, dtype=torch.int64, device=device)
+        self.pad = torch.zeros(1, dtype=torch.int64, device=device)
+        self.xpad = torch.zeros((self.rows.M, a.hidden_size), dtype=torch.bfloat16, device=device)
+        self.h_last = torch.zeros((B, a.hidden_size), dtype=torch.bfloat16, device=device)
+        self.graph = None
+        llm.model.rope(max_len)          # make sure the RoPE tables cover max_len before capture
+
+    def _body(self):
+        """pick token from h_last -> bookkeeping -> (embed -> layers) -> new h_last, advance device state."""
+        llm, B = self.llm, self.B
+        logits = llm.logits_rows(self.h_last)
+        nxt = ops.argmax_rows(logits)
+        nxt = nxt * self.unfinished + self.pad * (1 - self.unfinished)
+        self.out.index_copy_(0, self.step_idx, nxt.unsqueeze(0))
+        self.unfinished.mul_((nxt != self.eos).long())
+        self.alive.index_copy_(0, self.step_idx, self.unfinished.max().unsqueeze(0))
+        self.step_idx.add_(1)
+        # forward of the chosen token
+        x = ops.gather_rows(llm.model.embed_tokens.weight.data, nxt.contiguous())
+        self.xpad[:B].copy_(x)
+        self.cache.mask.index_fill_(3, self.cache.len_idx, True)       # the new key is visible to its own query
+        hid = llm.model.forward_packed(self.xpad, self.rows, self.cache)
+        self.h_last.copy_(hid[:B])
+        self.cache.len_idx.add_(1)
+        self.rows.pos.add_(1)
+
+    def start(self, task, prefill_len, h_last, eos, pad):
+        self.rows.tile_group.fill_(task)
+        self.rows.pos.fill_(prefill_len)
+        self.cache.len = prefill_len
+        self.cache.sync_device_state()
+        self.cache.graph_mode = True
+        self.tok.zero_()
+        self.unfinished.fill_(1)
+        self.step_idx.zero_()
+        self.alive.zero_()
+        self.eos.fill_(eos)
+        self.pad.fill_(pad)
+        self.h_last.copy_(h_last)
+
+    def run(self, steps):
+        if self.graph is None:
+            # warm-up on a side stream (allocator / lazy init), restoring the device state afterwards, then capture
+            snap = [t.clone() for t in self._state()]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()
+            torch.cuda.current_stream().wait_stream(s)
+            for t, v in zip(self._state(), snap):
+                t.copy_(v)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+            for t, v in zip(self._state(), snap):
+                t.copy_(v)
+        for _ in range(steps):
+            self.graph.replay()
+
+    def _state(self):
+        return [self.unfinished, self.out, self.alive, self.step_idx, self.cache.len_idx, self.cache.mask, self.rows.pos,
+                self.h_last, self.cache.k, self.cache.v]
+
+    def finish(self):
+        self.cache.graph_mode = False
+
+
+def _get_step(llm, B, max_len, max_new, device):
+    cache = getattr(llm, "_graphed_steps", None)
+    if cache is None:
+        cache = llm._graphed_steps = {}
+    key = (B, max_len, max_new)
+    if key not in cache:
+        if len(cache) >= 4:
+            cache.clear()
+        cache[key] = GraphedGreedyStep(llm, B, max_len, max_new, device)
+    return cache[key]
 
 
 @torch.no_grad()
-def greedy_generate(llm, inputs_embeds, max_new_tokens, eos_token_id, pad_token_id, modality=None, trim=True):
+def greedy_generate(llm, inputs_embeds, max_new_tokens, eos_token_id, pad_token_id, modality=None, trim=True,
+                    use_graph=True):
     ops.require_cuda(inputs_embeds)
     B, S0, H = inputs_embeds.shape
-    a = llm.config
     dev = inputs_embeds.device
     task = llm._task_of(modality)
-    cache = KVCache(a, B, S0 + max_new_tokens, dev)
+    if pad_token_id is None:
+        pad_token_id = eos_token_id
+    # bucket the cache length so that different prefill lengths share one captured graph
+    max_len = (S0 + max_new_tokens + 127) // 128 * 128
+    step = _get_step(llm, B, max_len, max_new_tokens, dev)
+    cache = step.cache
+    cache.graph_mode = False
+    cache.len = 0
     rows = PackedRows.get([(task, B, S0)], dev)
-    hid = llm.model.forward_packed(pack_segments([inputs_embeds.to(torch.bfloat16)], rows), rows, cache)
+    hid = llm.model.forward_packed(pack_segments([inputs_embeds.to(torch.bfloat16)], rows), rows, cache)   # prefill
     cache.advance(S0)
     last = (torch.arange(B, device=dev, dtype=torch.int64) * S0 + (S0 - 1)).contiguous()
     h_last = ops.gather_rows(hid, last)
-    if pad_token_id is None:
-        pad_token_id = eos_token_id
-    unfinished = torch.ones(B, dtype=torch.int64, device=dev)
-    toks, alive = [], []
-    for step in range(max_new_tokens):
-        logits = llm.logits_rows(h_last)
-        nxt = ops.argmax_rows(logits)
-        nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
-        toks.append(nxt)
-        unfinished = unfinished * (nxt != eos_token_id).long()
-        alive.append(unfinished.max())
-        if step == max_new_tokens - 1:
-            break
-        x = ops.gather_rows(llm.model.embed_tokens.weight.data, nxt.contiguous())
-        rows1 = PackedRows.get([(task, B, 1)], dev, pos_offset=cache.len)
-        hid = llm.model.forward_packed(pack_segments([x.view(B, 1, H)], rows1), rows1, cache)
-        cache.advance(1)
-        h_last = hid[:B]
-    out = torch.stack(toks, dim=1)
+    step.start(task, S0, h_last, eos_token_id, pad_token_id)
+    if use_graph:
+        step.run(max_new_tokens)
+    else:
+        for _ in range(max_new_tokens):
+            step._body()
+    step.finish()
+    out = step.out.t().contiguous()
     if trim:
-        alive = torch.stack(alive).tolist()        # the only host sync of the whole decode
+        alive = step.alive.tolist()                # the only host sync of the whole decode
         n = next((i + 1 for i, v in enumerate(alive) if v == 0), len(alive))
         out = out[:, :n]
-    return out
+    return out.clone()
