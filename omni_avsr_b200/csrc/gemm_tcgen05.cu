@@ -456,6 +456,188 @@ gemm_bf16_tn_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cluster variant: two CTAs (one per SM of a TPC pair) work on two vertically adjacent M tiles of the same N tile.
+// Each CTA loads its own A tile and HALF of the shared B tile; the TMA unit multicasts that half into both CTAs'
+// shared memory, so the L2 -> SM traffic per MAC drops by a third (48 KB -> 32 KB per 128x256x64 block).  A smem
+// slot may only be refilled when BOTH MMA warps are done with it: tcgen05.commit arrives on the empty barrier of
+// both CTAs (count 2).  Everything else (TMEM double buffering, epilogue) is the persistent kernel.
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                     const GemmKParams p, const int m_fast) {
+  using S = GemmSmemP<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int num_pairs = m_pairs * p.n_tiles;
+  constexpr int B_HALF_BYTES = S::B_BYTES / 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBh);
+    if (p.ext_table) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 2);      // both CTAs' MMA warps release a slot
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], 1);
+        mbar_init(&tmem_empty_bar[s], 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // partner's barriers are initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_pairs; t += num_clusters) {
+        int m_pair, n_tile;
+        tile_coords(t, m_pairs, p.n_tiles, m_fast, m_pair, n_tile);
+        const int m_tile = 2 * m_pair + rank;
+        const int m0 = m_tile * BM;                  // may be >= M for the phantom tile of an odd M: TMA zero-fills
+        const int n0 = n_tile * BN;
+        for (int it = 0; it < p.num_k_blocks; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * S::STAGE_BYTES;
+          uint8_t* sB = sA + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_2d(&tmA, &full_bar[stage], sA, it * BK, m0);
+          tma_load_2d_multicast(&tmBh, &full_bar[stage], sB + rank * B_HALF_BYTES, it * BK, n0 + rank * (BN / 2),
+                                static_cast<uint16_t>(3));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (p.ext_table) {
+          const int mt = m_tile < p.m_tiles ? m_tile : p.m_tiles - 1;
+          const int group = p.tile_group ? p.tile_group[mt] : 0;
+          const int4* ext = p.ext_table + static_cast<long long>(group * p.n_tiles + n_tile) * p.n_ext;
+          for (int j = 0; j < p.n_ext; ++j) {
+            const int4 e = ext[j];
+            if (e.y < 0) continue;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * S::STAGE_BYTES;
+            uint8_t* sB = sA + S::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            tma_load_2d(&tmA2, &full_bar[stage], sA, e.x, m0);
+            // the adapter (hence B2) may differ between the two CTAs: private, non-multicast load of both halves
+            tma_load_2d(&tmB2, &full_bar[stage], sB, e.z, e.y);
+            tma_load_2d(&tmB2, &full_bar[stage], sB + B_HALF_BYTES, e.z, e.y + BN / 2);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = cluster_id; t < num_pairs; t += num_clusters) {
+      int m_pair, n_tile;
+      tile_coords(t, m_pairs, p.n_tiles, m_fast, m_pair, n_tile);
+      int total_iters = p.num_k_blocks;
+      if (p.ext_table) {
+        // the number of extension blocks depends only on the N tile (Q / K / V column class), not on the task
+        const int4* ext = p.ext_table + static_cast<long long>(n_tile) * p.n_ext;
+        for (int j = 0; j < p.n_ext; ++j) total_iters += (ext[j].y >= 0) ? 1 : 0;
+      }
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int it = 0; it < total_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sB = sA + S::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(3));
+          if (it == total_iters - 1) umma_commit(&tmem_full_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    const float alpha = p.alpha;
+    for (int t = cluster_id; t < num_pairs; t += num_clusters) {
+      int m_pair, n_tile;
+      tile_coords(t, m_pairs, p.n_tiles, m_fast, m_pair, n_tile);
+      const int row = (2 * m_pair + rank) * BM + q * 32 + lane;
+      const int n0 = n_tile * BN;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+        epilogue_store_32(p, v, row, col0);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // nobody exits while the partner can still multicast into / arrive on it
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 static int omni_sm_count() {
   static int n = 0;   // immutable once resolved
   if (n == 0) {
@@ -516,6 +698,33 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     // (lm_head-like shapes: the big B operand is then streamed from HBM exactly once)
     const long long a_bytes = static_cast<long long>(a->M) * a->K * 2;
     const int m_fast = (!a->b_row_table && !a->ext_table && p.m_tiles < p.n_tiles && a_bytes <= (40ll << 20)) ? 1 : 0;
+    static const bool no_cluster = (getenv("OMNI_GEMM_NO_CLUSTER") != nullptr);
+    if (!no_cluster && BN >= 128 && !a->b_row_table && p.m_tiles >= 2 && tiles >= sms / 2) {
+      // 2-CTA clusters with TMA multicast of the shared B tile
+      auto kc = gemm_bf16_tn_cluster<BN, STAGES>;
+      static bool attr_set_c = false;
+      if (!attr_set_c) {
+        if (cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::TOTAL) != cudaSuccess)
+          return OMNI_ERR_CUDA;
+        attr_set_c = true;
+      }
+      CUtensorMap tmBh, tmB2h;
+      rc = omni_make_tmap_2d_bf16(&tmBh, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, BN / 2, BK, 1);
+      if (rc) return rc;
+      if (a->ext_table) {
+        rc = omni_make_tmap_2d_bf16(&tmB2h, a->B2, (uint64_t)a->b2_rows, (uint64_t)a->b2_cols, (uint64_t)a->ldb2,
+                                    BN / 2, BK, 1);
+        if (rc) return rc;
+      } else {
+        tmB2h = tmBh;
+      }
+      const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+      int clusters = sms / 2;
+      if (pairs < clusters) clusters = pairs;
+      kc<<<2 * clusters, GEMM_THREADS, SP::TOTAL, stream>>>(tmA, tmBh, tmA2, tmB2h, p, m_fast);
+      OMNI_LAUNCH_CHECK();
+      return OMNI_OK;
+    }
     kp<<<tiles < sms ? tiles : sms, GEMM_THREADS, SP::TOTAL, stream>>>(tmA, tmB, tmA2, tmB2, p, m_fast);
     OMNI_LAUNCH_CHECK();
     return OMNI_OK;

@@ -275,12 +275,61 @@ class _ResEncoder(nn.Module):
             nn.PReLU(widths[0]), nn.MaxPool3d((1, 3, 3), (1, 2, 2), (0, 1, 1)))
         self.trunk = _Trunk(widths)
 
+    # ---- eval-mode fast path: BatchNorm folded into the convolutions, Conv3d(C_in=1) as a channels-last Conv2d ----
+    @staticmethod
+    def _fold(conv_w, bn):
+        scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        w = (conv_w.float() * scale.view(-1, *([1] * (conv_w.dim() - 1)))).to(torch.bfloat16)
+        b = (bn.bias.float() - bn.running_mean.float() * scale).to(torch.bfloat16)
+        return w, b
+
+    def _prepare(self):
+        conv3, bn3 = self.frontend3D[0], self.frontend3D[1]
+        w3, b3 = self._fold(conv3.weight, bn3)                         # [C, 1, 5, 7, 7]
+        C = w3.shape[0]
+        w2d = torch.zeros((C, 8, 7, 7), device=w3.device, dtype=torch.bfloat16)
+        w2d[:, :5] = w3[:, 0]                                          # temporal taps become input channels (3 zero pads)
+        f = {"front": (w2d.contiguous(memory_format=torch.channels_last), b3)}
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
+                w1, b1 = self._fold(blk.conv1.weight, blk.bn1)
+                w2, b2 = self._fold(blk.conv2.weight, blk.bn2)
+                ds = None
+                if blk.downsample is not None:
+                    wd, bd = self._fold(blk.downsample[0].weight, blk.downsample[1])
+                    ds = (wd.contiguous(memory_format=torch.channels_last), bd, blk.downsample[0].stride)
+                f[(li, bi)] = (w1.contiguous(memory_format=torch.channels_last), b1, blk.conv1.stride,
+                               w2.contiguous(memory_format=torch.channels_last), b2, ds)
+        return f
+
     def forward(self, x):                       # [B, 1, T, 88, 88] -> [B*T, C]
-        B = x.shape[0]
-        x = self.frontend3D(x)
-        T = x.shape[2]
-        x = x.transpose(1, 2).reshape(B * T, *x.shape[1:2], *x.shape[3:])
-        return self.trunk(x.contiguous(memory_format=torch.channels_last))
+        if self.training:
+            B = x.shape[0]
+            x = self.frontend3D(x)
+            T = x.shape[2]
+            x = x.transpose(1, 2).reshape(B * T, *x.shape[1:2], *x.shape[3:])
+            return self.trunk(x.contiguous(memory_format=torch.channels_last))
+        if getattr(self, "_wt", None) is None:
+            self._wt = self._prepare()
+        f = self._wt
+        B, _, T, Hh, Ww = x.shape
+        # frame t sees frames t-2..t+2: build the 5 (+3 zero) "channels" of every frame as one strided copy
+        xp = F.pad(x[:, 0], (0, 0, 0, 0, 2, 2))                                  # [B, T+4, H, W]
+        x8 = torch.zeros((B, T, Hh, Ww, 8), device=x.device, dtype=torch.bfloat16)
+        x8[..., :5] = xp.unfold(1, 5, 1)                                          # [B, T, H, W, 5]
+        x8 = x8.view(B * T, Hh, Ww, 8).permute(0, 3, 1, 2)                        # NCHW view of channels-last data
+        w, b = f["front"]
+        y = F.conv2d(x8, w, b, stride=2, padding=3)        # TODO(round 2): implicit-GEMM tcgen05 kernel (conv mode)
+        y = F.prelu(y, self.frontend3D[2].weight)
+        y = F.max_pool2d(y, 3, 2, 1)
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
+                w1, b1, s1, w2, b2, ds = f[(li, bi)]
+                o = F.prelu(F.conv2d(y, w1, b1, stride=s1, padding=1), blk.relu1.weight)
+                o = F.conv2d(o, w2, b2, stride=1, padding=1)
+                res = y if ds is None else F.conv2d(y, ds[0], ds[1], stride=ds[2])
+                y = F.prelu(o + res, blk.relu2.weight)
+        return y.mean(dim=(2, 3))
 
 
 class _VideoFeatureExtractor(nn.Module):
@@ -399,7 +448,12 @@ class _AVHTransformerEncoder(nn.Module):
     def forward(self, x, B, T):                  # x [B*T, C]
         d = x.shape[1]
         with torch.no_grad():
-            xc = self.pos_conv(x.view(B, T, d).transpose(1, 2))      # TODO(round 2): grouped conv as GEMM
+            if getattr(self, "_wt", None) is None:                   # frozen: materialise g * v / ||v|| once
+                conv = self.pos_conv[0]
+                self._wt = (torch._weight_norm(conv.weight_v, conv.weight_g, 2).contiguous(), conv.bias,
+                            conv.padding[0], conv.groups)
+            w, bias, pad, groups = self._wt
+            xc = F.conv1d(x.view(B, T, d).transpose(1, 2), w, bias, padding=pad, groups=groups)  # TODO(round 2): as GEMM
             if self.remove:
                 xc = xc[:, :, : -self.remove]
             x = (x.view(B, T, d) + F.gelu(xc).transpose(1, 2)).reshape(B * T, d).contiguous()
@@ -425,6 +479,11 @@ class AVHubertVideoEncoder(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self.eval()
+
+    def train(self, mode: bool = True):
+        """The encoder always runs with eval semantics (no dropout/layerdrop, BatchNorm running statistics): the
+        deterministic configuration of SURVEY §5.8; `.train()` on a parent module must not flip it."""
+        return super().train(False)
 
     def lora_parameters(self):
         for layer in self.encoder.layers:
