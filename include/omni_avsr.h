@@ -66,6 +66,29 @@ typedef struct omni_gemm_args {
 int omni_gemm_bf16(const omni_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Weight-gradient GEMM (reduction over tokens, both operands token-major / "MN-major" for tcgen05):
+ *   out[z][i, j] = alpha * sum_{k in [k0[z], k1[z])} A[k, a_col0 + i] * B[k, b_col0 + j]   (+ out if accumulate)
+ * Replaces what autograd derives for the trainable tensors of the path: LoRA down/up of
+ * Llama_LoRA.py:246-259 / multihead_attention.py:485-494 (one token range per task run) and the projector
+ * linears of modeling_OmniAVSR.py:353,366.  omni_colsum_bf16 = bias gradient (sum over tokens).
+ * ---------------------------------------------------------------------------------------------- */
+#define OMNI_WGRAD_MAX_RANGES 8
+typedef struct omni_wgrad_args {
+  const void* A;  /* [K, a_cols] ld = lda, bf16 (e.g. dY) */
+  const void* B;  /* [K, b_cols] ld = ldb, bf16 (e.g. X)  */
+  void* out;      /* [n_ranges][Mo, No] ld = ldo, z stride out_zstride (elements); bf16 or fp32 */
+  int64_t lda, ldb, ldo, out_zstride;
+  int32_t K, a_cols, b_cols;
+  int32_t Mo, No, a_col0, b_col0;
+  int32_t n_ranges;
+  int32_t k0[OMNI_WGRAD_MAX_RANGES], k1[OMNI_WGRAD_MAX_RANGES];
+  int32_t out_fp32, accumulate;
+  float alpha;
+} omni_wgrad_args;
+int omni_gemm_wgrad_bf16(const omni_wgrad_args* args, void* stream);
+int omni_colsum_bf16(const void* x, void* out, int64_t rows, int32_t cols, int64_t ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Matryoshka compression of encoder features (truncate to n_tok, drop the remainder, pool/stack).
  *   x   [B, t_stride_rows, D] (only the first n_tok rows of each clip are read; batch stride x_bs elements)
  *   out [B, n_tok / rate, D]  (avg)   or   [B, n_tok / rate, rate*D]  (stack)

@@ -302,19 +302,37 @@ class LoraPlan:
         uv = up[ns * self.q_cols:].view(ns, self.v_cols, rp).transpose(1, 2).reshape(ns * rp, self.v_cols)
         return uq.contiguous(), uv.contiguous()
 
-    def accumulate_wgrads(self, d_down, d_up, h, T, dT, dout, runs):
-        """d_down[slot] += dT'[rows]^T h[rows];  d_up[slot] += dOut_part[rows]^T T[rows]  (per task run)."""
+    def _scatter_index(self, runs, device):
+        key = tuple(g for g, _, _ in runs)
+        cache = self.__dict__.setdefault("_idx_cache", {})
+        if key not in cache:
+            ns, na = self.n_slots, self.n_act
+            down = [part * ns + self.slot_of(a, g) for g in key for part in range(2) for a in range(na)]
+            up = [self.slot_of(a, g) for g in key for a in range(na)]
+            cache[key] = (torch.tensor(down, dtype=torch.int64, device=device),
+                          torch.tensor(up, dtype=torch.int64, device=device))
+        return cache[key]
+
+    def wgrads(self, h, T, dT, dout, runs):
+        """LoRA weight gradients with the MN-major tcgen05 kernel (csrc/gemm_wgrad.cu), one token range per task run:
+             d_down[slot] = sum_runs dT'[rows]^T h[rows]          d_up[slot] = sum_runs dOut_part[rows]^T T[rows]
+        fp32 partial results per run are scatter-added into their adapter slots (the shared adapter sums over runs)."""
         ns, rp, na = self.n_slots, self.rp, self.n_act
-        for (g, r0, r1) in runs:
-            hs, Ts, dTs, dos = h[r0:r1], T[r0:r1], dT[r0:r1], dout[r0:r1]
-            for part, (c0, width, ubase) in enumerate(((0, self.q_cols, 0), (self.v_col0, self.v_cols, ns * self.q_cols))):
-                for a in range(na):
-                    slot = self.slot_of(a, g)
-                    tc = (part * na + a) * rp
-                    drow = (part * ns + slot) * rp
-                    d_down[drow: drow + rp].addmm_(dTs[:, tc: tc + rp].t(), hs)
-                    urow = ubase + slot * width
-                    d_up[urow: urow + width].addmm_(dos[:, c0: c0 + width].t(), Ts[:, tc: tc + rp])
+        H = h.shape[1]
+        Z = len(runs)
+        ranges = [(r0, r1) for _, r0, r1 in runs]
+        idx_down, idx_up = self._scatter_index(runs, h.device)
+        pd = ops.gemm_wgrad(dT, h, mo=self.t_cols, no=H, ranges=ranges, out_dtype=torch.float32)        # [Z, 2*na*rp, H]
+        d_down = torch.zeros((2 * ns, rp, H), device=h.device, dtype=torch.float32)
+        d_down.index_add_(0, idx_down, pd.view(Z * 2 * na, rp, H))
+        ups = []
+        for part, (c0, width) in enumerate(((0, self.q_cols), (self.v_col0, self.v_cols))):
+            pu = ops.gemm_wgrad(dout, T, mo=width, no=na * rp, a_col0=c0, b_col0=part * na * rp, ranges=ranges,
+                                out_dtype=torch.float32)                                                 # [Z, width, na*rp]
+            du = torch.zeros((ns, width, rp), device=h.device, dtype=torch.float32)
+            du.index_add_(0, idx_up, pu.view(Z, width, na, rp).permute(0, 2, 1, 3).reshape(Z * na, width, rp))
+            ups.append(du.view(ns * width, rp))
+        return d_down.view(2 * ns * rp, H).to(torch.bfloat16), torch.cat(ups, dim=0).to(torch.bfloat16)
 
 
 class _LinearView(nn.Module):

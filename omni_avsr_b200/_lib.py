@@ -65,6 +65,22 @@ class SpliceArgs(C.Structure):
     ]
 
 
+WGRAD_MAX_RANGES = 8
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("ldo", C.c_int64), ("out_zstride", C.c_int64),
+        ("K", C.c_int32), ("a_cols", C.c_int32), ("b_cols", C.c_int32),
+        ("Mo", C.c_int32), ("No", C.c_int32), ("a_col0", C.c_int32), ("b_col0", C.c_int32),
+        ("n_ranges", C.c_int32),
+        ("k0", C.c_int32 * WGRAD_MAX_RANGES), ("k1", C.c_int32 * WGRAD_MAX_RANGES),
+        ("out_fp32", C.c_int32), ("accumulate", C.c_int32),
+        ("alpha", C.c_float),
+    ]
+
+
 def _sig(name, argtypes, restype=C.c_int):
     fn = getattr(lib, name)
     fn.argtypes = argtypes
@@ -101,6 +117,8 @@ _sig("omni_ce_bwd", [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P])
 _sig("omni_argmax", [_P, _P, _I64, _I32, _I64, _P])
 _sig("omni_sumsq", [_P, _I64, _P, _P])
 _sig("omni_adamw", [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _F, _P, _P])
+_sig("omni_gemm_wgrad_bf16", [C.POINTER(WgradArgs), _P])
+_sig("omni_colsum_bf16", [_P, _P, _I64, _I32, _I64, _P])
 
 # every symbol include/omni_avsr.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
@@ -108,7 +126,8 @@ EXPORTS = [
     "omni_matryoshka_compress_bwd", "omni_splice_seq_len", "omni_splice_prompt", "omni_splice_prompt_bwd",
     "omni_rmsnorm_fwd", "omni_rmsnorm_bwd", "omni_layernorm_fwd", "omni_layernorm_bwd", "omni_rope",
     "omni_swiglu_fwd", "omni_swiglu_bwd", "omni_gelu_fwd", "omni_gelu_bwd", "omni_gather_rows", "omni_scatter_rows",
-    "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw",
+    "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
+    "omni_colsum_bf16",
 ]
 
 

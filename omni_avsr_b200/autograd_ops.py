@@ -34,7 +34,7 @@ def frozen_linear(x, W, WT, bias=None, residual=None, block_n=0):
 
 class TrainableLinearFn(torch.autograd.Function):
     """Projector linear: y = act(x @ W^T + b); W, b trainable.  dx via our GEMM on W^T (transposed per call, the
-    weight changes every step); dW = dy^T x is a reduction over tokens (small) -- library GEMM for now."""
+    weight changes every step); dW = dy^T x runs on the MN-major tcgen05 weight-gradient kernel."""
 
     @staticmethod
     def forward(ctx, x, W, b, act):
@@ -50,8 +50,8 @@ class TrainableLinearFn(torch.autograd.Function):
         if ctx.act == "relu":
             dy = dy * (y > 0)
         dx = ops.gemm(dy, W.t().contiguous()) if ctx.needs_input_grad[0] else None
-        dW = torch.matmul(dy.t(), x)          # TODO(round 2): MN-major tcgen05 wgrad kernel
-        db = dy.sum(0, dtype=torch.float32).to(dy.dtype)
+        dW = ops.gemm_wgrad(dy, x, mo=W.shape[0], no=W.shape[1])[0]       # dY^T X, both operands token-major
+        db = ops.colsum(dy)
         return dx, dW, db, None
 
 
@@ -183,10 +183,8 @@ class LoraLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             downT = down.t().contiguous()
             dh = ops.gemm(dout, ctx.WT, tile_group=tile_group, ext=(dT, downT, plan.ext_bwd), block_n=plan.block_n_bwd)
-        # weight gradients: reductions over the tokens of each task (TODO(round 2): MN-major tcgen05 wgrad)
-        d_down = torch.zeros_like(down)
-        d_up = torch.zeros_like(up)
-        plan.accumulate_wgrads(d_down, d_up, h, T, dT, dout, ctx.rows.runs)
+        # weight gradients: reductions over the tokens of each task run (MN-major tcgen05 kernel)
+        d_down, d_up = plan.wgrads(h, T, dT, dout, ctx.rows.runs)
         return dh, None, None, None, d_down, d_up, None, None
 
 

@@ -386,3 +386,53 @@ def adamw_(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     check(lib.omni_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
                          weight_decay, step, grad_scale, max_norm, ptr(sumsq), stream_ptr()), "omni_adamw")
     _count()
+
+
+def gemm_wgrad(a, b, *, mo: int, no: int, a_col0: int = 0, b_col0: int = 0, ranges=None, out=None,
+               out_dtype=torch.bfloat16, alpha: float = 1.0, accumulate: bool = False):
+    """out[z][i, j] = alpha * sum_{k in ranges[z]} a[k, a_col0+i] * b[k, b_col0+j]  (tcgen05, MN-major operands).
+
+    a [K, *], b [K, *] token-major bf16; ranges = [(k0, k1), ...] (default: all tokens); out [Z, mo, no] (or [mo, no])."""
+    require_cuda(a, b, out)
+    a = _bf16_2d(a, "a")
+    b = _bf16_2d(b, "b")
+    K = a.shape[0]
+    if b.shape[0] != K:
+        raise ValueError("a and b must have the same number of token rows")
+    if ranges is None:
+        ranges = [(0, K)]
+    Z = len(ranges)
+    if Z > _lib.WGRAD_MAX_RANGES:
+        raise ValueError("too many token ranges")
+    if out is None:
+        out = torch.empty((Z, mo, no), device=a.device, dtype=out_dtype)
+    o3 = out if out.dim() == 3 else out.unsqueeze(0)
+    if o3.shape[0] != Z or o3.shape[1] != mo or o3.shape[2] != no or o3.stride(2) != 1:
+        raise ValueError("bad out tensor")
+    if o3.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("out must be bf16 or fp32")
+    g = _lib.WgradArgs()
+    g.A, g.B, g.out = a.data_ptr(), b.data_ptr(), o3.data_ptr()
+    g.lda, g.ldb, g.ldo, g.out_zstride = a.stride(0), b.stride(0), o3.stride(1), o3.stride(0) if Z > 1 else 0
+    g.K, g.a_cols, g.b_cols = K, a.shape[1], b.shape[1]
+    g.Mo, g.No, g.a_col0, g.b_col0 = mo, no, a_col0, b_col0
+    g.n_ranges = Z
+    for i, (k0, k1) in enumerate(ranges):
+        g.k0[i], g.k1[i] = int(k0), int(k1)
+    g.out_fp32 = 1 if o3.dtype == torch.float32 else 0
+    g.accumulate = 1 if accumulate else 0
+    g.alpha = float(alpha)
+    check(lib.omni_gemm_wgrad_bf16(C.byref(g), stream_ptr()), "omni_gemm_wgrad_bf16")
+    _count()
+    return out
+
+
+def colsum(x):
+    """Column sums (fp32 accumulate) of a bf16 [rows, cols] matrix -> bf16 [cols] (bias gradient)."""
+    x = _bf16_2d(x, "x")
+    require_cuda(x)
+    out = torch.empty(x.shape[1], device=x.device, dtype=torch.bfloat16)
+    check(lib.omni_colsum_bf16(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0), stream_ptr()),
+          "omni_colsum_bf16")
+    _count()
+    return out

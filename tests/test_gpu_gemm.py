@@ -134,3 +134,33 @@ def test_gemm_grouped_lora_extension():
     # and the adapters matter (guards against a silently skipped extension)
     base = ops.gemm(x, Wqkv)
     assert (qkv.float() - base.float()).abs().max().item() > 1e-2
+
+
+@pytest.mark.parametrize("K,Mo,No", [(128, 64, 64), (384, 128, 256), (1000, 200, 136), (4096, 256, 2048), (5000, 2048, 128)])
+def test_wgrad_mn_major(K, Mo, No):
+    """dW = dY^T X with both operands token-major (no transposed copies): tcgen05 MN-major operands."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(K + Mo)
+    dy = torch.randn(K, Mo + 64, device="cuda", generator=g).bfloat16()
+    x = torch.randn(K, No + 8, device="cuda", generator=g).bfloat16()
+    for dt in (torch.float32, torch.bfloat16):
+        out = ops.gemm_wgrad(dy, x, mo=Mo, no=No, a_col0=64, b_col0=8, out_dtype=dt, alpha=0.5)
+        ref = 0.5 * (dy[:, 64:64 + Mo].float().t() @ x[:, 8:8 + No].float())
+        _close(out[0], ref, tol=4e-3)
+
+
+def test_wgrad_ranges_and_accumulate():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    K, Mo, No = 1024, 128, 192
+    dy = torch.randn(K, Mo, device="cuda", generator=g).bfloat16()
+    x = torch.randn(K, No, device="cuda", generator=g).bfloat16()
+    ranges = [(0, 256), (256, 640), (640, 1024)]
+    out = ops.gemm_wgrad(dy, x, mo=Mo, no=No, ranges=ranges, out_dtype=torch.float32)
+    for z, (k0, k1) in enumerate(ranges):
+        _close(out[z], dy[k0:k1].float().t() @ x[k0:k1].float(), tol=4e-3)
+    acc = out[0].clone()
+    ops.gemm_wgrad(dy, x, mo=Mo, no=No, ranges=[(256, 640)], out=acc, accumulate=True)
+    _close(acc, (dy[:640].float().t() @ x[:640].float()), tol=4e-3)
+    cs = ops.colsum(dy)
+    _close(cs, dy.float().sum(0), tol=1e-2)
