@@ -191,6 +191,41 @@ class WhisperEncoder(nn.Module):
         self.layer_norm = _LN(d, device)
         self.requires_grad_(False)
 
+    def _conv_stem(self, feats):
+        """gelu(conv1) -> gelu(conv2, stride 2) -> + positions, with both convolutions on the tcgen05 GEMM: the
+        activations are kept channels-last with one zero row of padding on each side of every clip, so the im2col row of
+        output t is simply `k` CONSECUTIVE rows starting at row t*stride -- an overlapping-row view (row stride <
+        row length) that the TMA tensor map expresses directly; no im2col buffer, no cuDNN.
+        Rows that straddle two clips are garbage and land exactly on the padding rows, which are re-zeroed."""
+        B, C, L = feats.shape                       # [B, 80, 3000]
+        d = self.config.d_model
+        if getattr(self, "_wt", None) is None:
+            w1 = self.conv1.weight.data.permute(0, 2, 1).reshape(d, 3 * C).contiguous()      # [o, k*C + c]
+            w2 = self.conv2.weight.data.permute(0, 2, 1).reshape(d, 3 * d).contiguous()
+            self._wt = {"w1": w1, "w2": w2, "pos": {}}
+        w = self._wt
+        Lp = L + 2
+        T = L // 2
+        p1 = torch.zeros((B, Lp, C), device=feats.device, dtype=torch.bfloat16)
+        p1[:, 1: L + 1] = feats.transpose(1, 2)
+        p2 = torch.empty((B, Lp, d), device=feats.device, dtype=torch.bfloat16)
+        m1 = B * Lp - 2
+        a1 = torch.as_strided(p1, (m1, 3 * C), (C, 1))
+        ops.gemm(a1, w["w1"], bias=self.conv1.bias.data, act="gelu", out=p2.view(B * Lp, d)[1: 1 + m1], block_n=256)
+        p2[:, 0].zero_()
+        p2[:, Lp - 1].zero_()
+        Tp = Lp // 2                                # 1501 output slots per clip, the last one is garbage
+        if B not in w["pos"]:
+            pos = torch.zeros((B, Tp, d), device=feats.device, dtype=torch.bfloat16)
+            pos[:, :T] = self.embed_positions.weight.data[:T]
+            w["pos"] = {B: pos.view(B * Tp, d)}
+        m2 = B * Tp - 1
+        a2 = torch.as_strided(p2, (m2, 3 * d), (2 * d, 1))
+        y = torch.empty((B * Tp, d), device=feats.device, dtype=torch.bfloat16)
+        ops.gemm(a2, w["w2"], bias=self.conv2.bias.data, act="gelu", residual=w["pos"][B][:m2], out=y[:m2], block_n=256)
+        x = y.view(B, Tp, d)[:, :T].reshape(B * T, d)
+        return x, B, T
+
     @classmethod
     def from_pretrained(cls, name: str, device="cuda"):
         if name not in WHISPER_ARCHS:
@@ -200,10 +235,8 @@ class WhisperEncoder(nn.Module):
     @torch.no_grad()
     def forward(self, input_features: torch.Tensor) -> _EncOut:
         ops.require_cuda(input_features)
-        x = F.gelu(self.conv1(input_features.to(torch.bfloat16)))        # TODO(round 2): conv stem as TMA-strided GEMM
-        x = F.gelu(self.conv2(x))
-        B, d, T = x.shape
-        x = (x.permute(0, 2, 1) + self.embed_positions.weight).reshape(B * T, d).contiguous()
+        x, B, T = self._conv_stem(input_features.to(torch.bfloat16))
+        d = x.shape[1]
         for layer in self.layers:
             x = layer(x, B, T)
         x = self.layer_norm(x)
