@@ -493,40 +493,86 @@ class LlamaSdpaAttention_lora(nn.Module):
                                     rows, self.plan)
         n_rot = self.num_heads + self.num_key_value_heads
         if qkv.requires_grad:
-            qkv = ag.RopeFn.apply(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim)
+            qkv = ag.RopeFn.apply(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim, True)
         else:
             ops.rope_(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim)
         attn = attention_packed(qkv, rows, a, kv_cache, self.layer_idx)
         return ag.frozen_linear(attn, self.o_proj.weight.data, wt_o, residual=residual, block_n=256)
 
 
-def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
-    """Causal GQA attention per segment of the packed rows.
-    TODO(round 2): replace the library SDPA call with the tcgen05 flash kernel (csrc/attention.cu)."""
-    outs = []
-    for (task, B, S, off) in rows.segments:
+class PackedSdpaFn(torch.autograd.Function):
+    """Attention core over packed q|k|v rows -> [M, q_dim].
+
+    TODO(round 2): replace the library SDPA call with the tcgen05 flash kernel (csrc/attention.cu).
+    Forward: SDPA per segment on strided views of the packed buffer, written straight into the output rows.
+    Backward: the segment's SDPA is re-evaluated under a local graph and dq|dk|dv are copied into ONE packed dqkv
+    buffer -- autograd's own slice gradients would materialise three zero-filled [M, q+2kv] tensors per segment and
+    add them up."""
+
+    @staticmethod
+    def _views(qkv, B, S, off, nh, nkv, hd):
         blk = qkv[off: off + B * S]
-        q = blk[:, : a.q_dim].view(B, S, a.num_attention_heads, a.head_dim).transpose(1, 2)
-        k = blk[:, a.q_dim: a.q_dim + a.kv_dim].view(B, S, a.num_key_value_heads, a.head_dim).transpose(1, 2)
-        v = blk[:, a.q_dim + a.kv_dim:].view(B, S, a.num_key_value_heads, a.head_dim).transpose(1, 2)
-        mask = None
-        if kv_cache is not None:
-            k, v, mask = kv_cache.update(layer_idx, k, v)
+        q = blk[:, : nh * hd].view(B, S, nh, hd).transpose(1, 2)
+        k = blk[:, nh * hd: (nh + nkv) * hd].view(B, S, nkv, hd).transpose(1, 2)
+        v = blk[:, (nh + nkv) * hd:].view(B, S, nkv, hd).transpose(1, 2)
+        return q, k, v
+
+    @staticmethod
+    def _zero_pad_rows(t, segments):
+        cur = 0
+        for (_, B, S, off) in segments:
+            if off > cur:
+                t[cur:off].zero_()
+            cur = off + B * S
+        if cur < t.shape[0]:
+            t[cur:].zero_()
+
+    @staticmethod
+    def forward(ctx, qkv, segments, nh, nkv, hd, causal):
+        out = torch.empty((qkv.shape[0], nh * hd), device=qkv.device, dtype=torch.bfloat16)
+        for (_, B, S, off) in segments:
+            q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
+            o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
+            out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
+        PackedSdpaFn._zero_pad_rows(out, segments)
+        ctx.save_for_backward(qkv)
+        ctx.meta = (segments, nh, nkv, hd, causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        segments, nh, nkv, hd, causal = ctx.meta
+        dqkv = torch.empty_like(qkv)
+        for (_, B, S, off) in segments:
+            q, k, v = (t.detach().requires_grad_(True) for t in PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd))
+            with torch.enable_grad():
+                o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
+            do = dout[off: off + B * S].view(B, S, nh, hd).transpose(1, 2)
+            dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
+            gq, gk, gv = PackedSdpaFn._views(dqkv, B, S, off, nh, nkv, hd)
+            gq.copy_(dq)
+            gk.copy_(dk)
+            gv.copy_(dv)
+        PackedSdpaFn._zero_pad_rows(dqkv, segments)
+        return dqkv, None, None, None, None, None
+
+
+def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
+    """Causal GQA attention per segment of the packed rows (training / prefill without cache: PackedSdpaFn;
+    with a KV cache: SDPA against the cache, optionally under the graph-mode key mask)."""
+    nh, nkv, hd = a.num_attention_heads, a.num_key_value_heads, a.head_dim
+    if kv_cache is None:
+        return PackedSdpaFn.apply(qkv, rows.segments, nh, nkv, hd, True)
+    out = torch.empty((rows.M, a.q_dim), device=qkv.device, dtype=torch.bfloat16)
+    for (task, B, S, off) in rows.segments:
+        q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
+        k, v, mask = kv_cache.update(layer_idx, k, v)
         causal = S > 1 and k.shape[2] == S and mask is None
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal, enable_gqa=True)
-        outs.append((off, B * S, o.transpose(1, 2).reshape(B * S, a.q_dim)))
-    if len(outs) == 1 and outs[0][1] == rows.M:
-        return outs[0][2]
-    pieces, cur = [], 0
-    zeros = lambda n: torch.zeros((n, a.q_dim), device=qkv.device, dtype=torch.bfloat16)   # only the pad rows
-    for off, n, o in outs:
-        if off > cur:
-            pieces.append(zeros(off - cur))
-        pieces.append(o)
-        cur = off + n
-    if cur < rows.M:
-        pieces.append(zeros(rows.M - cur))
-    return torch.cat(pieces, dim=0)
+        out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
+    PackedSdpaFn._zero_pad_rows(out, rows.segments)
+    return out
 
 
 class KVCache:

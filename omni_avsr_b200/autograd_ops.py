@@ -97,9 +97,10 @@ class RopeFn(torch.autograd.Function):
     """RoPE applied in place on the q|k heads of the packed qkv buffer (the input buffer is consumed)."""
 
     @staticmethod
-    def forward(ctx, qkv, cos_t, sin_t, pos, n_heads_total, head_dim):
+    def forward(ctx, qkv, cos_t, sin_t, pos, n_heads_total, head_dim, grad_inplace=False):
         ctx.save_for_backward(cos_t, sin_t, pos)
         ctx.meta = (n_heads_total, head_dim)
+        ctx.grad_inplace = grad_inplace   # the consumer hands us a gradient buffer it owns (PackedSdpaFn)
         ctx.mark_dirty(qkv)
         ops.rope_(qkv, cos_t, sin_t, pos, n_heads_total, head_dim)
         return qkv
@@ -107,9 +108,10 @@ class RopeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d):
         cos_t, sin_t, pos = ctx.saved_tensors
-        d = d.clone(memory_format=torch.contiguous_format)
+        if not (ctx.grad_inplace and d.is_contiguous()):
+            d = d.clone(memory_format=torch.contiguous_format)
         ops.rope_(d, cos_t, sin_t, pos, ctx.meta[0], ctx.meta[1], inverse=True)
-        return d, None, None, None, None, None
+        return d, None, None, None, None, None, None
 
 
 class SwigluFn(torch.autograd.Function):

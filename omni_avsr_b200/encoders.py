@@ -27,7 +27,7 @@ from torch import nn
 
 from . import autograd_ops as ag
 from . import ops
-from .Llama_LoRA import FlatParams, LoraPlan, _LinearView
+from .Llama_LoRA import FlatParams, LoraPlan, PackedSdpaFn, _LinearView
 
 SAMPLE_RATE, N_FFT, HOP, N_MELS, N_SAMPLES = 16000, 400, 160, 80, 480000
 
@@ -140,12 +140,8 @@ class _PackedSelfAttention(nn.Module):
         return self._wt
 
     def sdpa(self, qkv, B, T):
-        d, h, hd = self.d, self.h, self.hd
-        q = qkv[:, :d].view(B, T, h, hd).transpose(1, 2)
-        k = qkv[:, d:2 * d].view(B, T, h, hd).transpose(1, 2)
-        v = qkv[:, 2 * d:].view(B, T, h, hd).transpose(1, 2)
-        o = F.scaled_dot_product_attention(q, k, v)           # TODO(round 2): tcgen05 flash kernel
-        return o.transpose(1, 2).reshape(B * T, d)
+        # non-causal attention over each clip (library SDPA core; TODO(round 2): tcgen05 flash kernel)
+        return PackedSdpaFn.apply(qkv, [(0, B, T, 0)], self.h, self.h, self.hd, False)
 
 
 class WhisperEncoderLayer(nn.Module):
