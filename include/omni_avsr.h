@@ -66,6 +66,15 @@ typedef struct omni_gemm_args {
 int omni_gemm_bf16(const omni_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Whisper log-mel front end on the device: audio [B, T] (fp32 or bf16, batch stride audio_bs) -> bf16 [B, 80, 3000].
+ * Replaces the host WhisperFeatureExtractor call + D2H/H2D round trip of modeling_OmniAVSR.py:531-534.
+ * mel_filters: fp32 [80, 201] slaney filter bank; workspace >= omni_logmel_workspace_bytes(B).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t omni_logmel_workspace_bytes(int32_t B);
+int omni_logmel(const void* audio, int32_t audio_is_bf16, int64_t audio_bs, int32_t B, int32_t T,
+                const float* mel_filters, void* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Weight-gradient GEMM (reduction over tokens, both operands token-major / "MN-major" for tcgen05):
  *   out[z][i, j] = alpha * sum_{k in [k0[z], k1[z])} A[k, a_col0 + i] * B[k, b_col0 + j]   (+ out if accumulate)
  * Replaces what autograd derives for the trainable tensors of the path: LoRA down/up of
@@ -161,6 +170,12 @@ int omni_swiglu_fwd(const void* gu, void* act, int64_t rows, int32_t I, void* st
 int omni_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, void* stream);
 int omni_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
 int omni_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
+/* ResNet front-end glue of AV-HuBERT (av_hubert/avhubert/resnet.py:35-74,131-169), channels-last [rows, C]:
+ * x <- PReLU(x (+ residual)) in place (per-channel slope), and PReLU + MaxPool(3x3, stride 2, pad 1) in one pass
+ * (frontend3D's PReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1))): x [N, H, W, C] -> y [N, Ho, Wo, C]. */
+int omni_prelu_res(void* x, const void* residual, const void* slope, int64_t rows, int32_t C, void* stream);
+int omni_prelu_maxpool3x3s2(const void* x, const void* slope, void* y, int64_t N, int32_t H, int32_t W, int32_t C,
+                            void* stream);
 /* out[i,:] = table[idx[i],:] (embed_tokens of the decode step, label-row selection); status as in the splice. */
 int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
                      int64_t table_rows, int32_t* status, void* stream);

@@ -119,6 +119,10 @@ _sig("omni_sumsq", [_P, _I64, _P, _P])
 _sig("omni_adamw", [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _F, _P, _P])
 _sig("omni_gemm_wgrad_bf16", [C.POINTER(WgradArgs), _P])
 _sig("omni_colsum_bf16", [_P, _P, _I64, _I32, _I64, _P])
+_sig("omni_prelu_res", [_P, _P, _P, _I64, _I32, _P])
+_sig("omni_prelu_maxpool3x3s2", [_P, _P, _P, _I64, _I32, _I32, _I32, _P])
+_sig("omni_logmel_workspace_bytes", [_I32], C.c_int64)
+_sig("omni_logmel", [_P, _I32, _I64, _I32, _I32, _P, _P, _P, _I64, _P])
 
 # every symbol include/omni_avsr.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
@@ -127,7 +131,7 @@ EXPORTS = [
     "omni_rmsnorm_fwd", "omni_rmsnorm_bwd", "omni_layernorm_fwd", "omni_layernorm_bwd", "omni_rope",
     "omni_swiglu_fwd", "omni_swiglu_bwd", "omni_gelu_fwd", "omni_gelu_bwd", "omni_gather_rows", "omni_scatter_rows",
     "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
-    "omni_colsum_bf16",
+    "omni_colsum_bf16", "omni_logmel_workspace_bytes", "omni_logmel", "omni_prelu_res", "omni_prelu_maxpool3x3s2",
 ]
 
 

@@ -481,3 +481,94 @@ extern "C" int omni_scatter_rows(const void* src, const int64_t* idx, void* out,
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// ResNet front-end glue (av_hubert/avhubert/resnet.py:35-74,131-169), channels-last activations [rows, C]:
+//   prelu_res_kernel:      x <- PReLU(x (+ residual)) in place, per-channel slope          (relu1 / `out += residual; relu2`)
+//   prelu_maxpool_kernel:  y[n, ho, wo, :] = max_{3x3, stride 2, pad 1} PReLU(x[n, h, w, :])  (frontend3D PReLU + MaxPool3d(1,3,3))
+// ------------------------------------------------------------------------------------------------
+namespace omni {
+
+__global__ void __launch_bounds__(EW_THREADS)
+prelu_res_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const bf16* __restrict__ slope, int C8,
+                 long long total8) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    float f[8], s[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[idx], f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(slope) + c), s);
+    if (res) {
+      float r[8];
+      unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(res) + idx), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = rbf(f[i] + r[i]);     // `out += residual` rounds to bf16 before the PReLU
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * s[i];
+    reinterpret_cast<uint4*>(x)[idx] = pack8(f);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+prelu_maxpool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ slope, bf16* __restrict__ y, int H, int W,
+                     int Ho, int Wo, int C8, long long total8) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    long long t = idx / C8;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    float s[8], m[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(slope) + c), s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int h = 2 * ho - 1 + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int w = 2 * wo - 1 + dx;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(x) + ((n * H + h) * W + w) * C8 + c), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = rbf(f[i] > 0.f ? f[i] : f[i] * s[i]);
+          m[i] = fmaxf(m[i], v);
+        }
+      }
+    }
+    st_na_u4(reinterpret_cast<uint4*>(y) + idx, pack8(m));
+  }
+}
+
+}  // namespace omni
+
+extern "C" int omni_prelu_res(void* x, const void* residual, const void* slope, int64_t rows, int32_t C, void* stream) {
+  OMNI_CHECK_ARG(x && slope && rows >= 0 && C > 0 && (C % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  const long long total8 = rows * (C / 8);
+  long long blocks = ceil_div_ll(total8, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  prelu_res_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((bf16*)x, (const bf16*)residual,
+                                                                          (const bf16*)slope, C / 8, total8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_prelu_maxpool3x3s2(const void* x, const void* slope, void* y, int64_t N, int32_t H, int32_t W,
+                                       int32_t C, void* stream) {
+  OMNI_CHECK_ARG(x && slope && y && N >= 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0);
+  if (N == 0) return OMNI_OK;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total8 = N * Ho * Wo * (C / 8);
+  long long blocks = ceil_div_ll(total8, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  prelu_maxpool_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)slope, (bf16*)y,
+                                                                              H, W, Ho, Wo, C / 8, total8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}

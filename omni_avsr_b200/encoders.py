@@ -10,8 +10,9 @@
   (modeling_OmniAVSR.py:127-142).
 
 Linear layers, LayerNorm, GELU and the LoRA-fused q|k|v projection run on our kernels (tcgen05 GEMM with bias /
-GELU / residual epilogues).  Still on library kernels in this round (TODO round 2): the STFT (cuFFT),
-the convolutions (cuDNN: Whisper stem, ResNet-18 front-end, grouped positional conv) and the attention core (SDPA).
+GELU / residual epilogues), the log-mel front end is our DFT kernel, the Whisper conv stem runs on the GEMM.
+Still on library kernels in this round (TODO round 2): the ResNet-18 / positional convolutions (cuDNN)
+and the attention core (SDPA).
 Encoders run in eval mode (no dropout / layerdrop, BatchNorm running statistics): SURVEY §5.8 / §7.
 """
 from __future__ import annotations
@@ -58,22 +59,11 @@ class LogMel(nn.Module):
 
     def __init__(self, device="cuda"):
         super().__init__()
-        self.register_buffer("window", torch.hann_window(N_FFT, device=device), persistent=False)
         self.register_buffer("filters", _slaney_mel_filters().to(device).t().contiguous(), persistent=False)
 
     @torch.no_grad()
     def forward(self, audio: torch.Tensor) -> torch.Tensor:
-        ops.require_cuda(audio)
-        B, T = audio.shape
-        wav = torch.zeros(B, N_SAMPLES, device=audio.device, dtype=torch.float32)
-        n = min(T, N_SAMPLES)
-        wav[:, :n] = audio[:, :n].float()
-        stft = torch.stft(wav, N_FFT, HOP, window=self.window, return_complex=True)   # TODO(round 2): own DFT kernel
-        mag = stft[..., :-1].abs() ** 2
-        mel = self.filters @ mag
-        log_spec = torch.clamp(mel, min=1e-10).log10()
-        log_spec = torch.maximum(log_spec, log_spec.amax(dim=(1, 2), keepdim=True) - 8.0)
-        return ((log_spec + 4.0) / 4.0).to(torch.bfloat16)
+        return ops.logmel(audio if audio.stride(-1) == 1 else audio.contiguous(), self.filters)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -349,15 +339,15 @@ class _ResEncoder(nn.Module):
         x8 = x8.view(B * T, Hh, Ww, 8).permute(0, 3, 1, 2)                        # NCHW view of channels-last data
         w, b = f["front"]
         y = F.conv2d(x8, w, b, stride=2, padding=3)        # TODO(round 2): implicit-GEMM tcgen05 kernel (conv mode)
-        y = F.prelu(y, self.frontend3D[2].weight)
-        y = F.max_pool2d(y, 3, 2, 1)
+        y = ops.prelu_maxpool3x3s2(y.contiguous(memory_format=torch.channels_last), self.frontend3D[2].weight.data)
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
                 w1, b1, s1, w2, b2, ds = f[(li, bi)]
-                o = F.prelu(F.conv2d(y, w1, b1, stride=s1, padding=1), blk.relu1.weight)
-                o = F.conv2d(o, w2, b2, stride=1, padding=1)
-                res = y if ds is None else F.conv2d(y, ds[0], ds[1], stride=ds[2])
-                y = F.prelu(o + res, blk.relu2.weight)
+                o = F.conv2d(y, w1, b1, stride=s1, padding=1).contiguous(memory_format=torch.channels_last)
+                ops.prelu_res_(o, blk.relu1.weight.data)
+                o = F.conv2d(o, w2, b2, stride=1, padding=1).contiguous(memory_format=torch.channels_last)
+                res = y if ds is None else F.conv2d(y, ds[0], ds[1], stride=ds[2]).contiguous(memory_format=torch.channels_last)
+                y = ops.prelu_res_(o, blk.relu2.weight.data, res)
         return y.mean(dim=(2, 3))
 
 

@@ -436,3 +436,51 @@ def colsum(x):
           "omni_colsum_bf16")
     _count()
     return out
+
+
+def _nhwc_rows(x):
+    """NCHW-shaped tensor stored channels-last -> (data pointer view as [N*H*W, C])."""
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last) or x.dtype != torch.bfloat16:
+        raise ValueError("expected a bf16 channels-last [N, C, H, W] tensor")
+    return x.shape[0] * x.shape[2] * x.shape[3], x.shape[1]
+
+
+def prelu_res_(x, slope, residual=None):
+    """x <- PReLU(x (+ residual)) in place; x / residual: bf16 channels-last [N, C, H, W]; slope bf16 [C]."""
+    require_cuda(x, slope, residual)
+    rows, Cc = _nhwc_rows(x)
+    if residual is not None and (_nhwc_rows(residual) != (rows, Cc)):
+        raise ValueError("residual shape mismatch")
+    check(lib.omni_prelu_res(x.data_ptr(), ptr(residual), slope.data_ptr(), rows, Cc, stream_ptr()), "omni_prelu_res")
+    _count()
+    return x
+
+
+def prelu_maxpool3x3s2(x, slope):
+    """PReLU then MaxPool2d(3, stride 2, padding 1) on a bf16 channels-last [N, C, H, W] tensor."""
+    require_cuda(x, slope)
+    _nhwc_rows(x)
+    N, Cc, H, W = x.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.empty((N, Cc, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    check(lib.omni_prelu_maxpool3x3s2(x.data_ptr(), slope.data_ptr(), y.data_ptr(), N, H, W, Cc, stream_ptr()),
+          "omni_prelu_maxpool3x3s2")
+    _count()
+    return y
+
+
+def logmel(audio, mel_filters):
+    """audio [B, T] (fp32 or bf16, unit inner stride) -> Whisper input features bf16 [B, 80, 3000] (on-device log-mel)."""
+    require_cuda(audio, mel_filters)
+    if audio.dim() != 2 or audio.stride(1) != 1 or audio.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("audio must be fp32/bf16 [B, T] with unit inner stride")
+    if mel_filters.dtype != torch.float32 or tuple(mel_filters.shape) != (80, 201) or not mel_filters.is_contiguous():
+        raise ValueError("mel_filters must be contiguous fp32 [80, 201]")
+    B, T = audio.shape
+    out = torch.empty((B, 80, 3000), device=audio.device, dtype=torch.bfloat16)
+    nbytes = int(lib.omni_logmel_workspace_bytes(B))
+    ws = torch.empty(nbytes, device=audio.device, dtype=torch.uint8)
+    check(lib.omni_logmel(audio.data_ptr(), 1 if audio.dtype == torch.bfloat16 else 0, audio.stride(0), B, T,
+                          mel_filters.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, stream_ptr()), "omni_logmel")
+    _count(3)
+    return out

@@ -3,7 +3,7 @@ configuration with identical weights: encoder features, the three task losses at
 gradients, greedy transcripts, and an optimisation sanity check.
 
 Tolerances (bf16 end to end on both sides): features / logits max|a-b| <= 2e-2*max|b|; losses |a-b| <= 5e-2;
-gradients max|a-b| <= 1e-1*max|b| (2.5e-1 for the ~1e-6-sized AV-HuBERT adapter gradients) and cosine >= 0.97; greedy tokens equal unless the oracle's own
+gradients max|a-b| <= 1e-1*max|b| and cosine >= 0.97 (AV-HuBERT adapter gradients: no further from the fp32 oracle than 1.5x the bf16 oracle); greedy tokens equal unless the oracle's own
 top-1/top-2 margin is below 2e-2 of its logit scale."""
 import pytest
 import torch
@@ -28,6 +28,14 @@ def pair():
     from oracle.pairing import oracle_from_product
     mod = small_module()
     return mod, oracle_from_product(mod)
+
+
+@pytest.fixture(scope="module")
+def oracle_fp32(pair):
+    """The same oracle evaluated in fp32: the yardstick for deep-chain gradients, where the reference's own bf16
+    execution is itself noisy."""
+    from oracle.pairing import oracle_from_product
+    return oracle_from_product(pair[0], dtype=torch.float32)
 
 
 def test_state_dict_uses_reference_key_names(pair):
@@ -64,9 +72,13 @@ def test_encoder_features(pair):
 
 
 @pytest.mark.parametrize("ra,rv", [(4, 2), (16, 5)])
-def test_three_task_losses_and_grads(pair, ra, rv):
+def test_three_task_losses_and_grads(pair, oracle_fp32, ra, rv):
     mod, oracle = pair
     cpu, gpu = _batch(mod)
+    oracle_fp32.zero_grad()
+    cpu32 = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in cpu.items()}
+    l32, _ = __import__("oracle.modeling", fromlist=["training_step"]).training_step(oracle_fp32, cpu32, ra, rv)
+    l32.backward()
     oracle.zero_grad()
     o_loss, o_parts = __import__("oracle.modeling", fromlist=["training_step"]).training_step(oracle, cpu, ra, rv)
     o_loss.backward()
@@ -89,19 +101,22 @@ def test_three_task_losses_and_grads(pair, ra, rv):
     r = round(m.llm.config.hidden_size / att.rank)
     checks.append((att.lora_down.grad[3 * p.rp: 3 * p.rp + r], oatt.lora_down_Q_shared.weight.grad, "llm.lora_down_Q_shared"))
     checks.append((att.lora_up.grad[2 * p.q_cols: 3 * p.q_cols, :r], oatt.lora_up_Q["audiovisual"].weight.grad, "llm.lora_up_Q.av"))
-    vatt = m.video_encoder.encoder.layers[1].self_attn
-    ovatt = oracle.video_encoder.encoder.layers[1].self_attn
-    rv_ = round(128 / 16)
-    checks.append((vatt.lora_up.grad[:128, :rv_], ovatt.lora_up_Q.weight.grad, "avh.lora_up_Q"))
-    checks.append((vatt.lora_down.grad[:rv_], ovatt.lora_down_Q.weight.grad, "avh.lora_down_Q"))
     for got, want, name in checks:
         assert want is not None, name
-        # AV-HuBERT adapter gradients are ~1e-6 in bf16 after the longest backward chain (LLM -> splice -> projector ->
-        # pool -> 2 transformer blocks) on BOTH sides: direction must agree, magnitude within 25 % of the max
-        tol = 2.5e-1 if name.startswith("avh.") else 1e-1
-        assert _rel(got, want) <= tol, (name, _rel(got, want))
+        assert _rel(got, want) <= 1e-1, (name, _rel(got, want))
         cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.float().flatten(), dim=0).item()
         assert cos >= 0.97, (name, cos)
+    # AV-HuBERT adapter gradients are ~1e-6 after the longest backward chain (LLM -> splice -> projector -> pool -> 2
+    # transformer blocks); the reference's own bf16 execution is noisy there, so both are measured against the fp32
+    # oracle: the CUDA path must be at least as close to it as the bf16 oracle is (x1.5 slack, floor 5e-2).
+    vatt = m.video_encoder.encoder.layers[1].self_attn
+    rv_ = round(128 / 16)
+    for got, key in ((vatt.lora_up.grad[:128, :rv_], "lora_up_Q"), (vatt.lora_down.grad[:rv_], "lora_down_Q"),
+                     (vatt.lora_up.grad[128:, :rv_], "lora_up_V")):
+        want16 = getattr(oracle.video_encoder.encoder.layers[1].self_attn, key).weight.grad
+        want32 = getattr(oracle_fp32.video_encoder.encoder.layers[1].self_attn, key).weight.grad
+        e_prod, e_ref = _rel(got, want32), _rel(want16, want32)
+        assert e_prod <= max(1.5 * e_ref, 5e-2), ("avh." + key, e_prod, e_ref)
     # projectors of the rates that were NOT selected get no gradient (why the reference needs find_unused_parameters)
     other = 1 - ia
     assert m.audio_proj[other][0].weight.grad.abs().max().item() == 0

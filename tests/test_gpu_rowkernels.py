@@ -176,3 +176,41 @@ def test_fused_clip_adamw_matches_torch():
                    max_norm=10.0, sumsq=acc)
         # the product keeps bf16 params: compare against the fp32 reference rounded, 1 bf16 ulp slack per step
         assert (p.cpu().float() - ref.data).abs().max().item() <= step * 2 ** -7 * ref.data.abs().max().item()
+
+
+def test_logmel_matches_oracle():
+    ops = _ops()
+    from oracle import encoders as oe
+    from omni_avsr_b200.encoders import LogMel
+    g = torch.Generator().manual_seed(12)
+    audio = torch.randn(2, 16000 * 2 + 123, generator=g)
+    audio[1, 20000:] = 0
+    want = oe.log_mel(audio)
+    fe = LogMel("cuda")
+    got = fe(audio.cuda())
+    assert got.shape == (2, 80, 3000)
+    assert (got.float().cpu() - want).abs().max().item() <= 1e-2          # bf16 output of values in [-1, 2]
+    got_bf = fe(audio.bfloat16().cuda().unsqueeze(-1).squeeze(-1))
+    want_bf = oe.log_mel(audio.bfloat16().float())
+    assert (got_bf.float().cpu() - want_bf).abs().max().item() <= 1e-2
+    # full-length (30 s) input exercises the reflect padding at the far end
+    long = torch.randn(1, 480000, generator=g)
+    assert (fe(long.cuda()).float().cpu() - oe.log_mel(long)).abs().max().item() <= 1e-2
+
+
+def test_prelu_kernels():
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(6, 64, 10, 12, generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    r = torch.randn(6, 64, 10, 12, generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    slope = (torch.rand(64, generator=g) * 0.5).bfloat16()
+    want = F.prelu(x + r, slope)
+    got = ops.prelu_res_(x.cuda().clone(memory_format=torch.channels_last), slope.cuda(), r.cuda())
+    assert torch.equal(_bits(got), _bits(want))
+    want1 = F.prelu(x, slope)
+    got1 = ops.prelu_res_(x.cuda().clone(memory_format=torch.channels_last), slope.cuda())
+    assert torch.equal(_bits(got1), _bits(want1))
+    wantp = F.max_pool2d(F.prelu(x, slope), 3, 2, 1)
+    gotp = ops.prelu_maxpool3x3s2(x.cuda(), slope.cuda())
+    assert gotp.shape == wantp.shape
+    assert torch.equal(_bits(gotp), _bits(wantp))
