@@ -176,6 +176,9 @@ int omni_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stre
 int omni_prelu_res(void* x, const void* residual, const void* slope, int64_t rows, int32_t C, void* stream);
 int omni_prelu_maxpool3x3s2(const void* x, const void* slope, void* y, int64_t N, int32_t H, int32_t W, int32_t C,
                             void* stream);
+/* im2col of the video front-end Conv3d(1,64,(5,7,7),stride (1,2,2),pad (2,3,3)) (resnet.py:137): video [B,T,H,W] bf16 ->
+ * out [B*T*Ho*Wo, 256] bf16 (245 taps + 11 zero columns), so the convolution runs as one omni_gemm_bf16 call. */
+int omni_im2col_front3d(const void* video, void* out, int32_t B, int32_t T, int32_t H, int32_t W, void* stream);
 /* out[i,:] = table[idx[i],:] (embed_tokens of the decode step, label-row selection); status as in the splice. */
 int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
                      int64_t table_rows, int32_t* status, void* stream);

@@ -572,3 +572,58 @@ extern "C" int omni_prelu_maxpool3x3s2(const void* x, const void* slope, void* y
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// im2col of AV-HuBERT's video front-end convolution (resnet.py:137: Conv3d(1, 64, (5,7,7), stride (1,2,2), pad (2,3,3))).
+// video [B, T, H, W] bf16 (C_in = 1)  ->  A [B*T*Ho*Wo, 256] bf16, column k = (kt*7 + ky)*7 + kx (245 taps, 11 zero pads),
+// so that the convolution becomes one tcgen05 GEMM against the [64, 256] (BatchNorm-folded) filter matrix.
+// One thread = 8 consecutive taps of one output position (one 16-byte store).
+// ------------------------------------------------------------------------------------------------
+namespace omni {
+
+__global__ void __launch_bounds__(EW_THREADS)
+im2col_front3d_kernel(const bf16* __restrict__ video, bf16* __restrict__ out, int T, int H, int W, int Ho, int Wo,
+                      long long total_chunks) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_chunks;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kc = static_cast<int>(idx & 31);          // 32 chunks of 8 taps per output position
+    long long m = idx >> 5;
+    const int xo = static_cast<int>(m % Wo); m /= Wo;
+    const int yo = static_cast<int>(m % Ho); m /= Ho;
+    const int t = static_cast<int>(m % T);
+    const long long b = m / T;
+    const bf16* clip = video + b * static_cast<long long>(T) * H * W;
+    __align__(16) bf16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kc * 8 + i;
+      bf16 val = __float2bfloat16_rn(0.f);
+      if (k < 245) {
+        const int kt = k / 49;
+        const int r = k - kt * 49;
+        const int ky = r / 7;
+        const int kx = r - ky * 7;
+        const int tt = t + kt - 2, yy = 2 * yo + ky - 3, xx = 2 * xo + kx - 3;
+        if (tt >= 0 && tt < T && yy >= 0 && yy < H && xx >= 0 && xx < W)
+          val = clip[(static_cast<long long>(tt) * H + yy) * W + xx];
+      }
+      v[i] = val;
+    }
+    st_na_u4(reinterpret_cast<uint4*>(out) + idx, *reinterpret_cast<const uint4*>(v));
+  }
+}
+
+}  // namespace omni
+
+extern "C" int omni_im2col_front3d(const void* video, void* out, int32_t B, int32_t T, int32_t H, int32_t W,
+                                   void* stream) {
+  OMNI_CHECK_ARG(video && out && B > 0 && T > 0 && H > 0 && W > 0);
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long total = static_cast<long long>(B) * T * Ho * Wo * 32;
+  long long blocks = ceil_div_ll(total, EW_THREADS);
+  if (blocks > kNumSMs * 32LL) blocks = kNumSMs * 32LL;
+  im2col_front3d_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)video, (bf16*)out, T, H, W, Ho,
+                                                                               Wo, total);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}

@@ -306,9 +306,9 @@ class _ResEncoder(nn.Module):
         conv3, bn3 = self.frontend3D[0], self.frontend3D[1]
         w3, b3 = self._fold(conv3.weight, bn3)                         # [C, 1, 5, 7, 7]
         C = w3.shape[0]
-        w2d = torch.zeros((C, 8, 7, 7), device=w3.device, dtype=torch.bfloat16)
-        w2d[:, :5] = w3[:, 0]                                          # temporal taps become input channels (3 zero pads)
-        f = {"front": (w2d.contiguous(memory_format=torch.channels_last), b3)}
+        wmat = torch.zeros((C, 256), device=w3.device, dtype=torch.bfloat16)
+        wmat[:, :245] = w3.reshape(C, 245)                             # k = (kt*7 + ky)*7 + kx, 11 zero pad columns
+        f = {"front": (wmat, b3)}
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
                 w1, b1 = self._fold(blk.conv1.weight, blk.bn1)
@@ -332,13 +332,10 @@ class _ResEncoder(nn.Module):
             self._wt = self._prepare()
         f = self._wt
         B, _, T, Hh, Ww = x.shape
-        # frame t sees frames t-2..t+2: build the 5 (+3 zero) "channels" of every frame as one strided copy
-        xp = F.pad(x[:, 0], (0, 0, 0, 0, 2, 2))                                  # [B, T+4, H, W]
-        x8 = torch.zeros((B, T, Hh, Ww, 8), device=x.device, dtype=torch.bfloat16)
-        x8[..., :5] = xp.unfold(1, 5, 1)                                          # [B, T, H, W, 5]
-        x8 = x8.view(B * T, Hh, Ww, 8).permute(0, 3, 1, 2)                        # NCHW view of channels-last data
+        # Conv3d(1 -> C, (5,7,7), stride (1,2,2)) = im2col kernel (245 taps padded to 256) + ONE tcgen05 GEMM against the
+        # BatchNorm-folded [C, 256] filter matrix; the GEMM output [B*T*Ho*Wo, C] IS the channels-last activation.
         w, b = f["front"]
-        y = F.conv2d(x8, w, b, stride=2, padding=3)        # TODO(round 2): implicit-GEMM tcgen05 kernel (conv mode)
+        y = ops.conv3d_front(x[:, 0].contiguous(), w, b)                                   # [B*T, C, Ho, Wo] (NHWC memory)
         y = ops.prelu_maxpool3x3s2(y.contiguous(memory_format=torch.channels_last), self.frontend3D[2].weight.data)
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):

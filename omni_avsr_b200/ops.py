@@ -484,3 +484,28 @@ def logmel(audio, mel_filters):
                           mel_filters.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, stream_ptr()), "omni_logmel")
     _count(3)
     return out
+
+
+def conv3d_front(video, wmat, bias):
+    """AV-HuBERT front-end Conv3d(1, C, (5,7,7), stride (1,2,2), pad (2,3,3)) on video [B, T, H, W] bf16:
+    im2col kernel + tcgen05 GEMM (bias = folded BatchNorm shift).  Returns [B*T, C, Ho, Wo] in channels-last memory."""
+    require_cuda(video, wmat, bias)
+    if video.dtype != torch.bfloat16 or video.dim() != 4 or not video.is_contiguous():
+        raise ValueError("video must be contiguous bf16 [B, T, H, W]")
+    if wmat.dtype != torch.bfloat16 or wmat.shape[1] != 256 or not wmat.is_contiguous():
+        raise ValueError("wmat must be contiguous bf16 [C, 256]")
+    B, T, H, W = video.shape
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    Cc = wmat.shape[0]
+    out = torch.empty((B * T * Ho * Wo, Cc), device=video.device, dtype=torch.bfloat16)
+    per_clip = T * Ho * Wo
+    clips = max(1, (4 << 20) // per_clip)          # <= ~4M im2col rows (2 GB) in flight; whole clips per chunk
+    cols = torch.empty((min(B, clips) * per_clip, 256), device=video.device, dtype=torch.bfloat16)
+    for b0 in range(0, B, clips):
+        nb = min(clips, B - b0)
+        check(lib.omni_im2col_front3d(video[b0:b0 + nb].data_ptr(), cols.data_ptr(), nb, T, H, W, stream_ptr()),
+              "omni_im2col_front3d")
+        _count()
+        gemm(cols[: nb * per_clip], wmat, bias=bias, out=out[b0 * per_clip:(b0 + nb) * per_clip],
+             block_n=64 if Cc <= 64 else 128)
+    return out.view(B * T, Ho, Wo, Cc).permute(0, 3, 1, 2)

