@@ -214,3 +214,24 @@ def test_prelu_kernels():
     gotp = ops.prelu_maxpool3x3s2(x.cuda(), slope.cuda())
     assert gotp.shape == wantp.shape
     assert torch.equal(_bits(gotp), _bits(wantp))
+
+
+def test_conv3d_front_matches_torch():
+    """im2col kernel + tcgen05 GEMM == Conv3d(1, C, (5,7,7), stride (1,2,2), pad (2,3,3)) (+ bias), incl. all borders."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    B, T, H, W, C = 2, 7, 88, 88, 64
+    video = torch.randn(B, T, H, W, generator=g).bfloat16()
+    w3 = (torch.randn(C, 1, 5, 7, 7, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(C, generator=g).bfloat16()
+    want = F.conv3d(video.float().unsqueeze(1), w3.float(), bias.float(), stride=(1, 2, 2), padding=(2, 3, 3))
+    want = want.transpose(1, 2).reshape(B * T, C, 44, 44)
+    wmat = torch.zeros(C, 256, dtype=torch.bfloat16)
+    wmat[:, :245] = w3.reshape(C, 245)
+    got = ops.conv3d_front(video.cuda(), wmat.cuda(), bias.cuda()).float().cpu()
+    assert got.shape == want.shape
+    err = (got - want).abs()
+    assert err.max().item() <= 1e-2 * want.abs().max().item(), err.max().item()
+    # borders and temporal edges individually
+    for sl in (got[0] - want[0], got[T - 1] - want[T - 1], got[:, :, 0] - want[:, :, 0], got[:, :, :, 43] - want[:, :, :, 43]):
+        assert sl.abs().max().item() <= 1e-2 * want.abs().max().item()
