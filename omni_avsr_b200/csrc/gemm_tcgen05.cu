@@ -638,6 +638,174 @@ gemm_bf16_tn_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05.mma.cta_group::2): the two SMs of a TPC compute one 256 x 256 output tile together.
+// Each CTA stages its own 128 rows of A and HALF (128 rows) of the B tile; the pair's tensor cores read both halves,
+// so shared-memory fill and operand-read traffic per MAC are halved w.r.t. the single-CTA kernels -- the single-CTA
+// 128x256 tile needs 96 B/clk of TMA fill + 96 B/clk of MMA operand reads against a 128 B/clk shared memory.
+// Protocol: both CTAs' TMA loads credit the LEADER's full barrier; the leader's MMA warp issues every MMA and
+// multicasts its commits to both CTAs' empty / tmem_full barriers; both epilogues arrive on the leader's tmem_empty.
+// Plain GEMMs only (no grouping tables / K-extension): those stay on the kernels above.
+// ---------------------------------------------------------------------------------------------------
+template <int STAGES>
+struct GemmSmem2 {
+  static constexpr int BN2 = 256;
+  static constexpr int A_BYTES = BM * BK * 2;            // own 128 rows of A
+  static constexpr int B_BYTES = (BN2 / 2) * BK * 2;     // own half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, const GemmKParams p,
+                  const int m_fast) {
+  using S = GemmSmem2<STAGES>;
+  constexpr int BN2 = S::BN2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;                                   // one per CTA
+  uint64_t* tmem_full_bar = empty_bar + STAGES;                              // [2], one set per CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                              // [2], used in the leader only (count 8)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int n_tiles2 = (p.N + BN2 - 1) / BN2;
+  const int num_pairs = m_pairs * n_tiles2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBh);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], 1);
+        mbar_init(&tmem_empty_bar[s], 8);   // 4 epilogue warps x 2 CTAs
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(tmem_ptr_smem, 2 * BN2);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_pairs; t += num_clusters) {
+        int m_pair, n_tile;
+        tile_coords(t, m_pairs, n_tiles2, m_fast, m_pair, n_tile);
+        const int m0 = (2 * m_pair + rank) * BM;
+        const int nrow = n_tile * BN2 + rank * (BN2 / 2);
+        for (int it = 0; it < p.num_k_blocks; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * S::STAGE_BYTES;
+          uint8_t* sB = sA + S::A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);   // bytes of BOTH CTAs land on this barrier
+          tma_load_2d_pair(&tmA, &full_bar[stage], sA, it * BK, m0);
+          tma_load_2d_pair(&tmBh, &full_bar[stage], sB, it * BK, nrow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN2, 0, 0);   // M = 256 across the pair
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = cluster_id; t < num_pairs; t += num_clusters) {
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN2);
+        for (int it = 0; it < p.num_k_blocks; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
+            const uint32_t sB = sA + S::A_BYTES;
+            const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair_multicast(&empty_bar[stage], static_cast<uint16_t>(3));
+            if (it == p.num_k_blocks - 1) umma_commit_pair_multicast(&tmem_full_bar[as], static_cast<uint16_t>(3));
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs: each drains its own 128 TMEM lanes) =====
+    const int q = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    const float alpha = p.alpha;
+    for (int t = cluster_id; t < num_pairs; t += num_clusters) {
+      int m_pair, n_tile;
+      tile_coords(t, m_pairs, n_tiles2, m_fast, m_pair, n_tile);
+      const int row = (2 * m_pair + rank) * BM + q * 32 + lane;
+      const int n0 = n_tile * BN2;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN2) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+        if (c == BN2 / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // leader's barrier
+        }
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+        epilogue_store_32(p, v, row, col0);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tmem_dealloc_pair(tmem_base, 2 * BN2);
+  }
+}
+
 static int omni_sm_count() {
   static int n = 0;   // immutable once resolved
   if (n == 0) {
@@ -698,6 +866,29 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     // (lm_head-like shapes: the big B operand is then streamed from HBM exactly once)
     const long long a_bytes = static_cast<long long>(a->M) * a->K * 2;
     const int m_fast = (!a->b_row_table && !a->ext_table && p.m_tiles < p.n_tiles && a_bytes <= (40ll << 20)) ? 1 : 0;
+    static const bool no_2cta = (getenv("OMNI_GEMM_NO_2CTA") != nullptr);
+    if (!no_2cta && BN == 256 && !a->b_row_table && !a->ext_table && p.m_tiles >= 2 && tiles >= sms / 2) {
+      // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
+      constexpr int ST2 = 6;
+      using S2 = GemmSmem2<ST2>;
+      auto k2 = gemm_bf16_tn_2cta<ST2>;
+      static bool attr_set_2 = false;
+      if (!attr_set_2) {
+        if (cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL) != cudaSuccess)
+          return OMNI_ERR_CUDA;
+        attr_set_2 = true;
+      }
+      CUtensorMap tmBh;
+      rc = omni_make_tmap_2d_bf16(&tmBh, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, 128, BK, 1);
+      if (rc) return rc;
+      const int pairs = ((p.m_tiles + 1) / 2) * ceil_div(a->N, 256);
+      int clusters = sms / 2;
+      if (pairs < clusters) clusters = pairs;
+      const int m_fast2 = (((p.m_tiles + 1) / 2) < ceil_div(a->N, 256) && a_bytes <= (40ll << 20)) ? 1 : 0;
+      k2<<<2 * clusters, GEMM_THREADS, S2::TOTAL, stream>>>(tmA, tmBh, p, m_fast2);
+      OMNI_LAUNCH_CHECK();
+      return OMNI_OK;
+    }
     static const bool no_cluster = (getenv("OMNI_GEMM_NO_CLUSTER") != nullptr);
     if (!no_cluster && BN >= 128 && !a->b_row_table && p.m_tiles >= 2 && tiles >= sms / 2) {
       // 2-CTA clusters with TMA multicast of the shared B tile
