@@ -61,6 +61,8 @@ typedef struct omni_gemm_args {
   int32_t act;             /* OMNI_ACT_* */
   int32_t out_fp32;
   float alpha;
+  int32_t pair_aligned;    /* 1: tile_group is constant over every pair of consecutive 128-row tiles (segments start on
+                              256-row boundaries), which lets the K-extended GEMM run on the CTA-pair kernel */
 } omni_gemm_args;
 
 int omni_gemm_bf16(const omni_gemm_args* args, void* stream);

@@ -168,9 +168,13 @@ class PackedRows:
         self.segments = []
         off = 0
         groups, pos = [], []
+        # segments start on 256-row boundaries when there are several of them: a CTA PAIR (two 128-row tiles) then never
+        # straddles two tasks and the K-extended LoRA GEMM can run on the cta_group::2 kernel
+        align = 2 * TILE if len(segments) > 1 else TILE
+        self.pair_aligned = True            # one segment = one task for every tile; several = 256-row aligned
         for (task, B, S) in segments:
             n = B * S
-            n_pad = (n + TILE - 1) // TILE * TILE
+            n_pad = (n + align - 1) // align * align
             self.segments.append((task, B, S, off))
             groups += [task] * (n_pad // TILE)
             p = (torch.arange(S, dtype=torch.int32) + pos_offset).repeat(B)
@@ -180,7 +184,7 @@ class PackedRows:
         self.max_pos = pos_offset + max(S for _, _, S in segments)
         self.runs = []                      # maximal runs of equal task id: (task, row0, row1)
         for (task, B, S, o) in self.segments:
-            end = o + (B * S + TILE - 1) // TILE * TILE
+            end = o + (B * S + align - 1) // align * align
             if self.runs and self.runs[-1][0] == task and self.runs[-1][2] == o:
                 self.runs[-1] = (task, self.runs[-1][1], end)
             else:

@@ -47,7 +47,7 @@ class GemmArgs(C.Structure):
         ("b_rows", C.c_int32),
         ("a2_cols", C.c_int32), ("b2_rows", C.c_int32), ("b2_cols", C.c_int32),
         ("n_ext", C.c_int32), ("block_n", C.c_int32), ("act", C.c_int32), ("out_fp32", C.c_int32),
-        ("alpha", C.c_float),
+        ("alpha", C.c_float), ("pair_aligned", C.c_int32),
     ]
 
 

@@ -160,7 +160,8 @@ class LoraLinearFn(torch.autograd.Function):
         tile_group = rows.tile_group
         T = ops.gemm(h, down, n=plan.t_cols, alpha=plan.scaling, tile_group=tile_group, b_row_table=plan.brow_fwd,
                      block_n=64)
-        out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd), block_n=plan.block_n)
+        out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd), block_n=plan.block_n,
+                       pair_aligned=getattr(rows, "pair_aligned", False))
         ctx.save_for_backward(h, T, down, up)
         ctx.WT, ctx.plan, ctx.rows = WT, plan, rows
         return out
@@ -184,7 +185,8 @@ class LoraLinearFn(torch.autograd.Function):
         dh = None
         if ctx.needs_input_grad[0]:
             downT = down.t().contiguous()
-            dh = ops.gemm(dout, ctx.WT, tile_group=tile_group, ext=(dT, downT, plan.ext_bwd), block_n=plan.block_n_bwd)
+            dh = ops.gemm(dout, ctx.WT, tile_group=tile_group, ext=(dT, downT, plan.ext_bwd), block_n=plan.block_n_bwd,
+                          pair_aligned=getattr(ctx.rows, "pair_aligned", False))
         # weight gradients: reductions over the tokens of each task run (MN-major tcgen05 kernel)
         d_down, d_up = plan.wgrads(h, T, dT, dout, ctx.rows.runs)
         return dh, None, None, None, d_down, d_up, None, None

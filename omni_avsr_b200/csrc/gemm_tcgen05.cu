@@ -659,7 +659,8 @@ struct GemmSmem2 {
 
 template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, const GemmKParams p,
+gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2h, const GemmKParams p,
                   const int m_fast) {
   using S = GemmSmem2<STAGES>;
   constexpr int BN2 = S::BN2;
@@ -684,6 +685,10 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmBh);
+    if (p.ext_table) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2h);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -726,6 +731,24 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_2d_pair(&tmBh, &full_bar[stage], sB, it * BK, nrow);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (p.ext_table) {
+          // K-extension (LoRA up-projection): both M tiles of a pair belong to the same task (256-row aligned
+          // segments), so the pair shares the adapter rows of B2; each CTA stages its half
+          const int mt = (2 * m_pair < p.m_tiles) ? 2 * m_pair : p.m_tiles - 1;
+          const int group = p.tile_group ? p.tile_group[mt] : 0;
+          const int4* ext = p.ext_table + static_cast<long long>(group * n_tiles2 + n_tile) * p.n_ext;
+          for (int j = 0; j < p.n_ext; ++j) {
+            const int4 e = ext[j];
+            if (e.y < 0) continue;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * S::STAGE_BYTES;
+            uint8_t* sB = sA + S::A_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            tma_load_2d_pair(&tmA2, &full_bar[stage], sA, e.x, m0);
+            tma_load_2d_pair(&tmB2h, &full_bar[stage], sB, e.z, e.y + rank * (BN2 / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -737,10 +760,17 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int as = 0;
       uint32_t aphase = 0;
       for (int t = cluster_id; t < num_pairs; t += num_clusters) {
+        int total_iters = p.num_k_blocks;
+        if (p.ext_table) {
+          int m_pair, n_tile;
+          tile_coords(t, m_pairs, n_tiles2, m_fast, m_pair, n_tile);
+          const int4* ext = p.ext_table + static_cast<long long>(n_tile) * p.n_ext;   // count depends on the N tile only
+          for (int j = 0; j < p.n_ext; ++j) total_iters += (ext[j].y >= 0) ? 1 : 0;
+        }
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN2);
-        for (int it = 0; it < p.num_k_blocks; ++it) {
+        for (int it = 0; it < total_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (lane == 0) {
@@ -752,7 +782,7 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
             umma_commit_pair_multicast(&empty_bar[stage], static_cast<uint16_t>(3));
-            if (it == p.num_k_blocks - 1) umma_commit_pair_multicast(&tmem_full_bar[as], static_cast<uint16_t>(3));
+            if (it == total_iters - 1) umma_commit_pair_multicast(&tmem_full_bar[as], static_cast<uint16_t>(3));
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -867,7 +897,8 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     const long long a_bytes = static_cast<long long>(a->M) * a->K * 2;
     const int m_fast = (!a->b_row_table && !a->ext_table && p.m_tiles < p.n_tiles && a_bytes <= (40ll << 20)) ? 1 : 0;
     static const bool no_2cta = (getenv("OMNI_GEMM_NO_2CTA") != nullptr);
-    if (!no_2cta && BN == 256 && !a->b_row_table && !a->ext_table && p.m_tiles >= 2 && tiles >= sms / 2) {
+    if (!no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) && p.m_tiles >= 2 &&
+        tiles >= sms / 2) {
       // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
       constexpr int ST2 = 6;
       using S2 = GemmSmem2<ST2>;
@@ -878,14 +909,21 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
           return OMNI_ERR_CUDA;
         attr_set_2 = true;
       }
-      CUtensorMap tmBh;
+      CUtensorMap tmBh, tmB2h2;
       rc = omni_make_tmap_2d_bf16(&tmBh, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, 128, BK, 1);
       if (rc) return rc;
+      if (a->ext_table) {
+        rc = omni_make_tmap_2d_bf16(&tmB2h2, a->B2, (uint64_t)a->b2_rows, (uint64_t)a->b2_cols, (uint64_t)a->ldb2, 128,
+                                    BK, 1);
+        if (rc) return rc;
+      } else {
+        tmB2h2 = tmBh;
+      }
       const int pairs = ((p.m_tiles + 1) / 2) * ceil_div(a->N, 256);
       int clusters = sms / 2;
       if (pairs < clusters) clusters = pairs;
       const int m_fast2 = (((p.m_tiles + 1) / 2) < ceil_div(a->N, 256) && a_bytes <= (40ll << 20)) ? 1 : 0;
-      k2<<<2 * clusters, GEMM_THREADS, S2::TOTAL, stream>>>(tmA, tmBh, p, m_fast2);
+      k2<<<2 * clusters, GEMM_THREADS, S2::TOTAL, stream>>>(tmA, tmBh, tmA2, tmB2h2, p, m_fast2);
       OMNI_LAUNCH_CHECK();
       return OMNI_OK;
     }

@@ -30,6 +30,7 @@ class _StepRows:
         self.valid_rows = B
         self.max_pos = max_pos
         self.runs = [(0, 0, self.M)]
+        self.pair_aligned = True
         self.tile_group = torch.zeros(self.M // TILE, dtype=torch.int32, device=device)
         self.pos = torch.zeros(self.M, dtype=torch.int32, device=device)
 

@@ -361,6 +361,7 @@ class _Rows:
     def __init__(self, M):
         self.tile_group = None
         self.runs = [(0, 0, M)]
+        self.pair_aligned = True
 
 
 class AVHAttention_lora(_PackedSelfAttention):
@@ -434,7 +435,7 @@ class AVHLayer(nn.Module):
             Tm = ops.gemm(h, att.lora_down.data, n=att.plan.t_cols, alpha=att.plan.scaling, b_row_table=att.plan.brow_fwd,
                           block_n=64)
             qkv = ops.gemm(h, att.qkv_weight, bias=att.qkv_bias, ext=(Tm, att.lora_up.data, att.plan.ext_fwd),
-                           block_n=att.plan.block_n)
+                           block_n=att.plan.block_n, pair_aligned=True)
         else:
             qkv = ops.gemm(h, att.qkv_weight, bias=att.qkv_bias, block_n=256)
         o = att.sdpa(qkv, B, T)       # q * head_dim^-0.5 (:511) is SDPA's default scale (exact: power of two)

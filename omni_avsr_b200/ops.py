@@ -36,7 +36,8 @@ def _bf16_2d(t: torch.Tensor, name: str) -> torch.Tensor:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
          alpha: float = 1.0, n: Optional[int] = None, tile_group: Optional[torch.Tensor] = None,
-         b_row_table: Optional[torch.Tensor] = None, ext: Optional[tuple] = None, block_n: int = 0) -> torch.Tensor:
+         b_row_table: Optional[torch.Tensor] = None, ext: Optional[tuple] = None, block_n: int = 0,
+         pair_aligned: bool = False) -> torch.Tensor:
     """out[M,N] = epi(alpha * (a[M,K] @ b[rows,K]^T (+ K-extension)))  -- tcgen05 kernel.
 
     ext = (a2 [M, a2_cols], b2 [b2_rows, b2_cols], ext_table int32 [groups, n_tiles, n_ext, 4]).
@@ -90,6 +91,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.a2_cols, g.b2_rows, g.b2_cols = a2.shape[1], b2.shape[0], b2.shape[1]
         g.n_ext = table.shape[-2]
     g.block_n = block_n
+    g.pair_aligned = 1 if pair_aligned else 0
     g.act = ACT[act]
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     g.alpha = float(alpha)
