@@ -181,7 +181,7 @@ def run_ours(args):
             k_ext = 0
             if kw.get("ext") is not None:
                 k_ext = kw["ext"][2].shape[-2] * 64
-            recs.append((s, e, 2.0 * a.shape[0] * n * (a.shape[1] + k_ext)))
+            recs.append((s, e, 2.0 * a.shape[0] * n * (a.shape[1] + k_ext), (a.shape[0], n, a.shape[1] + k_ext)))
             return out
         ops.gemm = traced
         import omni_avsr_b200.autograd_ops as ag
@@ -190,11 +190,22 @@ def run_ours(args):
             torch.cuda.synchronize()
         finally:
             ops.gemm = orig
-        tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-        tot_fl = sum(f for _, _, f in recs)
+        tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
+        tot_fl = sum(f for _, _, f, _ in recs)
+        if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            by_shape = {}
+            for s_, e_, f_, shp in recs:
+                d = by_shape.setdefault(shp, [0, 0.0, 0.0])
+                d[0] += 1
+                d[1] += s_.elapsed_time(e_)
+                d[2] += f_
+            rows_ = sorted(({"M": k[0], "N": k[1], "K": k[2], "launches": v[0], "ms": round(v[1], 3),
+                             "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)} for k, v in by_shape.items()),
+                           key=lambda r: -r["ms"])
+            json.dump(rows_, open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.json"), "w"), indent=0)
         peaks = load_peaks()
         ach = tot_fl / (tot_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "omni::gemm_bf16_tn_kernel (tcgen05)", "achieved": round(ach, 1),
+        roof = {"bound": "tensor", "kernel": "omni::gemm_bf16_tn_{2cta,cluster,persistent} (tcgen05)", "achieved": round(ach, 1),
                 "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["_source"] + " (sustained: timed inside a long step)",
                 "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 3), "traffic": None,
                 "launches": len(recs), "gemm_ms_per_step": round(tot_ms, 2),

@@ -148,6 +148,18 @@ int omni_splice_prompt_bwd(const omni_splice_args* args, const void* const dout[
                            void* d_video_tok, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Flash-attention forward (tcgen05, head_dim 64) over one segment of the packed q|k|v rows:
+ *   qkv [M, ld] bf16, every row = [q heads | k heads | v heads]; the segment is B clips x S tokens from row0.
+ *   out [M, out_ld] bf16 (n_heads*head_dim columns written for the segment's rows); lse optional fp32 [n_heads, M].
+ * Replaces F.scaled_dot_product_attention at Llama_LoRA.py:300 / Qwen_LoRA.py:606 (causal GQA), the HF Whisper encoder
+ * self-attention and fairseq multihead_attention.py:619-654 (non-causal).  Returns OMNI_ERR_UNSUPPORTED for
+ * head_dim != 64 (the host then uses the library SDPA; listed in DESIGN.md).
+ * ---------------------------------------------------------------------------------------------- */
+int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* out, int64_t out_ld, float* lse, int32_t row0,
+                       int32_t B, int32_t S, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t causal,
+                       float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Row kernels of the decoder / encoder blocks (all bf16 in/out, fp32 statistics).
  * Replace the transformers==4.43.1 ops reached from Llama_LoRA.py:624,643-644 (RMSNorm), :277 (RoPE),
  * LlamaMLP (SwiGLU), and the fairseq LayerNorm/GELU of the AV-HuBERT blocks

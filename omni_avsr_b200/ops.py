@@ -511,3 +511,22 @@ def conv3d_front(video, wmat, bias):
         gemm(cols[: nb * per_clip], wmat, bias=bias, out=out[b0 * per_clip:(b0 + nb) * per_clip],
              block_n=64 if Cc <= 64 else 128)
     return out.view(B * T, Ho, Wo, Cc).permute(0, 3, 1, 2)
+
+
+def attention_fwd(qkv, out, segments, n_heads: int, n_kv_heads: int, head_dim: int, causal: bool, lse=None,
+                  scale: Optional[float] = None):
+    """tcgen05 flash-attention forward over the packed q|k|v rows (head_dim 64).  segments = [(task, B, S, row0)];
+    out [M, n_heads*head_dim] bf16 (rows outside the segments untouched).  Raises for unsupported head dims."""
+    require_cuda(qkv, out, lse)
+    qkv = _bf16_2d(qkv, "qkv")
+    out = _bf16_2d(out, "out")
+    if head_dim != 64:
+        raise NotImplementedError("attention_fwd: head_dim 64 only in this round")
+    if scale is None:
+        scale = head_dim ** -0.5
+    for (_, B, S, row0) in segments:
+        check(lib.omni_attention_fwd(qkv.data_ptr(), qkv.shape[0], qkv.stride(0), out.data_ptr(), out.stride(0), ptr(lse),
+                                     row0, B, S, n_heads, n_kv_heads, head_dim, 1 if causal else 0, float(scale),
+                                     stream_ptr()), "omni_attention_fwd")
+        _count()
+    return out
