@@ -534,10 +534,15 @@ class PackedSdpaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, segments, nh, nkv, hd, causal):
         out = torch.empty((qkv.shape[0], nh * hd), device=qkv.device, dtype=torch.bfloat16)
-        for (_, B, S, off) in segments:
-            q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
-            o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
-            out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
+        if hd == 64:
+            # our tcgen05 flash-attention forward, straight from / into the packed rows
+            ops.attention_fwd(qkv, out, segments, nh, nkv, hd, causal)
+        else:
+            # TODO(round 2): head_dim 128 variant of csrc/attention.cu (Qwen2.5-3B, Llama-3.1-8B) -- library SDPA meanwhile
+            for (_, B, S, off) in segments:
+                q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
+                o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
+                out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
         PackedSdpaFn._zero_pad_rows(out, segments)
         ctx.save_for_backward(qkv)
         ctx.meta = (segments, nh, nkv, hd, causal)
@@ -571,7 +576,12 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
     out = torch.empty((rows.M, a.q_dim), device=qkv.device, dtype=torch.bfloat16)
     for (task, B, S, off) in rows.segments:
         q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
+        prefill = S > 1 and kv_cache.len == 0 and not kv_cache.graph_mode
         k, v, mask = kv_cache.update(layer_idx, k, v)
+        if prefill and hd == 64:
+            # prefill: keys == this segment's own rows -> our flash kernel on the packed buffer (cache filled above)
+            ops.attention_fwd(qkv, out, [(task, B, S, off)], nh, nkv, hd, True)
+            continue
         causal = S > 1 and k.shape[2] == S and mask is None
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal, enable_gqa=True)
         out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
@@ -836,12 +846,9 @@ class LlamaForCausalLM_lora(nn.Module):
             tgts.append(tgt[mask].contiguous())
             scales.append((w / mask.sum().clamp(min=1).float()).expand(b_idx.numel()).contiguous())
         hrows = GatherRowsFn.apply(hid, torch.cat(idxs).contiguous())      # one gather / one scatter for all tasks
-        out, start = [], 0
-        for tg, sc in zip(tgts, scales):
-            n = tg.numel()
-            out.append(ag.LmHeadCEFn.apply(hrows[start: start + n], W, WT, tg, sc))
-            start += n
-        return out
+        losses = ag.LmHeadCEFn.apply(hrows, W, WT, torch.cat(tgts).contiguous(), torch.cat(scales).contiguous(),
+                                     [int(t.numel()) for t in tgts])          # one logits GEMM + CE for all tasks
+        return list(losses.unbind(0))
 
     @torch.no_grad()
     def generate(self, inputs_embeds=None, max_new_tokens=32, num_beams=1, eos_token_id=None, bos_token_id=None,

@@ -194,10 +194,11 @@ class LoraLinearFn(torch.autograd.Function):
 
 class LmHeadCEFn(torch.autograd.Function):
     """lm_head + fp32 cross-entropy evaluated ONLY on the rows whose shifted label is not ignore_index
-    (identical loss to Llama_LoRA.py:372-386: ignored rows contribute nothing to the mean)."""
+    (identical loss to Llama_LoRA.py:372-386: ignored rows contribute nothing to the mean).  The label rows of all
+    task segments go through ONE logits GEMM / CE / dgrad GEMM; `seg_sizes` splits the rows back into per-task losses."""
 
     @staticmethod
-    def forward(ctx, hrows, W, WT, targets, row_scale):
+    def forward(ctx, hrows, W, WT, targets, row_scale, seg_sizes):
         # logits of the label rows, bf16 (as lm_head produces them before `.float()`)
         V = W.shape[0]
         Vp = (V + 7) // 8 * 8     # row stride must be a multiple of 16 bytes (vector stores, TMA in the backward)
@@ -205,13 +206,15 @@ class LmHeadCEFn(torch.autograd.Function):
         logits = ops.gemm(hrows, W, out=buf[:, :V], block_n=256 if V >= 256 else 0)
         loss_rows, lse = ops.ce_fwd(logits, targets)
         ctx.save_for_backward(logits, targets, lse, row_scale)
-        ctx.WT = WT
-        return (loss_rows * row_scale).sum()
+        ctx.WT, ctx.seg_sizes = WT, seg_sizes
+        return torch.stack([c.sum() for c in torch.split(loss_rows * row_scale, seg_sizes)])
 
     @staticmethod
     def backward(ctx, dloss):
         logits, targets, lse, row_scale = ctx.saved_tensors
-        scale = (row_scale * dloss.float()).contiguous()
+        per_row = torch.repeat_interleave(dloss.float(), torch.tensor(ctx.seg_sizes, device=dloss.device),
+                                          output_size=sum(ctx.seg_sizes))
+        scale = (row_scale * per_row).contiguous()
         ops.ce_bwd_(logits, targets, lse, scale)        # in place: logits -> dlogits
         dh = ops.gemm(logits, ctx.WT, block_n=256)
-        return dh, None, None, None, None
+        return dh, None, None, None, None, None

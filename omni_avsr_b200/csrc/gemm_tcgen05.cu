@@ -49,8 +49,36 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // +1024 for manual alignment
 };
 
+// Residual values of one 32-column chunk, fetched one chunk AHEAD of the TMEM read so that the (strided, 64 bytes per
+// thread) loads are in flight while the previous chunk is converted and stored -- without this the epilogue is
+// latency-bound on short-K GEMMs (8 serialized ~1 us round trips per 128x256 tile).
+struct ResPrefetch {
+  uint4 r[4];
+  bool valid;
+};
+__device__ __forceinline__ void res_prefetch(const GemmKParams& p, int row, int col0, bool row_ok, ResPrefetch& o) {
+  o.valid = p.residual != nullptr && row_ok && (col0 + 32 <= p.N);
+  if (o.valid) {
+    const uint4* rp4 = reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.r[i] = ld_nc_u4(rp4 + i);
+  }
+}
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one exp and
+  // one reciprocal instead of the ~40-instruction erff -- the epilogue evaluates 256 of these per thread per tile
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float erf_abs = 1.0f - poly * __expf(-z * z);
+  const float erfv = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erfv);
+}
+
 // Epilogue of 32 accumulator columns of one row: alpha, bias, rounding point, activation, residual, store.
-__device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&v)[32], int row, int col0) {
+__device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&v)[32], int row, int col0,
+                                                  const ResPrefetch* pre = nullptr) {
   const bool full = (col0 + 32 <= p.N);
   if (p.bias) {
     if (full) {
@@ -78,7 +106,7 @@ __device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&
       for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
     } else if (p.act == OMNI_ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_erf(v[i])));
+      for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_fast(v[i])));
     }
   }
   if (p.residual) {
@@ -87,7 +115,7 @@ __device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&
       const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint4 b = ld_nc_u4(rp4 + i);
+        uint4 b = (pre && pre->valid) ? pre->r[i] : ld_nc_u4(rp4 + i);
         float2 f;
         f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
         f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
@@ -423,11 +451,15 @@ gemm_bf16_tn_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int row = m_tile * BM + q * 32 + lane;
       const int n0 = n_tile * BN;
       const bool row_ok = row < p.M;
+      ResPrefetch res_cur, res_nxt;
+      res_prefetch(p, row, n0, row_ok, res_nxt);          // in flight while the main loop of this tile finishes
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        res_cur = res_nxt;
+        if (c + 1 < BN / 32) res_prefetch(p, row, n0 + (c + 1) * 32, row_ok, res_nxt);
         uint32_t r[32];
         tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
         tmem_ld_wait();
@@ -442,7 +474,7 @@ gemm_bf16_tn_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-        epilogue_store_32(p, v, row, col0);
+        epilogue_store_32(p, v, row, col0, &res_cur);
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -605,11 +637,15 @@ gemm_bf16_tn_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int row = (2 * m_pair + rank) * BM + q * 32 + lane;
       const int n0 = n_tile * BN;
       const bool row_ok = row < p.M;
+      ResPrefetch res_cur, res_nxt;
+      res_prefetch(p, row, n0, row_ok, res_nxt);          // in flight while the main loop of this tile finishes
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        res_cur = res_nxt;
+        if (c + 1 < BN / 32) res_prefetch(p, row, n0 + (c + 1) * 32, row_ok, res_nxt);
         uint32_t r[32];
         tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
         tmem_ld_wait();
@@ -623,7 +659,7 @@ gemm_bf16_tn_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-        epilogue_store_32(p, v, row, col0);
+        epilogue_store_32(p, v, row, col0, &res_cur);
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -803,11 +839,15 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row = (2 * m_pair + rank) * BM + q * 32 + lane;
       const int n0 = n_tile * BN2;
       const bool row_ok = row < p.M;
+      ResPrefetch res_cur, res_nxt;
+      res_prefetch(p, row, n0, row_ok, res_nxt);          // in flight while the main loop of this tile finishes
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN2) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN2 / 32; ++c) {
+        res_cur = res_nxt;
+        if (c + 1 < BN2 / 32) res_prefetch(p, row, n0 + (c + 1) * 32, row_ok, res_nxt);
         uint32_t r[32];
         tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
         tmem_ld_wait();
@@ -821,7 +861,7 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-        epilogue_store_32(p, v, row, col0);
+        epilogue_store_32(p, v, row, col0, &res_cur);
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
