@@ -534,11 +534,11 @@ class PackedSdpaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, segments, nh, nkv, hd, causal):
         out = torch.empty((qkv.shape[0], nh * hd), device=qkv.device, dtype=torch.bfloat16)
-        if hd == 64:
+        if hd in (64, 128):
             # our tcgen05 flash-attention forward, straight from / into the packed rows
             ops.attention_fwd(qkv, out, segments, nh, nkv, hd, causal)
         else:
-            # TODO(round 2): head_dim 128 variant of csrc/attention.cu (Qwen2.5-3B, Llama-3.1-8B) -- library SDPA meanwhile
+            # other head dims (none of the named architectures): library SDPA
             for (_, B, S, off) in segments:
                 q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
                 o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
@@ -578,7 +578,7 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
         q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
         prefill = S > 1 and kv_cache.len == 0 and not kv_cache.graph_mode
         k, v, mask = kv_cache.update(layer_idx, k, v)
-        if prefill and hd == 64:
+        if prefill and hd in (64, 128):
             # prefill: keys == this segment's own rows -> our flash kernel on the packed buffer (cache filled above)
             ops.attention_fwd(qkv, out, [(task, B, S, off)], nh, nkv, hd, True)
             continue

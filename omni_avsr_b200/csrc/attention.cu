@@ -1,4 +1,4 @@
-// Flash-attention forward on the sm_100a tensor cores (head_dim 64): S = Q.K^T and O += P.V are tcgen05.mma with the
+// Flash-attention forward on the sm_100a tensor cores (head_dim 64 or 128): S = Q.K^T and O += P.V are tcgen05.mma with the
 // accumulators in TMEM; the online softmax runs on 128 threads (one per query row) between the two MMAs.
 //
 // Replaces F.scaled_dot_product_attention of: Llama_LoRA.py:300 / Qwen_LoRA.py:606 (causal, GQA, no mask on this path),
@@ -11,8 +11,8 @@
 //   warps 2..5: softmax / accumulation, thread = query row.
 // Per KV tile of 128 keys:  S(TMEM) = Q K^T  ->  rows: m, l, P = exp2(s - m) (bf16, written to smem in the K-major
 // 128B-swizzled operand layout)  ->  O_tile(TMEM) = P V (V consumed as an MN-major operand straight from its
-// [keys, head_dim] TMA tile)  ->  rows: O = O * alpha + O_tile.   Two CTAs fit per SM (80 KB smem, 256 TMEM columns),
-// so one CTA's softmax overlaps the other's MMAs.
+// [keys, head_dim] TMA tile)  ->  rows: O = O * alpha + O_tile.   With head_dim 64 two CTAs fit per SM (80 KB smem, 256
+// TMEM columns), so one CTA's softmax overlaps the other's MMAs.
 #include "common.cuh"
 #include "../../include/omni_avsr.h"
 
@@ -20,18 +20,24 @@ namespace omni {
 
 constexpr int AT_BQ = 128;     // query rows per CTA
 constexpr int AT_BK = 128;     // keys per step
-constexpr int AT_HD = 64;      // head dim (one 128-byte swizzle row)
 constexpr int AT_THREADS = 192;
 
+template <int AT_HD>           // head dim: 64 or 128 (one or two 128-byte swizzle blocks per row)
 struct AttnSmem {
-  static constexpr int Q_BYTES = AT_BQ * AT_HD * 2;        // 16 KB
-  static constexpr int K_BYTES = AT_BK * AT_HD * 2;        // 16 KB
-  static constexpr int V_BYTES = AT_BK * AT_HD * 2;        // 16 KB
+  static constexpr int Q_BYTES = AT_BQ * AT_HD * 2;        // 16 / 32 KB
+  static constexpr int K_BYTES = AT_BK * AT_HD * 2;
+  static constexpr int V_BYTES = AT_BK * AT_HD * 2;
   static constexpr int P_BYTES = AT_BQ * AT_BK * 2;        // 32 KB (two [128 x 64] swizzled blocks)
   static constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + K_BYTES, OFF_P = OFF_V + V_BYTES;
   static constexpr int BAR_OFFSET = OFF_P + P_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 8 * 8 + 16 + 1024;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttnParams {
   bf16* out;             // [M, out_ld]
@@ -42,9 +48,11 @@ struct AttnParams {
   float scale_log2;      // softmax scale * log2(e)
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+template <int AT_HD>
+__global__ void __launch_bounds__(AT_THREADS, AT_HD == 64 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
-  using SM = AttnSmem;
+  using SM = AttnSmem<AT_HD>;
+  constexpr int NB = AT_HD / 64;     // 64-column TMA boxes per Q / K / V tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
@@ -92,12 +100,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, SM::Q_BYTES);
-      tma_load_2d(&tm, q_full, smem + SM::OFF_Q, col_q, clip_row0 + q0);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) tma_load_2d(&tm, q_full, smem + SM::OFF_Q + b * 16384, col_q + b * 64, clip_row0 + q0);
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(kv_empty, (j & 1) ^ 1);
         mbar_expect_tx(kv_full, SM::K_BYTES + SM::V_BYTES);
-        tma_load_2d(&tm, kv_full, smem + SM::OFF_K, col_k, clip_row0 + j * AT_BK);
-        tma_load_2d(&tm, kv_full, smem + SM::OFF_V, col_v, clip_row0 + j * AT_BK);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          tma_load_2d(&tm, kv_full, smem + SM::OFF_K + b * 16384, col_k + b * 64, clip_row0 + j * AT_BK);
+          tma_load_2d(&tm, kv_full, smem + SM::OFF_V + b * 16384, col_v + b * 64, clip_row0 + j * AT_BK);
+        }
       }
     }
   } else if (warp == 1) {
@@ -113,17 +125,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       mbar_wait(kv_full, ph);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t qd = make_smem_desc_sw128(sQ, 16, 1024);
-        const uint64_t kd = make_smem_desc_sw128(sK, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < AT_HD / 16; ++k) umma_bf16(tmem_s, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < AT_HD / 16; ++k) {
+          const uint64_t qd = make_smem_desc_sw128(sQ + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          const uint64_t kd = make_smem_desc_sw128(sK + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_s, qd, kd, idesc_s, k > 0 ? 1u : 0u);
+        }
         umma_commit(s_full);
       }
       __syncwarp();
       mbar_wait(p_full, ph);      // softmax consumed S and wrote P
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t vd = make_smem_desc_sw128(sV, 8192, 1024);   // MN-major: 8 key rows per 1 KB group
+        // MN-major V: 8 key rows per 1 KB group (SBO), next 64 head-dim columns one 16 KB box further (LBO)
+        const uint64_t vd = make_smem_desc_sw128(sV, 16384, 1024);
 #pragma unroll
         for (int k = 0; k < AT_BK / 16; ++k) {
           const uint64_t pd = make_smem_desc_sw128(sP + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
@@ -151,36 +166,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       const int k0 = j * AT_BK;
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // pass 1: row maximum of the (masked) scores
+      // pass 1: row maximum of the (masked) scores.  Interior tiles (every key visible) take the compare-free path.
       float mx = -INFINITY;
       const int kmax = p.causal ? min(qpos, p.S - 1) : (p.S - 1);      // last visible key position
+      const bool unmasked = (k0 + AT_BK - 1 <= kmax);
 #pragma unroll 1
       for (int c = 0; c < AT_BK / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
         tmem_ld_wait();
+        if (unmasked) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (k0 + c * 32 + i <= kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (k0 + c * 32 + i <= kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
       const float m_new = fmaxf(m, mx * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;          // fully masked row so far
-      const float alpha = exp2f(m - m_use);                            // m = -inf -> 0
+      const float alpha = ex2_approx(m - m_use);                       // m = -inf -> 0
       // pass 2: P = exp2(s * scale - m), row sum, bf16 P into the swizzled operand tile
       float sum = 0.f;
+      const float sc = p.scale_log2;
 #pragma unroll 1
       for (int c = 0; c < AT_BK / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
         tmem_ld_wait();
         uint32_t packed[16];
+        if (unmasked) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (k0 + c * 32 + i <= kmax) p0 = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_use);
-          if (k0 + c * 32 + i + 1 <= kmax) p1 = exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_use);
-          sum += p0 + p1;
-          packed[i >> 1] = f2_to_bf2(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_use));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -m_use));
+            sum += p0 + p1;
+            packed[i >> 1] = f2_to_bf2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = 0.f, p1 = 0.f;
+            if (k0 + c * 32 + i <= kmax) p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_use));
+            if (k0 + c * 32 + i + 1 <= kmax) p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -m_use));
+            sum += p0 + p1;
+            packed[i >> 1] = f2_to_bf2(p0, p1);
+          }
         }
         // 32 keys = 4 chunks of 16 bytes; key block (64 keys) = c >> 1, chunk index inside the 128-byte row = (c & 1) * 4 + t
         uint8_t* blk = sP + (c >> 1) * 16384 + r * 128;
@@ -233,6 +265,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
+template <int HD>
+static int launch_attn(const CUtensorMap& tm, const AttnParams& p, dim3 grid, cudaStream_t st) {
+  auto kfn = attn_fwd_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<HD>::TOTAL) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    attr_set = true;
+  }
+  kfn<<<grid, AT_THREADS, AttnSmem<HD>::TOTAL, st>>>(tm, p);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
 }  // namespace omni
 
 extern "C" int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* out, int64_t out_ld, float* lse,
@@ -242,10 +288,10 @@ extern "C" int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* 
   OMNI_CHECK_ARG(qkv && out && M > 0 && B > 0 && S > 0 && n_heads > 0 && n_kv_heads > 0);
   OMNI_CHECK_ARG(n_heads % n_kv_heads == 0 && row0 >= 0 && static_cast<int64_t>(row0) + static_cast<int64_t>(B) * S <= M);
   OMNI_CHECK_ARG((ld % 8) == 0 && (out_ld % 8) == 0 && ld >= static_cast<int64_t>(n_heads + 2 * n_kv_heads) * head_dim);
-  if (head_dim != AT_HD) return OMNI_ERR_UNSUPPORTED;
+  if (head_dim != 64 && head_dim != 128) return OMNI_ERR_UNSUPPORTED;
   CUtensorMap tm;
   int rc = omni_make_tmap_2d_bf16(&tm, qkv, (uint64_t)M, (uint64_t)(n_heads + 2 * n_kv_heads) * head_dim, (uint64_t)ld,
-                                  AT_BQ, AT_HD, 1);
+                                  AT_BQ, 64, 1);
   if (rc) return rc;
   AttnParams p;
   p.out = reinterpret_cast<bf16*>(out);
@@ -254,14 +300,7 @@ extern "C" int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* 
   p.M = M;
   p.row0 = row0; p.S = S; p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.causal = causal ? 1 : 0;
   p.scale_log2 = scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL) != cudaSuccess)
-      return OMNI_ERR_CUDA;
-    attr_set = true;
-  }
   dim3 grid(ceil_div(S, AT_BQ), n_heads, B);
-  attn_fwd_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
-  OMNI_LAUNCH_CHECK();
-  return OMNI_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return head_dim == 64 ? launch_attn<64>(tm, p, grid, st) : launch_attn<128>(tm, p, grid, st);
 }

@@ -515,13 +515,13 @@ def conv3d_front(video, wmat, bias):
 
 def attention_fwd(qkv, out, segments, n_heads: int, n_kv_heads: int, head_dim: int, causal: bool, lse=None,
                   scale: Optional[float] = None):
-    """tcgen05 flash-attention forward over the packed q|k|v rows (head_dim 64).  segments = [(task, B, S, row0)];
+    """tcgen05 flash-attention forward over the packed q|k|v rows (head_dim 64 / 128).  segments = [(task, B, S, row0)];
     out [M, n_heads*head_dim] bf16 (rows outside the segments untouched).  Raises for unsupported head dims."""
     require_cuda(qkv, out, lse)
     qkv = _bf16_2d(qkv, "qkv")
     out = _bf16_2d(out, "out")
-    if head_dim != 64:
-        raise NotImplementedError("attention_fwd: head_dim 64 only in this round")
+    if head_dim not in (64, 128):
+        raise NotImplementedError("attention_fwd: head_dim 64 or 128")
     if scale is None:
         scale = head_dim ** -0.5
     for (_, B, S, row0) in segments:

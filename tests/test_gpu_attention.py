@@ -25,12 +25,13 @@ def _ref(qkv, B, S, row0, nh, nkv, hd, causal):
     return o.transpose(1, 2).reshape(B * S, nh * hd), lse
 
 
-@pytest.mark.parametrize("B,S,nh,nkv,causal", [(2, 128, 4, 4, False), (2, 256, 8, 2, True), (3, 460, 32, 8, True),
-                                               (2, 1500, 16, 16, False), (2, 400, 16, 16, False), (1, 57, 4, 1, True),
-                                               (2, 190, 32, 8, True)])
-def test_attention_forward(B, S, nh, nkv, causal):
+@pytest.mark.parametrize("B,S,nh,nkv,causal,hd", [(2, 128, 4, 4, False, 64), (2, 256, 8, 2, True, 64),
+                                                  (3, 460, 32, 8, True, 64), (2, 1500, 16, 16, False, 64),
+                                                  (2, 400, 16, 16, False, 64), (1, 57, 4, 1, True, 64),
+                                                  (2, 190, 32, 8, True, 64), (2, 412, 16, 2, True, 128),
+                                                  (2, 300, 8, 8, False, 128), (1, 129, 32, 8, True, 128)])
+def test_attention_forward(B, S, nh, nkv, causal, hd):
     from omni_avsr_b200 import ops
-    hd = 64
     g = torch.Generator(device="cuda").manual_seed(S + nh)
     row0 = 128
     M = row0 + B * S + 70
