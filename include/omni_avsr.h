@@ -148,14 +148,23 @@ int omni_splice_prompt_bwd(const omni_splice_args* args, const void* const dout[
                            void* d_video_tok, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Flash-attention forward (tcgen05, head_dim 64) over one segment of the packed q|k|v rows:
+ * Flash-attention forward (tcgen05, head_dim 64 or 128) over one segment of the packed q|k|v rows:
  *   qkv [M, ld] bf16, every row = [q heads | k heads | v heads]; the segment is B clips x S tokens from row0.
  *   out [M, out_ld] bf16 (n_heads*head_dim columns written for the segment's rows); lse optional fp32 [n_heads, M].
  * Replaces F.scaled_dot_product_attention at Llama_LoRA.py:300 / Qwen_LoRA.py:606 (causal GQA), the HF Whisper encoder
  * self-attention and fairseq multihead_attention.py:619-654 (non-causal).  Returns OMNI_ERR_UNSUPPORTED for
- * head_dim != 64 (the host then uses the library SDPA; listed in DESIGN.md).
+ * any other head_dim (none of the named architectures).
  * ---------------------------------------------------------------------------------------------- */
 int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* out, int64_t out_ld, float* lse, int32_t row0,
+                       int32_t B, int32_t S, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t causal,
+                       float scale, void* stream);
+
+/* Flash-attention backward (tcgen05) of the same segment: dqkv [M, dqkv_ld] bf16 receives dQ | dK | dV in the column
+ * layout of qkv (the segment's rows only; GQA group sums included).  out / lse are the forward results, dout the
+ * gradient of out [M, dout_ld]; delta is caller-owned scratch, fp32 [n_heads, M].  Replaces what autograd derives for
+ * the SDPA calls listed above (Llama_LoRA.py:300, Qwen_LoRA.py:606, multihead_attention.py:619-654). */
+int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const void* out, int64_t out_ld, const void* dout,
+                       int64_t dout_ld, const float* lse, float* delta, void* dqkv, int64_t dqkv_ld, int32_t row0,
                        int32_t B, int32_t S, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t causal,
                        float scale, void* stream);
 

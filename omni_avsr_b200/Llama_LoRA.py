@@ -505,13 +505,12 @@ class LlamaSdpaAttention_lora(nn.Module):
 
 
 class PackedSdpaFn(torch.autograd.Function):
-    """Attention core over packed q|k|v rows -> [M, q_dim].
+    """Attention core over packed q|k|v rows -> [M, q_dim], on our tcgen05 flash kernels (csrc/attention.cu,
+    csrc/attention_bwd.cu) for head_dim 64 / 128 -- every named architecture.
 
-    TODO(round 2): replace the library SDPA call with the tcgen05 flash kernel (csrc/attention.cu).
-    Forward: SDPA per segment on strided views of the packed buffer, written straight into the output rows.
-    Backward: the segment's SDPA is re-evaluated under a local graph and dq|dk|dv are copied into ONE packed dqkv
-    buffer -- autograd's own slice gradients would materialise three zero-filled [M, q+2kv] tensors per segment and
-    add them up."""
+    Forward: one launch per segment, straight from / into the packed rows, log-sum-exp kept for the backward.
+    Backward: dQ | dK | dV written into ONE packed dqkv buffer (autograd's own slice gradients would materialise three
+    zero-filled [M, q+2kv] tensors per segment and add them up).  Other head dims fall to the library SDPA."""
 
     @staticmethod
     def _views(qkv, B, S, off, nh, nkv, hd):
@@ -534,35 +533,44 @@ class PackedSdpaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, segments, nh, nkv, hd, causal):
         out = torch.empty((qkv.shape[0], nh * hd), device=qkv.device, dtype=torch.bfloat16)
-        if hd in (64, 128):
-            # our tcgen05 flash-attention forward, straight from / into the packed rows
-            ops.attention_fwd(qkv, out, segments, nh, nkv, hd, causal)
+        ours = hd in (64, 128)
+        lse = None
+        if ours:
+            if ctx.needs_input_grad[0]:
+                lse = torch.empty((nh, qkv.shape[0]), device=qkv.device, dtype=torch.float32)
+            ops.attention_fwd(qkv, out, segments, nh, nkv, hd, causal, lse=lse)
         else:
-            # other head dims (none of the named architectures): library SDPA
             for (_, B, S, off) in segments:
                 q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
                 o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
                 out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
         PackedSdpaFn._zero_pad_rows(out, segments)
-        ctx.save_for_backward(qkv)
+        if lse is not None:
+            ctx.save_for_backward(qkv, out, lse)
+        else:
+            ctx.save_for_backward(qkv)
         ctx.meta = (segments, nh, nkv, hd, causal)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (qkv,) = ctx.saved_tensors
         segments, nh, nkv, hd, causal = ctx.meta
+        qkv = ctx.saved_tensors[0]
         dqkv = torch.empty_like(qkv)
-        for (_, B, S, off) in segments:
-            q, k, v = (t.detach().requires_grad_(True) for t in PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd))
-            with torch.enable_grad():
-                o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
-            do = dout[off: off + B * S].view(B, S, nh, hd).transpose(1, 2)
-            dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
-            gq, gk, gv = PackedSdpaFn._views(dqkv, B, S, off, nh, nkv, hd)
-            gq.copy_(dq)
-            gk.copy_(dk)
-            gv.copy_(dv)
+        if len(ctx.saved_tensors) == 3:
+            _, out, lse = ctx.saved_tensors
+            ops.attention_bwd(qkv, out, dout.contiguous(), lse, dqkv, segments, nh, nkv, hd, causal)
+        else:
+            for (_, B, S, off) in segments:
+                q, k, v = (t.detach().requires_grad_(True) for t in PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd))
+                with torch.enable_grad():
+                    o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
+                do = dout[off: off + B * S].view(B, S, nh, hd).transpose(1, 2)
+                dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
+                gq, gk, gv = PackedSdpaFn._views(dqkv, B, S, off, nh, nkv, hd)
+                gq.copy_(dq)
+                gk.copy_(dk)
+                gv.copy_(dv)
         PackedSdpaFn._zero_pad_rows(dqkv, segments)
         return dqkv, None, None, None, None, None
 

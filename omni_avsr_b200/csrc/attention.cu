@@ -33,12 +33,6 @@ struct AttnSmem {
   static constexpr int TOTAL = BAR_OFFSET + 8 * 8 + 16 + 1024;
 };
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 struct AttnParams {
   bf16* out;             // [M, out_ld]
   float* lse;            // optional [n_heads, M] (natural-log-sum-exp of the scaled scores) or nullptr

@@ -1,0 +1,555 @@
+// Flash-attention backward on the sm_100a tensor cores (head_dim 64 or 128), two kernels, no atomics:
+//   attn_bwd_dq_kernel   : CTA = one 128-query tile of one head;  loops over key tiles;     dQ accumulates in TMEM
+//   attn_bwd_dkv_kernel  : CTA = one 128-key tile of one KV head; loops over (query head of the group, query tile);
+//                          dK and dV accumulate in TMEM (the GQA group sum happens in the accumulator)
+// Both recompute S and dP on the tensor cores from the packed q|k|v rows and dOut, rebuild P = exp2(s*scale - lse)
+// from the log-sum-exp saved by the forward kernel, form dS = P o (dP - delta) per thread (thread = TMEM lane) and
+// feed bf16 P / dS back to tcgen05.mma as K-major operands through a 128B-swizzled shared-memory tile, exactly like
+// the forward kernel's P.  K / V / Q / dO tiles are used twice from the same TMA tile: K-major for the score GEMMs,
+// MN-major for the gradient GEMMs.  delta[h, row] = sum_d dO*O comes from a small HBM-bound pre-pass.
+//
+// Replaces what autograd derives for F.scaled_dot_product_attention at Llama_LoRA.py:300 / Qwen_LoRA.py:606 (causal GQA)
+// and fairseq multihead_attention.py:619-654 (non-causal, AV-HuBERT LoRA fine-tuning).
+#include "common.cuh"
+#include "../../include/omni_avsr.h"
+
+namespace omni {
+
+constexpr int AB_T = 128;          // queries per tile == keys per tile
+constexpr int AB_THREADS = 192;    // warp 0 TMA, warp 1 MMA, warps 2..5 compute (thread = TMEM lane)
+
+struct AttnBwdParams {
+  bf16* dqkv;            // [M, dqkv_ld] packed gradient rows, same column layout as qkv
+  long long dqkv_ld;
+  const float* lse;      // [n_heads, M] natural-log-sum-exp of the scaled scores (forward kernel)
+  const float* delta;    // [n_heads, M] rowsum(dO o O)
+  long long M;
+  int row0, S, n_heads, n_kv_heads, causal;
+  float scale, scale_log2;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// delta pre-pass: one warp per row, HD/8 lanes per head (16-byte loads), fp32 sum.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ dout, long long do_ld, const bf16* __restrict__ out, long long o_ld,
+                  float* __restrict__ delta, long long M, int row0, int rows, int n_heads, int hd) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  const long long row = static_cast<long long>(row0) + w;
+  const int lph = hd >> 3;                 // lanes per head
+  const int hpp = 32 / lph;                // heads per pass
+  const int sub = lane / lph, l = lane % lph;
+  for (int h0 = 0; h0 < n_heads; h0 += hpp) {
+    const int h = h0 + sub;
+    float acc = 0.f;
+    if (h < n_heads) {
+      const uint4 a = ld_nc_u4(dout + row * do_ld + h * hd + l * 8);
+      const uint4 b = ld_nc_u4(out + row * o_ld + h * hd + l * 8);
+      const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = bf2_to_f2(av[i]), y = bf2_to_f2(bv[i]);
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+      }
+    }
+    for (int o = lph >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (h < n_heads && l == 0) delta[static_cast<long long>(h) * M + row] = acc;
+  }
+}
+
+// write 32 bf16 (16 packed words) of row r, column block c (32 columns) into a [128 x 128] K-major operand tile made
+// of two 128B-swizzled [128 x 64] blocks
+__device__ __forceinline__ void store_operand_chunk(uint8_t* tile, int r, int c, const uint32_t (&w)[16]) {
+  uint8_t* blk = tile + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int chunk = (c & 1) * 4 + t;
+    *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dQ
+// ---------------------------------------------------------------------------------------------------------------
+template <int HD>
+struct BwdQSmem {
+  static constexpr int TILE = AB_T * HD * 2;
+  static constexpr int OFF_Q = 0, OFF_DO = TILE, OFF_K = 2 * TILE, OFF_V = 3 * TILE, OFF_DS = 4 * TILE;
+  static constexpr int BAR_OFFSET = OFF_DS + 32768;
+  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo,
+                   const AttnBwdParams p) {
+  using SM = BwdQSmem<HD>;
+  constexpr int NB = HD / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* ds_full = bars + 4;
+  uint64_t* dq_full = bars + 5;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, clip = blockIdx.z;
+  const int kvh = head / (p.n_heads / p.n_kv_heads);
+  const int q0 = qt * AB_T;
+  const int clip_row0 = p.row0 + clip * p.S;
+  const int n_kv = p.causal ? (qt + 1) : (p.S + AB_T - 1) / AB_T;
+  const int col_q = head * HD;
+  const int col_k = (p.n_heads + kvh) * HD;
+  const int col_v = (p.n_heads + p.n_kv_heads + kvh) * HD;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tmdo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      mbar_init(kv_full, 1);
+      mbar_init(kv_empty, 1);
+      mbar_init(s_full, 1);
+      mbar_init(ds_full, 4);
+      mbar_init(dq_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 512);    // S [0,128) | dP [128,256) | dQ [256, 256+HD)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * SM::TILE);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        tma_load_2d(&tm, q_full, smem + SM::OFF_Q + b * 16384, col_q + b * 64, clip_row0 + q0);
+        tma_load_2d(&tmdo, q_full, smem + SM::OFF_DO + b * 16384, col_q + b * 64, clip_row0 + q0);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(kv_empty, (j & 1) ^ 1);
+        mbar_expect_tx(kv_full, 2 * SM::TILE);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          tma_load_2d(&tm, kv_full, smem + SM::OFF_K + b * 16384, col_k + b * 64, clip_row0 + j * AB_T);
+          tma_load_2d(&tm, kv_full, smem + SM::OFF_V + b * 16384, col_v + b * 64, clip_row0 + j * AB_T);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(AB_T, AB_T, 0, 0);
+    constexpr uint32_t idesc_g = make_idesc_bf16(AB_T, HD, 0, 1);     // dS (K-major) x K tile (MN-major)
+    const uint32_t sQ = smem_u32(smem + SM::OFF_Q), sDO = smem_u32(smem + SM::OFF_DO);
+    const uint32_t sK = smem_u32(smem + SM::OFF_K), sV = smem_u32(smem + SM::OFF_V);
+    const uint32_t sDS = smem_u32(smem + SM::OFF_DS);
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(kv_full, ph);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint64_t ad = make_smem_desc_sw128(sQ + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          const uint64_t bd = make_smem_desc_sw128(sK + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_s, ad, bd, idesc_s, k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint64_t ad = make_smem_desc_sw128(sDO + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          const uint64_t bd = make_smem_desc_sw128(sV + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_dp, ad, bd, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(ds_full, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t kd = make_smem_desc_sw128(sK, 16384, 1024);      // MN-major [keys, HD]
+#pragma unroll
+        for (int k = 0; k < AB_T / 16; ++k) {
+          const uint64_t ad = make_smem_desc_sw128(sDS + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_dq, ad, kd + 128 * k, idesc_g, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(kv_empty);
+        if (j == n_kv - 1) umma_commit(dq_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qpos = q0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const long long row = static_cast<long long>(clip_row0) + qpos;
+    const bool row_ok = qpos < p.S;
+    const float lse2 = row_ok ? p.lse[static_cast<long long>(head) * p.M + row] * 1.4426950408889634f : 0.f;
+    const float dl = row_ok ? p.delta[static_cast<long long>(head) * p.M + row] : 0.f;
+    const int kmax = row_ok ? (p.causal ? qpos : (p.S - 1)) : -1;
+    const float sc = p.scale_log2;
+    uint8_t* sDS = smem + SM::OFF_DS;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int k0 = j * AB_T;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      const bool full = (k0 + AB_T - 1 <= kmax);
+#pragma unroll 1
+      for (int c = 0; c < AB_T / 32; ++c) {
+        uint32_t s[32], d[32], w[16];
+        tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
+        tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
+        tmem_ld_wait();
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), sc, -lse2));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sc, -lse2));
+            w[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(d[i]) - dl), p1 * (__uint_as_float(d[i + 1]) - dl));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float g0 = 0.f, g1 = 0.f;
+            if (k0 + c * 32 + i <= kmax)
+              g0 = ex2_approx(fmaf(__uint_as_float(s[i]), sc, -lse2)) * (__uint_as_float(d[i]) - dl);
+            if (k0 + c * 32 + i + 1 <= kmax)
+              g1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sc, -lse2)) * (__uint_as_float(d[i + 1]) - dl);
+            w[i >> 1] = f2_to_bf2(g0, g1);
+          }
+        }
+        store_operand_chunk(sDS, r, c, w);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    mbar_wait(dq_full, 0);
+    tc_fence_after();
+    bf16* op = p.dqkv + row * p.dqkv_ld + col_q;
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_dq + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = f2_to_bf2(__uint_as_float(v[i]) * p.scale, __uint_as_float(v[i + 1]) * p.scale);
+          u.y = f2_to_bf2(__uint_as_float(v[i + 2]) * p.scale, __uint_as_float(v[i + 3]) * p.scale);
+          u.z = f2_to_bf2(__uint_as_float(v[i + 4]) * p.scale, __uint_as_float(v[i + 5]) * p.scale);
+          u.w = f2_to_bf2(__uint_as_float(v[i + 6]) * p.scale, __uint_as_float(v[i + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(op + c * 32 + i) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dK, dV
+// ---------------------------------------------------------------------------------------------------------------
+template <int HD>
+struct BwdKVSmem {
+  static constexpr int TILE = AB_T * HD * 2;
+  static constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = 3 * TILE, OFF_P = 4 * TILE;
+  static constexpr int OFF_DS = OFF_P + 32768;
+  static constexpr int OFF_STAT = OFF_DS + 32768;          // [2 buffers][lse2 | delta][128] fp32
+  static constexpr int BAR_OFFSET = OFF_STAT + 2 * 2 * AB_T * 4;
+  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo,
+                    const AttnBwdParams p) {
+  using SM = BwdKVSmem<HD>;
+  constexpr int NB = HD / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* pds_full = bars + 4;
+  uint64_t* acc_full = bars + 5;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, kvh = blockIdx.y, clip = blockIdx.z;
+  const int G = p.n_heads / p.n_kv_heads;
+  const int k0 = jt * AB_T;
+  const int clip_row0 = p.row0 + clip * p.S;
+  const int n_qt = (p.S + AB_T - 1) / AB_T;
+  const int i0 = p.causal ? jt : 0;
+  const int per_head = n_qt - i0;
+  const int n_it = G * per_head;
+  const int col_k = (p.n_heads + kvh) * HD;
+  const int col_v = (p.n_heads + p.n_kv_heads + kvh) * HD;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tmdo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1);
+      mbar_init(q_full, 1);
+      mbar_init(q_empty, 1);
+      mbar_init(s_full, 1);
+      mbar_init(pds_full, 4);
+      mbar_init(acc_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 512);    // S^T [0,128) | dP^T [128,256) | dV [256,256+HD) | dK [256+HD, 256+2HD)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 256 + HD;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * SM::TILE);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        tma_load_2d(&tm, kv_full, smem + SM::OFF_K + b * 16384, col_k + b * 64, clip_row0 + k0);
+        tma_load_2d(&tm, kv_full, smem + SM::OFF_V + b * 16384, col_v + b * 64, clip_row0 + k0);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int head = kvh * G + it / per_head;
+        const int q0 = (i0 + it % per_head) * AB_T;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, 2 * SM::TILE);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          tma_load_2d(&tm, q_full, smem + SM::OFF_Q + b * 16384, head * HD + b * 64, clip_row0 + q0);
+          tma_load_2d(&tmdo, q_full, smem + SM::OFF_DO + b * 16384, head * HD + b * 64, clip_row0 + q0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(AB_T, AB_T, 0, 0);
+    constexpr uint32_t idesc_g = make_idesc_bf16(AB_T, HD, 0, 1);
+    const uint32_t sK = smem_u32(smem + SM::OFF_K), sV = smem_u32(smem + SM::OFF_V);
+    const uint32_t sQ = smem_u32(smem + SM::OFF_Q), sDO = smem_u32(smem + SM::OFF_DO);
+    const uint32_t sP = smem_u32(smem + SM::OFF_P), sDS = smem_u32(smem + SM::OFF_DS);
+    mbar_wait(kv_full, 0);
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = it & 1;
+      mbar_wait(q_full, ph);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {      // S^T = K Q^T
+          const uint64_t ad = make_smem_desc_sw128(sK + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          const uint64_t bd = make_smem_desc_sw128(sQ + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_s, ad, bd, idesc_s, k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {      // dP^T = V dO^T
+          const uint64_t ad = make_smem_desc_sw128(sV + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          const uint64_t bd = make_smem_desc_sw128(sDO + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_dp, ad, bd, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(pds_full, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dod = make_smem_desc_sw128(sDO, 16384, 1024);    // MN-major [queries, HD]
+        const uint64_t qd = make_smem_desc_sw128(sQ, 16384, 1024);
+#pragma unroll
+        for (int k = 0; k < AB_T / 16; ++k) {    // dV += P^T dO
+          const uint64_t ad = make_smem_desc_sw128(sP + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_dv, ad, dod + 128 * k, idesc_g, (it > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < AB_T / 16; ++k) {    // dK += dS^T Q
+          const uint64_t ad = make_smem_desc_sw128(sDS + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
+          umma_bf16(tmem_dk, ad, qd + 128 * k, idesc_g, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(q_empty);
+        if (it == n_it - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // key row inside the tile == TMEM lane
+    const int kpos = k0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const bool row_ok = kpos < p.S;
+    const int qlo = row_ok ? (p.causal ? kpos : 0) : 0x7fffffff;     // first query position that sees this key
+    const float sc = p.scale_log2;
+    uint8_t* sP = smem + SM::OFF_P;
+    uint8_t* sDS = smem + SM::OFF_DS;
+    float* stat = reinterpret_cast<float*>(smem + SM::OFF_STAT);
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = it & 1;
+      const int head = kvh * G + it / per_head;
+      const int q0 = (i0 + it % per_head) * AB_T;
+      float* st = stat + (it & 1) * 2 * AB_T;
+      {
+        const bool ok = q0 + r < p.S;
+        const long long idx = static_cast<long long>(head) * p.M + clip_row0 + q0 + r;
+        st[r] = ok ? p.lse[idx] * 1.4426950408889634f : 0.f;
+        st[AB_T + r] = ok ? p.delta[idx] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      const bool full = (qlo <= q0) && (q0 + AB_T - 1 < p.S);
+#pragma unroll 1
+      for (int c = 0; c < AB_T / 32; ++c) {
+        uint32_t s[32], d[32], wp[16], wd[16];
+        tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
+        tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
+        tmem_ld_wait();
+        const float4* L4 = reinterpret_cast<const float4*>(st + c * 32);
+        const float4* D4 = reinterpret_cast<const float4*>(st + AB_T + c * 32);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 l = L4[i4], dd = D4[i4];
+          const float ls[4] = {l.x, l.y, l.z, l.w}, ds[4] = {dd.x, dd.y, dd.z, dd.w};
+          float pv[4], gv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i4 * 4 + e;
+            const int qc = q0 + c * 32 + i;
+            const bool ok = full || (qc >= qlo && qc < p.S);
+            const float pe = ok ? ex2_approx(fmaf(__uint_as_float(s[i]), sc, -ls[e])) : 0.f;
+            pv[e] = pe;
+            gv[e] = ok ? pe * (__uint_as_float(d[i]) - ds[e]) : 0.f;
+          }
+          wp[i4 * 2] = f2_to_bf2(pv[0], pv[1]);
+          wp[i4 * 2 + 1] = f2_to_bf2(pv[2], pv[3]);
+          wd[i4 * 2] = f2_to_bf2(gv[0], gv[1]);
+          wd[i4 * 2 + 1] = f2_to_bf2(gv[2], gv[3]);
+        }
+        store_operand_chunk(sP, r, c, wp);
+        store_operand_chunk(sDS, r, c, wd);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const long long row = static_cast<long long>(clip_row0) + kpos;
+    bf16* ov = p.dqkv + row * p.dqkv_ld + col_v;
+    bf16* ok_ = p.dqkv + row * p.dqkv_ld + col_k;
+#pragma unroll
+    for (int c = 0; c < 2 * HD / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_dv + lane_addr + c * 32, v);      // dV columns first, dK right behind
+      tmem_ld_wait();
+      const bool is_k = c >= HD / 32;
+      const float mul = is_k ? p.scale : 1.0f;
+      bf16* op = is_k ? (ok_ + (c - HD / 32) * 32) : (ov + c * 32);
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = f2_to_bf2(__uint_as_float(v[i]) * mul, __uint_as_float(v[i + 1]) * mul);
+          u.y = f2_to_bf2(__uint_as_float(v[i + 2]) * mul, __uint_as_float(v[i + 3]) * mul);
+          u.z = f2_to_bf2(__uint_as_float(v[i + 4]) * mul, __uint_as_float(v[i + 5]) * mul);
+          u.w = f2_to_bf2(__uint_as_float(v[i + 6]) * mul, __uint_as_float(v[i + 7]) * mul);
+          *reinterpret_cast<uint4*>(op + i) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int HD>
+static int launch_attn_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdParams& p, int B, cudaStream_t st) {
+  auto kq = attn_bwd_dq_kernel<HD>;
+  auto kkv = attn_bwd_dkv_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdQSmem<HD>::TOTAL) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    if (cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdKVSmem<HD>::TOTAL) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    attr_set = true;
+  }
+  const int nt = ceil_div(p.S, AB_T);
+  kkv<<<dim3(nt, p.n_kv_heads, B), AB_THREADS, BwdKVSmem<HD>::TOTAL, st>>>(tm, tmdo, p);
+  OMNI_LAUNCH_CHECK();
+  kq<<<dim3(nt, p.n_heads, B), AB_THREADS, BwdQSmem<HD>::TOTAL, st>>>(tm, tmdo, p);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+}  // namespace omni
+
+extern "C" int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const void* out, int64_t out_ld,
+                                  const void* dout, int64_t dout_ld, const float* lse, float* delta, void* dqkv,
+                                  int64_t dqkv_ld, int32_t row0, int32_t B, int32_t S, int32_t n_heads,
+                                  int32_t n_kv_heads, int32_t head_dim, int32_t causal, float scale, void* stream) {
+  using namespace omni;
+  OMNI_CHECK_ARG(qkv && out && dout && lse && delta && dqkv && M > 0 && B > 0 && S > 0 && n_heads > 0 && n_kv_heads > 0);
+  OMNI_CHECK_ARG(n_heads % n_kv_heads == 0 && row0 >= 0 && static_cast<int64_t>(row0) + static_cast<int64_t>(B) * S <= M);
+  const int64_t width = static_cast<int64_t>(n_heads + 2 * n_kv_heads) * head_dim;
+  OMNI_CHECK_ARG((ld % 8) == 0 && (out_ld % 8) == 0 && (dout_ld % 8) == 0 && (dqkv_ld % 8) == 0 && ld >= width &&
+                 dqkv_ld >= width);
+  if (head_dim != 64 && head_dim != 128) return OMNI_ERR_UNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tm, tmdo;
+  int rc = omni_make_tmap_2d_bf16(&tm, qkv, (uint64_t)M, (uint64_t)width, (uint64_t)ld, AB_T, 64, 1);
+  if (rc) return rc;
+  rc = omni_make_tmap_2d_bf16(&tmdo, dout, (uint64_t)M, (uint64_t)n_heads * head_dim, (uint64_t)dout_ld, AB_T, 64, 1);
+  if (rc) return rc;
+  const int rows = B * S;
+  attn_delta_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(dout), dout_ld,
+                                                       reinterpret_cast<const bf16*>(out), out_ld, delta, M, row0, rows,
+                                                       n_heads, head_dim);
+  OMNI_LAUNCH_CHECK();
+  AttnBwdParams p;
+  p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  p.dqkv_ld = dqkv_ld;
+  p.lse = lse;
+  p.delta = delta;
+  p.M = M;
+  p.row0 = row0; p.S = S; p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.causal = causal ? 1 : 0;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  return head_dim == 64 ? launch_attn_bwd<64>(tm, tmdo, p, B, st) : launch_attn_bwd<128>(tm, tmdo, p, B, st);
+}

@@ -530,3 +530,25 @@ def attention_fwd(qkv, out, segments, n_heads: int, n_kv_heads: int, head_dim: i
                                      stream_ptr()), "omni_attention_fwd")
         _count()
     return out
+
+
+def attention_bwd(qkv, out, dout, lse, dqkv, segments, n_heads: int, n_kv_heads: int, head_dim: int, causal: bool,
+                  scale: Optional[float] = None):
+    """tcgen05 flash-attention backward over the packed rows: fills the segments' rows of dqkv [M, q+2kv] with
+    dQ | dK | dV.  out / lse [n_heads, M] are the forward results of attention_fwd."""
+    require_cuda(qkv, out, dout, lse, dqkv)
+    qkv, out, dout, dqkv = (_bf16_2d(t, n) for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")))
+    if head_dim not in (64, 128):
+        raise NotImplementedError("attention_bwd: head_dim 64 or 128")
+    if lse.dtype != torch.float32 or lse.shape != (n_heads, qkv.shape[0]) or not lse.is_contiguous():
+        raise ValueError("attention_bwd: lse must be contiguous fp32 [n_heads, M]")
+    if scale is None:
+        scale = head_dim ** -0.5
+    delta = torch.empty_like(lse)
+    for (_, B, S, row0) in segments:
+        check(lib.omni_attention_bwd(qkv.data_ptr(), qkv.shape[0], qkv.stride(0), out.data_ptr(), out.stride(0),
+                                     dout.data_ptr(), dout.stride(0), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(),
+                                     dqkv.stride(0), row0, B, S, n_heads, n_kv_heads, head_dim, 1 if causal else 0,
+                                     float(scale), stream_ptr()), "omni_attention_bwd")
+        _count(3)
+    return dqkv
