@@ -202,6 +202,14 @@ int omni_prelu_maxpool3x3s2(const void* x, const void* slope, void* y, int64_t N
 /* im2col of the video front-end Conv3d(1,64,(5,7,7),stride (1,2,2),pad (2,3,3)) (resnet.py:137): video [B,T,H,W] bf16 ->
  * out [B*T*Ho*Wo, 256] bf16 (245 taps + 11 zero columns), so the convolution runs as one omni_gemm_bf16 call. */
 int omni_im2col_front3d(const void* video, void* out, int32_t B, int32_t T, int32_t H, int32_t W, void* stream);
+
+/* Time-major variant (4x less traffic): out2 [B][Ho][Wo][T+4][64] holds the 49 spatial taps of every (position, padded
+ * time) row; the five temporal taps are the five consecutive rows, consumed by omni_gemm_bf16 through an overlapping-row
+ * view (lda = 64, K = 320).  omni_prelu_maxpool_front = PReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) (resnet.py:139-140)
+ * reading the GEMM output [B][H][W][T+4][C] and writing channels-last [B*T][Hp][Wp][C]. */
+int omni_im2col_front2d(const void* video, void* out2, int32_t B, int32_t T, int32_t H, int32_t W, void* stream);
+int omni_prelu_maxpool_front(const void* x, const void* slope, void* y, int32_t B, int32_t T, int32_t H, int32_t W,
+                             int32_t C, void* stream);
 /* out[i,:] = table[idx[i],:] (embed_tokens of the decode step, label-row selection); status as in the splice. */
 int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
                      int64_t table_rows, int32_t* status, void* stream);

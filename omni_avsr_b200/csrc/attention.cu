@@ -28,9 +28,14 @@ struct AttnSmem {
   static constexpr int K_BYTES = AT_BK * AT_HD * 2;
   static constexpr int V_BYTES = AT_BK * AT_HD * 2;
   static constexpr int P_BYTES = AT_BQ * AT_BK * 2;        // 32 KB (two [128 x 64] swizzled blocks)
-  static constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + K_BYTES, OFF_P = OFF_V + V_BYTES;
+  static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;    // K/V tiles are double-buffered: the TMA load of tile j+1
+  static constexpr int OFF_Q = 0, OFF_KV = Q_BYTES;        // runs under the softmax / MMAs of tile j
+  static constexpr int OFF_P = OFF_KV + 2 * STAGE_BYTES;
   static constexpr int BAR_OFFSET = OFF_P + P_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 8 * 8 + 16 + 1024;
+  // 2 CTAs / SM need <= 113 KB each: the 1024-byte alignment slack is trimmed to 768 (the kernel traps if the dynamic
+  // shared-memory base is less aligned than that allows; in practice it is 1024-aligned)
+  static constexpr int ALIGN_SLACK = AT_HD == 64 ? 768 : 1024;
+  static constexpr int TOTAL = BAR_OFFSET + 8 * 8 + 16 + ALIGN_SLACK;
 };
 
 struct AttnParams {
@@ -51,12 +56,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 2;
-  uint64_t* s_full = bars + 3;
-  uint64_t* p_full = bars + 4;
-  uint64_t* o_full = bars + 5;
+  uint64_t* kv_full = bars + 1;      // [2]
+  uint64_t* kv_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  if (static_cast<int>(smem - smem_raw) > SM::ALIGN_SLACK) __trap();
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,7 +80,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     if (lane == 0) {
       mbar_init(q_full, 1);
       mbar_init(kv_full, 1);
+      mbar_init(kv_full + 1, 1);
       mbar_init(kv_empty, 1);
+      mbar_init(kv_empty + 1, 1);
       mbar_init(s_full, 1);
       mbar_init(p_full, 4);      // one arrive per softmax warp
       mbar_init(o_full, 1);
@@ -97,12 +105,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 #pragma unroll
       for (int b = 0; b < NB; ++b) tma_load_2d(&tm, q_full, smem + SM::OFF_Q + b * 16384, col_q + b * 64, clip_row0 + q0);
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(kv_empty, (j & 1) ^ 1);
-        mbar_expect_tx(kv_full, SM::K_BYTES + SM::V_BYTES);
+        const int st = j & 1;
+        uint8_t* kv = smem + SM::OFF_KV + st * SM::STAGE_BYTES;
+        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full + st, SM::STAGE_BYTES);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          tma_load_2d(&tm, kv_full, smem + SM::OFF_K + b * 16384, col_k + b * 64, clip_row0 + j * AT_BK);
-          tma_load_2d(&tm, kv_full, smem + SM::OFF_V + b * 16384, col_v + b * 64, clip_row0 + j * AT_BK);
+          tma_load_2d(&tm, kv_full + st, kv + b * 16384, col_k + b * 64, clip_row0 + j * AT_BK);
+          tma_load_2d(&tm, kv_full + st, kv + SM::K_BYTES + b * 16384, col_v + b * 64, clip_row0 + j * AT_BK);
         }
       }
     }
@@ -110,13 +120,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     constexpr uint32_t idesc_s = make_idesc_bf16(AT_BQ, AT_BK, 0, 0);   // Q (K-major) x K (K-major)
     constexpr uint32_t idesc_o = make_idesc_bf16(AT_BQ, AT_HD, 0, 1);   // P (K-major) x V (MN-major: [keys, hd] tile)
     const uint32_t sQ = smem_u32(smem + SM::OFF_Q);
-    const uint32_t sK = smem_u32(smem + SM::OFF_K);
-    const uint32_t sV = smem_u32(smem + SM::OFF_V);
     const uint32_t sP = smem_u32(smem + SM::OFF_P);
     mbar_wait(q_full, 0);
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
-      mbar_wait(kv_full, ph);
+      const int st = j & 1;
+      const uint32_t sK = smem_u32(smem + SM::OFF_KV + st * SM::STAGE_BYTES);
+      const uint32_t sV = sK + SM::K_BYTES;
+      mbar_wait(kv_full + st, (j >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -139,7 +150,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
           umma_bf16(tmem_o, pd, vd + 128 * k, idesc_o, k > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
-        umma_commit(kv_empty);
+        umma_commit(kv_empty + st);
       }
       __syncwarp();
     }

@@ -1,7 +1,9 @@
 // Flash-attention backward on the sm_100a tensor cores (head_dim 64 or 128), two kernels, no atomics:
-//   attn_bwd_dq_kernel   : CTA = one 128-query tile of one head;  loops over key tiles;     dQ accumulates in TMEM
-//   attn_bwd_dkv_kernel  : CTA = one 128-key tile of one KV head; loops over (query head of the group, query tile);
+//   attn_bwd_dq_kernel   : CTA = one 128-query tile of one head;  loops over 64-key steps;  dQ accumulates in TMEM
+//   attn_bwd_dkv_kernel  : CTA = one 128-key tile of one KV head; loops over (query head of the group, 64-query step);
 //                          dK and dV accumulate in TMEM (the GQA group sum happens in the accumulator)
+// The 64-wide steps keep a CTA at 256 TMEM columns and < 113 KB of shared memory for head_dim 64, so two CTAs share
+// an SM and one CTA's exp2 / dS arithmetic runs under the other's MMAs; the streamed operand tiles are double-buffered.
 // Both recompute S and dP on the tensor cores from the packed q|k|v rows and dOut, rebuild P = exp2(s*scale - lse)
 // from the log-sum-exp saved by the forward kernel, form dS = P o (dP - delta) per thread (thread = TMEM lane) and
 // feed bf16 P / dS back to tcgen05.mma as K-major operands through a 128B-swizzled shared-memory tile, exactly like
@@ -60,15 +62,22 @@ attn_delta_kernel(const bf16* __restrict__ dout, long long do_ld, const bf16* __
   }
 }
 
-// write 32 bf16 (16 packed words) of row r, column block c (32 columns) into a [128 x 128] K-major operand tile made
-// of two 128B-swizzled [128 x 64] blocks
+// write 32 bf16 (16 packed words) of row r, column block c (32 columns, c = 0 or 1) into a [128 x 64] K-major
+// 128B-swizzled operand tile
 __device__ __forceinline__ void store_operand_chunk(uint8_t* tile, int r, int c, const uint32_t (&w)[16]) {
-  uint8_t* blk = tile + (c >> 1) * 16384 + r * 128;
+  uint8_t* blk = tile + r * 128;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const int chunk = (c & 1) * 4 + t;
+    const int chunk = c * 4 + t;
     *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
   }
+}
+
+constexpr int AB_STEP = 64;        // streamed rows (keys in the dQ kernel, queries in the dK/dV kernel) per step
+
+// K-major descriptor of k-step k (16 elements) inside a tile made of 64-column 128B-swizzled blocks of `blk_bytes`
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t base, int k, uint32_t blk_bytes) {
+  return make_smem_desc_sw128(base + (k >> 2) * blk_bytes, 16, 1024) + 2 * (k & 3);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -76,27 +85,32 @@ __device__ __forceinline__ void store_operand_chunk(uint8_t* tile, int r, int c,
 // ---------------------------------------------------------------------------------------------------------------
 template <int HD>
 struct BwdQSmem {
-  static constexpr int TILE = AB_T * HD * 2;
-  static constexpr int OFF_Q = 0, OFF_DO = TILE, OFF_K = 2 * TILE, OFF_V = 3 * TILE, OFF_DS = 4 * TILE;
-  static constexpr int BAR_OFFSET = OFF_DS + 32768;
-  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;
+  static constexpr int TILE = AB_T * HD * 2;               // Q, dO: [128 x HD]
+  static constexpr int STEP = AB_STEP * HD * 2;            // K, V step tiles: [64 x HD]
+  static constexpr int OFF_Q = 0, OFF_DO = TILE, OFF_KV = 2 * TILE;     // K/V: 2 stages of (K | V)
+  static constexpr int OFF_DS = OFF_KV + 4 * STEP;         // dS [128 x 64] bf16
+  static constexpr int BAR_OFFSET = OFF_DS + 16384;
+  static constexpr int ALIGN_SLACK = HD == 64 ? 768 : 1024;
+  static constexpr int TOTAL = BAR_OFFSET + 128 + ALIGN_SLACK;
+  static constexpr int TMEM_COLS = 256;                    // S [0,64) | dP [64,128) | dQ [128,128+HD)
 };
 
 template <int HD>
-__global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo,
-                   const AttnBwdParams p) {
+__global__ void __launch_bounds__(AB_THREADS, HD == 64 ? 2 : 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm64,
+                   const __grid_constant__ CUtensorMap tmdo, const AttnBwdParams p) {
   using SM = BwdQSmem<HD>;
   constexpr int NB = HD / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(smem - smem_raw) > SM::ALIGN_SLACK) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 2;
-  uint64_t* s_full = bars + 3;
-  uint64_t* ds_full = bars + 4;
-  uint64_t* dq_full = bars + 5;
+  uint64_t* kv_full = bars + 1;      // [2]
+  uint64_t* kv_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* ds_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -105,34 +119,38 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
   const int kvh = head / (p.n_heads / p.n_kv_heads);
   const int q0 = qt * AB_T;
   const int clip_row0 = p.row0 + clip * p.S;
-  const int n_kv = p.causal ? (qt + 1) : (p.S + AB_T - 1) / AB_T;
+  const int n_all = (p.S + AB_STEP - 1) / AB_STEP;
+  const int n_kv = p.causal ? min(2 * qt + 2, n_all) : n_all;
   const int col_q = head * HD;
   const int col_k = (p.n_heads + kvh) * HD;
   const int col_v = (p.n_heads + p.n_kv_heads + kvh) * HD;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tm64);
     tma_prefetch_desc(&tmdo);
   }
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(q_full, 1);
       mbar_init(kv_full, 1);
+      mbar_init(kv_full + 1, 1);
       mbar_init(kv_empty, 1);
+      mbar_init(kv_empty + 1, 1);
       mbar_init(s_full, 1);
       mbar_init(ds_full, 4);
       mbar_init(dq_full, 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, 512);    // S [0,128) | dP [128,256) | dQ [256, 256+HD)
+    tmem_alloc(tmem_ptr_smem, SM::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 64, tmem_dq = tmem_base + 128;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -143,52 +161,47 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         tma_load_2d(&tmdo, q_full, smem + SM::OFF_DO + b * 16384, col_q + b * 64, clip_row0 + q0);
       }
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(kv_empty, (j & 1) ^ 1);
-        mbar_expect_tx(kv_full, 2 * SM::TILE);
+        const int st = j & 1;
+        uint8_t* kv = smem + SM::OFF_KV + st * 2 * SM::STEP;
+        mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full + st, 2 * SM::STEP);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          tma_load_2d(&tm, kv_full, smem + SM::OFF_K + b * 16384, col_k + b * 64, clip_row0 + j * AB_T);
-          tma_load_2d(&tm, kv_full, smem + SM::OFF_V + b * 16384, col_v + b * 64, clip_row0 + j * AB_T);
+          tma_load_2d(&tm64, kv_full + st, kv + b * 8192, col_k + b * 64, clip_row0 + j * AB_STEP);
+          tma_load_2d(&tm64, kv_full + st, kv + SM::STEP + b * 8192, col_v + b * 64, clip_row0 + j * AB_STEP);
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = make_idesc_bf16(AB_T, AB_T, 0, 0);
-    constexpr uint32_t idesc_g = make_idesc_bf16(AB_T, HD, 0, 1);     // dS (K-major) x K tile (MN-major)
+    constexpr uint32_t idesc_s = make_idesc_bf16(AB_T, AB_STEP, 0, 0);
+    constexpr uint32_t idesc_g = make_idesc_bf16(AB_T, HD, 0, 1);     // dS (K-major) x K step tile (MN-major)
     const uint32_t sQ = smem_u32(smem + SM::OFF_Q), sDO = smem_u32(smem + SM::OFF_DO);
-    const uint32_t sK = smem_u32(smem + SM::OFF_K), sV = smem_u32(smem + SM::OFF_V);
     const uint32_t sDS = smem_u32(smem + SM::OFF_DS);
     mbar_wait(q_full, 0);
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
-      mbar_wait(kv_full, ph);
+      const int st = j & 1;
+      const uint32_t sK = smem_u32(smem + SM::OFF_KV + st * 2 * SM::STEP), sV = sK + SM::STEP;
+      mbar_wait(kv_full + st, (j >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t ad = make_smem_desc_sw128(sQ + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          const uint64_t bd = make_smem_desc_sw128(sK + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          umma_bf16(tmem_s, ad, bd, idesc_s, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_s, kmajor_desc(sQ, k, 16384), kmajor_desc(sK, k, 8192), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t ad = make_smem_desc_sw128(sDO + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          const uint64_t bd = make_smem_desc_sw128(sV + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          umma_bf16(tmem_dp, ad, bd, idesc_s, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_dp, kmajor_desc(sDO, k, 16384), kmajor_desc(sV, k, 8192), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
       }
       __syncwarp();
       mbar_wait(ds_full, ph);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t kd = make_smem_desc_sw128(sK, 16384, 1024);      // MN-major [keys, HD]
+        const uint64_t kd = make_smem_desc_sw128(sK, 8192, 1024);       // MN-major [64 keys, HD]
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k) {
-          const uint64_t ad = make_smem_desc_sw128(sDS + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          umma_bf16(tmem_dq, ad, kd + 128 * k, idesc_g, (j > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(kv_empty);
+        for (int k = 0; k < AB_STEP / 16; ++k)
+          umma_bf16(tmem_dq, kmajor_desc(sDS, k, 0), kd + 128 * k, idesc_g, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(kv_empty + st);
         if (j == n_kv - 1) umma_commit(dq_full);
       }
       __syncwarp();
@@ -207,12 +220,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     uint8_t* sDS = smem + SM::OFF_DS;
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
-      const int k0 = j * AB_T;
+      const int k0 = j * AB_STEP;
       mbar_wait(s_full, ph);
       tc_fence_after();
-      const bool full = (k0 + AB_T - 1 <= kmax);
-#pragma unroll 1
-      for (int c = 0; c < AB_T / 32; ++c) {
+      const bool full = (k0 + AB_STEP - 1 <= kmax);
+#pragma unroll
+      for (int c = 0; c < AB_STEP / 32; ++c) {
         uint32_t s[32], d[32], w[16];
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
         tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
@@ -267,7 +280,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, SM::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -275,29 +288,34 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------------
 template <int HD>
 struct BwdKVSmem {
-  static constexpr int TILE = AB_T * HD * 2;
-  static constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = 3 * TILE, OFF_P = 4 * TILE;
-  static constexpr int OFF_DS = OFF_P + 32768;
-  static constexpr int OFF_STAT = OFF_DS + 32768;          // [2 buffers][lse2 | delta][128] fp32
-  static constexpr int BAR_OFFSET = OFF_STAT + 2 * 2 * AB_T * 4;
-  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;
+  static constexpr int TILE = AB_T * HD * 2;               // K, V: [128 x HD]
+  static constexpr int STEP = AB_STEP * HD * 2;            // Q, dO step tiles: [64 x HD]
+  static constexpr int OFF_K = 0, OFF_V = TILE, OFF_QDO = 2 * TILE;     // 2 stages of (Q | dO)
+  static constexpr int OFF_P = OFF_QDO + 4 * STEP;         // P^T [128 x 64] bf16
+  static constexpr int OFF_DS = OFF_P + 16384;             // dS^T [128 x 64] bf16
+  static constexpr int OFF_STAT = OFF_DS + 16384;          // [2 buffers][lse2 | delta][64] fp32
+  static constexpr int BAR_OFFSET = OFF_STAT + 2 * 2 * AB_STEP * 4;
+  static constexpr int ALIGN_SLACK = HD == 64 ? 768 : 1024;
+  static constexpr int TOTAL = BAR_OFFSET + 128 + ALIGN_SLACK;
+  static constexpr int TMEM_COLS = HD == 64 ? 256 : 512;   // S^T [0,64) | dP^T [64,128) | dV [128,128+HD) | dK behind
 };
 
 template <int HD>
-__global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmdo,
-                    const AttnBwdParams p) {
+__global__ void __launch_bounds__(AB_THREADS, HD == 64 ? 2 : 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm64,
+                    const __grid_constant__ CUtensorMap tmdo64, const AttnBwdParams p) {
   using SM = BwdKVSmem<HD>;
   constexpr int NB = HD / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(smem - smem_raw) > SM::ALIGN_SLACK) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
   uint64_t* kv_full = bars + 0;
-  uint64_t* q_full = bars + 1;
-  uint64_t* q_empty = bars + 2;
-  uint64_t* s_full = bars + 3;
-  uint64_t* pds_full = bars + 4;
-  uint64_t* acc_full = bars + 5;
+  uint64_t* q_full = bars + 1;       // [2]
+  uint64_t* q_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* acc_full = bars + 7;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -306,36 +324,39 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
   const int G = p.n_heads / p.n_kv_heads;
   const int k0 = jt * AB_T;
   const int clip_row0 = p.row0 + clip * p.S;
-  const int n_qt = (p.S + AB_T - 1) / AB_T;
-  const int i0 = p.causal ? jt : 0;
-  const int per_head = n_qt - i0;
+  const int n_qs = (p.S + AB_STEP - 1) / AB_STEP;          // 64-query steps in the clip
+  const int i0 = p.causal ? 2 * jt : 0;                    // first step that sees any key of this tile
+  const int per_head = n_qs - i0;
   const int n_it = G * per_head;
   const int col_k = (p.n_heads + kvh) * HD;
   const int col_v = (p.n_heads + p.n_kv_heads + kvh) * HD;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm);
-    tma_prefetch_desc(&tmdo);
+    tma_prefetch_desc(&tm64);
+    tma_prefetch_desc(&tmdo64);
   }
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(kv_full, 1);
       mbar_init(q_full, 1);
+      mbar_init(q_full + 1, 1);
       mbar_init(q_empty, 1);
+      mbar_init(q_empty + 1, 1);
       mbar_init(s_full, 1);
       mbar_init(pds_full, 4);
       mbar_init(acc_full, 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, 512);    // S^T [0,128) | dP^T [128,256) | dV [256,256+HD) | dK [256+HD, 256+2HD)
+    tmem_alloc(tmem_ptr_smem, SM::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 256 + HD;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 64, tmem_dv = tmem_base + 128, tmem_dk = tmem_base + 128 + HD;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -347,59 +368,52 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
       }
       for (int it = 0; it < n_it; ++it) {
         const int head = kvh * G + it / per_head;
-        const int q0 = (i0 + it % per_head) * AB_T;
-        mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, 2 * SM::TILE);
+        const int q0 = (i0 + it % per_head) * AB_STEP;
+        const int st = it & 1;
+        uint8_t* qd = smem + SM::OFF_QDO + st * 2 * SM::STEP;
+        mbar_wait(q_empty + st, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(q_full + st, 2 * SM::STEP);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          tma_load_2d(&tm, q_full, smem + SM::OFF_Q + b * 16384, head * HD + b * 64, clip_row0 + q0);
-          tma_load_2d(&tmdo, q_full, smem + SM::OFF_DO + b * 16384, head * HD + b * 64, clip_row0 + q0);
+          tma_load_2d(&tm64, q_full + st, qd + b * 8192, head * HD + b * 64, clip_row0 + q0);
+          tma_load_2d(&tmdo64, q_full + st, qd + SM::STEP + b * 8192, head * HD + b * 64, clip_row0 + q0);
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = make_idesc_bf16(AB_T, AB_T, 0, 0);
+    constexpr uint32_t idesc_s = make_idesc_bf16(AB_T, AB_STEP, 0, 0);
     constexpr uint32_t idesc_g = make_idesc_bf16(AB_T, HD, 0, 1);
     const uint32_t sK = smem_u32(smem + SM::OFF_K), sV = smem_u32(smem + SM::OFF_V);
-    const uint32_t sQ = smem_u32(smem + SM::OFF_Q), sDO = smem_u32(smem + SM::OFF_DO);
     const uint32_t sP = smem_u32(smem + SM::OFF_P), sDS = smem_u32(smem + SM::OFF_DS);
     mbar_wait(kv_full, 0);
     for (int it = 0; it < n_it; ++it) {
       const uint32_t ph = it & 1;
-      mbar_wait(q_full, ph);
+      const int st = it & 1;
+      const uint32_t sQ = smem_u32(smem + SM::OFF_QDO + st * 2 * SM::STEP), sDO = sQ + SM::STEP;
+      mbar_wait(q_full + st, (it >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {      // S^T = K Q^T
-          const uint64_t ad = make_smem_desc_sw128(sK + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          const uint64_t bd = make_smem_desc_sw128(sQ + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          umma_bf16(tmem_s, ad, bd, idesc_s, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < HD / 16; ++k)        // S^T = K Q^T
+          umma_bf16(tmem_s, kmajor_desc(sK, k, 16384), kmajor_desc(sQ, k, 8192), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {      // dP^T = V dO^T
-          const uint64_t ad = make_smem_desc_sw128(sV + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          const uint64_t bd = make_smem_desc_sw128(sDO + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          umma_bf16(tmem_dp, ad, bd, idesc_s, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < HD / 16; ++k)        // dP^T = V dO^T
+          umma_bf16(tmem_dp, kmajor_desc(sV, k, 16384), kmajor_desc(sDO, k, 8192), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
       }
       __syncwarp();
       mbar_wait(pds_full, ph);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t dod = make_smem_desc_sw128(sDO, 16384, 1024);    // MN-major [queries, HD]
-        const uint64_t qd = make_smem_desc_sw128(sQ, 16384, 1024);
+        const uint64_t dod = make_smem_desc_sw128(sDO, 8192, 1024);     // MN-major [64 queries, HD]
+        const uint64_t qd = make_smem_desc_sw128(sQ, 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k) {    // dV += P^T dO
-          const uint64_t ad = make_smem_desc_sw128(sP + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          umma_bf16(tmem_dv, ad, dod + 128 * k, idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < AB_STEP / 16; ++k)   // dV += P^T dO
+          umma_bf16(tmem_dv, kmajor_desc(sP, k, 0), dod + 128 * k, idesc_g, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k) {    // dK += dS^T Q
-          const uint64_t ad = make_smem_desc_sw128(sDS + (k >> 2) * 16384, 16, 1024) + 2 * (k & 3);
-          umma_bf16(tmem_dk, ad, qd + 128 * k, idesc_g, (it > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(q_empty);
+        for (int k = 0; k < AB_STEP / 16; ++k)   // dK += dS^T Q
+          umma_bf16(tmem_dk, kmajor_desc(sDS, k, 0), qd + 128 * k, idesc_g, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(q_empty + st);
         if (it == n_it - 1) umma_commit(acc_full);
       }
       __syncwarp();
@@ -415,29 +429,39 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     uint8_t* sP = smem + SM::OFF_P;
     uint8_t* sDS = smem + SM::OFF_DS;
     float* stat = reinterpret_cast<float*>(smem + SM::OFF_STAT);
+    // per-query statistics of a step: threads 0..63 fetch them one step ahead (the global-load latency hides under
+    // the previous step's arithmetic) and publish them through a double-buffered shared-memory row
+    auto fetch_stat = [&](int it, float& l2, float& dl) {
+      const int head = kvh * G + it / per_head;
+      const int q0 = (i0 + it % per_head) * AB_STEP;
+      const bool ok = r < AB_STEP && it < n_it && q0 + r < p.S;
+      const long long idx = static_cast<long long>(head) * p.M + clip_row0 + q0 + r;
+      l2 = ok ? p.lse[idx] * 1.4426950408889634f : 0.f;
+      dl = ok ? p.delta[idx] : 0.f;
+    };
+    float nl2, ndl;
+    fetch_stat(0, nl2, ndl);
     for (int it = 0; it < n_it; ++it) {
       const uint32_t ph = it & 1;
-      const int head = kvh * G + it / per_head;
-      const int q0 = (i0 + it % per_head) * AB_T;
-      float* st = stat + (it & 1) * 2 * AB_T;
-      {
-        const bool ok = q0 + r < p.S;
-        const long long idx = static_cast<long long>(head) * p.M + clip_row0 + q0 + r;
-        st[r] = ok ? p.lse[idx] * 1.4426950408889634f : 0.f;
-        st[AB_T + r] = ok ? p.delta[idx] : 0.f;
+      const int q0 = (i0 + it % per_head) * AB_STEP;
+      float* st = stat + (it & 1) * 2 * AB_STEP;
+      if (r < AB_STEP) {
+        st[r] = nl2;
+        st[AB_STEP + r] = ndl;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      fetch_stat(it + 1, nl2, ndl);
       mbar_wait(s_full, ph);
       tc_fence_after();
-      const bool full = (qlo <= q0) && (q0 + AB_T - 1 < p.S);
-#pragma unroll 1
-      for (int c = 0; c < AB_T / 32; ++c) {
+      const bool full = (qlo <= q0) && (q0 + AB_STEP - 1 < p.S);
+#pragma unroll
+      for (int c = 0; c < AB_STEP / 32; ++c) {
         uint32_t s[32], d[32], wp[16], wd[16];
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
         tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
         tmem_ld_wait();
         const float4* L4 = reinterpret_cast<const float4*>(st + c * 32);
-        const float4* D4 = reinterpret_cast<const float4*>(st + AB_T + c * 32);
+        const float4* D4 = reinterpret_cast<const float4*>(st + AB_STEP + c * 32);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 l = L4[i4], dd = D4[i4];
@@ -495,11 +519,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, SM::TMEM_COLS);
 }
 
 template <int HD>
-static int launch_attn_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const AttnBwdParams& p, int B, cudaStream_t st) {
+static int launch_attn_bwd(const CUtensorMap& tm, const CUtensorMap& tm64, const CUtensorMap& tmdo,
+                           const CUtensorMap& tmdo64, const AttnBwdParams& p, int B, cudaStream_t st) {
   auto kq = attn_bwd_dq_kernel<HD>;
   auto kkv = attn_bwd_dkv_kernel<HD>;
   static bool attr_set = false;
@@ -511,9 +536,9 @@ static int launch_attn_bwd(const CUtensorMap& tm, const CUtensorMap& tmdo, const
     attr_set = true;
   }
   const int nt = ceil_div(p.S, AB_T);
-  kkv<<<dim3(nt, p.n_kv_heads, B), AB_THREADS, BwdKVSmem<HD>::TOTAL, st>>>(tm, tmdo, p);
+  kkv<<<dim3(nt, p.n_kv_heads, B), AB_THREADS, BwdKVSmem<HD>::TOTAL, st>>>(tm, tm64, tmdo64, p);
   OMNI_LAUNCH_CHECK();
-  kq<<<dim3(nt, p.n_heads, B), AB_THREADS, BwdQSmem<HD>::TOTAL, st>>>(tm, tmdo, p);
+  kq<<<dim3(nt, p.n_heads, B), AB_THREADS, BwdQSmem<HD>::TOTAL, st>>>(tm, tm64, tmdo, p);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
@@ -532,10 +557,14 @@ extern "C" int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const 
                  dqkv_ld >= width);
   if (head_dim != 64 && head_dim != 128) return OMNI_ERR_UNSUPPORTED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap tm, tmdo;
+  CUtensorMap tm, tm64, tmdo, tmdo64;
   int rc = omni_make_tmap_2d_bf16(&tm, qkv, (uint64_t)M, (uint64_t)width, (uint64_t)ld, AB_T, 64, 1);
   if (rc) return rc;
+  rc = omni_make_tmap_2d_bf16(&tm64, qkv, (uint64_t)M, (uint64_t)width, (uint64_t)ld, AB_STEP, 64, 1);
+  if (rc) return rc;
   rc = omni_make_tmap_2d_bf16(&tmdo, dout, (uint64_t)M, (uint64_t)n_heads * head_dim, (uint64_t)dout_ld, AB_T, 64, 1);
+  if (rc) return rc;
+  rc = omni_make_tmap_2d_bf16(&tmdo64, dout, (uint64_t)M, (uint64_t)n_heads * head_dim, (uint64_t)dout_ld, AB_STEP, 64, 1);
   if (rc) return rc;
   const int rows = B * S;
   attn_delta_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(dout), dout_ld,
@@ -551,5 +580,6 @@ extern "C" int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const 
   p.row0 = row0; p.S = S; p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.causal = causal ? 1 : 0;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
-  return head_dim == 64 ? launch_attn_bwd<64>(tm, tmdo, p, B, st) : launch_attn_bwd<128>(tm, tmdo, p, B, st);
+  return head_dim == 64 ? launch_attn_bwd<64>(tm, tm64, tmdo, tmdo64, p, B, st)
+                        : launch_attn_bwd<128>(tm, tm64, tmdo, tmdo64, p, B, st);
 }

@@ -306,9 +306,9 @@ class _ResEncoder(nn.Module):
         conv3, bn3 = self.frontend3D[0], self.frontend3D[1]
         w3, b3 = self._fold(conv3.weight, bn3)                         # [C, 1, 5, 7, 7]
         C = w3.shape[0]
-        wmat = torch.zeros((C, 256), device=w3.device, dtype=torch.bfloat16)
-        wmat[:, :245] = w3.reshape(C, 245)                             # k = (kt*7 + ky)*7 + kx, 11 zero pad columns
-        f = {"front": (wmat, b3)}
+        wmat = torch.zeros((C, 5, 64), device=w3.device, dtype=torch.bfloat16)
+        wmat[:, :, :49] = w3.reshape(C, 5, 49)                         # k = kt*64 + ky*7 + kx, 15 zero columns per kt
+        f = {"front": (wmat.view(C, 320), b3)}
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
                 w1, b1 = self._fold(blk.conv1.weight, blk.bn1)
@@ -332,11 +332,11 @@ class _ResEncoder(nn.Module):
             self._wt = self._prepare()
         f = self._wt
         B, _, T, Hh, Ww = x.shape
-        # Conv3d(1 -> C, (5,7,7), stride (1,2,2)) = im2col kernel (245 taps padded to 256) + ONE tcgen05 GEMM against the
-        # BatchNorm-folded [C, 256] filter matrix; the GEMM output [B*T*Ho*Wo, C] IS the channels-last activation.
+        # Conv3d(1 -> C, (5,7,7), stride (1,2,2)) = time-major im2col of the 49 spatial taps + ONE tcgen05 GEMM whose five
+        # K blocks (temporal taps) read five consecutive rows, against the BatchNorm-folded [C, 5*64] filter matrix; the
+        # pooling kernel turns the time-major GEMM output into the channels-last activation of the trunk.
         w, b = f["front"]
-        y = ops.conv3d_front(x[:, 0].contiguous(), w, b)                                   # [B*T, C, Ho, Wo] (NHWC memory)
-        y = ops.prelu_maxpool3x3s2(y.contiguous(memory_format=torch.channels_last), self.frontend3D[2].weight.data)
+        y = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data)  # [B*T, C, 22, 22] NHWC
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
                 w1, b1, s1, w2, b2, ds = f[(li, bi)]

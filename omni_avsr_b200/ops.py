@@ -513,6 +513,41 @@ def conv3d_front(video, wmat, bias):
     return out.view(B * T, Ho, Wo, Cc).permute(0, 3, 1, 2)
 
 
+def front3d_prelu_maxpool(video, wmat5, bias, slope):
+    """AV-HuBERT front-end Conv3d(1, C, (5,7,7), (1,2,2), (2,3,3)) (+ folded BatchNorm bias) + PReLU + MaxPool3d((1,3,3),
+    (1,2,2), (0,1,1)) on video [B, T, H, W] bf16.  wmat5 [C, 320]: column dt*64 + ky*7 + kx (49 taps + 15 zero columns
+    per temporal tap).  Time-major im2col of the 49 spatial taps, one tcgen05 GEMM whose five K blocks read five
+    consecutive rows (overlapping-row TMA view), pooling kernel.  Returns [B*T, C, Hp, Wp] in channels-last memory."""
+    require_cuda(video, wmat5, bias, slope)
+    if video.dtype != torch.bfloat16 or video.dim() != 4 or not video.is_contiguous():
+        raise ValueError("video must be contiguous bf16 [B, T, H, W]")
+    if wmat5.dtype != torch.bfloat16 or wmat5.shape[1] != 320 or not wmat5.is_contiguous():
+        raise ValueError("wmat5 must be contiguous bf16 [C, 320]")
+    B, T, H, W = video.shape
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
+    Cc = wmat5.shape[0]
+    Tp = T + 4
+    y = torch.empty((B * T, Cc, Hp, Wp), device=video.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    per_clip = Ho * Wo * Tp
+    clips = max(1, (16 << 20) // per_clip)          # <= ~16M rows (2 GB of taps + 2 GB of conv output) in flight
+    nb_max = min(B, clips)
+    cols = torch.empty((nb_max * per_clip + 8, 64), device=video.device, dtype=torch.bfloat16)
+    cols[nb_max * per_clip:].zero_()                 # rows read by the last line's scratch outputs
+    conv = torch.empty((nb_max * per_clip, Cc), device=video.device, dtype=torch.bfloat16)
+    for b0 in range(0, B, clips):
+        nb = min(clips, B - b0)
+        check(lib.omni_im2col_front2d(video[b0:b0 + nb].data_ptr(), cols.data_ptr(), nb, T, H, W, stream_ptr()),
+              "omni_im2col_front2d")
+        _count()
+        a = cols.as_strided((nb * per_clip, 320), (64, 1))
+        gemm(a, wmat5, bias=bias, out=conv[: nb * per_clip], block_n=64 if Cc <= 64 else 128)
+        check(lib.omni_prelu_maxpool_front(conv.data_ptr(), slope.data_ptr(), y[b0 * T:].data_ptr(), nb, T, Ho, Wo, Cc,
+                                           stream_ptr()), "omni_prelu_maxpool_front")
+        _count()
+    return y
+
+
 def attention_fwd(qkv, out, segments, n_heads: int, n_kv_heads: int, head_dim: int, causal: bool, lse=None,
                   scale: Optional[float] = None):
     """tcgen05 flash-attention forward over the packed q|k|v rows (head_dim 64 / 128).  segments = [(task, B, S, row0)];

@@ -235,3 +235,32 @@ def test_conv3d_front_matches_torch():
     # borders and temporal edges individually
     for sl in (got[0] - want[0], got[T - 1] - want[T - 1], got[:, :, 0] - want[:, :, 0], got[:, :, :, 43] - want[:, :, :, 43]):
         assert sl.abs().max().item() <= 1e-2 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("B,T", [(2, 7), (1, 3), (3, 12)])
+def test_front3d_prelu_maxpool_matches_torch(B, T):
+    """Time-major im2col (49 taps) + overlapping-row tcgen05 GEMM (5 temporal K blocks) + PReLU/MaxPool kernel ==
+    Conv3d(1, C, (5,7,7), (1,2,2), (2,3,3)) + bias -> PReLU -> MaxPool3d((1,3,3), (1,2,2), (0,1,1)) (resnet.py:137-140),
+    including the temporal edges (zero padding) and all spatial borders."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(23 + T)
+    H, W, C = 88, 88, 64
+    video = torch.randn(B, T, H, W, generator=g).bfloat16()
+    w3 = (torch.randn(C, 1, 5, 7, 7, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(C, generator=g).bfloat16()
+    slope = (torch.rand(C, generator=g) * 0.5).bfloat16()
+    conv = F.conv3d(video.float().unsqueeze(1), w3.float(), bias.float(), stride=(1, 2, 2), padding=(2, 3, 3))
+    conv = conv.bfloat16().float()                                     # the GEMM epilogue rounds to bf16
+    act = F.prelu(conv, slope.float())
+    want = F.max_pool3d(act, (1, 3, 3), (1, 2, 2), (0, 1, 1)).transpose(1, 2).reshape(B * T, C, 22, 22)
+    wmat = torch.zeros(C, 5, 64, dtype=torch.bfloat16)
+    wmat[:, :, :49] = w3.reshape(C, 5, 49)
+    got = ops.front3d_prelu_maxpool(video.cuda(), wmat.view(C, 320).cuda(), bias.cuda(), slope.cuda())
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    got = got.float().cpu()
+    assert got.shape == want.shape
+    tol = 1e-2 * want.abs().max().item()
+    assert (got - want).abs().max().item() <= tol
+    for sl in (got[0] - want[0], got[T - 1] - want[T - 1], got[B * T - 1] - want[B * T - 1],
+               got[:, :, 0] - want[:, :, 0], got[:, :, :, 21] - want[:, :, :, 21]):
+        assert sl.abs().max().item() <= tol

@@ -98,6 +98,38 @@ def bench_splice():
                           "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3)}), flush=True)
 
 
+def bench_attention():
+    """Path shapes at B=16: Whisper-medium (S=1500, non-causal), AV-HuBERT (S=400), Llama-1B segments (causal GQA),
+    plus the head_dim-128 shapes of Qwen2.5-3B / Llama-3.1-8B; cuDNN SDPA timed beside each."""
+    import torch.nn.functional as F
+    shapes = [("whisper-m", 16, 1500, 16, 16, 64, False), ("avhubert-l", 16, 400, 16, 16, 64, False),
+              ("llama1b-avsr", 16, 460, 32, 8, 64, True), ("llama1b-asr", 16, 256, 32, 8, 64, True),
+              ("qwen3b-avsr", 16, 460, 16, 2, 128, True), ("llama8b-avsr", 16, 460, 32, 8, 128, True)]
+    for name, B, S, nh, nkv, hd, causal in shapes:
+        M = B * S
+        qkv = torch.randn(M, (nh + 2 * nkv) * hd, device="cuda").bfloat16()
+        out = torch.empty(M, nh * hd, device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(nh, M, device="cuda")
+        dout = torch.randn(M, nh * hd, device="cuda").bfloat16()
+        dqkv = torch.empty_like(qkv)
+        seg = [(0, B, S, 0)]
+        fl = 4.0 * B * nh * S * S * hd * (0.5 if causal else 1.0)
+        med, _ = timeit(lambda: ops.attention_fwd(qkv, out, seg, nh, nkv, hd, causal, lse=lse))
+        medb, _ = timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, dqkv, seg, nh, nkv, hd, causal))
+        blk = qkv.view(B, S, -1)
+        q = blk[..., : nh * hd].view(B, S, nh, hd).transpose(1, 2).detach().requires_grad_(True)
+        k = blk[..., nh * hd: (nh + nkv) * hd].view(B, S, nkv, hd).transpose(1, 2).detach().requires_grad_(True)
+        v = blk[..., (nh + nkv) * hd:].view(B, S, nkv, hd).transpose(1, 2).detach().requires_grad_(True)
+        medl, _ = timeit(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=causal, enable_gqa=nh != nkv))
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=causal, enable_gqa=nh != nkv)
+        do = dout.view(B, S, nh, hd).transpose(1, 2)
+        medlb, _ = timeit(lambda: torch.autograd.grad(o, (q, k, v), do, retain_graph=True))
+        print(json.dumps({"kernel": "attention", "shape": name, "B": B, "S": S, "heads": nh, "kv_heads": nkv, "hd": hd,
+                          "causal": causal, "fwd_ms": round(med, 4), "fwd_tflops": round(fl / med / 1e9, 1),
+                          "bwd_ms": round(medb, 4), "bwd_tflops": round(2.5 * fl / medb / 1e9, 1),
+                          "sdpa_fwd_ms": round(medl, 4), "sdpa_bwd_ms": round(medlb, 4)}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "compress", "splice"]
     if "compress" in which:
@@ -106,3 +138,5 @@ if __name__ == "__main__":
         bench_splice()
     if "gemm" in which:
         bench_gemm()
+    if "attention" in which:
+        bench_attention()
