@@ -194,9 +194,11 @@ int omni_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, i
 int omni_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
 int omni_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
 /* ResNet front-end glue of AV-HuBERT (av_hubert/avhubert/resnet.py:35-74,131-169), channels-last [rows, C]:
- * x <- PReLU(x (+ residual)) in place (per-channel slope), and PReLU + MaxPool(3x3, stride 2, pad 1) in one pass
+ * x <- PReLU((x + bias) (+ residual + res_bias)) in place (per-channel slope; bias / res_bias = optional folded-BatchNorm
+ * shifts of the convolutions that produced x / residual), and PReLU + MaxPool(3x3, stride 2, pad 1) in one pass
  * (frontend3D's PReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1))): x [N, H, W, C] -> y [N, Ho, Wo, C]. */
-int omni_prelu_res(void* x, const void* residual, const void* slope, int64_t rows, int32_t C, void* stream);
+int omni_prelu_res(void* x, const void* residual, const void* slope, const void* bias, const void* res_bias,
+                   int64_t rows, int32_t C, void* stream);
 int omni_prelu_maxpool3x3s2(const void* x, const void* slope, void* y, int64_t N, int32_t H, int32_t W, int32_t C,
                             void* stream);
 /* im2col of the video front-end Conv3d(1,64,(5,7,7),stride (1,2,2),pad (2,3,3)) (resnet.py:137): video [B,T,H,W] bf16 ->

@@ -119,7 +119,7 @@ _sig("omni_sumsq", [_P, _I64, _P, _P])
 _sig("omni_adamw", [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _F, _F, _P, _P])
 _sig("omni_gemm_wgrad_bf16", [C.POINTER(WgradArgs), _P])
 _sig("omni_colsum_bf16", [_P, _P, _I64, _I32, _I64, _P])
-_sig("omni_prelu_res", [_P, _P, _P, _I64, _I32, _P])
+_sig("omni_prelu_res", [_P, _P, _P, _P, _P, _I64, _I32, _P])
 _sig("omni_prelu_maxpool3x3s2", [_P, _P, _P, _I64, _I32, _I32, _I32, _P])
 _sig("omni_im2col_front3d", [_P, _P, _I32, _I32, _I32, _I32, _P])
 _sig("omni_im2col_front2d", [_P, _P, _I32, _I32, _I32, _I32, _P])

@@ -490,17 +490,29 @@ extern "C" int omni_scatter_rows(const void* src, const int64_t* idx, void* out,
 namespace omni {
 
 __global__ void __launch_bounds__(EW_THREADS)
-prelu_res_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const bf16* __restrict__ slope, int C8,
-                 long long total8) {
+prelu_res_kernel(bf16* __restrict__ x, const bf16* __restrict__ res, const bf16* __restrict__ slope,
+                 const bf16* __restrict__ bias, const bf16* __restrict__ res_bias, int C8, long long total8) {
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(idx % C8);
     float f[8], s[8];
     unpack8(reinterpret_cast<const uint4*>(x)[idx], f);
     unpack8(__ldg(reinterpret_cast<const uint4*>(slope) + c), s);
+    if (bias) {                                                // folded-BatchNorm shift of the convolution that made x
+      float b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(bias) + c), b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = rbf(f[i] + b[i]);
+    }
     if (res) {
       float r[8];
       unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(res) + idx), r);
+      if (res_bias) {                                          // ... and of the 1x1 downsample convolution
+        float b[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(res_bias) + c), b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = rbf(r[i] + b[i]);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = rbf(f[i] + r[i]);     // `out += residual` rounds to bf16 before the PReLU
     }
@@ -547,14 +559,16 @@ prelu_maxpool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ slope,
 
 }  // namespace omni
 
-extern "C" int omni_prelu_res(void* x, const void* residual, const void* slope, int64_t rows, int32_t C, void* stream) {
+extern "C" int omni_prelu_res(void* x, const void* residual, const void* slope, const void* bias, const void* res_bias,
+                              int64_t rows, int32_t C, void* stream) {
   OMNI_CHECK_ARG(x && slope && rows >= 0 && C > 0 && (C % 8) == 0);
   if (rows == 0) return OMNI_OK;
   const long long total8 = rows * (C / 8);
   long long blocks = ceil_div_ll(total8, EW_THREADS);
   if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
   prelu_res_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((bf16*)x, (const bf16*)residual,
-                                                                          (const bf16*)slope, C / 8, total8);
+                                                                          (const bf16*)slope, (const bf16*)bias,
+                                                                          (const bf16*)res_bias, C / 8, total8);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }

@@ -3,9 +3,10 @@
 // `_torch_extract_fbank_features`):
 //   zero-pad / truncate to 30 s -> reflect-padded STFT (periodic hann 400, n_fft 400, hop 160), |.|^2, drop last frame
 //   -> 80 slaney mel bins -> log10(clamp 1e-10) -> max(x, max_utt - 8) -> (x + 4) / 4  -> bf16 [B, 80, 3000]
-// The 400-point DFT is evaluated directly in fp32 from shared-memory twiddles (400 x 201 MACs per frame is ~1 GFLOP per
-// utterance: negligible, and it needs no FFT library); pass 1 writes fp32 log-mel + the per-utterance maximum, pass 2
-// applies the dynamic-range clamp and the affine map.
+// The 400-point DFT is evaluated directly in fp32 from shared-memory twiddles, folded in half by the real-input symmetry
+// and register-tiled over 8 frames per thread (no FFT library); frames that lie entirely in the zero padding behind the
+// utterance are written as the constant they evaluate to.  Pass 1 writes fp32 log-mel + the per-utterance maximum,
+// pass 2 applies the dynamic-range clamp and the affine map.
 #include "common.cuh"
 #include "../../include/omni_avsr.h"
 
@@ -45,10 +46,19 @@ logmel_pass1_kernel(const void* __restrict__ audio, int is_bf16, long long audio
                     const float* __restrict__ mel_filters,   // [80, 201]
                     float* __restrict__ logmel,               // [B, 80, 3000]
                     float* __restrict__ utt_max) {            // [B], pre-filled with -inf
-  __shared__ float s_x[(LM_FPB - 1) * LM_HOP + LM_NFFT];      // windowless samples of the frame span
-  __shared__ float s_win[LM_NFFT];
+  // Real-input DFT folded in half: with e[n] = xw[n] + xw[400-n], o[n] = xw[n] - xw[400-n] (n = 1..199; e[0] = xw[0],
+  // e[200] = xw[200], o[0] = o[200] = 0):  Re X[k] = sum_{n<=200} e[n] cos(2 pi n k / 400),  Im X[k] = sum o[n] sin(..).
+  // Thread = one bin k, 8 frames at a time in registers; e / o are stored frame-fastest so one 16-byte shared load
+  // feeds four frames and the twiddle loads are amortised over eight.
+  constexpr int HALF = LM_NFFT / 2;                            // 200
+  constexpr int SPAN = (LM_FPB - 1) * LM_HOP + LM_NFFT;
+  constexpr int POW_LD = LM_BINS + 1;
+  __shared__ float s_xp[SPAN > LM_FPB * POW_LD ? SPAN : LM_FPB * POW_LD];   // samples, later the power spectrum
   __shared__ float s_cos[LM_NFFT], s_sin[LM_NFFT];
-  __shared__ float s_pow[LM_FPB][LM_BINS + 1];
+  __shared__ __align__(16) float s_e[(HALF + 1) * LM_FPB];     // [n][frame]
+  __shared__ __align__(16) float s_o[(HALF + 1) * LM_FPB];
+  float* s_x = s_xp;
+  float (*s_pow)[POW_LD] = reinterpret_cast<float (*)[POW_LD]>(s_xp);
   __shared__ float s_max[LM_THREADS / 32];
 
   const int b = blockIdx.y;
@@ -56,34 +66,63 @@ logmel_pass1_kernel(const void* __restrict__ audio, int is_bf16, long long audio
   const int tid = threadIdx.x;
   const long long base = static_cast<long long>(b) * audio_bs;
 
+  // frames that only see the zero padding behind the utterance (a 16 s clip fills 1600 of the 3000 frames):
+  // power 0 -> log10(clamp 1e-10) = -10, no transform needed
+  if (T <= LM_NSAMP - LM_NFFT && f0 * LM_HOP - HALF >= T) {
+    for (int p = tid; p < LM_FPB * LM_MELS; p += LM_THREADS) {
+      const int m = p / LM_FPB, frame = f0 + (p - m * LM_FPB);
+      if (frame < LM_FRAMES) logmel[(static_cast<long long>(b) * LM_MELS + m) * LM_FRAMES + frame] = -10.0f;
+    }
+    if (tid == 0) atomic_max_float(utt_max + b, -10.0f);
+    return;
+  }
+
   for (int i = tid; i < LM_NFFT; i += LM_THREADS) {
     const float ang = 6.283185307179586f * static_cast<float>(i) / static_cast<float>(LM_NFFT);
     float sn, cs;
     sincosf(ang, &sn, &cs);
     s_cos[i] = cs;
     s_sin[i] = sn;
-    s_win[i] = 0.5f - 0.5f * cs;   // periodic hann
   }
-  const int span = (LM_FPB - 1) * LM_HOP + LM_NFFT;
-  for (int i = tid; i < span; i += LM_THREADS)
-    s_x[i] = lm_sample(audio, is_bf16, base, T, f0 * LM_HOP + i - LM_NFFT / 2);
+  for (int i = tid; i < SPAN; i += LM_THREADS)
+    s_x[i] = lm_sample(audio, is_bf16, base, T, f0 * LM_HOP + i - HALF);
+  __syncthreads();
+  for (int p = tid; p < (HALF + 1) * LM_FPB; p += LM_THREADS) {
+    const int n = p / LM_FPB, f = p - n * LM_FPB;
+    const float* x = s_x + f * LM_HOP;
+    const float wn = 0.5f - 0.5f * s_cos[n];                   // periodic hann (symmetric: w[400-n] = w[n])
+    const float a = x[n] * wn;
+    const float c = (n == 0 || n == HALF) ? 0.f : x[LM_NFFT - n] * wn;
+    s_e[p] = a + c;
+    s_o[p] = (n == 0 || n == HALF) ? 0.f : a - c;
+  }
   __syncthreads();
 
-  // power spectrum: (frame, bin) pairs
-  for (int p = tid; p < LM_FPB * LM_BINS; p += LM_THREADS) {
-    const int f = p / LM_BINS;
-    const int k = p - f * LM_BINS;
-    const float* x = s_x + f * LM_HOP;
-    float re = 0.f, im = 0.f;
-    int idx = 0;
-    for (int n = 0; n < LM_NFFT; ++n) {
-      const float v = x[n] * s_win[n];
-      re = fmaf(v, s_cos[idx], re);
-      im = fmaf(v, s_sin[idx], im);
-      idx += k;
-      if (idx >= LM_NFFT) idx -= LM_NFFT;
+  if (tid < LM_BINS) {
+    const int k = tid;
+#pragma unroll 1
+    for (int g = 0; g < LM_FPB / 8; ++g) {
+      float re[8], im[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) re[i] = im[i] = 0.f;
+      int idx = 0;
+#pragma unroll 2
+      for (int n = 0; n <= HALF; ++n) {
+        const float cs = s_cos[idx], sn = s_sin[idx];
+        const float4 e0 = *reinterpret_cast<const float4*>(s_e + n * LM_FPB + g * 8);
+        const float4 e1 = *reinterpret_cast<const float4*>(s_e + n * LM_FPB + g * 8 + 4);
+        const float4 o0 = *reinterpret_cast<const float4*>(s_o + n * LM_FPB + g * 8);
+        const float4 o1 = *reinterpret_cast<const float4*>(s_o + n * LM_FPB + g * 8 + 4);
+        re[0] = fmaf(e0.x, cs, re[0]); re[1] = fmaf(e0.y, cs, re[1]); re[2] = fmaf(e0.z, cs, re[2]); re[3] = fmaf(e0.w, cs, re[3]);
+        re[4] = fmaf(e1.x, cs, re[4]); re[5] = fmaf(e1.y, cs, re[5]); re[6] = fmaf(e1.z, cs, re[6]); re[7] = fmaf(e1.w, cs, re[7]);
+        im[0] = fmaf(o0.x, sn, im[0]); im[1] = fmaf(o0.y, sn, im[1]); im[2] = fmaf(o0.z, sn, im[2]); im[3] = fmaf(o0.w, sn, im[3]);
+        im[4] = fmaf(o1.x, sn, im[4]); im[5] = fmaf(o1.y, sn, im[5]); im[6] = fmaf(o1.z, sn, im[6]); im[7] = fmaf(o1.w, sn, im[7]);
+        idx += k;
+        if (idx >= LM_NFFT) idx -= LM_NFFT;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_pow[g * 8 + i][k] = re[i] * re[i] + im[i] * im[i];
     }
-    s_pow[f][k] = re * re + im * im;
   }
   __syncthreads();
 

@@ -340,11 +340,15 @@ class _ResEncoder(nn.Module):
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
                 w1, b1, s1, w2, b2, ds = f[(li, bi)]
-                o = F.conv2d(y, w1, b1, stride=s1, padding=1).contiguous(memory_format=torch.channels_last)
-                ops.prelu_res_(o, blk.relu1.weight.data)
-                o = F.conv2d(o, w2, b2, stride=1, padding=1).contiguous(memory_format=torch.channels_last)
-                res = y if ds is None else F.conv2d(y, ds[0], ds[1], stride=ds[2]).contiguous(memory_format=torch.channels_last)
-                y = ops.prelu_res_(o, blk.relu2.weight.data, res)
+                # the folded-BatchNorm shifts ride in the PReLU kernel (a conv bias would cost one more elementwise pass)
+                o = F.conv2d(y, w1, None, stride=s1, padding=1).contiguous(memory_format=torch.channels_last)
+                ops.prelu_res_(o, blk.relu1.weight.data, bias=b1)
+                o = F.conv2d(o, w2, None, stride=1, padding=1).contiguous(memory_format=torch.channels_last)
+                if ds is None:
+                    y = ops.prelu_res_(o, blk.relu2.weight.data, y, bias=b2)
+                else:
+                    res = F.conv2d(y, ds[0], None, stride=ds[2]).contiguous(memory_format=torch.channels_last)
+                    y = ops.prelu_res_(o, blk.relu2.weight.data, res, bias=b2, res_bias=ds[1])
         return y.mean(dim=(2, 3))
 
 

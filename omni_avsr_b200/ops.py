@@ -447,13 +447,18 @@ def _nhwc_rows(x):
     return x.shape[0] * x.shape[2] * x.shape[3], x.shape[1]
 
 
-def prelu_res_(x, slope, residual=None):
-    """x <- PReLU(x (+ residual)) in place; x / residual: bf16 channels-last [N, C, H, W]; slope bf16 [C]."""
-    require_cuda(x, slope, residual)
+def prelu_res_(x, slope, residual=None, bias=None, res_bias=None):
+    """x <- PReLU((x + bias) (+ residual + res_bias)) in place; x / residual: bf16 channels-last [N, C, H, W]; slope, bias,
+    res_bias bf16 [C] (the biases are the folded-BatchNorm shifts of the convolutions that produced x / residual)."""
+    require_cuda(x, slope, residual, bias, res_bias)
     rows, Cc = _nhwc_rows(x)
     if residual is not None and (_nhwc_rows(residual) != (rows, Cc)):
         raise ValueError("residual shape mismatch")
-    check(lib.omni_prelu_res(x.data_ptr(), ptr(residual), slope.data_ptr(), rows, Cc, stream_ptr()), "omni_prelu_res")
+    for b in (bias, res_bias):
+        if b is not None and (b.dtype != torch.bfloat16 or b.numel() != Cc or not b.is_contiguous()):
+            raise ValueError("bias must be contiguous bf16 [C]")
+    check(lib.omni_prelu_res(x.data_ptr(), ptr(residual), slope.data_ptr(), ptr(bias), ptr(res_bias), rows, Cc,
+                             stream_ptr()), "omni_prelu_res")
     _count()
     return x
 

@@ -210,6 +210,13 @@ def test_prelu_kernels():
     want1 = F.prelu(x, slope)
     got1 = ops.prelu_res_(x.cuda().clone(memory_format=torch.channels_last), slope.cuda())
     assert torch.equal(_bits(got1), _bits(want1))
+    # folded-BatchNorm shifts of both convolutions applied in the same pass (bit-exact with the separate bf16 adds)
+    b1 = torch.randn(64, generator=g).bfloat16()
+    b2 = torch.randn(64, generator=g).bfloat16()
+    want2 = F.prelu((x + b1.view(1, -1, 1, 1)) + (r + b2.view(1, -1, 1, 1)), slope)
+    got2 = ops.prelu_res_(x.cuda().clone(memory_format=torch.channels_last), slope.cuda(), r.cuda(), bias=b1.cuda(),
+                          res_bias=b2.cuda())
+    assert torch.equal(_bits(got2), _bits(want2))
     wantp = F.max_pool2d(F.prelu(x, slope), 3, 2, 1)
     gotp = ops.prelu_maxpool3x3s2(x.cuda(), slope.cuda())
     assert gotp.shape == wantp.shape
