@@ -22,6 +22,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue
+constexpr int GEMM2_THREADS = 320; // CTA-pair kernel: warps 2..9 epilogue (two warps per TMEM lane quarter, 128 columns each)
 
 struct GemmKParams {
   int M, N, K;
@@ -154,6 +155,96 @@ __device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&
         if (col0 + i < p.N) op[i] = __float2bfloat16_rn(v[i]);
     }
   }
+}
+
+
+// ---- coalesced epilogue of the CTA-pair kernel ------------------------------------------------------------------
+// A thread owns one accumulator row (TMEM lane), so direct global accesses are 16 bytes per thread at the row pitch:
+// 32 different 128-byte lines per warp instruction, and the LSU retires about one line per clock -- on short-K GEMMs
+// (K = 1024: 8192 clk of MMA per 256x256 tile) the residual loads + output stores alone cost as much as the main loop.
+// Each epilogue warp therefore transposes 32 rows x 64 columns through a private padded shared-memory tile (pitch
+// 144 B: conflict-free for the 16-byte row writes and for the 8-lanes-per-row reads), so that global loads / stores are
+// full 128-byte row segments (4 lines per warp instruction).
+constexpr int EPI_PITCH = 144;
+constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
+
+struct ResTile {            // residual of a 32-row x 64-column block in the coalesced layout: lane -> (row l/8 + 4*pass, 16 B l%8)
+  uint4 r[8];
+};
+__device__ __forceinline__ void res_tile_prefetch(const GemmKParams& p, int row0, int col0, int lane, ResTile& o) {
+  const bf16* rp = p.residual + static_cast<long long>(row0 + (lane >> 3)) * p.ldr + col0 + (lane & 7) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const bool ok = (row0 + (lane >> 3) + 4 * pass) < p.M;
+    o.r[pass] = ok ? ld_nc_u4(rp + static_cast<long long>(4 * pass) * p.ldr) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// publish a prefetched residual block into the warp's transposition tile (frees its registers for the next prefetch)
+__device__ __forceinline__ void res_tile_publish(uint8_t* stage, int lane, const ResTile& res) {
+  uint8_t* co_ptr = stage + (lane >> 3) * EPI_PITCH + (lane & 7) * 16;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) *reinterpret_cast<uint4*>(co_ptr + 4 * pass * EPI_PITCH) = res.r[pass];
+  __syncwarp();
+}
+
+__device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* stage, float (&v)[64], int lane, int row0,
+                                                int col0, bool res_staged) {
+  if (p.bias) {
+    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 b = __ldg(bp + i);
+      float2 f;
+      f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+      f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+      f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+      f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+    }
+  }
+  if (p.act != OMNI_ACT_NONE || p.residual) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    if (p.act == OMNI_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (p.act == OMNI_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_fast(v[i])));
+    }
+  }
+  uint8_t* my_row = stage + lane * EPI_PITCH;
+  uint8_t* co_ptr = stage + (lane >> 3) * EPI_PITCH + (lane & 7) * 16;
+  if (res_staged) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 b = *reinterpret_cast<const uint4*>(my_row + 16 * i);
+      float2 f;
+      f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+      f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+      f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+      f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 o;
+    o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
+    o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
+    o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
+    o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(my_row + 16 * i) = o;
+  }
+  __syncwarp();
+  bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row0 + (lane >> 3)) * p.ldo + col0 + (lane & 7) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    if (row0 + (lane >> 3) + 4 * pass < p.M)
+      *reinterpret_cast<uint4*>(op + static_cast<long long>(4 * pass) * p.ldo) =
+          *reinterpret_cast<const uint4*>(co_ptr + 4 * pass * EPI_PITCH);
+  }
+  __syncwarp();
 }
 
 template <int BN, int STAGES>
@@ -689,12 +780,13 @@ struct GemmSmem2 {
   static constexpr int A_BYTES = BM * BK * 2;            // own 128 rows of A
   static constexpr int B_BYTES = (BN2 / 2) * BK * 2;     // own half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;                    // 8 per-warp transposition tiles
+  static constexpr int BAR_OFFSET = EPI_OFFSET + 8 * EPI_WARP_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
 template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2h, const GemmKParams p,
                   const int m_fast) {
@@ -734,7 +826,7 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tmem_full_bar[s], 1);
-        mbar_init(&tmem_empty_bar[s], 8);   // 4 epilogue warps x 2 CTAs
+        mbar_init(&tmem_empty_bar[s], 16);  // 8 epilogue warps x 2 CTAs
       }
       fence_mbar_init();
     }
@@ -829,39 +921,75 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===== epilogue (both CTAs: each drains its own 128 TMEM lanes) =====
+    // Eight warps: warp w reads TMEM lane quarter w % 4 (hardware rule) and the column half (w - 2) / 4, so a thread
+    // owns 128 of the 256 accumulator columns of its row.  All four residual chunks of the tile are requested before
+    // the wait on the accumulator: the (strided, 64 bytes per thread) loads fly under the tile's main loop.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CH = BN2 / 64;            // 32-column chunks per thread
+    uint8_t* stage_tile = smem + S::EPI_OFFSET + (warp - 2) * EPI_WARP_BYTES;
     int as = 0;
     uint32_t aphase = 0;
     const float alpha = p.alpha;
     for (int t = cluster_id; t < num_pairs; t += num_clusters) {
       int m_pair, n_tile;
       tile_coords(t, m_pairs, n_tiles2, m_fast, m_pair, n_tile);
-      const int row = (2 * m_pair + rank) * BM + q * 32 + lane;
-      const int n0 = n_tile * BN2;
+      const int row0 = (2 * m_pair + rank) * BM + q * 32;        // first of this warp's 32 rows
+      const int row = row0 + lane;
+      const int n0 = n_tile * BN2 + half * (BN2 / 2);
       const bool row_ok = row < p.M;
-      ResPrefetch res_cur, res_nxt;
-      res_prefetch(p, row, n0, row_ok, res_nxt);          // in flight while the main loop of this tile finishes
+      // fast path: bf16 output and both 64-column blocks inside N -> coalesced through the transposition tile
+      const bool fast = !p.out_fp32 && (n0 + BN2 / 2 <= p.N);
+      const bool use_res = fast && p.residual != nullptr && row0 < p.M;
+      ResTile rt;
+      if (use_res) res_tile_prefetch(p, row0, n0, lane, rt);       // in flight under the rest of this tile's main loop
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN2) + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN2 / 32; ++c) {
-        res_cur = res_nxt;
-        if (c + 1 < BN2 / 32) res_prefetch(p, row, n0 + (c + 1) * 32, row_ok, res_nxt);
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
-        tmem_ld_wait();
-        if (c == BN2 / 32 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // leader's barrier
-        }
-        const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= p.N) continue;
-        float v[32];
+      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN2 + half * (BN2 / 2)) +
+                                (static_cast<uint32_t>(q * 32) << 16);
+      if (fast) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-        epilogue_store_32(p, v, row, col0, &res_cur);
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c2 * 64), r0);
+          tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c2 * 64 + 32), r1);
+          tmem_ld_wait();
+          if (c2 == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // leader's barrier
+          }
+          if (row0 >= p.M) continue;                                      // warp-uniform
+          float v[64];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r0[i]) * alpha;
+            v[32 + i] = __uint_as_float(r1[i]) * alpha;
+          }
+          if (use_res) {
+            res_tile_publish(stage_tile, lane, rt);
+            if (c2 == 0) res_tile_prefetch(p, row0, n0 + 64, lane, rt);   // lands while block 0 is converted and stored
+          }
+          epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c * 32), r);
+          tmem_ld_wait();
+          if (c == CH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // leader's barrier
+          }
+          const int col0 = n0 + c * 32;
+          if (!row_ok || col0 >= p.N) continue;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+          epilogue_store_32(p, v, row, col0);      // edge tiles / fp32 output: direct row-per-thread path
+        }
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -940,7 +1068,7 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     if (!no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) && p.m_tiles >= 2 &&
         tiles >= sms / 2) {
       // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
-      constexpr int ST2 = 6;
+      constexpr int ST2 = 5;     // 5 x 32 KB operand stages + 36 KB of epilogue transposition tiles
       using S2 = GemmSmem2<ST2>;
       auto k2 = gemm_bf16_tn_2cta<ST2>;
       static bool attr_set_2 = false;
@@ -963,7 +1091,7 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
       int clusters = sms / 2;
       if (pairs < clusters) clusters = pairs;
       const int m_fast2 = (((p.m_tiles + 1) / 2) < ceil_div(a->N, 256) && a_bytes <= (40ll << 20)) ? 1 : 0;
-      k2<<<2 * clusters, GEMM_THREADS, S2::TOTAL, stream>>>(tmA, tmBh, tmA2, tmB2h2, p, m_fast2);
+      k2<<<2 * clusters, GEMM2_THREADS, S2::TOTAL, stream>>>(tmA, tmBh, tmA2, tmB2h2, p, m_fast2);
       OMNI_LAUNCH_CHECK();
       return OMNI_OK;
     }
