@@ -15,6 +15,8 @@ advance (cache write index, key mask, RoPE positions, output slot) lives in devi
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -149,7 +151,7 @@ def greedy_generate(llm, inputs_embeds, max_new_tokens, eos_token_id, pad_token_
     last = (torch.arange(B, device=dev, dtype=torch.int64) * S0 + (S0 - 1)).contiguous()
     h_last = ops.gather_rows(hid, last)
     step.start(task, S0, h_last, eos_token_id, pad_token_id)
-    if use_graph:
+    if use_graph and not os.environ.get("OMNI_DECODE_NO_GRAPH"):     # (eager steps: profiling aid)
         step.run(max_new_tokens)
     else:
         for _ in range(max_new_tokens):

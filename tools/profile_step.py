@@ -17,6 +17,7 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--decode", action="store_true", help="profile one greedy decode instead of a train step")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_profile.json"))
     args = ap.parse_args()
     from omni_avsr_b200.synthetic import synthetic_batch, to_device
@@ -24,14 +25,30 @@ def main():
     torch.cuda.set_device(0)
     mod = bench.build_module(args, dev)
     batch = to_device(synthetic_batch(args.batch, mod.tokenizer, seed=1234), dev)
-    for k in range(5):
-        mod.train_step(batch, rates=bench.RATE_GRID[k % 4], lr=1e-4)
-    torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.decode:
+        # one greedy decode (audiovisual, rates 4/2, 32 new tokens) of `batch` utterances
+        batch["tokens"] = batch["tokens"][:, :1].contiguous()
+        mod.args.modality = "audiovisual"
+        mod.args.downsample_ratio_test_matry_audio, mod.args.downsample_ratio_test_matry_video = 4, 2
+        mod.on_test_epoch_start()
+        mod.model.decode_no_trim = True
+
+        def run():
+            with torch.no_grad():
+                mod.test_step(batch)
+        for _ in range(2):
+            run()
+    else:
+        def run():
+            mod.train_step(batch, rates=(4, 2), lr=1e-4)
+        for k in range(5):
+            mod.train_step(batch, rates=bench.RATE_GRID[k % 4], lr=1e-4)
+    torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         s.record()
-        mod.train_step(batch, rates=(4, 2), lr=1e-4)
+        run()
         e.record()
         torch.cuda.synchronize()
     step_ms = s.elapsed_time(e)
