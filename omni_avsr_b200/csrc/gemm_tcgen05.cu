@@ -580,6 +580,160 @@ gemm_bf16_tn_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Split-K variant for the decode step (M <= 128: one tile of activation rows, the weight matrix streamed once).
+// Measured (profiles/decode_gemm_r1): one SM pulls only ~25 B/clk of HBM-missing TMA traffic, so a [2048 x 2048] weight
+// spread over 8..32 CTAs streams at 0.4-1.5 TB/s.  Here a cluster of SPLIT CTAs shares one 128 x 64 output tile, each
+// CTA accumulating a K slice in its own TMEM; ranks 1.. push their fp32 partials into rank 0's shared memory over DSMEM
+// (column-major: 32 lanes = 32 consecutive floats), one cluster barrier, and rank 0 runs the usual epilogue on the sum.
+// ---------------------------------------------------------------------------------------------------
+template <int SPLIT, int STAGES>
+struct GemmSmemSK {
+  static constexpr int BN = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PART_OFFSET = STAGES * STAGE_BYTES;                 // [SPLIT-1][64 cols][128 rows] fp32
+  static constexpr int PART_BYTES = (SPLIT - 1) * BN * BM * 4;
+  static constexpr int BAR_OFFSET = PART_OFFSET + PART_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int SPLIT, int STAGES>
+__global__ void __cluster_dims__(SPLIT, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  using S = GemmSmemSK<SPLIT, STAGES>;
+  constexpr int BN = S::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* part = reinterpret_cast<float*>(smem + S::PART_OFFSET);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int n_tile = blockIdx.x / SPLIT;
+  const int kb_per = p.num_k_blocks / SPLIT;
+  const int kb0 = rank * kb_per;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < kb_per; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * S::STAGE_BYTES;
+        uint8_t* sB = sA + S::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+        tma_load_2d(&tmB, &full_bar[stage], sB, (kb0 + it) * BK, n_tile * BN);     // the HBM stream first
+        tma_load_2d(&tmA, &full_bar[stage], sA, (kb0 + it) * BK, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < kb_per; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint32_t sB = sA + S::A_BYTES;
+        const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (it == kb_per - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (rank != 0) {
+    // ===== partial producer: TMEM -> rank 0's shared memory =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(part)), "r"(0));
+    remote += static_cast<uint32_t>(((rank - 1) * BN * BM + r) * 4);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + static_cast<uint32_t>((c * 32 + i) * BM * 4)), "r"(v[i])
+                     : "memory");
+    }
+    tc_fence_before();
+  }
+
+  // partials published (release) / visible to rank 0 (acquire)
+  cluster_sync_all();
+
+  if (rank == 0 && warp >= 2) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int row = r;
+    const int n0 = n_tile * BN;
+    const bool row_ok = row < p.M;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), acc);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (!row_ok || col0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float a = __uint_as_float(acc[i]);
+#pragma unroll
+        for (int s2 = 0; s2 < SPLIT - 1; ++s2) a += part[(s2 * BN + c * 32 + i) * BM + r];
+        v[i] = a * p.alpha;
+      }
+      epilogue_store_32(p, v, row, col0);
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Cluster variant: two CTAs (one per SM of a TPC pair) work on two vertically adjacent M tiles of the same N tile.
 // Each CTA loads its own A tile and HALF of the shared B tile; the TMA unit multicasts that half into both CTAs'
 // shared memory, so the L2 -> SM traffic per MAC drops by a third (48 KB -> 32 KB per 128x256x64 block).  A smem
@@ -1048,6 +1202,25 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
   p.ldo = a->ldo; p.ldr = a->ldr;
   p.act = a->act; p.out_fp32 = a->out_fp32; p.alpha = a->alpha;
 
+  if constexpr (BN == 64) {
+    // decode step: one tile of rows, few N tiles -> split K over a 4-CTA cluster so that enough SMs pull on HBM
+    constexpr int SPLIT = 4, SKST = 4;
+    static const bool no_splitk = (getenv("OMNI_GEMM_NO_SPLITK") != nullptr);
+    if (!no_splitk && p.m_tiles == 1 && !a->ext_table && !a->b_row_table && !a->tile_group && p.n_tiles * SPLIT <= 160 &&
+        p.num_k_blocks % SPLIT == 0 && p.num_k_blocks >= 4 * SPLIT && (a->K % BK) == 0) {
+      using SK = GemmSmemSK<SPLIT, SKST>;
+      auto ks = gemm_bf16_tn_splitk<SPLIT, SKST>;
+      static bool attr_set_sk = false;
+      if (!attr_set_sk) {
+        if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, SK::TOTAL) != cudaSuccess)
+          return OMNI_ERR_CUDA;
+        attr_set_sk = true;
+      }
+      ks<<<p.n_tiles * SPLIT, GEMM_THREADS, SK::TOTAL, stream>>>(tmA, tmB, p);
+      OMNI_LAUNCH_CHECK();
+      return OMNI_OK;
+    }
+  }
   static const bool use_v1 = (getenv("OMNI_GEMM_V1") != nullptr);   // debugging switch: one tile per CTA
   if (!use_v1) {
     using SP = GemmSmemP<BN, STAGES>;
