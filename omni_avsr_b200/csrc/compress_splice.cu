@@ -54,6 +54,35 @@ compress_avg_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int n_ou
   }
 }
 
+// Same, with the window length known at compile time: all RATE 16-byte loads of a window are issued before the first
+// add (one DRAM round trip per output instead of RATE/4), the sum still runs in window order (bit-exact with ATen).
+template <int RATE>
+__global__ void __launch_bounds__(CS_THREADS)
+compress_avg_fixed_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int n_out, int D8, long long x_bs,
+                          long long total) {
+  constexpr float frate = static_cast<float>(RATE);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(idx % D8);
+    const long long t = idx / D8;
+    const int j = static_cast<int>(t % n_out);
+    const int b = static_cast<int>(t / n_out);
+    const uint4* src = reinterpret_cast<const uint4*>(x + b * x_bs) + (static_cast<long long>(j) * RATE) * D8 + c8;
+    uint4 u[RATE];
+#pragma unroll
+    for (int i = 0; i < RATE; ++i) u[i] = ld_nc_u4(src + static_cast<long long>(i) * D8);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < RATE; ++i) acc8(a, u[i]);
+    uint4 o;
+    o.x = f2_to_bf2(a[0] / frate, a[1] / frate);
+    o.y = f2_to_bf2(a[2] / frate, a[3] / frate);
+    o.z = f2_to_bf2(a[4] / frate, a[5] / frate);
+    o.w = f2_to_bf2(a[6] / frate, a[7] / frate);
+    st_na_u4(reinterpret_cast<uint4*>(out) + idx, o);
+  }
+}
+
 // stack = per-clip contiguous copy of the first n_out*rate rows (row-major [n_out, rate*D] == [n_out*rate, D])
 __global__ void __launch_bounds__(CS_THREADS)
 compress_stack_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long per_clip8, long long x_bs,
@@ -362,8 +391,18 @@ extern "C" int omni_matryoshka_compress(const void* x, void* out, int32_t B, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mode == OMNI_COMPRESS_AVG) {
     const long long total = static_cast<long long>(B) * n_out * D8;
-    compress_avg_kernel<<<grid_for(total, CS_THREADS), CS_THREADS, 0, st>>>(
-        reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n_out, D8, x_bs, rate, total);
+    const bf16* xp = reinterpret_cast<const bf16*>(x);
+    bf16* op = reinterpret_cast<bf16*>(out);
+    const int grid = grid_for(total, CS_THREADS);
+    switch (rate) {   // the rates of the reference's recipes (README: audio 4/16, video 2/5) + neighbours
+      case 2: compress_avg_fixed_kernel<2><<<grid, CS_THREADS, 0, st>>>(xp, op, n_out, D8, x_bs, total); break;
+      case 3: compress_avg_fixed_kernel<3><<<grid, CS_THREADS, 0, st>>>(xp, op, n_out, D8, x_bs, total); break;
+      case 4: compress_avg_fixed_kernel<4><<<grid, CS_THREADS, 0, st>>>(xp, op, n_out, D8, x_bs, total); break;
+      case 5: compress_avg_fixed_kernel<5><<<grid, CS_THREADS, 0, st>>>(xp, op, n_out, D8, x_bs, total); break;
+      case 8: compress_avg_fixed_kernel<8><<<grid, CS_THREADS, 0, st>>>(xp, op, n_out, D8, x_bs, total); break;
+      case 16: compress_avg_fixed_kernel<16><<<grid, CS_THREADS, 0, st>>>(xp, op, n_out, D8, x_bs, total); break;
+      default: compress_avg_kernel<<<grid, CS_THREADS, 0, st>>>(xp, op, n_out, D8, x_bs, rate, total);
+    }
   } else {
     const long long per_clip8 = static_cast<long long>(n_out) * rate * D8;
     const long long total = per_clip8 * B;

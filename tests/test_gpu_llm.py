@@ -25,8 +25,17 @@ def _build(family, task_specific, shared, layers=2):
         lc = pl.LoRA_config(4, 2, True, False, task_specific, shared)
         olc = ol.LoRA_config(4, 2, True, False, task_specific, shared)
         model = pl.LlamaForCausalLM_lora(arch, lc)
+    elif family == "llama8b":
+        # Llama-3.1-8B geometry in small: head_dim 128, GQA 4:1, rope factor 8, untied head (BASELINE config 5)
+        arch = pl.LLMArch("llama", 512, 1024, layers, 4, 1, 1005, 1e-5, 500000.0, 128,
+                          dict(factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
+                               original_max_position_embeddings=8192), False, False, inv_freq_dtype="bf16")
+        lc = pl.LoRA_config(4, 2, True, False, task_specific, shared)
+        olc = ol.LoRA_config(4, 2, True, False, task_specific, shared)
+        model = pl.LlamaForCausalLM_lora(arch, lc)
     else:
-        arch = pl.LLMArch("qwen2", 512, 1024, layers, 8, 1, 1003, 1e-6, 1000000.0, 64, None, True, True,
+        hd = 128 if family == "qwen2_hd128" else 64       # Qwen2.5-3B's real head_dim is 128 (BASELINE config 4)
+        arch = pl.LLMArch("qwen2", 512 * (hd // 64), 1024, layers, 8, 1, 1003, 1e-6, 1000000.0, hd, None, True, True,
                           max_position_embeddings=32768, inv_freq_dtype="fp32")
         lc = pq.QwenLoRA_config(8, 4, IS_QWEN25_3B=True, IS_TASK_SPECIFIC=task_specific, SHARED_LORA=shared)
         olc = ol.QwenLoRA_config(8, 4, IS_QWEN25_3B=True, IS_TASK_SPECIFIC=task_specific, SHARED_LORA=shared)
@@ -37,8 +46,8 @@ def _build(family, task_specific, shared, layers=2):
             layer.self_attn.qkv_bias.normal_(0, 0.05)
     ocfg = ol.LLMConfig(arch.family, arch.hidden_size, arch.intermediate_size, arch.num_hidden_layers,
                         arch.num_attention_heads, arch.num_key_value_heads, arch.vocab_size, arch.rms_norm_eps,
-                        arch.rope_theta, arch.head_dim, arch.rope_scaling, arch.attention_bias, True,
-                        inv_freq_dtype=arch.inv_freq_dtype)
+                        arch.rope_theta, arch.head_dim, arch.rope_scaling, arch.attention_bias,
+                        arch.tie_word_embeddings, inv_freq_dtype=arch.inv_freq_dtype)
     oracle = ol.ForCausalLM_lora(ocfg, olc).bfloat16()
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     missing, unexpected = oracle.load_state_dict(sd, strict=False)
@@ -52,6 +61,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("family,ts,sh", [("llama", False, False), ("llama", True, False), ("llama", True, True),
+                                          ("llama8b", True, True), ("qwen2_hd128", True, False),
                                           ("qwen2", True, True)])
 def test_forward_logits_and_loss(family, ts, sh):
     model, oracle, arch = _build(family, ts, sh)
@@ -82,7 +92,8 @@ def test_cpu_tensor_is_refused():
         model(inputs_embeds=torch.zeros(1, 4, arch.hidden_size, dtype=torch.bfloat16))
 
 
-@pytest.mark.parametrize("family,ts,sh", [("llama", True, True), ("llama", False, False), ("qwen2", True, False)])
+@pytest.mark.parametrize("family,ts,sh", [("llama", True, True), ("llama", False, False), ("qwen2", True, False),
+                                          ("llama8b", True, True), ("qwen2_hd128", True, True)])
 def test_packed_three_task_step_grads(family, ts, sh):
     """One packed pass over ASR+VSR+AVSR segments == three separate oracle passes (losses and LoRA grads)."""
     from omni_avsr_b200 import Llama_LoRA as pl
