@@ -583,6 +583,11 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
         return PackedSdpaFn.apply(qkv, rows.segments, nh, nkv, hd, True)
     out = torch.empty((rows.M, a.q_dim), device=qkv.device, dtype=torch.bfloat16)
     for (task, B, S, off) in rows.segments:
+        if kv_cache.graph_mode and S == 1 and kv_cache.native_step:
+            # decode step: our single-token kernel appends K / V to the cache and attends over it in one launch
+            ops.decode_attention(qkv[off: off + B], kv_cache.k[layer_idx], kv_cache.v[layer_idx], kv_cache.len_idx,
+                                 out[off: off + B], B, nh, nkv, hd)
+            continue
         q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
         prefill = S > 1 and kv_cache.len == 0 and not kv_cache.graph_mode
         k, v, mask = kv_cache.update(layer_idx, k, v)
@@ -612,6 +617,9 @@ class KVCache:
         self.max_len = max_len
         self.graph_mode = False
         self.len_idx = torch.zeros(1, device=device, dtype=torch.int64)            # device copy of `len`
+        # single-token steps run on csrc/decode_attention.cu when the geometry is covered (every named architecture)
+        self.native_step = a.head_dim in (64, 128) and \
+            (a.num_attention_heads // a.num_key_value_heads) in ops.DECODE_ATTN_GROUPS
         self.mask = torch.zeros((B, 1, 1, max_len), device=device, dtype=torch.bool)
 
     def update(self, layer, k, v):

@@ -1,0 +1,201 @@
+// Single-token (decode-step) attention over the static KV cache, HBM-bound: one CTA per (clip, KV head) streams that
+// head's K and V rows exactly once for all G query heads of the GQA group, and writes the new token's K / V into the
+// cache on the way (replaces the index_copy_ + key-mask + F.scaled_dot_product_attention sequence of the eager step;
+// reference call sites: Llama_LoRA.py:284-300 / Qwen_LoRA.py:590-606 with past_key_value during HF generate).
+//
+// Layout: HD/8 lanes cover one key row (one 16-byte load each, so a warp instruction reads 32/(HD/8) whole rows);
+// the query fragments of all G heads live in registers.  Pass 1: scores -> shared memory; softmax per head by one
+// warp; pass 2: P.V with per-thread partial sums over its key slots, reduced across the slots / warps at the end.
+// The position of the new token is read from device memory (the decode step is replayed from a CUDA graph).
+#include "common.cuh"
+#include "../../include/omni_avsr.h"
+
+namespace omni {
+
+constexpr int DA_THREADS = 128;
+constexpr int DA_WARPS = DA_THREADS / 32;
+constexpr int DA_UNROLL = 8;       // key rows in flight per lane
+
+__device__ __forceinline__ void unpack_u4(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = bf2_to_f2(u.x); f[0] = t.x; f[1] = t.y;
+  t = bf2_to_f2(u.y); f[2] = t.x; f[3] = t.y;
+  t = bf2_to_f2(u.z); f[4] = t.x; f[5] = t.y;
+  t = bf2_to_f2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+template <int HD, int G>
+__global__ void __launch_bounds__(DA_THREADS)
+decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict__ kc, bf16* __restrict__ vc,
+                   const long long* __restrict__ len_idx, bf16* __restrict__ out, long long out_ld, int n_kv_heads,
+                   int max_len, float scale_log2) {
+  constexpr int LPK = HD / 8;          // lanes per key row
+  constexpr int KPW = 32 / LPK;        // key rows per warp instruction
+  extern __shared__ float sm[];
+  float* sc = sm;                                   // [G][max_len] scores, then unnormalised probabilities
+  float* red = sm + G * max_len;                    // [DA_WARPS][G][HD] partial outputs
+  float* inv_sum = red + DA_WARPS * G * HD;         // [G]
+
+  const int b = blockIdx.x / n_kv_heads, kvh = blockIdx.x - b * n_kv_heads;
+  const int n_heads = n_kv_heads * G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPK, l = lane - sub * LPK;
+  const int pos = static_cast<int>(*len_idx);       // position of the new token == number of cached keys
+  if (pos >= max_len) return;                       // cache full: the host sized max_len = prefill + max_new_tokens
+  const int n_keys = pos + 1;
+
+  const bf16* row = qkv + static_cast<long long>(b) * ld;
+  float q[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    unpack_u4(*reinterpret_cast<const uint4*>(row + (kvh * G + g) * HD + l * 8), q[g]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[g][i] *= scale_log2;
+  }
+  const uint4 k_new = *reinterpret_cast<const uint4*>(row + (n_heads + kvh) * HD + l * 8);
+  const uint4 v_new = *reinterpret_cast<const uint4*>(row + (n_heads + n_kv_heads + kvh) * HD + l * 8);
+  bf16* krow = kc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
+  bf16* vrow = vc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
+  if (threadIdx.x < LPK) {                          // append the new token to the cache (read back by later steps only)
+    *reinterpret_cast<uint4*>(krow + static_cast<long long>(pos) * HD + l * 8) = k_new;
+    *reinterpret_cast<uint4*>(vrow + static_cast<long long>(pos) * HD + l * 8) = v_new;
+  }
+
+  // ---- pass 1: scores (DA_UNROLL independent 16-byte loads in flight per lane: the kernel is latency-bound otherwise) ----
+  for (int p0 = warp * KPW; p0 < n_keys; p0 += DA_UNROLL * DA_WARPS * KPW) {
+    uint4 kk[DA_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DA_UNROLL; ++u) {
+      const int p = p0 + u * DA_WARPS * KPW + sub;
+      kk[u] = k_new;
+      if (p < n_keys && p != pos) kk[u] = ld_nc_u4(krow + static_cast<long long>(p) * HD + l * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < DA_UNROLL; ++u) {
+      const int p = p0 + u * DA_WARPS * KPW + sub;
+      float kf[8];
+      unpack_u4(kk[u], kf);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(q[g][i], kf[i], s);
+#pragma unroll
+        for (int o = LPK >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (p < n_keys && l == 0) sc[g * max_len + p] = s;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax: warp w handles heads w, w + DA_WARPS, ... ----
+  for (int g = warp; g < G; g += DA_WARPS) {
+    float* s = sc + g * max_len;
+    float mx = -INFINITY;
+    for (int p = lane; p < n_keys; p += 32) mx = fmaxf(mx, s[p]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int p = lane; p < n_keys; p += 32) {
+      const float e = ex2_approx(s[p] - mx);
+      s[p] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) inv_sum[g] = 1.0f / sum;
+  }
+  __syncthreads();
+
+  // ---- pass 2: P.V ----
+  float acc[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+  for (int p0 = warp * KPW; p0 < n_keys; p0 += DA_UNROLL * DA_WARPS * KPW) {
+    uint4 vv[DA_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DA_UNROLL; ++u) {
+      const int p = p0 + u * DA_WARPS * KPW + sub;
+      vv[u] = v_new;
+      if (p < n_keys && p != pos) vv[u] = ld_nc_u4(vrow + static_cast<long long>(p) * HD + l * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < DA_UNROLL; ++u) {
+      const int p = p0 + u * DA_WARPS * KPW + sub;
+      if (p < n_keys) {
+        float vf[8];
+        unpack_u4(vv[u], vf);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float pg = sc[g * max_len + p];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(pg, vf[i], acc[g][i]);
+        }
+      }
+    }
+  }
+  // sum the key slots of a warp (lanes with equal l), then the warps through shared memory
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = acc[g][i];
+#pragma unroll
+      for (int o = LPK; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc[g][i] = a;
+    }
+  if (sub == 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[(warp * G + g) * HD + l * 8 + i] = acc[g][i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < G * HD; e += DA_THREADS) {
+    const int g = e / HD;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) a += red[w * G * HD + e];
+    out[static_cast<long long>(b) * out_ld + (kvh * G + g) * HD + (e - g * HD)] = __float2bfloat16_rn(a * inv_sum[g]);
+  }
+}
+
+template <int HD, int G>
+static int launch_decode_attn(const bf16* qkv, long long ld, bf16* kc, bf16* vc, const long long* len_idx, bf16* out,
+                              long long out_ld, int B, int n_kv_heads, int max_len, float scale, cudaStream_t st) {
+  auto kfn = decode_attn_kernel<HD, G>;
+  const int smem = (G * max_len + DA_WARPS * G * HD + G) * 4;
+  if (smem > 200 * 1024) return OMNI_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return OMNI_ERR_CUDA;
+  kfn<<<B * n_kv_heads, DA_THREADS, smem, st>>>(qkv, ld, kc, vc, len_idx, out, out_ld, n_kv_heads, max_len,
+                                                scale * 1.4426950408889634f);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+}  // namespace omni
+
+extern "C" int omni_decode_attention(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx,
+                                     void* out, int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads,
+                                     int32_t head_dim, int32_t max_len, float scale, void* stream) {
+  using namespace omni;
+  OMNI_CHECK_ARG(qkv && k_cache && v_cache && len_idx && out && B > 0 && n_heads > 0 && n_kv_heads > 0 && max_len > 0);
+  OMNI_CHECK_ARG(n_heads % n_kv_heads == 0 && (ld % 8) == 0 && (out_ld % 8) == 0);
+  OMNI_CHECK_ARG(ld >= static_cast<int64_t>(n_heads + 2 * n_kv_heads) * head_dim);
+  const int G = n_heads / n_kv_heads;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  bf16* kc = reinterpret_cast<bf16*>(k_cache);
+  bf16* vc = reinterpret_cast<bf16*>(v_cache);
+  const long long* li = reinterpret_cast<const long long*>(len_idx);
+  bf16* o = reinterpret_cast<bf16*>(out);
+#define OMNI_DA(HD_, G_) \
+  if (head_dim == HD_ && G == G_) \
+    return launch_decode_attn<HD_, G_>(q, ld, kc, vc, li, o, out_ld, B, n_kv_heads, max_len, scale, st);
+  OMNI_DA(64, 1) OMNI_DA(64, 2) OMNI_DA(64, 4) OMNI_DA(64, 8)
+  OMNI_DA(128, 1) OMNI_DA(128, 2) OMNI_DA(128, 4) OMNI_DA(128, 8)
+#undef OMNI_DA
+  return OMNI_ERR_UNSUPPORTED;
+}

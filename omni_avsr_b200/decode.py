@@ -70,7 +70,8 @@ class GraphedGreedyStep:
         # forward of the chosen token
         x = ops.gather_rows(llm.model.embed_tokens.weight.data, nxt.contiguous())
         self.xpad[:B].copy_(x)
-        self.cache.mask.index_fill_(3, self.cache.len_idx, True)       # the new key is visible to its own query
+        if not self.cache.native_step:                                     # (library-SDPA fallback only)
+            self.cache.mask.index_fill_(3, self.cache.len_idx, True)       # the new key is visible to its own query
         hid = llm.model.forward_packed(self.xpad, self.rows, self.cache)
         self.h_last.copy_(hid[:B])
         self.cache.len_idx.add_(1)

@@ -596,3 +596,28 @@ def attention_bwd(qkv, out, dout, lse, dqkv, segments, n_heads: int, n_kv_heads:
                                      float(scale), stream_ptr()), "omni_attention_bwd")
         _count(3)
     return dqkv
+
+
+DECODE_ATTN_GROUPS = (1, 2, 4, 8)
+
+
+def decode_attention(qkv, k_cache, v_cache, len_idx, out, B: int, n_heads: int, n_kv_heads: int, head_dim: int,
+                     scale: Optional[float] = None):
+    """Single-token attention over the static KV cache [B, n_kv_heads, max_len, head_dim] (one layer): appends the new
+    token's K / V (from the packed q|k|v rows, RoPE applied) at position len_idx[0] (int64, device) and attends over
+    positions 0..len_idx[0].  out [>=B, n_heads*head_dim] bf16; rows >= B untouched."""
+    require_cuda(qkv, k_cache, v_cache, len_idx, out)
+    qkv = _bf16_2d(qkv, "qkv")
+    out = _bf16_2d(out, "out")
+    if len_idx.dtype != torch.int64:
+        raise TypeError("len_idx must be int64")
+    if k_cache.dtype != torch.bfloat16 or not k_cache.is_contiguous() or not v_cache.is_contiguous() \
+            or tuple(k_cache.shape[:2]) != (B, n_kv_heads) or k_cache.shape[3] != head_dim or k_cache.shape != v_cache.shape:
+        raise ValueError("k_cache / v_cache must be contiguous bf16 [B, n_kv_heads, max_len, head_dim]")
+    if scale is None:
+        scale = head_dim ** -0.5
+    check(lib.omni_decode_attention(qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
+                                    len_idx.data_ptr(), out.data_ptr(), out.stride(0), B, n_heads, n_kv_heads, head_dim,
+                                    k_cache.shape[2], float(scale), stream_ptr()), "omni_decode_attention")
+    _count()
+    return out

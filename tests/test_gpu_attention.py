@@ -106,3 +106,37 @@ def test_packed_sdpa_autograd_matches_reference():
     err = (qkv.grad.float() - x.grad).abs().max().item()
     assert err <= 2e-2 * max(1.0, x.grad.abs().max().item()), err
     assert (qkv.grad[200:256] == 0).all() and (qkv.grad[536:] == 0).all()
+
+
+@pytest.mark.parametrize("B,nh,nkv,hd,max_len,pos", [(3, 32, 8, 64, 384, 300), (2, 16, 2, 128, 256, 255), (5, 4, 4, 64, 128, 0),
+                                                     (64, 32, 8, 64, 512, 37), (2, 8, 4, 128, 640, 513)])
+def test_decode_attention_step(B, nh, nkv, hd, max_len, pos):
+    """Single-token attention over the static KV cache (csrc/decode_attention.cu): cache append + softmax(q.K^T).V for all
+    heads of a GQA group, against fp32 torch on the same cache contents."""
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(pos + nh)
+    kc = torch.randn(B, nkv, max_len, hd, device="cuda", generator=g).bfloat16()
+    vc = torch.randn(B, nkv, max_len, hd, device="cuda", generator=g).bfloat16()
+    kc0, vc0 = kc.clone(), vc.clone()
+    M = 128
+    qkv = (torch.randn(M, (nh + 2 * nkv) * hd, device="cuda", generator=g) * 1.2).bfloat16()
+    out = torch.full((M, nh * hd), 5.0, device="cuda", dtype=torch.bfloat16)
+    len_idx = torch.tensor([pos], device="cuda", dtype=torch.int64)
+    ops.decode_attention(qkv[:B], kc, vc, len_idx, out[:B], B, nh, nkv, hd)
+    torch.cuda.synchronize()
+    q = qkv[:B, : nh * hd].float().view(B, nh, hd)
+    k_new = qkv[:B, nh * hd: (nh + nkv) * hd].view(B, nkv, hd)
+    v_new = qkv[:B, (nh + nkv) * hd:].view(B, nkv, hd)
+    # the cache now holds the new token at `pos`, everything else untouched
+    assert torch.equal(kc[:, :, pos], k_new) and torch.equal(vc[:, :, pos], v_new)
+    keep = torch.ones(max_len, dtype=torch.bool, device="cuda")
+    keep[pos] = False
+    assert torch.equal(kc[:, :, keep], kc0[:, :, keep]) and torch.equal(vc[:, :, keep], vc0[:, :, keep])
+    G = nh // nkv
+    K = kc[:, :, : pos + 1].float().repeat_interleave(G, dim=1)          # [B, nh, n, hd]
+    V = vc[:, :, : pos + 1].float().repeat_interleave(G, dim=1)
+    s = torch.einsum("bhd,bhnd->bhn", q, K) / math.sqrt(hd)
+    want = torch.einsum("bhn,bhnd->bhd", torch.softmax(s, dim=-1), V).reshape(B, nh * hd)
+    err = (out[:B].float() - want).abs().max().item()
+    assert err <= 1e-2 * max(1.0, want.abs().max().item()), err
+    assert (out[B:] == 5.0).all()
