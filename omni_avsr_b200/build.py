@@ -36,11 +36,13 @@ def _nvcc() -> str:
 
 
 def _digest(paths) -> str:
+    """Content hash of the sources + flags.  Location-independent (the repo is copied to a scratch path on the GPU box:
+    an absolute include path in the hash would force a rebuild there -- and a rebuild race between ranks)."""
     h = hashlib.sha256()
     for p in sorted(paths):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())
     return h.hexdigest()
 
 
@@ -52,6 +54,19 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     dig = _digest(sources + headers)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
         return LIB
+    # one builder at a time (several ranks may import the package at once); the others wait, then find the stamp
+    import fcntl
+    with open(BUILD / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+                return LIB
+            return _build_locked(sources, stamp, dig, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(sources, stamp, dig, verbose) -> Path:
     nvcc = _nvcc()
 
     def compile_one(src: Path) -> Path:
@@ -67,10 +82,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *[str(o) for o in objs], "-cudart", "static"]
+    tmp = LIB.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *[str(o) for o in objs], "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr}")
+    os.replace(tmp, LIB)            # atomic: a process that already mapped the old library keeps its inode
     stamp.write_text(dig)
     return LIB
 

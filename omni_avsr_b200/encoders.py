@@ -10,9 +10,10 @@
   (modeling_OmniAVSR.py:127-142).
 
 Linear layers, LayerNorm, GELU and the LoRA-fused q|k|v projection run on our kernels (tcgen05 GEMM with bias /
-GELU / residual epilogues), the log-mel front end is our DFT kernel, the Whisper conv stem runs on the GEMM.
-Still on library kernels in this round (TODO round 2): the ResNet-18 / positional convolutions (cuDNN)
-and the attention core (SDPA).
+GELU / residual epilogues), the attention core is the tcgen05 flash kernel (forward and backward), the log-mel front end
+is our DFT kernel, the Whisper conv stem and the AV-HuBERT Conv3d front-end run on the GEMM.
+Still on library kernels in this round (TODO round 2): the ResNet-18 trunk and the grouped positional
+convolution (cuDNN).
 Encoders run in eval mode (no dropout / layerdrop, BatchNorm running statistics): SURVEY §5.8 / §7.
 """
 from __future__ import annotations
@@ -130,7 +131,7 @@ class _PackedSelfAttention(nn.Module):
         return self._wt
 
     def sdpa(self, qkv, B, T):
-        # non-causal attention over each clip (library SDPA core; TODO(round 2): tcgen05 flash kernel)
+        # non-causal attention over each clip: tcgen05 flash kernels (csrc/attention.cu, csrc/attention_bwd.cu)
         return PackedSdpaFn.apply(qkv, [(0, B, T, 0)], self.h, self.h, self.hd, False)
 
 
