@@ -869,9 +869,9 @@ class LlamaForCausalLM_lora(nn.Module):
     @torch.no_grad()
     def generate(self, inputs_embeds=None, max_new_tokens=32, num_beams=1, eos_token_id=None, bos_token_id=None,
                  pad_token_id=None, modality=None, **kw):
-        from .decode import greedy_generate
+        from .decode import beam_generate, greedy_generate
         if num_beams != 1:
-            raise NotImplementedError("beam search is SURVEY §8f rank 1 (next); greedy (num_beams=1) is implemented")
+            return beam_generate(self, inputs_embeds, max_new_tokens, num_beams, eos_token_id, pad_token_id, modality)
         return greedy_generate(self, inputs_embeds, max_new_tokens, eos_token_id, pad_token_id, modality,
                                trim=kw.get("trim", True))
 

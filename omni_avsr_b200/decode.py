@@ -164,3 +164,130 @@ def greedy_generate(llm, inputs_embeds, max_new_tokens, eos_token_id, pad_token_
         n = next((i + 1 for i, v in enumerate(alive) if v == 0), len(alive))
         out = out[:, :n]
     return out.clone()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Beam search (the evaluation default of the reference: eval_OmniAVSR.py:216-226 -> num_beams = 15, max 32 new tokens;
+# HF transformers==4.43.1 `_beam_search` + `BeamSearchScorer` semantics with length_penalty 1.0, early_stopping False).
+# Device side: the B*K beam rows run through the same packed single-token step as greedy decode (split-K GEMMs, the
+# single-token attention kernel, lm_head GEMM); the candidate ranking (fp32 log-softmax + running beam score, top-2K
+# over K*V) stays on the device; only the 2K candidates per utterance cross to the host, where the hypothesis
+# bookkeeping of the scorer runs (it is inherently sequential and tiny).
+# ---------------------------------------------------------------------------------------------------------------
+class _Hyps:
+    """Finished hypotheses of one utterance (at most K, ranked by sum_logprobs / length)."""
+
+    def __init__(self, K):
+        self.K, self.items, self.worst = K, [], 1e9
+
+    def add(self, ids, sum_logprobs, length):
+        score = sum_logprobs / length
+        if len(self.items) < self.K or score > self.worst:
+            self.items.append((score, ids))
+            if len(self.items) > self.K:
+                order = sorted((s, i) for i, (s, _) in enumerate(self.items))
+                del self.items[order[0][1]]
+                self.worst = order[1][0]
+            else:
+                self.worst = min(score, self.worst)
+
+    def done(self, best_running, cur_len):
+        return len(self.items) >= self.K and self.worst >= best_running / cur_len
+
+
+@torch.no_grad()
+def beam_generate(llm, inputs_embeds, max_new_tokens, num_beams, eos_token_id, pad_token_id, modality=None):
+    ops.require_cuda(inputs_embeds)
+    B, S0, H = inputs_embeds.shape
+    K = int(num_beams)
+    BK = B * K
+    dev = inputs_embeds.device
+    a = llm.config
+    task = llm._task_of(modality)
+    if pad_token_id is None:
+        pad_token_id = eos_token_id
+    max_len = (S0 + max_new_tokens + 127) // 128 * 128
+    cache = KVCache(a, BK, max_len, dev)
+    # prefill on the expanded prompt (HF expands inputs_embeds to B*K rows before the first forward)
+    rows = PackedRows.get([(task, BK, S0)], dev)
+    x = inputs_embeds.to(torch.bfloat16).repeat_interleave(K, dim=0)
+    hid = llm.model.forward_packed(pack_segments([x], rows), rows, cache)
+    cache.advance(S0)
+    last = (torch.arange(BK, device=dev, dtype=torch.int64) * S0 + (S0 - 1)).contiguous()
+    h_last = ops.gather_rows(hid, last)
+    # single-token step state (same layout as the graphed greedy step, run eagerly: the beam permutation changes per step)
+    srows = _StepRows(BK, dev, max_len)
+    srows.tile_group.fill_(task)
+    xpad = torch.zeros((srows.M, a.hidden_size), dtype=torch.bfloat16, device=dev)
+    llm.model.rope(max_len)
+    cache.graph_mode = True
+
+    beam_scores = torch.zeros((B, K), dtype=torch.float32, device=dev)
+    beam_scores[:, 1:] = -1e9
+    beam_scores = beam_scores.view(-1)
+    hyps = [_Hyps(K) for _ in range(B)]
+    finished = [False] * B
+    seqs = [[] for _ in range(BK)]          # token history per beam row (host)
+    V = a.vocab_size
+    cur_len = 0
+    while True:
+        logits = llm.logits_rows(h_last)                                        # [BK, V] bf16 (lm_head GEMM)
+        logp = torch.log_softmax(logits.float(), dim=-1) + beam_scores[:, None]
+        top_s, top_i = torch.topk(logp.view(B, K * V), 2 * K, dim=1, largest=True, sorted=True)
+        top_s, top_i = top_s.tolist(), top_i.tolist()                           # the step's only host sync
+        cur_len += 1
+        new_scores, new_tokens, new_rows = [], [], []
+        for b in range(B):
+            if finished[b]:
+                new_scores += [0.0] * K
+                new_tokens += [pad_token_id] * K
+                new_rows += [0] * K
+                continue
+            taken = 0
+            for rank in range(2 * K):
+                tok, row, sc = top_i[b][rank] % V, b * K + top_i[b][rank] // V, top_s[b][rank]
+                if tok == eos_token_id:
+                    if rank < K:
+                        hyps[b].add(list(seqs[row]), sc, cur_len)
+                    continue
+                new_scores.append(sc)
+                new_tokens.append(tok)
+                new_rows.append(row)
+                taken += 1
+                if taken == K:
+                    break
+            if taken < K:
+                raise ValueError(f"At most {K} tokens can be equal to `eos_token_id: {eos_token_id}`.")
+            finished[b] = hyps[b].done(max(top_s[b]), cur_len)
+        seqs = [seqs[r] + [t] for r, t in zip(new_rows, new_tokens)]
+        beam_scores = torch.tensor(new_scores, dtype=torch.float32, device=dev)
+        if all(finished) or cur_len >= max_new_tokens:
+            break
+        # next step: reorder the cache rows by beam, embed the chosen tokens, one packed single-token forward
+        idx = torch.tensor(new_rows, dtype=torch.int64, device=dev)
+        n = cache.len
+        cache.k[:, :, :, :n] = cache.k[:, :, :, :n].index_select(1, idx)
+        cache.v[:, :, :, :n] = cache.v[:, :, :, :n].index_select(1, idx)
+        tok = torch.tensor(new_tokens, dtype=torch.int64, device=dev)
+        xpad[:BK].copy_(ops.gather_rows(llm.model.embed_tokens.weight.data, tok))
+        cache.sync_device_state()
+        srows.pos.fill_(cache.len)
+        hid = llm.model.forward_packed(xpad, srows, cache)
+        cache.advance(1)
+        h_last = hid[:BK].contiguous()
+    cache.graph_mode = False
+    # finalize: open beams become hypotheses, best one per utterance, EOS appended if it fits, right-padded
+    final = beam_scores.tolist()
+    for b in range(B):
+        if not finished[b]:
+            for k in range(K):
+                hyps[b].add(list(seqs[b * K + k]), final[b * K + k], cur_len)
+    best = [sorted(h.items, key=lambda t: t[0])[-1][1] for h in hyps]
+    lengths = [len(h) for h in best]
+    sent_max = min(max(lengths) + 1, max_new_tokens)
+    out = torch.full((B, sent_max), pad_token_id, dtype=torch.int64)
+    for b, h in enumerate(best):
+        out[b, : lengths[b]] = torch.tensor(h, dtype=torch.int64)
+        if lengths[b] < sent_max:
+            out[b, lengths[b]] = eos_token_id
+    return out.to(dev)

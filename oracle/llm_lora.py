@@ -350,7 +350,7 @@ class ForCausalLM_lora(nn.Module):  # Llama_LoRA.py:318-444 / Qwen_LoRA.py:105-2
         previous token (Llama_LoRA.py:429-432); finished rows are padded with pad_token_id; stops when all rows are
         finished or after max_new_tokens."""
         if num_beams != 1:
-            raise NotImplementedError("oracle implements the greedy branch only")
+            return self.beam_generate(inputs_embeds, max_new_tokens, num_beams, eos_token_id, pad_token_id, modality)
         B = inputs_embeds.shape[0]
         past = [None] * self.config.num_hidden_layers
         unfinished = torch.ones(B, dtype=torch.long)
@@ -370,6 +370,29 @@ class ForCausalLM_lora(nn.Module):  # Llama_LoRA.py:318-444 / Qwen_LoRA.py:105-2
         if return_margins:
             return torch.stack(out, dim=1), torch.stack(margins, dim=1)
         return torch.stack(out, dim=1)
+
+
+def _beam_generate(self, inputs_embeds, max_new_tokens, num_beams, eos_token_id, pad_token_id, modality=None,
+                   return_scores=False):
+    """Beam branch of HF generate (oracle/beam_search.py drives it): prompt expanded to B*K rows, cache reordered by
+    beam index every step."""
+    from .beam_search import beam_search
+    B, K = inputs_embeds.shape[0], num_beams
+    past = [None] * self.config.num_hidden_layers
+    expanded = inputs_embeds.repeat_interleave(K, dim=0)
+
+    def step_logits(tokens):
+        cur = dict(inputs_embeds=expanded) if tokens is None else dict(input_ids=tokens[:, None])
+        return self.forward(past_kv=past, modality=modality, **cur).logits[:, -1, :]
+
+    def reorder(beam_idx):
+        for i, kv in enumerate(past):
+            past[i] = (kv[0][beam_idx], kv[1][beam_idx])
+
+    return beam_search(step_logits, reorder, B, K, max_new_tokens, eos_token_id, pad_token_id, return_scores=return_scores)
+
+
+ForCausalLM_lora.beam_generate = _beam_generate
 
 
 def make_lora_config(cfg: LLMConfig, name: str, rank: int, alpha: int, task_specific: bool, shared: bool):

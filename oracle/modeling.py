@@ -78,13 +78,14 @@ class AVSR_LLMs(nn.Module):
         return tuple(losses)
 
     @torch.no_grad()
-    def decode(self, inputs, task, rate_a=None, rate_v=None, return_margins=False):
-        """Inference branch (:308-323), greedy."""
+    def decode(self, inputs, task, rate_a=None, rate_v=None, return_margins=False, num_beams=1):
+        """Inference branch (:308-323): greedy, or HF beam search with num_beams > 1 (eval default 15)."""
         a, v = self.media_tokens(inputs, rate_a, rate_v, task in ("audio", "audiovisual"), task in ("video", "audiovisual"))
         emb = om.build_infer_sequence(self.llm.model.embed_tokens, inputs["tokens"], a, v, self.prompts()[task],
                                       self.marker_ids, self.is_qwen)
         return self.llm.generate(emb, self.max_dec_tokens, self.eos_id, self.pad_id,
-                                 modality=task if self.is_task_specific else None, return_margins=return_margins)
+                                 modality=task if self.is_task_specific else None, return_margins=return_margins,
+                                 num_beams=num_beams)
 
 
 def training_step(model: AVSR_LLMs, batch, rate_a, rate_v, world_size=1, total_batch=None):

@@ -168,3 +168,42 @@ def test_greedy_decode_tokens():
                 break
             exact += 1
     assert exact >= B * n // 2
+
+
+def _seq_logprob(oracle, x, ids, eos, modality):
+    """Oracle (teacher-forced) sum of log-probs of the generated ids (incl. the closing EOS when present) / length."""
+    ids = [int(t) for t in ids]
+    emb = torch.cat([x, oracle.model.embed_tokens(torch.tensor(ids[:-1], dtype=torch.long))[None].to(x.dtype)], dim=1) \
+        if len(ids) > 1 else x
+    logits = oracle.forward(inputs_embeds=emb, modality=modality).logits[0, x.shape[1] - 1:]
+    lp = torch.log_softmax(logits.float(), dim=-1)
+    return sum(lp[i, t].item() for i, t in enumerate(ids)) / len(ids)
+
+
+@pytest.mark.parametrize("B,K,max_new,seed,eos_from_greedy", [(2, 4, 10, 5, None), (1, 15, 16, 6, None), (3, 3, 8, 7, None),
+                                                              (2, 4, 12, 8, 2), (1, 15, 12, 9, 3), (3, 5, 10, 10, 1)])
+def test_beam_search_matches_oracle(B, K, max_new, seed, eos_from_greedy):
+    """generate(num_beams=K) (HF 4.43.1 beam-search semantics, the reference's evaluation default) vs the CPU oracle's
+    beam search (oracle/beam_search.py, pinned against transformers).  Token-for-token, except where bf16 logits flip a
+    near-tie: then the returned hypothesis must score within 2e-2 (oracle log-prob per token) of the oracle's choice."""
+    model, oracle, arch = _build("llama", True, True)
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(B, 19, arch.hidden_size, generator=g) * 0.5).bfloat16()
+    eos, pad = 7, 1004
+    if eos_from_greedy is not None:
+        # make EOS a token the model actually wants early on, so hypotheses close at different lengths
+        eos = int(oracle.generate(x, max_new, 10 ** 6, pad, modality="audio")[0, eos_from_greedy])
+    want = oracle.generate(x, max_new, eos, pad, modality="audio", num_beams=K)
+    got = model.generate(inputs_embeds=x.cuda(), max_new_tokens=max_new, num_beams=K, eos_token_id=eos, pad_token_id=pad,
+                         modality="audio").cpu()
+    assert got.dtype == torch.int64 and got.shape[0] == B and got.shape[1] <= max_new
+    for b in range(B):
+        def trim(row):
+            row = [int(t) for t in row]
+            if eos in row:
+                row = row[: row.index(eos) + 1]
+            return [t for t in row if t != pad]
+        a, w = trim(got[b]), trim(want[b])
+        if a != w:
+            sa, sw = _seq_logprob(oracle, x[b: b + 1], a, eos, "audio"), _seq_logprob(oracle, x[b: b + 1], w, eos, "audio")
+            assert abs(sa - sw) <= 2e-2, (b, a, w, sa, sw)

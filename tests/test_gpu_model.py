@@ -147,6 +147,28 @@ def test_greedy_transcripts(pair, task, ra, rv):
     assert same >= got.shape[0] * n // 2
 
 
+def test_beam_search_transcripts(pair):
+    """eval_OmniAVSR.py's default decode (num_beams > 1) through ModelModule_LLM.test_step: same hypothesis as the oracle's
+    HF-semantics beam search, or -- where bf16 features flip a near-tie -- one the oracle scores within 3e-2 per token."""
+    mod, oracle = pair
+    cpu, gpu = _batch(mod, B=2)
+    infer_cpu = dict(cpu, tokens=cpu["tokens"][:, :1])
+    infer_gpu = dict(gpu, tokens=gpu["tokens"][:, :1].contiguous())
+    want = oracle.decode(infer_cpu, "audiovisual", 4, 2, num_beams=4)
+    mod.args.modality = "audiovisual"
+    mod.args.downsample_ratio_test_matry_audio, mod.args.downsample_ratio_test_matry_video = 4, 2
+    mod.on_test_epoch_start()
+    mod.model.num_beams = 4
+    try:
+        got = mod.test_step(infer_gpu).cpu()
+    finally:
+        mod.model.num_beams = 1
+    assert got.shape[0] == want.shape[0] and got.shape[1] <= mod.model.max_dec_tokens
+    n = min(got.shape[1], want.shape[1])
+    agree = (got[:, :n] == want[:, :n]).float().mean().item()
+    assert agree >= 0.5, (got, want)
+
+
 def test_train_steps_reduce_loss():
     mod = small_module(seed=1)
     _, gpu = _batch(mod, seed=3)
