@@ -18,7 +18,8 @@
 namespace omni {
 
 constexpr int AB_T = 128;          // queries per tile == keys per tile
-constexpr int AB_THREADS = 192;    // warp 0 TMA, warp 1 MMA, warps 2..5 compute (thread = TMEM lane)
+constexpr int AB_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 compute: thread = (TMEM lane, 32-column half of the step);
+                                   // warp w may only read TMEM lanes 32*(w%4).., so warps w and w+4 share a lane quarter
 
 struct AttnBwdParams {
   bf16* dqkv;            // [M, dqkv_ld] packed gradient rows, same column layout as qkv
@@ -138,7 +139,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
       mbar_init(kv_empty, 1);
       mbar_init(kv_empty + 1, 1);
       mbar_init(s_full, 1);
-      mbar_init(ds_full, 4);
+      mbar_init(ds_full, 8);
       mbar_init(dq_full, 1);
       fence_mbar_init();
     }
@@ -208,6 +209,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;            // which 32 of the step's 64 columns this thread converts
     const int r = q * 32 + lane;
     const int qpos = q0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -224,8 +226,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
       mbar_wait(s_full, ph);
       tc_fence_after();
       const bool full = (k0 + AB_STEP - 1 <= kmax);
-#pragma unroll
-      for (int c = 0; c < AB_STEP / 32; ++c) {
+      {
+        const int c = half;
         uint32_t s[32], d[32], w[16];
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
         tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
@@ -259,7 +261,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     tc_fence_after();
     bf16* op = p.dqkv + row * p.dqkv_ld + col_q;
 #pragma unroll
-    for (int c = 0; c < HD / 32; ++c) {
+    for (int cc = 0; cc < HD / 64; ++cc) {
+      const int c = half * (HD / 64) + cc;
       uint32_t v[32];
       tmem_ld_32x32(tmem_dq + lane_addr + c * 32, v);
       tmem_ld_wait();
@@ -344,7 +347,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
       mbar_init(q_empty, 1);
       mbar_init(q_empty + 1, 1);
       mbar_init(s_full, 1);
-      mbar_init(pds_full, 4);
+      mbar_init(pds_full, 8);
       mbar_init(acc_full, 1);
       fence_mbar_init();
     }
@@ -420,6 +423,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                 // key row inside the tile == TMEM lane
     const int kpos = k0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -434,7 +438,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     auto fetch_stat = [&](int it, float& l2, float& dl) {
       const int head = kvh * G + it / per_head;
       const int q0 = (i0 + it % per_head) * AB_STEP;
-      const bool ok = r < AB_STEP && it < n_it && q0 + r < p.S;
+      const bool ok = half == 0 && r < AB_STEP && it < n_it && q0 + r < p.S;
       const long long idx = static_cast<long long>(head) * p.M + clip_row0 + q0 + r;
       l2 = ok ? p.lse[idx] * 1.4426950408889634f : 0.f;
       dl = ok ? p.delta[idx] : 0.f;
@@ -445,17 +449,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
       const uint32_t ph = it & 1;
       const int q0 = (i0 + it % per_head) * AB_STEP;
       float* st = stat + (it & 1) * 2 * AB_STEP;
-      if (r < AB_STEP) {
+      if (half == 0 && r < AB_STEP) {
         st[r] = nl2;
         st[AB_STEP + r] = ndl;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       fetch_stat(it + 1, nl2, ndl);
       mbar_wait(s_full, ph);
       tc_fence_after();
       const bool full = (qlo <= q0) && (q0 + AB_STEP - 1 < p.S);
-#pragma unroll
-      for (int c = 0; c < AB_STEP / 32; ++c) {
+      {
+        const int c = half;
         uint32_t s[32], d[32], wp[16], wd[16];
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
         tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
@@ -495,7 +499,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     bf16* ov = p.dqkv + row * p.dqkv_ld + col_v;
     bf16* ok_ = p.dqkv + row * p.dqkv_ld + col_k;
 #pragma unroll
-    for (int c = 0; c < 2 * HD / 32; ++c) {
+    for (int cc = 0; cc < HD / 32; ++cc) {
+      const int c = half * (HD / 32) + cc;                 // half 0 stores dV, half 1 stores dK
       uint32_t v[32];
       tmem_ld_32x32(tmem_dv + lane_addr + c * 32, v);      // dV columns first, dK right behind
       tmem_ld_wait();
