@@ -435,26 +435,29 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     float* stat = reinterpret_cast<float*>(smem + SM::OFF_STAT);
     // per-query statistics of a step: threads 0..63 fetch them one step ahead (the global-load latency hides under
     // the previous step's arithmetic) and publish them through a double-buffered shared-memory row
-    auto fetch_stat = [&](int it, float& l2, float& dl) {
-      const int head = kvh * G + it / per_head;
-      const int q0 = (i0 + it % per_head) * AB_STEP;
+    // (head, step) of an iteration advance as counters: no integer division in the loop
+    auto fetch_stat = [&](int it, int head, int step, float& l2, float& dl) {
+      const int q0 = (i0 + step) * AB_STEP;
       const bool ok = half == 0 && r < AB_STEP && it < n_it && q0 + r < p.S;
       const long long idx = static_cast<long long>(head) * p.M + clip_row0 + q0 + r;
       l2 = ok ? p.lse[idx] * 1.4426950408889634f : 0.f;
       dl = ok ? p.delta[idx] : 0.f;
     };
     float nl2, ndl;
-    fetch_stat(0, nl2, ndl);
+    int cur_step = 0, nxt_head = kvh * G, nxt_step = 0;
+    fetch_stat(0, nxt_head, nxt_step, nl2, ndl);
     for (int it = 0; it < n_it; ++it) {
       const uint32_t ph = it & 1;
-      const int q0 = (i0 + it % per_head) * AB_STEP;
+      cur_step = nxt_step;
+      const int q0 = (i0 + cur_step) * AB_STEP;
+      if (++nxt_step == per_head) { nxt_step = 0; ++nxt_head; }
       float* st = stat + (it & 1) * 2 * AB_STEP;
       if (half == 0 && r < AB_STEP) {
         st[r] = nl2;
         st[AB_STEP + r] = ndl;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      fetch_stat(it + 1, nl2, ndl);
+      fetch_stat(it + 1, nxt_head, nxt_step, nl2, ndl);
       mbar_wait(s_full, ph);
       tc_fence_after();
       const bool full = (qlo <= q0) && (q0 + AB_STEP - 1 < p.S);
