@@ -275,6 +275,7 @@ class LoraPlan:
                         ext[g, nt, a * cb + c] = torch.tensor(
                             [(part * self.n_act + a) * rp + c * 64, base + self.slot_of(a, g) * width + nn0, c * 64, 0])
         self.ext_fwd = ext.contiguous().to(device)
+        self.ext_fwd_step = self.ext_fwd if bn == 64 else self._ext_table(64).to(device)   # decode step: 64-column tiles
         # backward phase 1': dT_part = s * dOut_part @ upT_part, upT_part [n_slots*rp, width]; tile -> (a, c)
         nt1b = self.n_act * cb
         browb = torch.zeros((3, nt1b), dtype=torch.int32)
@@ -299,6 +300,26 @@ class LoraPlan:
                                  (part * ns + self.slot_of(a, g)) * rp + c * 64, 0])
                             j += 1
         self.ext_bwd = extb.contiguous().to(device)
+
+    def _ext_table(self, bn: int) -> torch.Tensor:
+        """K-extension blocks per (group, n_tile) for an N tile width of bn (same content as ext_fwd, other tiling)."""
+        rp, cb, ns = self.rp, self.cb, self.n_slots
+        nt2 = self.N // bn
+        ext = torch.full((3, nt2, self.n_act * cb, 4), -1, dtype=torch.int32)
+        for g in range(3):
+            for nt in range(nt2):
+                n0 = nt * bn
+                if n0 < self.q_cols:
+                    part, nn0, width, base = 0, n0, self.q_cols, 0
+                elif n0 >= self.v_col0:
+                    part, nn0, width, base = 1, n0 - self.v_col0, self.v_cols, ns * self.q_cols
+                else:
+                    continue
+                for a in range(self.n_act):
+                    for c in range(cb):
+                        ext[g, nt, a * cb + c] = torch.tensor(
+                            [(part * self.n_act + a) * rp + c * 64, base + self.slot_of(a, g) * width + nn0, c * 64, 0])
+        return ext.contiguous()
 
     def transposed_up(self, up: torch.Tensor):
         ns, rp = self.n_slots, self.rp

@@ -160,8 +160,12 @@ class LoraLinearFn(torch.autograd.Function):
         tile_group = rows.tile_group
         T = ops.gemm(h, down, n=plan.t_cols, alpha=plan.scaling, tile_group=tile_group, b_row_table=plan.brow_fwd,
                      block_n=64)
-        out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd), block_n=plan.block_n,
-                       pair_aligned=getattr(rows, "pair_aligned", False))
+        if h.shape[0] <= 128 and not h.requires_grad:
+            # decode step (one tile of rows): 64-column tiles put 4x the CTAs on the weight stream (N = 3072: 48, not 12)
+            out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd_step), block_n=64)
+        else:
+            out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd), block_n=plan.block_n,
+                           pair_aligned=getattr(rows, "pair_aligned", False))
         ctx.save_for_backward(h, T, down, up)
         ctx.WT, ctx.plan, ctx.rows = WT, plan, rows
         return out

@@ -93,7 +93,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if block_n == 256 and M <= 128 and N < 32768 and ext is None and b_row_table is None:
         # decode-step GEMMs (one 128-row tile of activations): the weight matrix is streamed once, so what matters is
         # how many SMs pull on HBM -- 64-column tiles give 4x the CTAs of 256-column ones (N = 2048: 32 instead of 8)
-        block_n = 64
+        block_n = 64 if N < 8192 else 128     # wide outputs: 128 columns halve the activation re-reads per weight byte
     g.block_n = block_n
     g.pair_aligned = 1 if pair_aligned else 0
     g.act = ACT[act]
