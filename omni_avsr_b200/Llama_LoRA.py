@@ -344,6 +344,15 @@ class LoraPlan:
         fp32 partial results per run are scatter-added into their adapter slots (the shared adapter sums over runs)."""
         ns, rp, na = self.n_slots, self.rp, self.n_act
         H = h.shape[1]
+        # the outputs are small ([256, H] / [Hq, 128] per run): a run per CTA column leaves most SMs idle, so long runs are
+        # cut into 128-row-aligned pieces (more token ranges = more CTAs; the pieces land in the same adapter slot below)
+        pieces = max(1, min(8 // max(len(runs), 1), 4))
+        if pieces > 1:
+            cut = []
+            for g, r0, r1 in runs:
+                step = ((r1 - r0 + pieces - 1) // pieces + 127) // 128 * 128
+                cut += [(g, a, min(a + step, r1)) for a in range(r0, r1, max(step, 128))]
+            runs = cut[:8] if len(cut) <= 8 else runs
         Z = len(runs)
         ranges = [(r0, r1) for _, r0, r1 in runs]
         idx_down, idx_up = self._scatter_index(runs, h.device)
@@ -696,6 +705,10 @@ class _NormWeight(nn.Module):
     def forward(self, x):
         return ag.rmsnorm(x, self.weight.data, self.variance_epsilon)
 
+    def with_residual(self, x):
+        """(residual branch, normed) -- the backward adds the residual-path gradient inside the norm-backward kernel."""
+        return ag.rmsnorm_residual(x, self.weight.data, self.variance_epsilon)
+
 
 class LlamaDecoderLayer_lora(nn.Module):
     attention_cls = LlamaSdpaAttention_lora
@@ -710,10 +723,10 @@ class LlamaDecoderLayer_lora(nn.Module):
         self.post_attention_layernorm = _NormWeight(config.hidden_size, config.rms_norm_eps, device)
 
     def forward(self, x, rows, cos_t, sin_t, kv_cache=None):
-        h = self.input_layernorm(x)
-        x = self.self_attn(h, rows, cos_t, sin_t, kv_cache, residual=x)       # x + attn  (residual in the epilogue)
-        h = self.post_attention_layernorm(x)
-        return self.mlp(h, residual=x)                                       # x + mlp
+        res, h = self.input_layernorm.with_residual(x)
+        x = self.self_attn(h, rows, cos_t, sin_t, kv_cache, residual=res)     # x + attn  (residual in the epilogue)
+        res, h = self.post_attention_layernorm.with_residual(x)
+        return self.mlp(h, residual=res)                                     # x + mlp
 
 
 class _Embedding(nn.Module):

@@ -74,6 +74,32 @@ def rmsnorm(x, w, eps):
     return RMSNormFn.apply(x, w, eps)
 
 
+class RMSNormResidualFn(torch.autograd.Function):
+    """Pre-norm block entry: returns (x, norm(x)) where the first output is the residual branch.  Autograd would
+    otherwise add the two gradients of x (residual path + norm path) with a separate elementwise kernel per block; here
+    the backward hands the residual-path gradient to the norm-backward kernel, which adds it on the way out."""
+
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        y, rstd = ops.rmsnorm_fwd(x, w, eps, want_rstd=True)
+        ctx.save_for_backward(x, w, rstd)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        x, w, rstd = ctx.saved_tensors
+        if dy is None:
+            return dres, None, None
+        return ops.rmsnorm_bwd(dy, x, w, rstd, dx_add=dres), None, None
+
+
+def rmsnorm_residual(x, w, eps):
+    """(residual, normed) with the fused gradient add; plain forward when no gradient is needed."""
+    if not x.requires_grad:
+        return x, ops.rmsnorm_fwd(x, w, eps)
+    return RMSNormResidualFn.apply(x, w, eps)
+
+
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):
@@ -91,6 +117,29 @@ def layernorm(x, w, b, eps):
     if not x.requires_grad:
         return ops.layernorm_fwd(x, w, b, eps)
     return LayerNormFn.apply(x, w, b, eps)
+
+
+class LayerNormResidualFn(torch.autograd.Function):
+    """LayerNorm twin of RMSNormResidualFn (AV-HuBERT pre-norm blocks)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, eps, want_stats=True)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        if dy is None:
+            return dres, None, None, None
+        return ops.layernorm_bwd(dy, x, w, mean, rstd, dx_add=dres), None, None, None
+
+
+def layernorm_residual(x, w, b, eps):
+    if not x.requires_grad:
+        return x, ops.layernorm_fwd(x, w, b, eps)
+    return LayerNormResidualFn.apply(x, w, b, eps)
 
 
 class RopeFn(torch.autograd.Function):

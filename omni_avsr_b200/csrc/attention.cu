@@ -66,7 +66,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, clip = blockIdx.z;
+  // grid (head, clip, tile): blocks are dispatched x-fastest, so all CTAs of the heaviest tile (the last one under the causal
+  // mask: it sees every key) start first and the light ones fill the tail of the launch
+  const int head = blockIdx.x, clip = blockIdx.y;
+  const int qt = p.causal ? static_cast<int>(gridDim.z - 1 - blockIdx.z) : static_cast<int>(blockIdx.z);
   const int kvh = head / (p.n_heads / p.n_kv_heads);
   const int q0 = qt * AT_BQ;
   const int clip_row0 = p.row0 + clip * p.S;
@@ -313,7 +316,10 @@ attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, clip = blockIdx.z;
+  // grid (head, clip, tile): blocks are dispatched x-fastest, so all CTAs of the heaviest tile (the last one under the causal
+  // mask: it sees every key) start first and the light ones fill the tail of the launch
+  const int head = blockIdx.x, clip = blockIdx.y;
+  const int qt = p.causal ? static_cast<int>(gridDim.z - 1 - blockIdx.z) : static_cast<int>(blockIdx.z);
   const int kvh = head / (p.n_heads / p.n_kv_heads);
   const int q0 = qt * AT_BQ;
   const int clip_row0 = p.row0 + clip * p.S;
@@ -575,6 +581,7 @@ extern "C" int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* 
                                   int32_t head_dim, int32_t causal, float scale, void* stream) {
   using namespace omni;
   OMNI_CHECK_ARG(qkv && out && M > 0 && B > 0 && S > 0 && n_heads > 0 && n_kv_heads > 0);
+  OMNI_CHECK_ARG(B <= 65535);   // clip index rides in gridDim.y
   OMNI_CHECK_ARG(n_heads % n_kv_heads == 0 && row0 >= 0 && static_cast<int64_t>(row0) + static_cast<int64_t>(B) * S <= M);
   OMNI_CHECK_ARG((ld % 8) == 0 && (out_ld % 8) == 0 && ld >= static_cast<int64_t>(n_heads + 2 * n_kv_heads) * head_dim);
   if (head_dim != 64 && head_dim != 128) return OMNI_ERR_UNSUPPORTED;
@@ -589,7 +596,7 @@ extern "C" int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* 
   p.M = M;
   p.row0 = row0; p.S = S; p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.causal = causal ? 1 : 0;
   p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(ceil_div(S, AT_BQ), n_heads, B);
+  dim3 grid(n_heads, B, ceil_div(S, AT_BQ));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) return launch_attn<64>(tm, p, grid, st);
   auto kfn = attn_fwd_pipe_kernel<128>;

@@ -116,7 +116,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, clip = blockIdx.z;
+  // grid (head, clip, tile), heaviest query tile (the last one under the causal mask) dispatched first
+  const int head = blockIdx.x, clip = blockIdx.y;
+  const int qt = p.causal ? static_cast<int>(gridDim.z - 1 - blockIdx.z) : static_cast<int>(blockIdx.z);
   const int kvh = head / (p.n_heads / p.n_kv_heads);
   const int q0 = qt * AB_T;
   const int clip_row0 = p.row0 + clip * p.S;
@@ -323,7 +325,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, kvh = blockIdx.y, clip = blockIdx.z;
+  // grid (KV head, clip, tile): key tile 0 is the heaviest under the causal mask (every query sees it) and goes first
+  const int kvh = blockIdx.x, clip = blockIdx.y, jt = blockIdx.z;
   const int G = p.n_heads / p.n_kv_heads;
   const int k0 = jt * AB_T;
   const int clip_row0 = p.row0 + clip * p.S;
@@ -544,9 +547,9 @@ static int launch_attn_bwd(const CUtensorMap& tm, const CUtensorMap& tm64, const
     attr_set = true;
   }
   const int nt = ceil_div(p.S, AB_T);
-  kkv<<<dim3(nt, p.n_kv_heads, B), AB_THREADS, BwdKVSmem<HD>::TOTAL, st>>>(tm, tm64, tmdo64, p);
+  kkv<<<dim3(p.n_kv_heads, B, nt), AB_THREADS, BwdKVSmem<HD>::TOTAL, st>>>(tm, tm64, tmdo64, p);
   OMNI_LAUNCH_CHECK();
-  kq<<<dim3(nt, p.n_heads, B), AB_THREADS, BwdQSmem<HD>::TOTAL, st>>>(tm, tm64, tmdo, p);
+  kq<<<dim3(p.n_heads, B, nt), AB_THREADS, BwdQSmem<HD>::TOTAL, st>>>(tm, tm64, tmdo, p);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
@@ -559,6 +562,7 @@ extern "C" int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const 
                                   int32_t n_kv_heads, int32_t head_dim, int32_t causal, float scale, void* stream) {
   using namespace omni;
   OMNI_CHECK_ARG(qkv && out && dout && lse && delta && dqkv && M > 0 && B > 0 && S > 0 && n_heads > 0 && n_kv_heads > 0);
+  OMNI_CHECK_ARG(B <= 65535);   // clip index rides in gridDim.y
   OMNI_CHECK_ARG(n_heads % n_kv_heads == 0 && row0 >= 0 && static_cast<int64_t>(row0) + static_cast<int64_t>(B) * S <= M);
   const int64_t width = static_cast<int64_t>(n_heads + 2 * n_kv_heads) * head_dim;
   OMNI_CHECK_ARG((ld % 8) == 0 && (out_ld % 8) == 0 && (dout_ld % 8) == 0 && (dqkv_ld % 8) == 0 && ld >= width &&

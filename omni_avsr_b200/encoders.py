@@ -110,6 +110,9 @@ class _LN(nn.Module):
     def forward(self, x):
         return ag.layernorm(x, self.weight.data, self.bias.data, self.eps)
 
+    def with_residual(self, x):
+        return ag.layernorm_residual(x, self.weight.data, self.bias.data, self.eps)
+
 
 class _PackedSelfAttention(nn.Module):
     """q|k|v packed into one [3D, D] weight (+[3D] bias); reference-named views q_proj/k_proj/v_proj/out_proj."""
@@ -433,7 +436,7 @@ class AVHLayer(nn.Module):
         att = self.self_attn
         wt_qkv, wt_o = att.transposed()
         wt1, wt2 = self.transposed()
-        h = self.self_attn_layer_norm(x)
+        res, h = self.self_attn_layer_norm.with_residual(x)
         if att.use_lora and (torch.is_grad_enabled() and att.lora_down.requires_grad):
             qkv = ag.LoraLinearFn.apply(h, att.qkv_weight, wt_qkv, att.qkv_bias, att.lora_down, att.lora_up, rows, att.plan)
         elif att.use_lora:
@@ -444,14 +447,14 @@ class AVHLayer(nn.Module):
         else:
             qkv = ops.gemm(h, att.qkv_weight, bias=att.qkv_bias, block_n=256)
         o = att.sdpa(qkv, B, T)       # q * head_dim^-0.5 (:511) is SDPA's default scale (exact: power of two)
-        x = ag.frozen_linear(o, att.out_proj.weight.data, wt_o, bias=att.out_proj.bias.data, residual=x, block_n=256)
-        h = self.final_layer_norm(x)
+        x = ag.frozen_linear(o, att.out_proj.weight.data, wt_o, bias=att.out_proj.bias.data, residual=res, block_n=256)
+        res, h = self.final_layer_norm.with_residual(x)
         if h.requires_grad:
             f = ag.frozen_linear(h, self.fc1.weight.data, wt1, bias=self.fc1.bias.data, block_n=256)
             f = ag.gelu(f)
         else:
             f = ops.gemm(h, self.fc1.weight.data, bias=self.fc1.bias.data, act="gelu", block_n=256)
-        return ag.frozen_linear(f, self.fc2.weight.data, wt2, bias=self.fc2.bias.data, residual=x, block_n=256)
+        return ag.frozen_linear(f, self.fc2.weight.data, wt2, bias=self.fc2.bias.data, residual=res, block_n=256)
 
 
 class _AVHTransformerEncoder(nn.Module):
