@@ -14,7 +14,10 @@ Video: AV-HuBERT video-only path, vendored in the reference:
 Eval-mode semantics (dropout / layerdrop off, BatchNorm running statistics) -- the deterministic configuration the
 parity runs use (SURVEY §7 "hard parts").
 
-Parity status: UNPINNED by the reference itself (no tests exist); pinned here against transformers and resnet.py.
+Parity status: pinned against transformers (log-mel, Whisper encoder), the reference's own resnet.py (imported by
+path) and the reference's own fairseq MultiheadAttention.forward_lora (executed from /root/reference by
+tests/golden/make_reference_golden.py, checked in tests/test_reference_golden.py).  The fairseq TransformerEncoder
+wrapper (wav2vec2.py) cannot be imported here (omegaconf / hydra absent): restated from the cited lines, unpinned.
 """
 from __future__ import annotations
 

@@ -11,7 +11,11 @@ repeat_kv and the Qwen2 twins; their published algorithm is restated here and cr
 tests/test_oracle_llm.py against the installed transformers (5.5.0) LlamaForCausalLM / Qwen2ForCausalLM built
 from config with the adapters switched off (lora_down == 0 => adapted model == base model, Llama_LoRA.py:166-175).
 
-Parity status: UNPINNED by the reference itself (no tests / golden vectors exist for this path).
+Parity status: PINNED against outputs of the reference itself.  The reference ships no tests / golden vectors, so
+tests/golden/make_reference_golden.py executes the unmodified Llama_LoRA.py / Qwen_LoRA.py from /root/reference in the
+build container (name-only transformers 4.43.1 -> 5.5 shims, tests/golden/_ref_compat.py) and freezes logits, losses
+and greedy tokens for the S / T / ST adapter modes; tests/test_reference_golden.py holds this file to them (observed:
+bit-identical logits on CPU).
 """
 from __future__ import annotations
 

@@ -3,9 +3,12 @@ projector and prompt-splice arithmetic of the reference, op for op.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
 
-Parity status: UNPINNED by the reference (it ships no tests / golden vectors for this path, SURVEY.md §4,
-§8c); the restatement below follows the cited lines literally (same torch ops in the same order), and is
-pinned by tests/golden fixtures generated from it plus the structural anchors of SURVEY.md §8c.
+Parity status: PINNED against outputs of the reference itself: tests/golden/reference_golden.pt holds what the
+unmodified AVSR_LLMs.encode_audio / encode_video / prepare_inputs / forward of /root/reference produced on seeded
+inputs (generator: tests/golden/make_reference_golden.py) and tests/test_reference_golden.py requires this file to
+reproduce every byte of the three LLM input sequences, every label and the compressed features (avg-pooling and
+stack, Llama and Qwen layouts, train and infer branches).  The older oracle-generated fixture
+(tests/golden/omni_golden.pt) and the structural anchors of SURVEY.md §8c are kept as regression checks.
 
 Reference lines (relative to /root/reference):
   token-count rule / truncation ... Omni_AVSR/modeling_OmniAVSR.py:537

@@ -5,8 +5,10 @@ log-mel and the three separate LLM passes; encoders in eval mode, rates passed e
 the reference offers through validation_step, lightning_OmniAVSR.py:180).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
-Parity status: UNPINNED by the reference itself (it has no tests); the parts are pinned against transformers /
-resnet.py in tests/test_oracle_*.py.
+Parity status: the parts are PINNED against outputs of the reference's own sources (tests/test_reference_golden.py:
+splice / labels / compression bit-exact, the three task losses incl. matry_weights, greedy ids of the inference
+branch) and against transformers / resnet.py (tests/test_oracle_*.py).  The full composition with the real Whisper /
+AV-HuBERT encoders cannot be run from the reference here (no fairseq, no checkpoints): that seam is unpinned.
 """
 from __future__ import annotations
 
