@@ -156,7 +156,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 64, tmem_dq = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * SM::TILE);
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
@@ -187,7 +187,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
       const uint32_t sK = smem_u32(smem + SM::OFF_KV + st * 2 * SM::STEP), sV = sK + SM::STEP;
       mbar_wait(kv_full + st, (j >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(tmem_s, kmajor_desc(sQ, k, 16384), kmajor_desc(sK, k, 8192), idesc_s, k > 0 ? 1u : 0u);
@@ -199,7 +199,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
       __syncwarp();
       mbar_wait(ds_full, ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t kd = make_smem_desc_sw128(sK, 8192, 1024);       // MN-major [64 keys, HD]
 #pragma unroll
         for (int k = 0; k < AB_STEP / 16; ++k)
@@ -365,7 +365,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 64, tmem_dv = tmem_base + 128, tmem_dk = tmem_base + 128 + HD;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * SM::TILE);
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
@@ -398,7 +398,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
       const uint32_t sQ = smem_u32(smem + SM::OFF_QDO + st * 2 * SM::STEP), sDO = sQ + SM::STEP;
       mbar_wait(q_full + st, (it >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)        // S^T = K Q^T
           umma_bf16(tmem_s, kmajor_desc(sK, k, 16384), kmajor_desc(sQ, k, 8192), idesc_s, k > 0 ? 1u : 0u);
@@ -410,7 +410,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
       __syncwarp();
       mbar_wait(pds_full, ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t dod = make_smem_desc_sw128(sDO, 8192, 1024);     // MN-major [64 queries, HD]
         const uint64_t qd = make_smem_desc_sw128(sQ, 8192, 1024);
 #pragma unroll

@@ -313,7 +313,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < p.num_k_blocks; ++it) {
@@ -346,7 +346,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int it = 0; it < total_iters; ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
         const uint32_t sB = sA + S::A_BYTES;
         const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
@@ -464,7 +464,7 @@ gemm_bf16_tn_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -521,7 +521,7 @@ gemm_bf16_tn_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int it = 0; it < total_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t sB = sA + S::A_BYTES;
           const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
@@ -649,7 +649,7 @@ gemm_bf16_tn_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < kb_per; ++it) {
@@ -669,7 +669,7 @@ gemm_bf16_tn_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int it = 0; it < kb_per; ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
         const uint32_t sB = sA + S::A_BYTES;
         const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
@@ -802,7 +802,7 @@ gemm_bf16_tn_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_pairs; t += num_clusters) {
@@ -862,7 +862,7 @@ gemm_bf16_tn_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int it = 0; it < total_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t sB = sA + S::A_BYTES;
           const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);
@@ -1004,7 +1004,7 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_pairs; t += num_clusters) {
@@ -1063,7 +1063,7 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int it = 0; it < total_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
             const uint32_t sB = sA + S::A_BYTES;
             const uint64_t adesc = make_smem_desc_sw128(sA, 16, 1024);

@@ -78,7 +78,7 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   if (num_k_blocks > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < num_k_blocks; ++it) {
@@ -103,7 +103,7 @@ gemm_bf16_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int it = 0; it < num_k_blocks; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t sB = sA + S::A_BYTES;
           // MN-major, 128B swizzle: LBO = stride between 64-wide MN chunks (one TMA box, 8 KB),
