@@ -112,7 +112,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
   uint64_t* s_full = bars + 5;
   uint64_t* ds_full = bars + 6;
   uint64_t* dq_full = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sd_read = bars + 8;      // compute warps hold S / dP of the step in registers: the TMEM buffers are free
+  uint64_t* ds_free = bars + 9;      // dQ MMAs of the step finished reading the dS tile
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,6 +145,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
       mbar_init(s_full, 1);
       mbar_init(ds_full, 8);
       mbar_init(dq_full, 1);
+      mbar_init(sd_read, 8);
+      mbar_init(ds_free, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -180,9 +184,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     constexpr uint32_t idesc_g = make_idesc_bf16(AB_T, HD, 0, 1);     // dS (K-major) x K step tile (MN-major)
     const uint32_t sQ = smem_u32(smem + SM::OFF_Q), sDO = smem_u32(smem + SM::OFF_DO);
     const uint32_t sDS = smem_u32(smem + SM::OFF_DS);
-    mbar_wait(q_full, 0);
-    for (int j = 0; j < n_kv; ++j) {
-      const uint32_t ph = j & 1;
+    // Issue order: S,dP(0) | S,dP(1) dQ(0) | S,dP(2) dQ(1) | ...  The score MMAs of step j+1 go out as soon as the compute
+    // warps hold step j's S / dP in registers (sd_read), i.e. they run under step j's exp2 / dS arithmetic.
+    auto issue_scores = [&](int j) {
       const int st = j & 1;
       const uint32_t sK = smem_u32(smem + SM::OFF_KV + st * 2 * SM::STEP), sV = sK + SM::STEP;
       mbar_wait(kv_full + st, (j >> 1) & 1);
@@ -197,6 +201,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         umma_commit(s_full);
       }
       __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_scores(0);
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int st = j & 1;
+      const uint32_t sK = smem_u32(smem + SM::OFF_KV + st * 2 * SM::STEP);
+      if (j + 1 < n_kv) {
+        mbar_wait(sd_read, ph);
+        tc_fence_after();
+        issue_scores(j + 1);
+      }
       mbar_wait(ds_full, ph);
       tc_fence_after();
       if (elect_one()) {
@@ -205,6 +221,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         for (int k = 0; k < AB_STEP / 16; ++k)
           umma_bf16(tmem_dq, kmajor_desc(sDS, k, 0), kd + 128 * k, idesc_g, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(kv_empty + st);
+        umma_commit(ds_free);
         if (j == n_kv - 1) umma_commit(dq_full);
       }
       __syncwarp();
@@ -234,6 +251,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
         tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sd_read);     // S / dP are in registers: the next step's score MMAs may overwrite TMEM
         if (full) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -252,6 +272,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             w[i >> 1] = f2_to_bf2(g0, g1);
           }
         }
+        if (j > 0) mbar_wait(ds_free, (j - 1) & 1);      // the previous step's dQ MMAs are done with the dS tile
         store_operand_chunk(sDS, r, c, w);
       }
       fence_proxy_async_smem();
@@ -321,7 +342,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
   uint64_t* s_full = bars + 5;
   uint64_t* pds_full = bars + 6;
   uint64_t* acc_full = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sd_read = bars + 8;      // compute warps hold S^T / dP^T of the step in registers
+  uint64_t* pds_free = bars + 9;     // dV / dK MMAs of the step finished reading the P^T / dS^T tiles
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -352,6 +375,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
       mbar_init(s_full, 1);
       mbar_init(pds_full, 8);
       mbar_init(acc_full, 1);
+      mbar_init(sd_read, 8);
+      mbar_init(pds_free, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -391,9 +416,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     constexpr uint32_t idesc_g = make_idesc_bf16(AB_T, HD, 0, 1);
     const uint32_t sK = smem_u32(smem + SM::OFF_K), sV = smem_u32(smem + SM::OFF_V);
     const uint32_t sP = smem_u32(smem + SM::OFF_P), sDS = smem_u32(smem + SM::OFF_DS);
-    mbar_wait(kv_full, 0);
-    for (int it = 0; it < n_it; ++it) {
-      const uint32_t ph = it & 1;
+    // Issue order: S,dP(0) | S,dP(1) dV,dK(0) | S,dP(2) dV,dK(1) | ...  (see the dQ kernel)
+    auto issue_scores = [&](int it) {
       const int st = it & 1;
       const uint32_t sQ = smem_u32(smem + SM::OFF_QDO + st * 2 * SM::STEP), sDO = sQ + SM::STEP;
       mbar_wait(q_full + st, (it >> 1) & 1);
@@ -408,6 +432,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         umma_commit(s_full);
       }
       __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    if (n_it > 0) issue_scores(0);
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = it & 1;
+      const int st = it & 1;
+      const uint32_t sQ = smem_u32(smem + SM::OFF_QDO + st * 2 * SM::STEP), sDO = sQ + SM::STEP;
+      if (it + 1 < n_it) {
+        mbar_wait(sd_read, ph);
+        tc_fence_after();
+        issue_scores(it + 1);
+      }
       mbar_wait(pds_full, ph);
       tc_fence_after();
       if (elect_one()) {
@@ -420,6 +456,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         for (int k = 0; k < AB_STEP / 16; ++k)   // dK += dS^T Q
           umma_bf16(tmem_dk, kmajor_desc(sDS, k, 0), qd + 128 * k, idesc_g, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(q_empty + st);
+        umma_commit(pds_free);
         if (it == n_it - 1) umma_commit(acc_full);
       }
       __syncwarp();
@@ -470,6 +507,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         tmem_ld_32x32(tmem_s + lane_addr + c * 32, s);
         tmem_ld_32x32(tmem_dp + lane_addr + c * 32, d);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sd_read);     // the next step's score MMAs may overwrite S^T / dP^T
         const float4* L4 = reinterpret_cast<const float4*>(st + c * 32);
         const float4* D4 = reinterpret_cast<const float4*>(st + AB_STEP + c * 32);
 #pragma unroll
@@ -491,6 +531,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
           wd[i4 * 2] = f2_to_bf2(gv[0], gv[1]);
           wd[i4 * 2 + 1] = f2_to_bf2(gv[2], gv[3]);
         }
+        if (it > 0) mbar_wait(pds_free, (it - 1) & 1);   // the previous step's dV / dK MMAs are done with the tiles
         store_operand_chunk(sP, r, c, wp);
         store_operand_chunk(sDS, r, c, wd);
       }
