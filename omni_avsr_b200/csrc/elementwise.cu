@@ -37,9 +37,31 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------
-// RMSNorm:  y = w * bf16(x * rsqrt(mean(x^2) + eps))     (fp32 statistics)
+// Norm kernels.  NPL = 16-byte chunks per lane (row width = 256 * NPL elements: 4 -> 1024, 8 -> 2048, 16 -> 4096): the
+// row (and dy) is loaded ONCE with all NPL (2 NPL) loads of a lane in flight and kept in registers for the statistics
+// and the output pass.  NPL = 0 is the generic width (runtime loops, the row is re-read from L1/L2 for each pass).  Both
+// forms accumulate in the same order (chunk c = lane, lane + 32, ...), so they produce identical bits.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EW_THREADS)
+template <int NPL>
+struct RowRegs {
+  uint4 v[NPL > 0 ? NPL : 1];
+  __device__ __forceinline__ void load(const uint4* row, int lane) {
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) v[k] = __ldg(row + lane + 32 * k);
+  }
+  // Opaque to the optimiser: the next pass has to unpack the bf16 pairs again instead of keeping 8 fp32 registers per
+  // chunk alive across the warp reduction (which would not fit in the register file).
+  __device__ __forceinline__ void pin() {
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) asm volatile("" : "+r"(v[k].x), "+r"(v[k].y), "+r"(v[k].z), "+r"(v[k].w));
+  }
+};
+#define OMNI_ROW_LOOP(k, c) \
+  _Pragma("unroll") for (int k = 0, c = lane; NPL > 0 ? k < NPL : c < H8; ++k, c += 32)
+
+// RMSNorm:  y = w * bf16(x * rsqrt(mean(x^2) + eps))     (fp32 statistics)
+template <int NPL>
+__global__ void __launch_bounds__(EW_THREADS, 1)
 rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                    float* __restrict__ rstd_out, long long rows, int H8, long long ldx, long long ldy, float eps) {
   const int lane = threadIdx.x & 31;
@@ -47,20 +69,23 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
   const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long r = wg; r < rows; r += nw) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
+    RowRegs<NPL> X;
+    X.load(xr, lane);
     float ss = 0.f;
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8];
-      unpack8(__ldg(xr + c), f);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
     }
     ss = warp_sum(ss);
+    X.pin();
     const float rstd = rsqrtf(ss / static_cast<float>(H8 * 8) + eps);
     if (lane == 0 && rstd_out) rstd_out[r] = rstd;
     uint4* yr = reinterpret_cast<uint4*>(y + r * ldy);
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8], g[8];
-      unpack8(__ldg(xr + c), f);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
       unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = g[i] * rbf(f[i] * rstd);
@@ -70,7 +95,8 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
 }
 
 // dx = rstd * (g - xhat * mean(g * xhat)),  g = dy * w, xhat = x * rstd   (weights are frozen: no dw)
-__global__ void __launch_bounds__(EW_THREADS)
+template <int NPL>
+__global__ void __launch_bounds__(EW_THREADS, 1)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                    const float* __restrict__ rstd_in, bf16* __restrict__ dx, const bf16* __restrict__ dx_add,
                    long long rows, int H8) {
@@ -81,28 +107,35 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
   for (long long r = wg; r < rows; r += nw) {
     const uint4* xr = reinterpret_cast<const uint4*>(x) + r * H8;
     const uint4* dr = reinterpret_cast<const uint4*>(dy) + r * H8;
+    const uint4* ar = dx_add ? reinterpret_cast<const uint4*>(dx_add) + r * H8 : nullptr;
+    RowRegs<NPL> X, D, A;
+    X.load(xr, lane);
+    D.load(dr, lane);
+    if (ar) A.load(ar, lane);
     const float rstd = rstd_in[r];
     float dot = 0.f;
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8], d[8], g[8];
-      unpack8(__ldg(xr + c), f);
-      unpack8(__ldg(dr + c), d);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
+      unpack8(NPL > 0 ? D.v[NPL > 0 ? k : 0] : __ldg(dr + c), d);
       unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dot += d[i] * g[i] * f[i] * rstd;
     }
     dot = warp_sum(dot) * invH;
+    X.pin();
+    D.pin();
     uint4* outr = reinterpret_cast<uint4*>(dx) + r * H8;
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8], d[8], g[8], a[8];
-      unpack8(__ldg(xr + c), f);
-      unpack8(__ldg(dr + c), d);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
+      unpack8(NPL > 0 ? D.v[NPL > 0 ? k : 0] : __ldg(dr + c), d);
       unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
-      if (dx_add) unpack8(__ldg(reinterpret_cast<const uint4*>(dx_add) + r * H8 + c), a);
+      if (ar) unpack8(NPL > 0 ? A.v[NPL > 0 ? k : 0] : __ldg(ar + c), a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float v = rstd * (d[i] * g[i] - f[i] * rstd * dot);
-        if (dx_add) v += a[i];
+        if (ar) v += a[i];
         f[i] = v;
       }
       outr[c] = pack8(f);
@@ -113,7 +146,8 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (fp32 statistics, eps inside sqrt), affine w/b:  y = bf16( (x-mean)*rstd * w + b )
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EW_THREADS)
+template <int NPL>
+__global__ void __launch_bounds__(EW_THREADS, 1)
 layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
                      bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      long long rows, int H8, long long ldx, long long ldy, float eps) {
@@ -123,30 +157,34 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, con
   const float invH = 1.0f / static_cast<float>(H8 * 8);
   for (long long r = wg; r < rows; r += nw) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + r * ldx);
+    RowRegs<NPL> X;
+    X.load(xr, lane);
     float s = 0.f;
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8];
-      unpack8(__ldg(xr + c), f);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += f[i];
     }
     const float mean = warp_sum(s) * invH;
+    X.pin();
     float v = 0.f;
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8];
-      unpack8(__ldg(xr + c), f);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { const float d = f[i] - mean; v += d * d; }
     }
     const float rstd = rsqrtf(warp_sum(v) * invH + eps);
+    X.pin();
     if (lane == 0) {
       if (mean_out) mean_out[r] = mean;
       if (rstd_out) rstd_out[r] = rstd;
     }
     uint4* yr = reinterpret_cast<uint4*>(y + r * ldy);
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8], g[8], bb[8];
-      unpack8(__ldg(xr + c), f);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
       unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
       unpack8(__ldg(reinterpret_cast<const uint4*>(b) + c), bb);
 #pragma unroll
@@ -157,7 +195,8 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, con
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*w   (frozen affine: no dw/db)
-__global__ void __launch_bounds__(EW_THREADS)
+template <int NPL>
+__global__ void __launch_bounds__(EW_THREADS, 1)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dx,
                      const bf16* __restrict__ dx_add, long long rows, int H8) {
@@ -168,12 +207,17 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   for (long long r = wg; r < rows; r += nw) {
     const uint4* xr = reinterpret_cast<const uint4*>(x) + r * H8;
     const uint4* dr = reinterpret_cast<const uint4*>(dy) + r * H8;
+    const uint4* ar = dx_add ? reinterpret_cast<const uint4*>(dx_add) + r * H8 : nullptr;
+    RowRegs<NPL> X, D, A;
+    X.load(xr, lane);
+    D.load(dr, lane);
+    if (ar) A.load(ar, lane);
     const float mean = mean_in[r], rstd = rstd_in[r];
     float s1 = 0.f, s2 = 0.f;
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8], d[8], g[8];
-      unpack8(__ldg(xr + c), f);
-      unpack8(__ldg(dr + c), d);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
+      unpack8(NPL > 0 ? D.v[NPL > 0 ? k : 0] : __ldg(dr + c), d);
       unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -184,23 +228,35 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     }
     s1 = warp_sum(s1) * invH;
     s2 = warp_sum(s2) * invH;
+    X.pin();
+    D.pin();
     uint4* outr = reinterpret_cast<uint4*>(dx) + r * H8;
-    for (int c = lane; c < H8; c += 32) {
+    OMNI_ROW_LOOP(k, c) {
       float f[8], d[8], g[8], a[8];
-      unpack8(__ldg(xr + c), f);
-      unpack8(__ldg(dr + c), d);
+      unpack8(NPL > 0 ? X.v[NPL > 0 ? k : 0] : __ldg(xr + c), f);
+      unpack8(NPL > 0 ? D.v[NPL > 0 ? k : 0] : __ldg(dr + c), d);
       unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), g);
-      if (dx_add) unpack8(__ldg(reinterpret_cast<const uint4*>(dx_add) + r * H8 + c), a);
+      if (ar) unpack8(NPL > 0 ? A.v[NPL > 0 ? k : 0] : __ldg(ar + c), a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float v = rstd * (d[i] * g[i] - s1 - (f[i] - mean) * rstd * s2);
-        if (dx_add) v += a[i];
+        if (ar) v += a[i];
         f[i] = v;
       }
       outr[c] = pack8(f);
     }
   }
 }
+#undef OMNI_ROW_LOOP
+
+// picks the register-resident instantiation for the row widths of the named architectures
+// (H = 1024 and 2048; wider rows -- Llama-3.1-8B's 4096 -- would need more than the 128 registers two blocks per SM leave)
+#define OMNI_NPL_DISPATCH(KERNEL, H8, ...)                                        \
+  do {                                                                            \
+    if ((H8) == 128) KERNEL<4><<<__VA_ARGS__;                                     \
+    else if ((H8) == 256) KERNEL<8><<<__VA_ARGS__;                                \
+    else KERNEL<0><<<__VA_ARGS__;                                                 \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // RoPE on the q and k parts of a packed [rows, ld] qkv buffer, in place.
@@ -247,19 +303,36 @@ rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos_t, const bf16* 
 // ------------------------------------------------------------------------------------------------
 // SwiGLU: gu [rows, 2I] = [gate | up]  ->  act [rows, I] = bf16( bf16(silu(g)) * u )
 // ------------------------------------------------------------------------------------------------
+// One block walks rows (grid-stride); a thread owns up to four 16-byte column chunks of the row, 256 chunks apart, and has
+// all of their loads in flight before the first use (no per-element 64-bit division, 8 / 12 independent loads per thread).
 __global__ void __launch_bounds__(EW_THREADS)
-swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, long long rows, int I8, long long total) {
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % I8);
-    const long long r = idx / I8;
+swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, long long rows, int I8) {
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     const uint4* g4 = reinterpret_cast<const uint4*>(gu) + r * (2LL * I8);
-    float g[8], u[8];
-    unpack8(ld_nc_u4(g4 + c), g);
-    unpack8(ld_nc_u4(g4 + I8 + c), u);
+    uint4* o4 = reinterpret_cast<uint4*>(act) + r * static_cast<long long>(I8);
+    for (int c0 = threadIdx.x; c0 < I8; c0 += 4 * EW_THREADS) {
+      uint4 gv[4], uv[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = rbf(silu(g[i])) * u[i];
-    st_na_u4(reinterpret_cast<uint4*>(act) + idx, pack8(g));
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k * EW_THREADS;
+        if (c < I8) {
+          gv[k] = ld_nc_u4(g4 + c);
+          uv[k] = ld_nc_u4(g4 + I8 + c);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k * EW_THREADS;
+        if (c < I8) {
+          float g[8], u[8];
+          unpack8(gv[k], g);
+          unpack8(uv[k], u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = rbf(silu(g[i])) * u[i];
+          st_na_u4(o4 + c, pack8(g));
+        }
+      }
+    }
   }
 }
 
@@ -366,8 +439,8 @@ extern "C" int omni_rmsnorm_fwd(const void* x, const void* w, void* y, float* rs
                                 int64_t ldy, float eps, void* stream) {
   OMNI_CHECK_ARG(x && w && y && rows >= 0 && H > 0 && (H % 8) == 0 && (ldx % 8) == 0 && (ldy % 8) == 0);
   if (rows == 0) return OMNI_OK;
-  rmsnorm_fwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H / 8, ldx, ldy, eps);
+  OMNI_NPL_DISPATCH(rmsnorm_fwd_kernel, H / 8, rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H / 8, ldx, ldy, eps));
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
@@ -376,8 +449,8 @@ extern "C" int omni_rmsnorm_bwd(const void* dy, const void* x, const void* w, co
                                 const void* dx_add, int64_t rows, int32_t H, void* stream) {
   OMNI_CHECK_ARG(dy && x && w && rstd && dx && rows >= 0 && H > 0 && (H % 8) == 0);
   if (rows == 0) return OMNI_OK;
-  rmsnorm_bwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (bf16*)dx, (const bf16*)dx_add, rows, H / 8);
+  OMNI_NPL_DISPATCH(rmsnorm_bwd_kernel, H / 8, rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (bf16*)dx, (const bf16*)dx_add, rows, H / 8));
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
@@ -386,8 +459,8 @@ extern "C" int omni_layernorm_fwd(const void* x, const void* w, const void* b, v
                                   int64_t rows, int32_t H, int64_t ldx, int64_t ldy, float eps, void* stream) {
   OMNI_CHECK_ARG(x && w && b && y && rows >= 0 && H > 0 && (H % 8) == 0 && (ldx % 8) == 0 && (ldy % 8) == 0);
   if (rows == 0) return OMNI_OK;
-  layernorm_fwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, mean, rstd, rows, H / 8, ldx, ldy, eps);
+  OMNI_NPL_DISPATCH(layernorm_fwd_kernel, H / 8, rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, mean, rstd, rows, H / 8, ldx, ldy, eps));
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
@@ -396,8 +469,8 @@ extern "C" int omni_layernorm_bwd(const void* dy, const void* x, const void* w, 
                                   void* dx, const void* dx_add, int64_t rows, int32_t H, void* stream) {
   OMNI_CHECK_ARG(dy && x && w && mean && rstd && dx && rows >= 0 && H > 0 && (H % 8) == 0);
   if (rows == 0) return OMNI_OK;
-  layernorm_bwd_kernel<<<rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, (const bf16*)dx_add, rows, H / 8);
+  OMNI_NPL_DISPATCH(layernorm_bwd_kernel, H / 8, rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)w, mean, rstd, (bf16*)dx, (const bf16*)dx_add, rows, H / 8));
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
@@ -420,11 +493,8 @@ extern "C" int omni_rope(void* qkv, const void* cos_t, const void* sin_t, const 
 extern "C" int omni_swiglu_fwd(const void* gu, void* act, int64_t rows, int32_t I, void* stream) {
   OMNI_CHECK_ARG(gu && act && rows >= 0 && I > 0 && (I % 8) == 0);
   if (rows == 0) return OMNI_OK;
-  const long long total = rows * (I / 8);
-  long long blocks = ceil_div_ll(total, EW_THREADS);
-  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
-  swiglu_fwd_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)gu, (bf16*)act, rows, I / 8,
-                                                                           total);
+  const long long blocks = rows < kNumSMs * 8LL ? rows : kNumSMs * 8LL;
+  swiglu_fwd_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)gu, (bf16*)act, rows, I / 8);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }
