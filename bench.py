@@ -38,10 +38,12 @@ WORKLOAD = ("Omni-AVSR AVSR train step: Whisper-medium + AV-HuBERT-Large + Llama
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-# capture (three consecutive launches of gemm_bf16_tn_2cta inside a B=16 train step: 1461 / 595 / 148 MB)
-NCU_TRAFFIC_BYTES = 734.8e6
-NCU_TRAFFIC_SOURCE = ("profiles/gemm2cta_r1_ncu_full_summary.csv: mean of 3 captured launches; the largest (gate_up, "
-                      "M=15616 N=16384 K=2048) moves 1461 MB against 643 MB algorithmic (B panel re-read from HBM 7x)")
+# capture (three consecutive launches of gemm_bf16_tn_2cta inside a B=32 train step: 2893 / 1191 / 315 MB)
+NCU_TRAFFIC_BYTES = 1466.4e6
+NCU_TRAFFIC_SOURCE = ("profiles/gemm2cta_r1b_ncu_full_summary.csv: mean of 3 captured launches (B=32); tensor pipe active "
+                      "93-97 %, DRAM throughput 15-25 %; the largest (gate_up, M=31232 N=16384 K=2048) moves 2893 MB against "
+                      "1218 MB algorithmic: the weight panel is re-read from HBM because 74 CTA pairs sweep all 64 N tiles "
+                      "per M wave -- not the limiter at 25 % DRAM utilisation")
 
 
 def load_peaks():
