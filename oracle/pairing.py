@@ -47,6 +47,8 @@ def oracle_from_product(module, dtype=torch.bfloat16):
     oracle = oracle.to(dtype).eval()
     # the product's prompt buffers must equal the oracle's embedded prompts
     for k, p in oracle.prompts().items():
+        if not hasattr(m, "prompt_" + k):          # Llama-AVSR mirror: the prompt is embedded per call, no buffers
+            continue
         if not torch.equal(getattr(m, "prompt_" + k).cpu().to(dtype), p.to(dtype)):
             raise RuntimeError("prompt buffer mismatch: " + k)
     return oracle

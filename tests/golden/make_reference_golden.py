@@ -11,6 +11,8 @@ What runs is the unmodified reference code, imported through the name-only shims
     encode_video for avg-pooling and stack Matryoshka compression, Llama and Qwen layouts.  `from_pretrained` and the
     fairseq checkpoint loader are patched to return tiny random-init models (there are no checkpoints offline), the video
     encoder is a stand-in (its output is stored, the test feeds it back), `.cuda()` is patched to a no-op;
+  * `Omni_AVSR/modeling_LlamaAVSR.py`  AVSR_LLMs (Llama-AVSR and Llama-MTSK: every rate / rate pair per step), same
+    stand-ins;
   * `av_hubert/fairseq/fairseq/modules/multihead_attention.py`  MultiheadAttention.forward_lora.
 
 Weights are NOT stored: they are regenerated from a seed by `golden_weights` (CPU mt19937 `randn`), a checksum guards
@@ -314,6 +316,101 @@ def build_omni_cases(ll, ql, mo):
     return cases
 
 
+def build_llamaavsr_cases(ll, ql, mla):
+    """Executes the reference's Omni_AVSR/modeling_LlamaAVSR.py AVSR_LLMs (Llama-AVSR / Llama-MTSK): real constructor,
+    prepare_inputs (train + infer), forward, with the same stand-ins as build_omni_cases."""
+    from transformers import LlamaConfig, Qwen2Config, WhisperConfig, WhisperFeatureExtractor, WhisperModel
+    cases = {}
+    prompts = {"P": [11, 12, 13, 14, 15, 16]}
+    wcfg = WhisperConfig(d_model=64, encoder_layers=2, encoder_attention_heads=2, encoder_ffn_dim=128, decoder_layers=1,
+                         decoder_attention_heads=2, decoder_ffn_dim=64, num_mel_bins=80, max_source_positions=1500,
+                         vocab_size=100, pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=1)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    specs = [  # name, llm, modality, mode, matryoshka, remove_ln, rates_a, rates_v, test_ratio
+        ("mtsk_av_avg", "meta-llama/Llama-3.2-1B", "audiovisual", "avg-pooling", True, False, [4, 16], [2, 5], [5, 4]),
+        ("mtsk_audio_stack", "meta-llama/Llama-3.2-1B", "audio", "stack", True, True, [4, 16], [2, 5], 16),
+        ("avsr_video_qwen", "Qwen/Qwen2.5-3B", "video", "avg-pooling", False, False, 4, 2, None),
+        ("avsr_av_llama", "meta-llama/Llama-3.2-1B", "audiovisual", "avg-pooling", False, False, 4, 2, None),
+    ]
+    for i, (name, llm_name, modality, mode, matry, rm_ln, ra, rv, test_ratio) in enumerate(specs):
+        is_qwen = "Qwen" in llm_name
+        torch.manual_seed(1300 + i)
+        fake_video = _FakeVideoEncoder()
+        mla.WhisperModel = types.SimpleNamespace(from_pretrained=lambda _n: WhisperModel(wcfg))
+        mla.AutoFeatureExtractor = types.SimpleNamespace(from_pretrained=lambda _n: WhisperFeatureExtractor())
+        mla.fairseq = types.SimpleNamespace(checkpoint_utils=types.SimpleNamespace(
+            load_model_ensemble_and_task=lambda paths: ([fake_video], None, None)))
+        if is_qwen:
+            lc = ql.QwenLoRA_config(8, 2, False, False, True, False)
+            ql.Qwen2ForCausalLM_lora.from_pretrained = classmethod(lambda cls, _n, lcfg: cls(Qwen2Config(**QWEN), lcfg))
+        else:
+            lc = ll.LoRA_config(4, 2, True, False)
+            ll.LlamaForCausalLM_lora.from_pretrained = classmethod(lambda cls, _n, lcfg: cls(LlamaConfig(**LLAMA), lcfg))
+        tok = _Tok(200, is_qwen, prompts)
+        model = mla.AVSR_LLMs(modality=modality, pretrain_avhubert_enc_video="base_fake.pt", use_lora_avhubert=False,
+                              llm_model=llm_name, hidden_size=(QWEN if is_qwen else LLAMA)["hidden_size"],
+                              intermediate_size=96, tokenizer=tok, prompt="P", pad_id=tok.vocab["<pad>"],
+                              downsample_ratio_audio=ra, downsample_ratio_video=rv, audio_encoder_name="openai/whisper-fake",
+                              compression_mode=mode, unfrozen_modules=["peft_llm"], max_dec_tokens=6, num_beams=1,
+                              PETF_LLM_name="lora", peft_config_llm=lc, remove_layernorm_from_projector=rm_ln,
+                              is_matryoshka=matry)
+        model.llm.tie_weights()
+        model = model.bfloat16().eval()
+        assert model.llm.lm_head.weight is model.llm.model.embed_tokens.weight
+        named_llm, csum_llm = load_golden_weights(model.llm, 1400 + i)
+        named, csums = {"llm": named_llm}, {"llm": csum_llm}
+        for key, seed in (("audio_proj", 1500 + i), ("video_proj", 1600 + i)):
+            if hasattr(model, key):
+                named[key], csums[key] = load_golden_weights(getattr(model, key), seed)
+        g = torch.Generator().manual_seed(1700 + i)
+        B, L, T, n_samples = 2, 9, 23, 20000
+        audio = torch.randn(B, n_samples, 1, generator=g)
+        audio[1, 15000:] = 0
+        video = ((torch.rand(B, T, 1, 88, 88, generator=g) - 0.421) / 0.165).bfloat16()
+        lengths = torch.tensor([n_samples, 15000])
+        tokens = torch.randint(4, 200, (B, L), generator=g)
+        if not is_qwen:
+            tokens[:, 0] = 1
+        tokens[0, -1] = 2
+        tokens[1, -3] = 2
+        tokens[1, -2:] = tok.vocab["<pad>"]
+        labels = tokens.clone()
+        labels[labels == tok.vocab["<pad>"]] = -100
+        inputs = dict(audio=audio.bfloat16(), video=video, lengths=lengths, tokens=tokens, labels=labels)
+        feats = {}
+        hook = None
+        if hasattr(model, "audio_encoder"):
+            hook = model.audio_encoder.register_forward_hook(
+                lambda m_, a, o: feats.__setitem__("audio_enc", o.last_hidden_state[:, :100].clone()))
+        orig_ef = fake_video.extract_finetune
+
+        def ef(source, **kw):
+            o = orig_ef(source, **kw)
+            feats["video_enc"] = o[0].clone()
+            return o
+        fake_video.extract_finetune = ef
+        c = dict(llm_name=llm_name, modality=modality, mode=mode, is_matryoshka=matry, remove_layernorm=rm_ln,
+                 rates_audio=ra, rates_video=rv, test_ratio=test_ratio, lora=dict(vars(lc)),
+                 seeds=dict(llm=1400 + i, audio_proj=1500 + i, video_proj=1600 + i), named=named, checksum=csums,
+                 inputs={k: v for k, v in inputs.items() if k != "video"}, prompt_ids=prompts["P"], vocab=dict(tok.vocab),
+                 n_vocab=len(tok))
+        with torch.no_grad():
+            emb, lab = model.prepare_inputs(inputs, True)
+            loss = model(inputs, is_trainval=True)
+            as_list = lambda x: [t.clone() for t in x] if isinstance(x, list) else x.clone()
+            c["train"] = dict(embeddings=as_list(emb), labels=as_list(lab), loss=loss.clone())
+            c.update({k: v.clone() for k, v in feats.items()})       # encoder outputs of the TRAIN batch (B = 2)
+            one = dict(audio=inputs["audio"][:1], video=inputs["video"][:1], lengths=lengths[:1],
+                       tokens=(torch.zeros(1, 0, dtype=torch.long) if is_qwen else torch.tensor([[1]])), labels=None)
+            e_inf, _ = model.prepare_inputs(one, False, test_ratio_matry=test_ratio)
+            ids, mg = _greedy(model.llm, e_inf, 6, 2, 2 if is_qwen else tok.vocab["<pad>"], None)
+            c["infer"] = dict(embeddings=e_inf.clone(), greedy=ids, margins=mg)
+        if hook is not None:
+            hook.remove()
+        cases[name] = c
+    return cases
+
+
 def build_mha_case(mha):
     torch.manual_seed(900)
     E, Hh, T, B = 128, 2, 11, 2
@@ -339,7 +436,9 @@ def main():
     assert rc.available(), "needs /root/reference (build container only)"
     ll, ql, mo, mha = rc.import_reference()
     _patch_ref(ll, ql)
-    out = dict(llm=build_llm_cases(ll, ql), omni=build_omni_cases(ll, ql, mo), mha=build_mha_case(mha),
+    mla = rc.load_by_path("Omni_AVSR.modeling_LlamaAVSR", "Omni_AVSR/modeling_LlamaAVSR.py", "Omni_AVSR")
+    out = dict(llm=build_llm_cases(ll, ql), omni=build_omni_cases(ll, ql, mo), llamaavsr=build_llamaavsr_cases(ll, ql, mla),
+               mha=build_mha_case(mha),
                meta=dict(torch=torch.__version__, note="outputs of /root/reference sources executed on CPU, bf16"))
     torch.save(out, OUT)
     print("written", OUT, os.path.getsize(OUT))

@@ -351,3 +351,177 @@ def test_gpu_avhubert_lora_attention_matches_reference():
         y = ops.gemm(o, att.out_proj.weight.data, bias=att.out_proj.bias.data, block_n=64)
     y = y.float().cpu().view(B, T, E).transpose(0, 1)
     assert rel_err(y, c["y_nomask"]) <= 2e-2, rel_err(y, c["y_nomask"])
+
+
+# ------------------------------------------------------------------------------------------------ Llama-AVSR / Llama-MTSK
+# (Omni_AVSR/modeling_LlamaAVSR.py executed from the reference tree; fixtures under GOLD["llamaavsr"])
+from oracle import llama_avsr as ola  # noqa: E402
+
+LA_CASES = ["mtsk_av_avg", "mtsk_audio_stack", "avsr_video_qwen", "avsr_av_llama"]
+
+
+def _la_media_slices(c, emb, is_trainval, ra, rv):
+    """Positions of the projected media tokens inside a reference sequence [bos?, <a> A </a>, <v> V </v>, prompt, ...]."""
+    is_qwen = "Qwen" in c["llm_name"]
+    stack = c["mode"] == "stack"
+    pos = 0 if is_qwen else 1
+    a_tok = v_tok = None
+    if c["modality"] in ("audio", "audiovisual"):
+        na = 62 // ra
+        a_tok = emb[:, pos + 1: pos + 1 + na].contiguous()
+        pos += na + 2
+    if c["modality"] in ("video", "audiovisual"):
+        nv = 23 // rv
+        v_tok = emb[:, pos + 1: pos + 1 + nv].contiguous()
+        pos += nv + 2
+    return a_tok, v_tok
+
+
+def _la_rate_grid(c):
+    if not c["is_matryoshka"]:
+        return [(c["rates_audio"], c["rates_video"])]
+    if c["modality"] == "audiovisual":
+        return [(a, v) for v in c["rates_video"] for a in c["rates_audio"]]        # video outer, audio inner (:312-324)
+    if c["modality"] == "audio":
+        return [(a, None) for a in c["rates_audio"]]
+    return [(None, v) for v in c["rates_video"]]
+
+
+def _la_embed(c):
+    H = (QWEN_CFG if "Qwen" in c["llm_name"] else LLAMA_CFG)["hidden_size"]
+    w = fixture_weights(c["named"]["llm"], c["seeds"]["llm"], c["checksum"]["llm"])
+    embed = torch.nn.Embedding(c["n_vocab"], H).bfloat16()
+    embed.weight.data.copy_(w["model.embed_tokens.weight"])
+    return embed
+
+
+@pytest.mark.parametrize("name", LA_CASES)
+def test_oracle_llamaavsr_sequences_labels_bit_exact_vs_reference(name):
+    c = GOLD["llamaavsr"][name]
+    is_qwen = "Qwen" in c["llm_name"]
+    embed = _la_embed(c)
+    v = c["vocab"]
+    marker = (v["<audio>"], v["</audio>"], v["<video>"], v["</video>"])
+    prompt_ids = torch.tensor([c["prompt_ids"]])
+    tr = c["train"]
+    seqs = tr["embeddings"] if c["is_matryoshka"] else [tr["embeddings"]]
+    labs = tr["labels"] if c["is_matryoshka"] else [tr["labels"]]
+    grid = _la_rate_grid(c)
+    assert len(seqs) == len(grid)
+    # compression: the reference's media rows are projector(compress(encoder output)) -- check the compressed lengths and
+    # (avg-pooling, LN-free stack) the projector output against the oracle projector on the oracle compression
+    a_list, v_list = [], []
+    for (ra, rv), e in zip(grid, seqs):
+        a_tok, v_tok = _la_media_slices(c, e, True, ra or 1, rv or 1)
+        a_list.append(a_tok)
+        v_list.append(v_tok)
+    for which, enc_key, rates, n_in in (("audio_proj", "audio_enc", c["rates_audio"], 62), ("video_proj", "video_enc", c["rates_video"], 23)):
+        if which not in c["named"]:
+            continue
+        wts = fixture_weights(c["named"][which], c["seeds"][which], c["checksum"][which])
+        rl = rates if c["is_matryoshka"] else [rates]
+        for i, r in enumerate(rl):
+            comp = om.compress(c[enc_key][:, :n_in], r, c["mode"])
+            ln = not c["remove_layernorm"]
+            proj = om.make_projector(comp.shape[-1], 96, embed.weight.shape[1], ln).bfloat16()
+            pre = f"{i}." if c["is_matryoshka"] else ""
+            load_named(proj, {k[len(pre):]: t for k, t in wts.items() if k.startswith(pre)})
+            with torch.no_grad():
+                want = proj(comp)
+            k = next(j for j, (ra, rv) in enumerate(grid) if (ra if which == "audio_proj" else rv) == r)
+            got = (a_list if which == "audio_proj" else v_list)[k]
+            assert rel_err(want, got) <= 1e-2, (name, which, r)
+    # splice + labels from the reference's own projected tokens: every byte equal
+    if c["is_matryoshka"]:
+        ua = [a_list[k] for k in range(len(c["rates_audio"]))] if c["modality"] != "video" else None
+        if c["modality"] == "audiovisual":
+            uv = [v_list[k * len(c["rates_audio"])] for k in range(len(c["rates_video"]))]
+        else:
+            uv = v_list if c["modality"] == "video" else None
+        with torch.no_grad():
+            mine, mlab = ola.prepare_inputs(embed, c["inputs"]["tokens"], c["inputs"]["labels"], ua, uv, prompt_ids, marker,
+                                            is_qwen, c["modality"], True, True)
+    else:
+        with torch.no_grad():
+            s, l = ola.prepare_inputs(embed, c["inputs"]["tokens"], c["inputs"]["labels"], a_list[0], v_list[0], prompt_ids,
+                                      marker, is_qwen, c["modality"], False, True)
+        mine, mlab = [s], [l]
+    for a, b, la, lb in zip(mine, seqs, mlab, labs):
+        assert bits_equal(a, b), name
+        assert torch.equal(la, lb), name
+    # inference layout
+    inf = c["infer"]["embeddings"]
+    tr_ = c["test_ratio"]
+    if c["is_matryoshka"]:
+        ra, rv = (tr_[1], tr_[0]) if c["modality"] == "audiovisual" else (tr_, tr_)
+    else:
+        ra, rv = c["rates_audio"], c["rates_video"]
+    a_tok, v_tok = _la_media_slices(c, inf, False, ra, rv)
+    toks = torch.zeros(1, 0, dtype=torch.long) if is_qwen else torch.tensor([[1]])
+    with torch.no_grad():
+        s, _ = ola.prepare_inputs(embed, toks, None, a_tok, v_tok, prompt_ids, marker, is_qwen, c["modality"], False, False)
+    assert bits_equal(s, inf), name
+
+
+@pytest.mark.parametrize("name", LA_CASES)
+def test_oracle_llamaavsr_loss_and_decode_vs_reference(name):
+    c = GOLD["llamaavsr"][name]
+    fam = "qwen2" if "Qwen" in c["llm_name"] else "llama"
+    m, _ = oracle_llm(fam, c["lora"], c["n_vocab"], c["named"]["llm"], c["seeds"]["llm"], c["checksum"]["llm"])
+    with torch.no_grad():
+        loss = ola.train_loss(m, c["train"]["embeddings"], c["train"]["labels"], c["is_matryoshka"])
+        assert abs(float(loss) - float(c["train"]["loss"])) <= 2e-2, name
+        inf = c["infer"]
+        ids = m.generate(inf["embeddings"], 6, 2, 2 if fam == "qwen2" else c["vocab"]["<pad>"], modality=None)
+        n = min(ids.shape[1], inf["greedy"].shape[1])
+        differs = ids[:, :n] != inf["greedy"][:, :n]
+        if differs.any():
+            assert inf["margins"][0, int(differs[0].float().argmax())] < 0.05, (name, ids, inf["greedy"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", LA_CASES)
+def test_gpu_llamaavsr_splice_loss_decode_vs_reference(name):
+    """CUDA path of the Llama-AVSR / Llama-MTSK step against the reference's outputs: splice + labels of every Matryoshka
+    sequence bit-exact, ONE packed LLM pass over all sequences -> mean loss within 5e-2, greedy ids token-for-token."""
+    from omni_avsr_b200 import ops
+    from omni_avsr_b200.Llama_LoRA import PackedRows, pack_segments
+    c = GOLD["llamaavsr"][name]
+    is_qwen = "Qwen" in c["llm_name"]
+    fam = "qwen2" if is_qwen else "llama"
+    model, _ = product_llm(fam, c["lora"], c["n_vocab"], c["named"]["llm"], c["seeds"]["llm"], c["checksum"]["llm"])
+    embed_w = model.model.embed_tokens.weight.data
+    v = c["vocab"]
+    marker = (v["<audio>"], v["</audio>"], v["<video>"], v["</video>"])
+    prompt = embed_w[torch.tensor(c["prompt_ids"], device="cuda")].contiguous()
+    t = TASKS.index(c["modality"])
+    tr = c["train"]
+    seqs = tr["embeddings"] if c["is_matryoshka"] else [tr["embeddings"]]
+    labs = tr["labels"] if c["is_matryoshka"] else [tr["labels"]]
+    tokens, labels = c["inputs"]["tokens"].cuda(), c["inputs"]["labels"].cuda()
+    mine, mlab = [], []
+    for (ra, rv), e in zip(_la_rate_grid(c), seqs):
+        a_tok, v_tok = _la_media_slices(c, e, True, ra or 1, rv or 1)
+        lay = ops.SpliceLayout(tokens=tokens, labels=labels, embed=embed_w,
+                               audio_tok=None if a_tok is None else a_tok.cuda(),
+                               video_tok=None if v_tok is None else v_tok.cuda(), prompts=[prompt] * 3, marker_ids=marker,
+                               has_bos=not is_qwen, task_mask=1 << t)
+        outs, outl = [None] * 3, [None] * 3
+        outs[t] = torch.empty(2, lay.seq_len[t], embed_w.shape[1], device="cuda", dtype=torch.bfloat16)
+        outl[t] = torch.empty(2, lay.seq_len[t], device="cuda", dtype=torch.int64)
+        ops.splice_prompt(lay, outs, outl)
+        mine.append(outs[t])
+        mlab.append(outl[t])
+    for a, b, la, lb in zip(mine, seqs, mlab, labs):
+        assert bits_equal(a.cpu(), b), name
+        assert torch.equal(la.cpu(), lb), name
+    with torch.no_grad():
+        rows = PackedRows.get([(0, 2, s.shape[1]) for s in mine], "cuda")
+        hid = model.model.forward_packed(pack_segments(mine, rows), rows)
+        losses = model.loss_from_hidden(hid, [(b, s, off) for (_, b, s, off) in rows.segments], mlab, [1.0] * len(mine))
+        loss = sum(float(l) for l in losses) / len(mine)
+        assert abs(loss - float(tr["loss"])) <= 5e-2, (name, loss, float(tr["loss"]))
+        inf = c["infer"]
+        ids = model.generate(inputs_embeds=inf["embeddings"].cuda(), max_new_tokens=6, num_beams=1, eos_token_id=2,
+                             pad_token_id=2 if is_qwen else v["<pad>"])
+        _greedy_ok(ids, inf["greedy"], inf["margins"], name)
