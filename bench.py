@@ -98,9 +98,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+MTSK_WORKLOAD = ("Llama-MTSK AVSR train step (SURVEY 8f rank 2): Whisper-medium + AV-HuBERT-Large + Llama-3.2-1B, shared LoRA "
+                 "(r=64), audiovisual, ALL audio rates {4,16} x video rates {2,5} in every step (4 sequences/utterance, "
+                 "one packed LLM pass), bf16")
+
+
 def build_module(args, device):
-    from omni_avsr_b200 import lightning_OmniAVSR as L
-    margs = L.make_args(num_beams=1, max_dec_tokens=32)
+    if getattr(args, "workload", "omni") == "mtsk":
+        from omni_avsr_b200 import lightning_LlamaAVSR as L
+        margs = L.make_args(modality="audiovisual", is_matryoshka=True, downsample_ratio_audio=[4, 16],
+                            downsample_ratio_video=[2, 5], num_beams=1, max_dec_tokens=32, no_layernorm_projector=True,
+                            downsample_ratio_test_matry=[2, 4])
+    else:
+        from omni_avsr_b200 import lightning_OmniAVSR as L
+        margs = L.make_args(num_beams=1, max_dec_tokens=32)
     torch.manual_seed(0)
     mod = L.ModelModule_LLM(margs, device=device)
     with torch.no_grad():   # non-degenerate adapters (LoRA down AND up ~ N(0, 0.02))
@@ -223,7 +234,7 @@ def run_ours(args):
 
     # ---- greedy decode (second half of the BASELINE metric): elastic sweep over the 8 (task, rate) settings -------
     decode = None
-    if not args.no_decode:
+    if not args.no_decode and args.workload == "omni":
         Bd = args.decode_batch
         dhost = synthetic_batch(Bd, mod.tokenizer, seconds=16.0, text_len=48, seed=4321 + rank, pin=True)
         dres = to_device(dhost, device)
@@ -267,7 +278,7 @@ def run_ours(args):
         "metric": "utterances/sec (train step)", "value": round(value, 3), "unit": "utterances/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": 16,
+        "config": {"workload": WORKLOAD if args.workload == "omni" else MTSK_WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": 16,
                    "text_tokens": 48, "parallelism": f"dp{world}", "l2": "256 MiB buffer written between timed steps",
                    "optimizer": "fused all-reduce + clip(10) + AdamW", "random_init": True},
         "e2e": {"value": round(e2e, 3), "unit": "utterances/s", "h2d_bytes_per_step": host_bytes(host),
@@ -277,7 +288,7 @@ def run_ours(args):
         "roofline": roof,
         "decode": decode,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "omni":
         line["cpu_baseline"] = cpu_baseline(steps=1, warmup=0)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -360,6 +371,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--decode-batch", type=int, default=64)
+    ap.add_argument("--workload", default="omni", choices=["omni", "mtsk"],
+                    help="omni = BASELINE config 2 (default, the judged line); mtsk = Llama-MTSK train step (extra line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
