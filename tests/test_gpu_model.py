@@ -190,3 +190,39 @@ def test_qwen_stack_mode_step():
     loss = mod.training_step(gpu, 0, rates=(4, 5))
     for a, b in zip(mod.last_losses, o_parts):
         assert abs(a.item() - b.item()) <= 5e-2, (a.item(), b.item())
+
+
+def test_ragged_batch_like_collate_llm(pair):
+    """Variable-length batch as `collate_LLM` builds it (datamodule/data_module.py:19-79): media zero-padded to the batch
+    maximum, text right-padded with <pad> and labels -100 there, `lengths` = true sample counts.  Only max(lengths) enters
+    the model (modeling_OmniAVSR.py:537: token count 93 for 29999 samples, not a multiple of either rate), the padded media
+    of the short clips goes through the encoders like any other input, and the reference passes no attention mask --
+    the three task losses must still match the oracle."""
+    from oracle.modeling import training_step
+    mod, oracle = pair
+    cpu, _ = _batch(mod, B=3, seconds=2.0, L=12, seed=11)
+    from omni_avsr_b200.synthetic import to_device
+    pad = mod.tokenizer.pad_token_id
+    cpu = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in cpu.items()}
+    n = 29999                                                  # longest clip; int(29999/16000*50) = 93 tokens
+    cpu["audio"] = cpu["audio"][:, :n].contiguous()
+    cpu["lengths"] = torch.tensor([n, 21000, 12345])
+    cpu["audio"][1, 21000:] = 0
+    cpu["audio"][2, 12345:] = 0
+    cpu["video"][1, 33:] = 0
+    cpu["video"][2, 19:] = 0
+    cpu["tokens"][1, 9:] = pad
+    cpu["tokens"][1, 8] = mod.tokenizer.eos_token_id
+    cpu["tokens"][2, 6:] = pad
+    cpu["tokens"][2, 5] = mod.tokenizer.eos_token_id
+    cpu["labels"] = cpu["tokens"].clone()
+    cpu["labels"][cpu["labels"] == pad] = -100
+    gpu = to_device(cpu, "cuda")
+    with torch.no_grad():
+        o_loss, o_parts = training_step(oracle, cpu, 4, 5)
+        loss = mod.training_step(gpu, 0, rates=(4, 5))
+    for a, b in zip(mod.last_losses, o_parts):
+        assert abs(a.item() - b.item()) <= 5e-2, (a.item(), b.item())
+    out = mod.model.prepare_inputs(gpu, True, test_ratio_matry_audio=4, test_ratio_matry_video=5)
+    assert out["labels_audio"].shape[1] == 1 + (93 // 4 + 2) + mod.model.prompt_audio_len + 11
+    assert (out["labels_audio"][2, -6:] == -100).all()
