@@ -26,6 +26,12 @@ extern "C" {
 #define OMNI_ACT_NONE 0
 #define OMNI_ACT_RELU 1
 #define OMNI_ACT_GELU 2
+/* SwiGLU pair epilogue (LlamaMLP / Qwen2MLP, transformers modeling_llama.py `down_proj(act_fn(gate_proj(x)) * up_proj(x))`):
+ * the N columns are [gate 64 | up 64] blocks (weight rows interleaved in 64-row blocks by the caller); `out` receives the
+ * bf16 gate|up tile as usual and `out2` [M, N/2] = bf16( bf16(silu(gate)) * up ) computed from the ROUNDED gate / up values,
+ * i.e. bit-identical to omni_swiglu_fwd on `out`.  CTA-pair kernel only (N % 256 == 0, no bias / residual / fp32 output);
+ * OMNI_ERR_UNSUPPORTED otherwise. */
+#define OMNI_ACT_SWIGLU64 3
 
 #define OMNI_COMPRESS_AVG 0   /* nn.AvgPool1d(r)  : modeling_OmniAVSR.py:544-546 (audio), :469-471 (video) */
 #define OMNI_COMPRESS_STACK 1 /* frame stacking   : modeling_OmniAVSR.py:562-568 (audio), :487-493 (video) */
@@ -63,6 +69,8 @@ typedef struct omni_gemm_args {
   float alpha;
   int32_t pair_aligned;    /* 1: tile_group is constant over every pair of consecutive 128-row tiles (segments start on
                               256-row boundaries), which lets the K-extended GEMM run on the CTA-pair kernel */
+  void* out2;              /* OMNI_ACT_SWIGLU64: [M, N/2] bf16, ld = ldo2; else NULL */
+  int64_t ldo2;
 } omni_gemm_args;
 
 int omni_gemm_bf16(const omni_gemm_args* args, void* stream);
@@ -200,6 +208,9 @@ int omni_rope(void* qkv, const void* cos_t, const void* sin_t, const int32_t* po
 /* gu [rows, 2I] = [gate | up] -> act [rows, I] = bf16(bf16(silu(gate)) * up), and its backward. */
 int omni_swiglu_fwd(const void* gu, void* act, int64_t rows, int32_t I, void* stream);
 int omni_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, void* stream);
+/* Same for the [gate blk | up blk] block-interleaved layout OMNI_ACT_SWIGLU64 produces (blk = 64; blk = I is the plain
+ * [gate | up] layout of omni_swiglu_bwd). */
+int omni_swiglu_bwd_blocked(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, int32_t blk, void* stream);
 int omni_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
 int omni_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
 /* ResNet front-end glue of AV-HuBERT (av_hubert/avhubert/resnet.py:35-74,131-169), channels-last [rows, C]:

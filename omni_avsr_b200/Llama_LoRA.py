@@ -683,16 +683,32 @@ class LlamaMLP(nn.Module):
         self.up_proj = _LinearView(self.gate_up_weight[I:])
         self.down_proj = _LinearView((torch.randn(H, I, device=device) * std).to(torch.bfloat16))
         self._wt = None
+        self._il = None
 
     def transposed(self):
         if self._wt is None:
             self._wt = (self.gate_up_weight.t().contiguous(), self.down_proj.weight.data.t().contiguous())
+            self._il = None
         return self._wt
+
+    def interleaved(self):
+        """gate|up weight with 64-row gate / up blocks interleaved (+ its transpose) for the fused SwiGLU epilogue of the
+        training forward; derived copies like `_wt`, rebuilt after a state-dict load."""
+        self.transposed()
+        if self._il is None:
+            w = ag.interleave_gate_up(self.gate_up_weight)
+            self._il = (w, w.t().contiguous())
+        return self._il
 
     def forward(self, h, residual):
         wt_gu, wt_d = self.transposed()
-        gu = ag.frozen_linear(h, self.gate_up_weight, wt_gu, block_n=256)
-        act = ag.swiglu(gu)
+        I = self.gate_up_weight.shape[0] // 2
+        if h.requires_grad and I % 64 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I):
+            w_il, wt_il = self.interleaved()
+            act = ag.GateUpSwigluFn.apply(h, w_il, wt_il)          # SwiGLU in the gate_up GEMM's epilogue
+        else:
+            gu = ag.frozen_linear(h, self.gate_up_weight, wt_gu, block_n=256)
+            act = ag.swiglu(gu)
         return ag.frozen_linear(act, self.down_proj.weight.data, wt_d, residual=residual, block_n=256)
 
 

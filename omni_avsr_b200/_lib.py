@@ -48,6 +48,7 @@ class GemmArgs(C.Structure):
         ("a2_cols", C.c_int32), ("b2_rows", C.c_int32), ("b2_cols", C.c_int32),
         ("n_ext", C.c_int32), ("block_n", C.c_int32), ("act", C.c_int32), ("out_fp32", C.c_int32),
         ("alpha", C.c_float), ("pair_aligned", C.c_int32),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64),
     ]
 
 
@@ -108,6 +109,7 @@ _sig("omni_layernorm_bwd", [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P])
 _sig("omni_rope", [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P])
 _sig("omni_swiglu_fwd", [_P, _P, _I64, _I32, _P])
 _sig("omni_swiglu_bwd", [_P, _P, _P, _I64, _I32, _P])
+_sig("omni_swiglu_bwd_blocked", [_P, _P, _P, _I64, _I32, _I32, _P])
 _sig("omni_gelu_fwd", [_P, _P, _I64, _P])
 _sig("omni_gelu_bwd", [_P, _P, _P, _I64, _P])
 _sig("omni_gather_rows", [_P, _P, _P, _I64, _I32, _I64, _I64, _P, _P])
@@ -136,7 +138,7 @@ EXPORTS = [
     "omni_abi_version", "omni_device_cc", "omni_gemm_bf16", "omni_matryoshka_compress",
     "omni_matryoshka_compress_bwd", "omni_splice_seq_len", "omni_splice_prompt", "omni_splice_prompt_bwd",
     "omni_rmsnorm_fwd", "omni_rmsnorm_bwd", "omni_layernorm_fwd", "omni_layernorm_bwd", "omni_rope",
-    "omni_swiglu_fwd", "omni_swiglu_bwd", "omni_gelu_fwd", "omni_gelu_bwd", "omni_gather_rows", "omni_scatter_rows",
+    "omni_swiglu_fwd", "omni_swiglu_bwd", "omni_swiglu_bwd_blocked", "omni_gelu_fwd", "omni_gelu_bwd", "omni_gather_rows", "omni_scatter_rows",
     "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
     "omni_colsum_bf16", "omni_logmel_workspace_bytes", "omni_logmel", "omni_prelu_res", "omni_prelu_maxpool3x3s2",
     "omni_im2col_front3d", "omni_im2col_front2d", "omni_prelu_maxpool_front", "omni_attention_fwd", "omni_attention_bwd", "omni_decode_attention",

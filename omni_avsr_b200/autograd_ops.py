@@ -179,6 +179,41 @@ def swiglu(gu):
     return SwigluFn.apply(gu) if gu.requires_grad else ops.swiglu_fwd(gu)
 
 
+def interleave_gate_up(w_gu: torch.Tensor, blk: int = ops.SWIGLU_BLK) -> torch.Tensor:
+    """[gate I rows ; up I rows] -> [gate blk ; up blk ; gate blk ; ...] (the row order OMNI_ACT_SWIGLU64 expects)."""
+    I = w_gu.shape[0] // 2
+    g = w_gu[:I].reshape(I // blk, blk, -1)
+    u = w_gu[I:].reshape(I // blk, blk, -1)
+    return torch.stack((g, u), dim=1).reshape(2 * I, -1).contiguous()
+
+
+class GateUpSwigluFn(torch.autograd.Function):
+    """act = silu(x Wg^T) * (x Wu^T) with FROZEN weights in ONE GEMM launch: the SwiGLU runs in the epilogue of the gate_up
+    GEMM (block-interleaved weight rows), which also writes the gate|up tile the backward needs.  Backward:
+    d(gate|up) = swiglu_bwd(dact, gate|up) on the interleaved layout, dx = d(gate|up) @ W_il (pre-transposed copy)."""
+
+    @staticmethod
+    def forward(ctx, x, W_il, WT_il):
+        M, N = x.shape[0], W_il.shape[0]
+        gu = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+        act = torch.empty((M, N // 2), device=x.device, dtype=torch.bfloat16)
+        ops.gemm(x, W_il, out=gu, out2=act, act="swiglu64", block_n=256)
+        ctx.save_for_backward(gu)
+        ctx.WT = WT_il
+        return act
+
+    @staticmethod
+    def backward(ctx, dact):
+        (gu,) = ctx.saved_tensors
+        dgu = ops.swiglu_bwd(dact, gu, blk=ops.SWIGLU_BLK)
+        return ops.gemm(dgu, ctx.WT, block_n=256), None, None
+
+
+def gate_up_swiglu_supported(M: int, N: int) -> bool:
+    """Shapes the CTA-pair kernel takes for the fused epilogue (mirrors the dispatch in csrc/gemm_tcgen05.cu)."""
+    return N % 256 == 0 and M > 128 and ((M + 127) // 128) * (N // 256) >= 74
+
+
 class GeluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

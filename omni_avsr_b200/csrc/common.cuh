@@ -334,7 +334,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with the hardware reciprocal (MUFU.RCP, <= 1 ulp): an IEEE division costs ~12 instructions plus a
+// slow-path subroutine per element, which made the SwiGLU epilogue of the gate_up GEMM longer than its main loop.
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace omni
 

@@ -336,19 +336,21 @@ swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, long long
   }
 }
 
-// d_gu [rows, 2I] from d_act [rows, I] and the saved gu
+// d_gu [rows, 2I] from d_act [rows, I] and the saved gu.  gu / d_gu columns are [gate blk | up blk] blocks of blk8 16-byte
+// chunks (blk8 = I8: the plain [gate | up] halves; blk8 = 8: the 64-column interleave of OMNI_ACT_SWIGLU64).
 __global__ void __launch_bounds__(EW_THREADS)
 swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf16* __restrict__ dgu, long long rows,
-                  int I8, long long total) {
+                  int I8, int blk8, long long total) {
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(idx % I8);
     const long long r = idx / I8;
+    const int cg = (c / blk8) * 2 * blk8 + (c % blk8);
     const uint4* g4 = reinterpret_cast<const uint4*>(gu) + r * (2LL * I8);
     uint4* o4 = reinterpret_cast<uint4*>(dgu) + r * (2LL * I8);
     float g[8], u[8], d[8], dg[8], du[8];
-    unpack8(ld_nc_u4(g4 + c), g);
-    unpack8(ld_nc_u4(g4 + I8 + c), u);
+    unpack8(ld_nc_u4(g4 + cg), g);
+    unpack8(ld_nc_u4(g4 + cg + blk8), u);
     unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(dact) + idx), d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -357,8 +359,8 @@ swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __restrict__ gu, bf
       du[i] = d[i] * s;
       dg[i] = d[i] * u[i] * (sg * (1.0f + g[i] * (1.0f - sg)));
     }
-    st_na_u4(o4 + c, pack8(dg));
-    st_na_u4(o4 + I8 + c, pack8(du));
+    st_na_u4(o4 + cg, pack8(dg));
+    st_na_u4(o4 + cg + blk8, pack8(du));
   }
 }
 
@@ -499,16 +501,21 @@ extern "C" int omni_swiglu_fwd(const void* gu, void* act, int64_t rows, int32_t 
   return OMNI_OK;
 }
 
-extern "C" int omni_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, void* stream) {
-  OMNI_CHECK_ARG(dact && gu && dgu && rows >= 0 && I > 0 && (I % 8) == 0);
+extern "C" int omni_swiglu_bwd_blocked(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, int32_t blk,
+                                       void* stream) {
+  OMNI_CHECK_ARG(dact && gu && dgu && rows >= 0 && I > 0 && (I % 8) == 0 && blk > 0 && (blk % 8) == 0 && (I % blk) == 0);
   if (rows == 0) return OMNI_OK;
   const long long total = rows * (I / 8);
   long long blocks = ceil_div_ll(total, EW_THREADS);
   if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
   swiglu_bwd_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)dact, (const bf16*)gu,
-                                                                           (bf16*)dgu, rows, I / 8, total);
+                                                                           (bf16*)dgu, rows, I / 8, blk / 8, total);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
+}
+
+extern "C" int omni_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t I, void* stream) {
+  return omni_swiglu_bwd_blocked(dact, gu, dgu, rows, I, I, stream);
 }
 
 extern "C" int omni_gelu_fwd(const void* x, void* y, int64_t n, void* stream) {

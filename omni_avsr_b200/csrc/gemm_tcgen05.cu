@@ -39,6 +39,8 @@ struct GemmKParams {
   int act;
   int out_fp32;
   float alpha;
+  bf16* out2;        // OMNI_ACT_SWIGLU64: [M, N/2]
+  long long ldo2;
 };
 
 template <int BN, int STAGES>
@@ -196,6 +198,32 @@ __device__ __forceinline__ void res_tile_publish(uint8_t* stage, int lane, const
   __syncwarp();
 }
 
+// 32 rows x 64 bf16 columns held one row per thread -> global memory as full 128-byte rows through the warp's padded
+// transposition tile.
+__device__ __forceinline__ void store_tile64(bf16* out, long long ldo, int M, uint8_t* stage, const float (&v)[64], int lane,
+                                             int row0, int col0) {
+  uint8_t* my_row = stage + lane * EPI_PITCH;
+  const uint8_t* co_ptr = stage + (lane >> 3) * EPI_PITCH + (lane & 7) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 o;
+    o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
+    o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
+    o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
+    o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(my_row + 16 * i) = o;
+  }
+  __syncwarp();
+  bf16* op = out + static_cast<long long>(row0 + (lane >> 3)) * ldo + col0 + (lane & 7) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    if (row0 + (lane >> 3) + 4 * pass < M)
+      *reinterpret_cast<uint4*>(op + static_cast<long long>(4 * pass) * ldo) =
+          *reinterpret_cast<const uint4*>(co_ptr + 4 * pass * EPI_PITCH);
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* stage, float (&v)[64], int lane, int row0,
                                                 int col0, bool res_staged) {
   if (p.bias) {
@@ -235,24 +263,7 @@ __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* s
     }
     __syncwarp();
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    uint4 o;
-    o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
-    o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
-    o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
-    o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
-    *reinterpret_cast<uint4*>(my_row + 16 * i) = o;
-  }
-  __syncwarp();
-  bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row0 + (lane >> 3)) * p.ldo + col0 + (lane & 7) * 8;
-#pragma unroll
-  for (int pass = 0; pass < 8; ++pass) {
-    if (row0 + (lane >> 3) + 4 * pass < p.M)
-      *reinterpret_cast<uint4*>(op + static_cast<long long>(4 * pass) * p.ldo) =
-          *reinterpret_cast<const uint4*>(co_ptr + 4 * pass * EPI_PITCH);
-  }
-  __syncwarp();
+  store_tile64(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage, v, lane, row0, col0);
 }
 
 template <int BN, int STAGES>
@@ -947,8 +958,8 @@ struct GemmSmem2 {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
+template <int STAGES, bool SWIGLU = false>     // SWIGLU: the OMNI_ACT_SWIGLU64 epilogue (own instantiation: its 64 extra
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)   // registers stay out of the plain kernel)
 gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2h, const GemmKParams p,
                   const int m_fast) {
@@ -1110,6 +1121,7 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN2 + half * (BN2 / 2)) +
                                 (static_cast<uint32_t>(q * 32) << 16);
       if (fast) {
+        uint32_t gate[SWIGLU ? 32 : 1];       // the rounded gate block, packed bf16 pairs
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t r0[32], r1[32];
@@ -1132,7 +1144,22 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             res_tile_publish(stage_tile, lane, rt);
             if (c2 == 0) res_tile_prefetch(p, row0, n0 + 64, lane, rt);   // lands while block 0 is converted and stored
           }
-          epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);
+          epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);     // rounds v to bf16 when act != NONE
+          if constexpr (SWIGLU) {
+            // this thread's 128 columns are [gate 64 | up 64] of the same 64 intermediate channels
+            if (c2 == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) gate[i] = f2_to_bf2(v[2 * i], v[2 * i + 1]);      // exact: v is already rounded
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float2 g = bf2_to_f2(gate[i]);
+                v[2 * i] = __bfloat162float(__float2bfloat16_rn(silu(g.x))) * v[2 * i];
+                v[2 * i + 1] = __bfloat162float(__float2bfloat16_rn(silu(g.y))) * v[2 * i + 1];
+              }
+              store_tile64(p.out2, p.ldo2, p.M, stage_tile, v, lane, row0, n0 >> 1);
+            }
+          }
         }
       } else {
 #pragma unroll
@@ -1209,6 +1236,7 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
   p.out = a->out;
   p.ldo = a->ldo; p.ldr = a->ldr;
   p.act = a->act; p.out_fp32 = a->out_fp32; p.alpha = a->alpha;
+  p.out2 = reinterpret_cast<bf16*>(a->out2); p.ldo2 = a->ldo2;
 
   if constexpr (BN == 64) {
     // decode step: one tile of rows, few N tiles -> split K over a 4-CTA cluster so that enough SMs pull on HBM
@@ -1246,17 +1274,20 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     const long long a_bytes = static_cast<long long>(a->M) * a->K * 2;
     const int m_fast = (!a->b_row_table && !a->ext_table && p.m_tiles < p.n_tiles && a_bytes <= (40ll << 20)) ? 1 : 0;
     static const bool no_2cta = (getenv("OMNI_GEMM_NO_2CTA") != nullptr);
-    if (!no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) && p.m_tiles >= 2 &&
-        tiles >= sms / 2) {
+    const bool pair_ok = !no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) && p.m_tiles >= 2 &&
+                         tiles >= sms / 2;
+    if (a->act == OMNI_ACT_SWIGLU64 && !pair_ok) return OMNI_ERR_UNSUPPORTED;
+    if (pair_ok) {
       // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
       constexpr int ST2 = 5;     // 5 x 32 KB operand stages + 36 KB of epilogue transposition tiles
       using S2 = GemmSmem2<ST2>;
-      auto k2 = gemm_bf16_tn_2cta<ST2>;
-      static bool attr_set_2 = false;
-      if (!attr_set_2) {
+      const bool swiglu = a->act == OMNI_ACT_SWIGLU64;
+      auto k2 = swiglu ? gemm_bf16_tn_2cta<ST2, true> : gemm_bf16_tn_2cta<ST2, false>;
+      static bool attr_set_2[2] = {false, false};
+      if (!attr_set_2[swiglu]) {
         if (cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL) != cudaSuccess)
           return OMNI_ERR_CUDA;
-        attr_set_2 = true;
+        attr_set_2[swiglu] = true;
       }
       CUtensorMap tmBh, tmB2h2;
       rc = omni_make_tmap_2d_bf16(&tmBh, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, 128, BK, 1);
@@ -1338,6 +1369,11 @@ extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
     OMNI_CHECK_ARG((a->lda2 % 8) == 0 && (a->ldb2 % 8) == 0);
   }
   if (a->b_row_table || a->ext_table) OMNI_CHECK_ARG(a->block_n == 64 || a->block_n == 128 || a->block_n == 256);
+  if (a->act == OMNI_ACT_SWIGLU64) {
+    OMNI_CHECK_ARG(a->out2 && (a->ldo2 % 8) == 0 && a->ldo2 >= a->N / 2 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);
+    if (a->block_n != 256 || (a->N % 256) != 0 || a->out_fp32 || a->residual || a->bias || a->ext_table || a->b_row_table)
+      return OMNI_ERR_UNSUPPORTED;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
   if (bn == 0) bn = (a->N <= 64) ? 64 : 128;

@@ -11,7 +11,8 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, SpliceArgs, check, lib, ptr, require_cuda, stream_ptr
 
-ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3}
+SWIGLU_BLK = 64          # gate / up interleave of the OMNI_ACT_SWIGLU64 epilogue
 COMPRESS = {"avg-pooling": 0, "avg": 0, "stack": 1}
 
 # number of kernel launches issued through this module (bench.py reports it as gpu_launches)
@@ -37,10 +38,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
          alpha: float = 1.0, n: Optional[int] = None, tile_group: Optional[torch.Tensor] = None,
          b_row_table: Optional[torch.Tensor] = None, ext: Optional[tuple] = None, block_n: int = 0,
-         pair_aligned: bool = False) -> torch.Tensor:
+         pair_aligned: bool = False, out2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epi(alpha * (a[M,K] @ b[rows,K]^T (+ K-extension)))  -- tcgen05 kernel.
 
     ext = (a2 [M, a2_cols], b2 [b2_rows, b2_cols], ext_table int32 [groups, n_tiles, n_ext, 4]).
+    act="swiglu64": b's rows are [gate 64 | up 64] interleaved blocks; out2 [M, N/2] (required) receives
+    bf16(bf16(silu(gate)) * up); raises OmniKernelError(OMNI_ERR_UNSUPPORTED) when the shape is not one the CTA-pair
+    kernel takes -- the caller then runs the unfused gemm + swiglu_fwd pair.
     """
     require_cuda(a, b, bias, residual, out, tile_group, b_row_table)
     a = _bf16_2d(a, "a")
@@ -97,6 +101,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     g.block_n = block_n
     g.pair_aligned = 1 if pair_aligned else 0
     g.act = ACT[act]
+    if act == "swiglu64":
+        require_cuda(out2)
+        if out2 is None or out2.dtype != torch.bfloat16 or out2.shape != (M, N // 2) or out2.stride(1) != 1:
+            raise ValueError("swiglu64 needs out2: bf16 [M, N/2]")
+        g.out2, g.ldo2 = out2.data_ptr(), out2.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     g.alpha = float(alpha)
     check(lib.omni_gemm_bf16(C.byref(g), stream_ptr()), "omni_gemm_bf16")
@@ -301,12 +310,14 @@ def swiglu_fwd(gu):
     return act
 
 
-def swiglu_bwd(dact, gu):
+def swiglu_bwd(dact, gu, blk: Optional[int] = None):
+    """blk: gate / up column interleave of `gu` (None = the plain [gate | up] halves, 64 = the swiglu64 GEMM layout)."""
+    require_cuda(dact, gu)
     dact = dact.contiguous()
     rows, I2 = gu.shape
     dgu = torch.empty_like(gu)
-    check(lib.omni_swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, I2 // 2, stream_ptr()),
-          "omni_swiglu_bwd")
+    check(lib.omni_swiglu_bwd_blocked(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, I2 // 2,
+                                      I2 // 2 if blk is None else blk, stream_ptr()), "omni_swiglu_bwd_blocked")
     _count()
     return dgu
 
