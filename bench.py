@@ -286,6 +286,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,
+        "hbm_kernels": hbm_kernel_rooflines(B, device, load_peaks()) if args.workload == "omni" else None,
         "decode": decode,
     }
     if world == 1 and not args.no_cpu_baseline and args.workload == "omni":
@@ -293,6 +294,51 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_kernel_rooflines(B, device, peaks):
+    """Live CUDA-event timings (L2 flushed) of the HBM-bound kernels of north_star subsystem (1) at the bench batch:
+    Matryoshka compression (avg-pool, audio rate 4 / video rate 2 from the untruncated encoder outputs) and the splice /
+    label kernel (rates (4, 2): 200 audio + 200 video tokens).  Algorithmic bytes as in SURVEY.md 8(d)."""
+    from omni_avsr_b200 import ops
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def timeit(fn, iters=9):
+        fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return sorted(ts)[len(ts) // 2]
+    out = {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["_source"], "batch": B,
+           "how": "median of 9 launches, CUDA events, 256 MiB written between launches; bytes = algorithmic read + write"}
+    for name, T, n_tok, rate in (("compress_avg_audio_r4", 1500, 800, 4), ("compress_avg_video_r2", 400, 400, 2)):
+        x = torch.randn(B, T, 1024, device=device).bfloat16()
+        ms = timeit(lambda: ops.matryoshka_compress(x, n_tok, rate, "avg-pooling"))
+        n = n_tok // rate
+        byts = B * n * rate * 1024 * 2 + B * n * 1024 * 2
+        out[name] = {"us": round(ms * 1e3, 1), "GBs": round(byts / ms / 1e6, 1), "frac": round(byts / ms / 1e6 / peaks["hbm_gbs"], 3)}
+    H, V, L, n_a, n_v = 2048, 128261, 48, 200, 200
+    embed = torch.randn(V, H, device=device).bfloat16()
+    tokens = torch.randint(0, V, (B, L), device=device)
+    a = torch.randn(B, n_a, H, device=device).bfloat16()
+    v = torch.randn(B, n_v, H, device=device).bfloat16()
+    prompts = [torch.randn(pl, H, device=device).bfloat16() for pl in (6, 6, 8)]
+    lay = ops.SpliceLayout(tokens=tokens, labels=tokens, embed=embed, audio_tok=a, video_tok=v, prompts=prompts,
+                           marker_ids=(V - 4, V - 3, V - 2, V - 1), has_bos=True)
+    outs = [torch.empty(B, sl, H, device=device, dtype=torch.bfloat16) for sl in lay.seq_len]
+    outl = [torch.empty(B, sl, device=device, dtype=torch.int64) for sl in lay.seq_len]
+    ms = timeit(lambda: ops.splice_prompt(lay, outs, outl))
+    rows = B * sum(lay.seq_len)
+    byts = rows * H * 2 + rows * 8 + (B * (n_a + n_v) + rows - 2 * B * (n_a + n_v)) * H * 2
+    out["splice_train_3tasks"] = {"us": round(ms * 1e3, 1), "GBs": round(byts / ms / 1e6, 1),
+                                  "frac": round(byts / ms / 1e6 / peaks["hbm_gbs"], 3), "rows": rows}
+    return out
 
 
 def build_oracle():
