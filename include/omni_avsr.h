@@ -32,6 +32,10 @@ extern "C" {
  * i.e. bit-identical to omni_swiglu_fwd on `out`.  CTA-pair kernel only (N % 256 == 0, no bias / residual / fp32 output);
  * OMNI_ERR_UNSUPPORTED otherwise. */
 #define OMNI_ACT_SWIGLU64 3
+/* GELU with the pre-activation kept (AV-HuBERT fc1 while its LoRA adapters train: the backward needs x): `out` [M, N] =
+ * bf16(A.B^T + bias), `out2` [M, N] (ld = ldo2) = bf16(gelu(out)) with the same erf formula as OMNI_ACT_GELU.  CTA-pair
+ * kernel only; OMNI_ERR_UNSUPPORTED otherwise. */
+#define OMNI_ACT_GELU_KEEP 4
 
 #define OMNI_COMPRESS_AVG 0   /* nn.AvgPool1d(r)  : modeling_OmniAVSR.py:544-546 (audio), :469-471 (video) */
 #define OMNI_COMPRESS_STACK 1 /* frame stacking   : modeling_OmniAVSR.py:562-568 (audio), :487-493 (video) */
@@ -69,7 +73,7 @@ typedef struct omni_gemm_args {
   float alpha;
   int32_t pair_aligned;    /* 1: tile_group is constant over every pair of consecutive 128-row tiles (segments start on
                               256-row boundaries), which lets the K-extended GEMM run on the CTA-pair kernel */
-  void* out2;              /* OMNI_ACT_SWIGLU64: [M, N/2] bf16, ld = ldo2; else NULL */
+  void* out2;              /* OMNI_ACT_SWIGLU64: [M, N/2] bf16; OMNI_ACT_GELU_KEEP: [M, N] bf16; ld = ldo2; else NULL */
   int64_t ldo2;
 } omni_gemm_args;
 

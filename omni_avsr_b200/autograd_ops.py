@@ -211,7 +211,7 @@ class GateUpSwigluFn(torch.autograd.Function):
 
 def gate_up_swiglu_supported(M: int, N: int) -> bool:
     """Shapes the CTA-pair kernel takes for the fused epilogue (mirrors the dispatch in csrc/gemm_tcgen05.cu)."""
-    return N % 256 == 0 and M > 128 and ((M + 127) // 128) * (N // 256) >= 74
+    return pair_kernel_shape(M, N)
 
 
 class GeluFn(torch.autograd.Function):
@@ -228,6 +228,31 @@ class GeluFn(torch.autograd.Function):
 
 def gelu(x):
     return GeluFn.apply(x) if x.requires_grad else ops.gelu_fwd(x)
+
+
+class FrozenLinearGeluFn(torch.autograd.Function):
+    """gelu(x @ W^T + b) with a FROZEN weight while something upstream trains (AV-HuBERT fc1 under LoRA fine-tuning): ONE
+    GEMM launch writes the pre-activation (saved for the backward) and the activation; backward = gelu_bwd + dgrad GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, W, WT, bias):
+        M, N = x.shape[0], W.shape[0]
+        pre = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+        act = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+        ops.gemm(x, W, bias=bias, out=pre, out2=act, act="gelu_keep", block_n=256)
+        ctx.save_for_backward(pre)
+        ctx.WT = WT
+        return act
+
+    @staticmethod
+    def backward(ctx, dact):
+        (pre,) = ctx.saved_tensors
+        return ops.gemm(ops.gelu_bwd(dact.contiguous(), pre), ctx.WT, block_n=256), None, None, None
+
+
+def pair_kernel_shape(M: int, N: int) -> bool:
+    """Shapes omni_gemm_bf16 runs on the CTA-pair kernel with 256-column tiles (the only one with the fused epilogues)."""
+    return N % 256 == 0 and M > 128 and ((M + 127) // 128) * (N // 256) >= 74
 
 
 class LoraLinearFn(torch.autograd.Function):

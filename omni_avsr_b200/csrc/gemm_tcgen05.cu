@@ -958,8 +958,10 @@ struct GemmSmem2 {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-template <int STAGES, bool SWIGLU = false>     // SWIGLU: the OMNI_ACT_SWIGLU64 epilogue (own instantiation: its 64 extra
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)   // registers stay out of the plain kernel)
+// EPI: 0 plain epilogue, 1 OMNI_ACT_SWIGLU64, 2 OMNI_ACT_GELU_KEEP (own instantiations: their extra registers stay out of
+// the plain kernel)
+template <int STAGES, int EPI = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2h, const GemmKParams p,
                   const int m_fast) {
@@ -1121,7 +1123,7 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN2 + half * (BN2 / 2)) +
                                 (static_cast<uint32_t>(q * 32) << 16);
       if (fast) {
-        uint32_t gate[SWIGLU ? 32 : 1];       // the rounded gate block, packed bf16 pairs
+        uint32_t gate[EPI == 1 ? 32 : 1];     // the rounded gate block, packed bf16 pairs
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t r0[32], r1[32];
@@ -1145,7 +1147,13 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (c2 == 0) res_tile_prefetch(p, row0, n0 + 64, lane, rt);   // lands while block 0 is converted and stored
           }
           epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);     // rounds v to bf16 when act != NONE
-          if constexpr (SWIGLU) {
+          if constexpr (EPI == 2) {
+            // v holds the rounded pre-activation that was just stored: second output = gelu of it
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = gelu_fast(v[i]);
+            store_tile64(p.out2, p.ldo2, p.M, stage_tile, v, lane, row0, n0 + c2 * 64);
+          }
+          if constexpr (EPI == 1) {
             // this thread's 128 columns are [gate 64 | up 64] of the same 64 intermediate channels
             if (c2 == 0) {
 #pragma unroll
@@ -1276,18 +1284,18 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     static const bool no_2cta = (getenv("OMNI_GEMM_NO_2CTA") != nullptr);
     const bool pair_ok = !no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) && p.m_tiles >= 2 &&
                          tiles >= sms / 2;
-    if (a->act == OMNI_ACT_SWIGLU64 && !pair_ok) return OMNI_ERR_UNSUPPORTED;
+    if ((a->act == OMNI_ACT_SWIGLU64 || a->act == OMNI_ACT_GELU_KEEP) && !pair_ok) return OMNI_ERR_UNSUPPORTED;
     if (pair_ok) {
       // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
       constexpr int ST2 = 5;     // 5 x 32 KB operand stages + 36 KB of epilogue transposition tiles
       using S2 = GemmSmem2<ST2>;
-      const bool swiglu = a->act == OMNI_ACT_SWIGLU64;
-      auto k2 = swiglu ? gemm_bf16_tn_2cta<ST2, true> : gemm_bf16_tn_2cta<ST2, false>;
-      static bool attr_set_2[2] = {false, false};
-      if (!attr_set_2[swiglu]) {
+      const int epi = a->act == OMNI_ACT_SWIGLU64 ? 1 : a->act == OMNI_ACT_GELU_KEEP ? 2 : 0;
+      auto k2 = epi == 1 ? gemm_bf16_tn_2cta<ST2, 1> : epi == 2 ? gemm_bf16_tn_2cta<ST2, 2> : gemm_bf16_tn_2cta<ST2, 0>;
+      static bool attr_set_2[3] = {false, false, false};
+      if (!attr_set_2[epi]) {
         if (cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL) != cudaSuccess)
           return OMNI_ERR_CUDA;
-        attr_set_2[swiglu] = true;
+        attr_set_2[epi] = true;
       }
       CUtensorMap tmBh, tmB2h2;
       rc = omni_make_tmap_2d_bf16(&tmBh, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, 128, BK, 1);
@@ -1369,6 +1377,11 @@ extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
     OMNI_CHECK_ARG((a->lda2 % 8) == 0 && (a->ldb2 % 8) == 0);
   }
   if (a->b_row_table || a->ext_table) OMNI_CHECK_ARG(a->block_n == 64 || a->block_n == 128 || a->block_n == 256);
+  if (a->act == OMNI_ACT_GELU_KEEP) {
+    OMNI_CHECK_ARG(a->out2 && (a->ldo2 % 8) == 0 && a->ldo2 >= a->N && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);
+    if (a->block_n != 256 || (a->N % 256) != 0 || a->out_fp32 || a->residual || a->ext_table || a->b_row_table)
+      return OMNI_ERR_UNSUPPORTED;
+  }
   if (a->act == OMNI_ACT_SWIGLU64) {
     OMNI_CHECK_ARG(a->out2 && (a->ldo2 % 8) == 0 && a->ldo2 >= a->N / 2 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);
     if (a->block_n != 256 || (a->N % 256) != 0 || a->out_fp32 || a->residual || a->bias || a->ext_table || a->b_row_table)

@@ -449,7 +449,9 @@ class AVHLayer(nn.Module):
         o = att.sdpa(qkv, B, T)       # q * head_dim^-0.5 (:511) is SDPA's default scale (exact: power of two)
         x = ag.frozen_linear(o, att.out_proj.weight.data, wt_o, bias=att.out_proj.bias.data, residual=res, block_n=256)
         res, h = self.final_layer_norm.with_residual(x)
-        if h.requires_grad:
+        if h.requires_grad and ag.pair_kernel_shape(h.shape[0], self.fc1.weight.shape[0]):
+            f = ag.FrozenLinearGeluFn.apply(h, self.fc1.weight.data, wt1, self.fc1.bias.data)   # GELU in the GEMM epilogue
+        elif h.requires_grad:
             f = ag.frozen_linear(h, self.fc1.weight.data, wt1, bias=self.fc1.bias.data, block_n=256)
             f = ag.gelu(f)
         else:

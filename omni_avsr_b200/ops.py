@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, SpliceArgs, check, lib, ptr, require_cuda, stream_ptr
 
-ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3}
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3, "gelu_keep": 4}
 SWIGLU_BLK = 64          # gate / up interleave of the OMNI_ACT_SWIGLU64 epilogue
 COMPRESS = {"avg-pooling": 0, "avg": 0, "stack": 1}
 
@@ -45,6 +45,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     act="swiglu64": b's rows are [gate 64 | up 64] interleaved blocks; out2 [M, N/2] (required) receives
     bf16(bf16(silu(gate)) * up); raises OmniKernelError(OMNI_ERR_UNSUPPORTED) when the shape is not one the CTA-pair
     kernel takes -- the caller then runs the unfused gemm + swiglu_fwd pair.
+    act="gelu_keep": out = bf16(a @ b^T + bias) (the pre-activation the backward needs), out2 [M, N] = bf16(gelu(out)).
     """
     require_cuda(a, b, bias, residual, out, tile_group, b_row_table)
     a = _bf16_2d(a, "a")
@@ -101,10 +102,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     g.block_n = block_n
     g.pair_aligned = 1 if pair_aligned else 0
     g.act = ACT[act]
-    if act == "swiglu64":
+    if act in ("swiglu64", "gelu_keep"):
         require_cuda(out2)
-        if out2 is None or out2.dtype != torch.bfloat16 or out2.shape != (M, N // 2) or out2.stride(1) != 1:
-            raise ValueError("swiglu64 needs out2: bf16 [M, N/2]")
+        n2 = N // 2 if act == "swiglu64" else N
+        if out2 is None or out2.dtype != torch.bfloat16 or out2.shape != (M, n2) or out2.stride(1) != 1:
+            raise ValueError(f"{act} needs out2: bf16 [M, {n2}]")
         g.out2, g.ldo2 = out2.data_ptr(), out2.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     g.alpha = float(alpha)

@@ -59,3 +59,29 @@ def test_unsupported_shapes_are_refused():
     W = torch.zeros(512, 256, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(OmniKernelError):
         ops.gemm(x, W, act="swiglu64", block_n=256, out2=torch.empty(64, 256, device="cuda", dtype=torch.bfloat16))
+
+
+def test_gelu_keep_epilogue_matches_separate_kernels():
+    """OMNI_ACT_GELU_KEEP: pre-activation bit-identical to the plain bias GEMM, activation bit-identical to the fused-GELU
+    GEMM (same erf formula), and within 1e-2 of torch's exact GELU; backward through FrozenLinearGeluFn matches the unfused
+    chain bit for bit (same kernels, same order)."""
+    from omni_avsr_b200 import autograd_ops as ag
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, K, N = 12800, 1024, 4096
+    x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = (torch.randn(N, device="cuda", generator=g) * 0.1).bfloat16()
+    assert ag.pair_kernel_shape(M, N)
+    pre = ops.gemm(x, W, bias=b, block_n=256)
+    act = ops.gemm(x, W, bias=b, act="gelu", block_n=256)
+    xg = x.clone().requires_grad_(True)
+    WT = W.t().contiguous()
+    act_f = ag.FrozenLinearGeluFn.apply(xg, W, WT, b)
+    assert _bits(act_f.detach(), act)
+    ref = torch.nn.functional.gelu(pre[:256].float())
+    assert ((act_f[:256].float() - ref).abs().max() / ref.abs().max()).item() <= 1e-2
+    dact = (torch.randn(M, N, device="cuda", generator=g) * 0.1).bfloat16()
+    act_f.backward(dact)
+    dx = ops.gemm(ops.gelu_bwd(dact, pre), WT, block_n=256)
+    assert _bits(xg.grad, dx)
