@@ -261,6 +261,24 @@ int omni_sumsq(const void* g, int64_t n, float* acc, void* stream);
 int omni_adamw(void* p, const void* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int32_t step, float grad_scale, float max_norm, const float* sumsq, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-device input pipeline (datamodule/transforms.py of the reference), one utterance per call.
+ * omni_video_transform: VideoTransform (:83-104): uint8 frames [T, C (1 or 3), H, W] -> x/255 -> crop 88x88 at
+ *   (crop_i, crop_j) (RandomCrop / CenterCrop offsets chosen by the caller) -> torchvision Grayscale -> AdaptiveTimeMask
+ *   (:36-56: frames t in [spans[2k], spans[2k+1]) zeroed) -> Normalize(0.421, 0.165); out [T, 1, 88, 88] fp32 (bit-exact
+ *   with the reference's fp32 result) or bf16 (out_bf16 = 1: the cast Lightning's bf16-true applies next).
+ * omni_audio_transform: AudioTransform (:107-131): wave [T] fp32 -> AdaptiveTimeMask (samples in the spans zeroed) ->
+ *   AddNoise (:59-80, torchaudio.functional.add_noise at snr_db; noise = NULL skips it) -> layer_norm over the whole
+ *   utterance (eps 1e-8).  `spans` are HOST arrays of [start, end) pairs (at most OMNI_MAX_MASK_SPANS, passed by value to
+ *   the kernels); workspace >= omni_audio_transform_workspace_bytes() device bytes.
+ * ---------------------------------------------------------------------------------------------- */
+#define OMNI_MAX_MASK_SPANS 48
+int omni_video_transform(const void* frames, int32_t T, int32_t C, int32_t H, int32_t W, int32_t crop_i, int32_t crop_j,
+                         const int32_t* spans, int32_t n_spans, void* out, int32_t out_bf16, void* stream);
+int64_t omni_audio_transform_workspace_bytes(void);
+int omni_audio_transform(const float* wave, const float* noise, int64_t T, float snr_db, const int32_t* spans,
+                         int32_t n_spans, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,8 @@ What runs is the unmodified reference code, imported through the name-only shims
     encoder is a stand-in (its output is stored, the test feeds it back), `.cuda()` is patched to a no-op;
   * `Omni_AVSR/modeling_LlamaAVSR.py`  AVSR_LLMs (Llama-AVSR and Llama-MTSK: every rate / rate pair per step), same
     stand-ins;
-  * `av_hubert/fairseq/fairseq/modules/multihead_attention.py`  MultiheadAttention.forward_lora.
+  * `av_hubert/fairseq/fairseq/modules/multihead_attention.py`  MultiheadAttention.forward_lora;
+  * `datamodule/transforms.py`  VideoTransform / AudioTransform (train and val pipelines, seeded RNGs).
 
 Weights are NOT stored: they are regenerated from a seed by `golden_weights` (CPU mt19937 `randn`), a checksum guards
 against RNG drift.  tests/test_reference_golden.py compares the oracle with this file on CPU and the CUDA path with it
@@ -411,6 +412,43 @@ def build_llamaavsr_cases(ll, ql, mla):
     return cases
 
 
+def build_transform_cases():
+    """Executes the reference's datamodule/transforms.py (VideoTransform / AudioTransform pipelines) on seeded inputs.
+    AddNoise.__init__ loads babble_noise.wav (absent from the tree, and torchaudio.load needs torchcodec here): the module
+    is built without calling it and given a synthetic noise waveform; its forward is the reference's."""
+    import _ref_compat as rc
+    tr = rc.load_by_path("ref_datamodule_transforms", "datamodule/transforms.py")
+    g = torch.Generator().manual_seed(2100)
+    video = torch.randint(0, 256, (8, 3, 96, 96), generator=g, dtype=torch.uint8)
+    gray = torch.randint(0, 256, (16, 1, 90, 92), generator=g, dtype=torch.uint8)
+    wave = torch.randn(24000, 1, generator=g) * 0.1
+    noise = torch.randn(1, 40000, generator=g) * 0.3
+    out = dict(video=video, gray=gray, wave=wave, noise=noise, cases={})
+
+    def seeded(seed, fn):
+        torch.manual_seed(seed)
+        random.seed(seed)
+        return fn()
+    out["cases"]["video_train"] = dict(seed=11, out=seeded(11, lambda: tr.VideoTransform("train")(video)))
+    out["cases"]["video_val"] = dict(seed=12, out=seeded(12, lambda: tr.VideoTransform("val")(video)))
+    out["cases"]["gray_train"] = dict(seed=13, out=seeded(13, lambda: tr.VideoTransform("train")(gray)))
+
+    def add_noise_module(snr_target=None):
+        m = tr.AddNoise.__new__(tr.AddNoise)
+        nn.Module.__init__(m)
+        m.snr_levels = [snr_target] if snr_target else [-5, 0, 5, 10, 15, 20, 999999]      # transforms.py:66
+        m.noise = noise
+        return m
+    ln = tr.FunctionalModule(lambda x: torch.nn.functional.layer_norm(x, x.shape, eps=1e-8))
+    train_pipe = nn.Sequential(tr.AdaptiveTimeMask(6400, 16000), add_noise_module(), ln)       # :110-117
+    out["cases"]["audio_train"] = dict(seed=21, out=seeded(21, lambda: train_pipe(wave)))
+    out["cases"]["audio_train2"] = dict(seed=22, out=seeded(22, lambda: train_pipe(wave)))
+    out["cases"]["audio_val"] = dict(seed=23, out=seeded(23, lambda: tr.AudioTransform("val")(wave)))
+    snr_pipe = nn.Sequential(add_noise_module(5), ln)                                          # :119-128 with snr_target
+    out["cases"]["audio_val_snr5"] = dict(seed=24, out=seeded(24, lambda: snr_pipe(wave)))
+    return out
+
+
 def build_mha_case(mha):
     torch.manual_seed(900)
     E, Hh, T, B = 128, 2, 11, 2
@@ -438,7 +476,7 @@ def main():
     _patch_ref(ll, ql)
     mla = rc.load_by_path("Omni_AVSR.modeling_LlamaAVSR", "Omni_AVSR/modeling_LlamaAVSR.py", "Omni_AVSR")
     out = dict(llm=build_llm_cases(ll, ql), omni=build_omni_cases(ll, ql, mo), llamaavsr=build_llamaavsr_cases(ll, ql, mla),
-               mha=build_mha_case(mha),
+               mha=build_mha_case(mha), transforms=build_transform_cases(),
                meta=dict(torch=torch.__version__, note="outputs of /root/reference sources executed on CPU, bf16"))
     torch.save(out, OUT)
     print("written", OUT, os.path.getsize(OUT))

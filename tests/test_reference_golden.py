@@ -525,3 +525,68 @@ def test_gpu_llamaavsr_splice_loss_decode_vs_reference(name):
         ids = model.generate(inputs_embeds=inf["embeddings"].cuda(), max_new_tokens=6, num_beams=1, eos_token_id=2,
                              pad_token_id=2 if is_qwen else v["<pad>"])
         _greedy_ok(ids, inf["greedy"], inf["margins"], name)
+
+
+# ------------------------------------------------------------------------------------------------ input pipeline
+# (datamodule/transforms.py executed from the reference tree; fixtures under GOLD["transforms"])
+def _seed(s):
+    import random
+    torch.manual_seed(s)
+    random.seed(s)
+
+
+def test_oracle_transforms_match_reference_bit_for_bit():
+    from oracle import transforms as otr
+    t = GOLD["transforms"]
+    c = t["cases"]
+    _seed(c["video_train"]["seed"])
+    assert torch.equal(otr.video_transform(t["video"], "train"), c["video_train"]["out"])
+    _seed(c["video_val"]["seed"])
+    assert torch.equal(otr.video_transform(t["video"], "val"), c["video_val"]["out"])
+    _seed(c["gray_train"]["seed"])
+    assert torch.equal(otr.video_transform(t["gray"], "train"), c["gray_train"]["out"])
+    for name in ("audio_train", "audio_train2"):
+        _seed(c[name]["seed"])
+        assert torch.equal(otr.audio_transform(t["wave"], "train", noise=t["noise"]), c[name]["out"])
+    _seed(c["audio_val"]["seed"])
+    assert torch.equal(otr.audio_transform(t["wave"], "val"), c["audio_val"]["out"])
+    _seed(c["audio_val_snr5"]["seed"])
+    assert torch.equal(otr.audio_transform(t["wave"], "val", noise=t["noise"], snr_target=5), c["audio_val_snr5"]["out"])
+    # the fixture exercises the masks: some but not all frames / samples are zeroed before normalisation
+    masked = (c["gray_train"]["out"] == (0.0 - 0.421) / 0.165).flatten(1).all(1)
+    assert 0 < int(masked.sum()) < masked.numel()
+
+
+@pytest.mark.gpu
+def test_gpu_video_transform_bit_exact_vs_reference():
+    """CUDA VideoTransform (x/255, crop, grayscale, time mask, normalise in one kernel) against the reference's torchvision
+    pipeline: every fp32 value identical; same seeds -> same RandomCrop offsets and mask spans."""
+    from omni_avsr_b200 import transforms as ptr
+    t = GOLD["transforms"]
+    c = t["cases"]
+    for name, clip, subset in (("video_train", "video", "train"), ("video_val", "video", "val"), ("gray_train", "gray", "train")):
+        _seed(c[name]["seed"])
+        got = ptr.VideoTransform(subset)(t[clip])
+        assert got.shape == c[name]["out"].shape and got.dtype == torch.float32
+        assert torch.equal(got.cpu(), c[name]["out"]), name
+    _seed(c["video_train"]["seed"])
+    got16 = ptr.VideoTransform("train", out_dtype=torch.bfloat16)(t["video"])
+    assert torch.equal(got16.cpu(), c["video_train"]["out"].bfloat16())
+
+
+@pytest.mark.gpu
+def test_gpu_audio_transform_vs_reference():
+    """CUDA AudioTransform (time mask, add_noise at the sampled SNR, utterance layer-norm) against the reference's
+    torchaudio pipeline.  The reductions run in fp64 on the device and in fp32 on the CPU: max|a-b| <= 1e-4 on unit-variance
+    output; samples inside a mask span of the noise-free pipeline are the same constant."""
+    from omni_avsr_b200 import transforms as ptr
+    t = GOLD["transforms"]
+    c = t["cases"]
+    for name, kw in (("audio_train", dict(subset="train", noise=t["noise"])), ("audio_train2", dict(subset="train", noise=t["noise"])),
+                     ("audio_val", dict(subset="val")), ("audio_val_snr5", dict(subset="val", snr_target=5, noise=t["noise"]))):
+        tr = ptr.AudioTransform(**kw)
+        _seed(c[name]["seed"])
+        got = tr(t["wave"])
+        want = c[name]["out"]
+        assert got.shape == want.shape
+        assert (got.cpu() - want).abs().max().item() <= 1e-4, (name, (got.cpu() - want).abs().max().item())

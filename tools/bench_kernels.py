@@ -130,6 +130,24 @@ def bench_attention():
                           "sdpa_fwd_ms": round(medl, 4), "sdpa_bwd_ms": round(medlb, 4)}), flush=True)
 
 
+def bench_transforms():
+    """Input-pipeline kernels on one 16 s utterance (400 RGB 96x96 frames, 256000 samples), train pipelines."""
+    from omni_avsr_b200 import transforms as ptr
+    video = torch.randint(0, 256, (400, 3, 96, 96), dtype=torch.uint8, device="cuda")
+    vt = ptr.VideoTransform("train", out_dtype=torch.bfloat16)
+    med, _ = timeit(lambda: vt(video))
+    byts = 400 * 3 * 88 * 88 + 400 * 88 * 88 * 2
+    print(json.dumps({"kernel": "video_transform(train, bf16 out)", "frames": 400, "ms": round(med, 4),
+                      "GBs": round(byts / med / 1e6, 1), "note": "includes the host-side RNG draws of the mirror"}), flush=True)
+    wave = torch.randn(256000, 1, device="cuda") * 0.1
+    at = ptr.AudioTransform("train", noise=torch.randn(1, 400000) * 0.3)
+    med, _ = timeit(lambda: at(wave))
+    byts = 256000 * 4 * (2 + 2 + 1)
+    print(json.dumps({"kernel": "audio_transform(train)", "samples": 256000, "ms": round(med, 4),
+                      "GBs": round(byts / med / 1e6, 1), "note": "two passes (sums, apply); includes host-side RNG draws"}),
+          flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "compress", "splice"]
     if "compress" in which:
@@ -140,3 +158,5 @@ if __name__ == "__main__":
         bench_gemm()
     if "attention" in which:
         bench_attention()
+    if "transforms" in which:
+        bench_transforms()
