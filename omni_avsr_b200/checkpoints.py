@@ -101,25 +101,34 @@ def load_avhubert(video_encoder, checkpoint) -> Tuple[List[str], List[str]]:
     return missing, ignored
 
 
+def _model_states(ckpt) -> Dict[str, torch.Tensor]:
+    """The `model.`-prefixed entries of a Lightning checkpoint, prefix removed (what ModelModule_LLM.model holds)."""
+    if isinstance(ckpt, (str, os.PathLike)):
+        ckpt = torch.load(ckpt, map_location="cpu")
+    return {k[len("model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("model.")}
+
+
 def average_checkpoints(last):
-    """utils/avg_checkpoints.py:14-31.  `last`: paths of Lightning checkpoints (or already loaded dicts)."""
-    avg = None
-    for path in last:
-        ck = torch.load(path, map_location=lambda storage, loc: storage) if isinstance(path, (str, os.PathLike)) else path
-        states = ck["state_dict"]
-        states = {k[6:]: v.clone() for k, v in states.items() if k.startswith("model.")}
-        if avg is None:
-            avg = states
+    """Element-wise mean of the model tensors of several Lightning checkpoints, with the arithmetic of
+    utils/avg_checkpoints.py:14-31: a running sum in each tensor's own dtype (bf16 sums round at every addition), then a true
+    division for floating-point tensors and a floor division for integer ones.  `last`: paths or loaded checkpoint dicts."""
+    count = len(last)
+    total: Dict[str, torch.Tensor] = {}
+    for n, item in enumerate(last):
+        states = _model_states(item)
+        if n == 0:
+            total = {k: v.clone() for k, v in states.items()}
         else:
-            for k in avg.keys():
-                avg[k] += states[k]
-    for k in avg.keys():
-        if avg[k] is not None:
-            if avg[k].is_floating_point():
-                avg[k] /= len(last)
-            else:
-                avg[k] //= len(last)
-    return avg
+            for k in total:
+                total[k].add_(states[k])
+    for k, v in total.items():
+        if v is None:
+            continue
+        if v.is_floating_point():
+            v.div_(count)
+        else:
+            v.floor_divide_(count)
+    return total
 
 
 def ensemble_original(args, num_average_epochs=10):

@@ -26,18 +26,15 @@ MAX_SPANS = 48
 def adaptive_time_mask_spans(length: int, window: int, stride: int) -> List[Tuple[int, int]]:
     """AdaptiveTimeMask.forward (:42-56) without touching the data: the [start, end) spans it would zero."""
     n_mask = int((length + stride - 0.1) // stride)
-    ts = torch.randint(0, window, size=(n_mask, 2))
+    draws = torch.randint(0, window, size=(n_mask, 2)).tolist()      # column 0 bounds the start, column 1 is the width
     spans = []
-    for t, t_end in ts:
-        t, t_end = int(t), int(t_end)
-        if length - t <= 0:
+    for bound, width in draws:
+        if bound >= length:                                           # reference: `length - t <= 0`
             continue
-        t_start = random.randrange(0, length - t)
-        if t_start == t_start + t:
+        start = random.randrange(0, length - bound)                   # drawn even when the row is then discarded
+        if bound == 0 or width == 0:                                  # `t_start == t_start + t` / empty slice
             continue
-        t_end += t_start
-        if t_end > t_start:
-            spans.append((t_start, min(t_end, length)))
+        spans.append((start, min(start + width, length)))
     return spans
 
 

@@ -12,20 +12,30 @@ import torchaudio
 import torchvision
 
 
-def adaptive_time_mask(x, window, stride):                         # :36-56
-    cloned = x.clone()
-    length = cloned.size(0)
+def time_mask_spans(length, window, stride):
+    """The [start, stop) ranges AdaptiveTimeMask (:36-56) zeroes, with its RNG draws in its order: one
+    `torch.randint(0, window, (n_mask, 2))` (column 0 bounds the start, column 1 is the span length), then one
+    `random.randrange` per usable row."""
     n_mask = int((length + stride - 0.1) // stride)
-    ts = torch.randint(0, window, size=(n_mask, 2))
-    for t, t_end in ts:
-        if length - t <= 0:
+    draws = torch.randint(0, window, size=(n_mask, 2)).tolist()
+    spans = []
+    for bound, width in draws:
+        if bound >= length:                       # `length - t <= 0`
             continue
-        t_start = random.randrange(0, length - t)
-        if t_start == t_start + t:
+        start = random.randrange(0, length - bound)
+        if bound == 0:                            # `t_start == t_start + t`
             continue
-        t_end += t_start
-        cloned[t_start:t_end] = 0
-    return cloned
+        spans.append((start, start + width))
+    return spans
+
+
+def adaptive_time_mask(x, window, stride):
+    keep = torch.ones(x.size(0), dtype=torch.bool)
+    for a, b in time_mask_spans(x.size(0), window, stride):
+        keep[a:b] = False
+    out = x.clone()
+    out[~keep] = 0
+    return out
 
 
 def video_transform(sample, subset):                               # :83-104
