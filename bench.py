@@ -112,6 +112,9 @@ def build_module(args, device):
     else:
         from omni_avsr_b200 import lightning_OmniAVSR as L
         margs = L.make_args(num_beams=1, max_dec_tokens=32)
+    llm = getattr(args, "llm", None)
+    if llm:                                  # BASELINE configs 4 / 5 (Qwen2.5-3B, Llama-3.1-8B): extra lines, not the judged one
+        margs.llm_model = llm
     torch.manual_seed(0)
     mod = L.ModelModule_LLM(margs, device=device)
     with torch.no_grad():   # non-degenerate adapters (LoRA down AND up ~ N(0, 0.02))
@@ -262,7 +265,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         decode = {"metric": "utterances/sec (greedy decode, 32 new tokens, sweep over 8 task x rate settings)",
                   "value": round(Bd * world * len(settings) / (t.item() * 1e-3), 2), "unit": "utterances/s",
-                  "batch_per_gpu": Bd, "ms_per_sweep": round(t.item(), 2), "llm": "Llama-3.2-1B",
+                  "batch_per_gpu": Bd, "ms_per_sweep": round(t.item(), 2), "llm": (args.llm or "meta-llama/Llama-3.2-1B"),
                   "includes": "encoders + compression + projector + splice + prefill + 32 decode steps"}
 
     if world > 1:
@@ -278,7 +281,8 @@ def run_ours(args):
         "metric": "utterances/sec (train step)", "value": round(value, 3), "unit": "utterances/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.workload == "omni" else MTSK_WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": 16,
+        "config": {"workload": (WORKLOAD if args.workload == "omni" else MTSK_WORKLOAD) +
+                   (f" [LLM replaced by {args.llm}]" if args.llm else ""), "per_gpu_batch": B, "global_batch": B * world, "clip_seconds": 16,
                    "text_tokens": 48, "parallelism": f"dp{world}", "l2": "256 MiB buffer written between timed steps",
                    "optimizer": "fused all-reduce + clip(10) + AdamW", "random_init": True},
         "e2e": {"value": round(e2e, 3), "unit": "utterances/s", "h2d_bytes_per_step": host_bytes(host),
@@ -417,6 +421,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--decode-batch", type=int, default=64)
+    ap.add_argument("--llm", default=None, help="other backbone of the reference's table, e.g. Qwen/Qwen2.5-3B (BASELINE config "
+                    "4) or meta-llama/Meta-Llama-3.1-8B (config 5); default = the judged Llama-3.2-1B line")
     ap.add_argument("--workload", default="omni", choices=["omni", "mtsk"],
                     help="omni = BASELINE config 2 (default, the judged line); mtsk = Llama-MTSK train step (extra line)")
     args = ap.parse_args()
