@@ -47,3 +47,38 @@ def to_device(batch, device, non_blocking=True):
 
 def host_bytes(batch) -> int:
     return sum(v.numel() * v.element_size() for k, v in batch.items() if torch.is_tensor(v) and k != "lengths")
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device feed: the copy of batch k+1 (from pinned host memory, on its own stream) runs under
+    the compute of batch k.  `next()` returns the device copy of the batch whose transfer was started by the previous call
+    (or starts one if there is none) and immediately starts the transfer of the following batch.
+
+        feed = DevicePrefetcher(lambda k: host_batches[k % n], device)
+        for k in range(steps):
+            loss = module.train_step(feed.next())
+    """
+
+    def __init__(self, host_batch_fn, device):
+        self.fn, self.device = host_batch_fn, torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.k = 0
+        self._pending = None
+
+    def _start(self):
+        host = self.fn(self.k)
+        self.k += 1
+        with torch.cuda.stream(self.stream):
+            dev = to_device(host, self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def next(self):
+        dev, ev = self._pending if self._pending is not None else self._start()
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        for v in dev.values():                    # the consumer stream now owns these buffers (caching-allocator safety)
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(torch.cuda.current_stream(self.device))
+        self._pending = self._start()
+        return dev
