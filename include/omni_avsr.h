@@ -239,6 +239,9 @@ int omni_prelu_maxpool_front(const void* x, const void* slope, void* y, int32_t 
 /* out[i,:] = table[idx[i],:] (embed_tokens of the decode step, label-row selection); status as in the splice. */
 int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
                      int64_t table_rows, int32_t* status, void* stream);
+/* Batched transpose: in [Z, R, C] bf16 -> out [Z, C, R] (per-step transposed copies of the trainable LoRA / projector
+ * matrices for the dgrad GEMMs; autograd's `.t().contiguous()`). */
+int omni_transpose_bf16(const void* in, void* out, int32_t Z, int32_t R, int32_t C, void* stream);
 /* out[idx[i],:] = src[i,:] for unique idx. */
 int omni_scatter_rows(const void* src, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_out,
                       void* stream);

@@ -323,9 +323,10 @@ class LoraPlan:
 
     def transposed_up(self, up: torch.Tensor):
         ns, rp = self.n_slots, self.rp
-        uq = up[: ns * self.q_cols].view(ns, self.q_cols, rp).transpose(1, 2).reshape(ns * rp, self.q_cols)
-        uv = up[ns * self.q_cols:].view(ns, self.v_cols, rp).transpose(1, 2).reshape(ns * rp, self.v_cols)
-        return uq.contiguous(), uv.contiguous()
+        up = up.detach()
+        uq = ops.transpose(up[: ns * self.q_cols].view(ns, self.q_cols, rp)).view(ns * rp, self.q_cols)
+        uv = ops.transpose(up[ns * self.q_cols:].view(ns, self.v_cols, rp)).view(ns * rp, self.v_cols)
+        return uq, uv
 
     def _scatter_index(self, runs, device):
         key = tuple(g for g, _, _ in runs)

@@ -114,6 +114,7 @@ _sig("omni_gelu_fwd", [_P, _P, _I64, _P])
 _sig("omni_gelu_bwd", [_P, _P, _P, _I64, _P])
 _sig("omni_gather_rows", [_P, _P, _P, _I64, _I32, _I64, _I64, _P, _P])
 _sig("omni_scatter_rows", [_P, _P, _P, _I64, _I32, _I64, _P])
+_sig("omni_transpose_bf16", [_P, _P, _I32, _I32, _I32, _P])
 _sig("omni_ce_fwd", [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P])
 _sig("omni_ce_bwd", [_P, _P, _P, _P, _I64, _I32, _I64, _I64, _P])
 _sig("omni_argmax", [_P, _P, _I64, _I32, _I64, _P])
@@ -145,7 +146,7 @@ EXPORTS = [
     "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
     "omni_colsum_bf16", "omni_logmel_workspace_bytes", "omni_logmel", "omni_prelu_res", "omni_prelu_maxpool3x3s2",
     "omni_im2col_front3d", "omni_im2col_front2d", "omni_prelu_maxpool_front", "omni_attention_fwd", "omni_attention_bwd", "omni_decode_attention",
-    "omni_video_transform", "omni_audio_transform_workspace_bytes", "omni_audio_transform",
+    "omni_transpose_bf16", "omni_video_transform", "omni_audio_transform_workspace_bytes", "omni_audio_transform",
 ]
 
 

@@ -49,7 +49,7 @@ class TrainableLinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         if ctx.act == "relu":
             dy = dy * (y > 0)
-        dx = ops.gemm(dy, W.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dx = ops.gemm(dy, ops.transpose(W.detach().contiguous())) if ctx.needs_input_grad[0] else None
         dW = ops.gemm_wgrad(dy, x, mo=W.shape[0], no=W.shape[1])[0]       # dY^T X, both operands token-major
         db = ops.colsum(dy)
         return dx, dW, db, None
@@ -297,7 +297,7 @@ class LoraLinearFn(torch.autograd.Function):
         # dh = dOut @ W + dT' @ down[sel]   (K-extension again)
         dh = None
         if ctx.needs_input_grad[0]:
-            downT = down.t().contiguous()
+            downT = ops.transpose(down.detach().contiguous())
             dh = ops.gemm(dout, ctx.WT, tile_group=tile_group, ext=(dT, downT, plan.ext_bwd), block_n=plan.block_n_bwd,
                           pair_aligned=getattr(ctx.rows, "pair_aligned", False))
         # weight gradients: reductions over the tokens of each task run (MN-major tcgen05 kernel)

@@ -433,9 +433,65 @@ scatter_rows_kernel(const bf16* __restrict__ src, const int64_t* __restrict__ id
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched 2-D transpose of bf16 matrices: in [Z, R, C] -> out [Z, C, R], 64 x 64 tiles through padded shared memory with
+// 4-byte accesses on both sides.  Used for the transposed copies of the TRAINABLE matrices (LoRA down / up, projector
+// weights) that the dgrad GEMMs need every step (the frozen weights keep a cached transposed copy instead).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int C) {
+  __shared__ uint32_t tile[64][33];               // 64 rows x 64 bf16 (32 words) + 1 word of padding
+  const long long z = blockIdx.z;
+  const bf16* src = in + z * static_cast<long long>(R) * C;
+  bf16* dst = out + z * static_cast<long long>(R) * C;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+  const bool c_even = (C & 1) == 0, r_even = (R & 1) == 0;
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    uint32_t w = 0;
+    if (r < R) {
+      const bf16* pp = src + static_cast<long long>(r) * C + c;
+      if (c + 1 < C && c_even) {
+        w = *reinterpret_cast<const uint32_t*>(pp);
+      } else {
+        const uint32_t lo = c < C ? *reinterpret_cast<const uint16_t*>(pp) : 0u;
+        const uint32_t hi = c + 1 < C ? *reinterpret_cast<const uint16_t*>(pp + 1) : 0u;
+        w = lo | (hi << 16);
+      }
+    }
+    tile[i][tx] = w;
+  }
+  __syncthreads();
+  // out row = input column c0 + j, out columns = input rows r0 + 2*tx, r0 + 2*tx + 1
+  for (int j = ty; j < 64; j += 8) {
+    const int oc = c0 + j, orow = r0 + 2 * tx;
+    if (oc >= C) continue;
+    const uint32_t a = tile[2 * tx][j >> 1], b = tile[2 * tx + 1][j >> 1];
+    const uint32_t lo = (j & 1) ? (a >> 16) : (a & 0xffffu);
+    const uint32_t hi = (j & 1) ? (b >> 16) : (b & 0xffffu);
+    bf16* pp = dst + static_cast<long long>(oc) * R + orow;
+    if (orow + 1 < R && r_even) {
+      *reinterpret_cast<uint32_t*>(pp) = lo | (hi << 16);
+    } else {
+      if (orow < R) *reinterpret_cast<uint16_t*>(pp) = static_cast<uint16_t>(lo);
+      if (orow + 1 < R) *reinterpret_cast<uint16_t*>(pp + 1) = static_cast<uint16_t>(hi);
+    }
+  }
+}
+
 }  // namespace omni
 
 using namespace omni;
+
+extern "C" int omni_transpose_bf16(const void* in, void* out, int32_t Z, int32_t R, int32_t C, void* stream) {
+  OMNI_CHECK_ARG(in && out && Z > 0 && R > 0 && C > 0 && Z <= 65535);
+  OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0);
+  dim3 grid((C + 63) / 64, (R + 63) / 64, Z);
+  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, R, C);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
 
 extern "C" int omni_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int32_t H, int64_t ldx,
                                 int64_t ldy, float eps, void* stream) {

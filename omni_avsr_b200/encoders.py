@@ -197,7 +197,7 @@ class WhisperEncoder(nn.Module):
         Lp = L + 2
         T = L // 2
         p1 = torch.zeros((B, Lp, C), device=feats.device, dtype=torch.bfloat16)
-        p1[:, 1: L + 1] = feats.transpose(1, 2)
+        p1[:, 1: L + 1] = ops.transpose(feats.contiguous())     # [B, 80, 3000] -> time-major rows (tiled transpose kernel)
         p2 = torch.empty((B, Lp, d), device=feats.device, dtype=torch.bfloat16)
         m1 = B * Lp - 2
         a1 = torch.as_strided(p1, (m1, 3 * C), (C, 1))

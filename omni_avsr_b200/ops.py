@@ -446,6 +446,19 @@ def gemm_wgrad(a, b, *, mo: int, no: int, a_col0: int = 0, b_col0: int = 0, rang
     return out
 
 
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """[R, C] or [Z, R, C] contiguous bf16 -> contiguous [C, R] / [Z, C, R] (tiled shared-memory transpose)."""
+    require_cuda(x)
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.dim() not in (2, 3):
+        raise ValueError("transpose needs a contiguous bf16 [R, C] or [Z, R, C] tensor")
+    Z = x.shape[0] if x.dim() == 3 else 1
+    R, Cc = x.shape[-2], x.shape[-1]
+    out = torch.empty((*x.shape[:-2], Cc, R), device=x.device, dtype=torch.bfloat16)
+    check(lib.omni_transpose_bf16(x.data_ptr(), out.data_ptr(), Z, R, Cc, stream_ptr()), "omni_transpose_bf16")
+    _count()
+    return out
+
+
 def colsum(x):
     """Column sums (fp32 accumulate) of a bf16 [rows, cols] matrix -> bf16 [cols] (bias gradient)."""
     x = _bf16_2d(x, "x")

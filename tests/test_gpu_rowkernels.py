@@ -271,3 +271,13 @@ def test_front3d_prelu_maxpool_matches_torch(B, T):
     for sl in (got[0] - want[0], got[T - 1] - want[T - 1], got[B * T - 1] - want[B * T - 1],
                got[:, :, 0] - want[:, :, 0], got[:, :, :, 21] - want[:, :, :, 21]):
         assert sl.abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("shape", [(512, 2048), (3, 100, 64), (4, 2048, 64), (1, 67, 130), (2, 129, 63)])
+def test_transpose_bit_exact(shape):
+    from omni_avsr_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).bfloat16().cuda()
+    got = ops.transpose(x)
+    want = x.transpose(-1, -2).contiguous()
+    assert got.shape == want.shape and torch.equal(got.view(torch.int16), want.view(torch.int16))
