@@ -472,18 +472,38 @@ class _AVHTransformerEncoder(nn.Module):
         self.layers = nn.ModuleList([AVHLayer(a, device, flat, use_lora, i) for i in range(a.encoder_layers)])
         self.layer_norm = _LN(d, device)
 
+    def _pos_conv_weights(self):
+        """Frozen positional convolution (wav2vec2.py:829-841: weight-normed grouped Conv1d + SamePad + GELU) as per-group GEMM
+        operands: g * v / ||v|| materialised once, group G's filter as a K-major [gw, k * gw] matrix (K = (tap, in-channel))."""
+        if getattr(self, "_wt", None) is None:
+            conv = self.pos_conv[0]
+            w = torch._weight_norm(conv.weight_v, conv.weight_g, 2)              # [d, gw, k]
+            groups, k = conv.groups, conv.kernel_size[0]
+            d, gw = w.shape[0], w.shape[1]
+            if gw % 8 != 0:
+                raise ValueError("positional-conv group width must be a multiple of 8 (TMA row stride)")
+            wg = w.view(groups, gw, gw, k).permute(0, 1, 3, 2).reshape(groups, gw, k * gw).contiguous()
+            self._wt = (wg, conv.bias.data.contiguous(), k, groups, gw)
+        return self._wt
+
     def forward(self, x, B, T):                  # x [B*T, C]
         d = x.shape[1]
         with torch.no_grad():
-            if getattr(self, "_wt", None) is None:                   # frozen: materialise g * v / ||v|| once
-                conv = self.pos_conv[0]
-                self._wt = (torch._weight_norm(conv.weight_v, conv.weight_g, 2).contiguous(), conv.bias,
-                            conv.padding[0], conv.groups)
-            w, bias, pad, groups = self._wt
-            xc = F.conv1d(x.view(B, T, d).transpose(1, 2), w, bias, padding=pad, groups=groups)  # TODO(round 2): as GEMM
-            if self.remove:
-                xc = xc[:, :, : -self.remove]
-            x = (x.view(B, T, d) + F.gelu(xc).transpose(1, 2)).reshape(B * T, d).contiguous()
+            # x + gelu(pos_conv(x)) on the tcgen05 GEMM: the activations of one group, zero-padded per clip and stored
+            # group-major, make the im2col row of output t simply the k CONSECUTIVE rows starting at row t (overlapping-row
+            # TMA view, row stride gw < row length k * gw); bias + GELU run in the epilogue, which writes the group's gw
+            # columns of the [B * Tp, d] result directly.  Rows t >= T of a clip are garbage and never read.
+            wg, bias, k, groups, gw = self._pos_conv_weights()
+            Tp = T + k
+            xp = torch.zeros((B, Tp, d), device=x.device, dtype=torch.bfloat16)
+            xp[:, k // 2: k // 2 + T] = x.view(B, T, d)
+            xg = xp.view(B * Tp, groups, gw).permute(1, 0, 2).contiguous()          # [groups, B*Tp, gw]
+            M = B * Tp - (k - 1)
+            y = torch.empty((B * Tp, d), device=x.device, dtype=torch.bfloat16)
+            for g in range(groups):
+                a = torch.as_strided(xg[g], (M, k * gw), (gw, 1))
+                ops.gemm(a, wg[g], bias=bias[g * gw: (g + 1) * gw], act="gelu", out=y[:M, g * gw: (g + 1) * gw], block_n=64)
+            x = (x.view(B, T, d) + y.view(B, Tp, d)[:, :T]).reshape(B * T, d)
         rows = _Rows(B * T)
         for i, layer in enumerate(self.layers):
             x = layer(x, B, T, rows, i == 0)
