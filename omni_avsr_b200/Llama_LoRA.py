@@ -850,12 +850,14 @@ class LlamaForCausalLM_lora(nn.Module):
     def head_transposed(self):
         """lm_head weight transposed [H, Vp] (Vp = V rounded up to 8 so the TMA row stride is 16-byte aligned)."""
         W = self.lm_head.weight.data
-        if self._head_t is None or self._head_t[1] is not W:
+        # `.data` is a fresh tensor object every time: compare storage + version (load_state_dict copies in place), not identity
+        key = (W.data_ptr(), tuple(W.shape), self.lm_head.weight._version)
+        if self._head_t is None or self._head_t[1] != key:
             V, H = W.shape
             Vp = (V + 7) // 8 * 8
             buf = torch.zeros((H, Vp), device=W.device, dtype=torch.bfloat16)
             buf[:, :V] = W.t()
-            self._head_t = (buf[:, :V], W)
+            self._head_t = (buf[:, :V], key)      # frozen weight: rebuilt only after load_state_dict / resize (they reset it)
         return self._head_t[0]
 
     def logits_rows(self, hrows):

@@ -208,12 +208,16 @@ class WhisperEncoder(nn.Module):
         if B not in w["pos"]:
             pos = torch.zeros((B, Tp, d), device=feats.device, dtype=torch.bfloat16)
             pos[:, :T] = self.embed_positions.weight.data[:T]
-            w["pos"] = {B: pos.view(B * Tp, d)}
+            w["pos"] = {B: pos.view(B * Tp, d)}      # (one batch size cached at a time)
         m2 = B * Tp - 1
         a2 = torch.as_strided(p2, (m2, 3 * d), (2 * d, 1))
         y = torch.empty((B * Tp, d), device=feats.device, dtype=torch.bfloat16)
         ops.gemm(a2, w["w2"], bias=self.conv2.bias.data, act="gelu", residual=w["pos"][B][:m2], out=y[:m2], block_n=256)
-        x = y.view(B, Tp, d)[:, :T].reshape(B * T, d)
+        # drop the one garbage slot per clip: row gather with a cached index (vectorised, HBM speed) instead of ATen's strided copy
+        if ("rows", B) not in w["pos"]:
+            w["pos"][("rows", B)] = (torch.arange(B, device=feats.device)[:, None] * Tp +
+                                     torch.arange(T, device=feats.device)[None, :]).reshape(-1).contiguous()
+        x = ops.gather_rows(y, w["pos"][("rows", B)])
         return x, B, T
 
     @classmethod
