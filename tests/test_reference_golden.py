@@ -590,3 +590,26 @@ def test_gpu_audio_transform_vs_reference():
         want = c[name]["out"]
         assert got.shape == want.shape
         assert (got.cpu() - want).abs().max().item() <= 1e-4, (name, (got.cpu() - want).abs().max().item())
+
+
+def test_product_span_sampler_draws_like_the_reference():
+    """Host logic of the on-device transforms (no GPU needed): with the same seeds the product's mask-span sampler consumes the
+    RNGs exactly like the reference's AdaptiveTimeMask (executed through the oracle restatement, itself pinned bit for bit
+    above) and yields the same zeroed ranges -- checked by applying both to an all-ones signal."""
+    import random
+    from oracle import transforms as otr
+    from omni_avsr_b200.transforms import adaptive_time_mask_spans
+    for seed, length, window, stride in [(1, 400, 10, 25), (2, 256000, 6400, 16000), (3, 7, 10, 25), (4, 24000, 6400, 16000),
+                                         (5, 30, 10, 25), (6, 100001, 6400, 16000)]:
+        _seed(seed)
+        want = otr.adaptive_time_mask(torch.ones(length), window, stride)
+        after_ref = (torch.rand(1).item(), random.random())
+        _seed(seed)
+        spans = adaptive_time_mask_spans(length, window, stride)
+        after_prod = (torch.rand(1).item(), random.random())
+        got = torch.ones(length)
+        for a, b in spans:
+            assert 0 <= a < b <= length
+            got[a:b] = 0
+        assert torch.equal(got, want), (seed, spans)
+        assert after_ref == after_prod, "RNG streams diverged"
