@@ -208,7 +208,8 @@ def run_ours(args):
             k_ext = 0
             if kw.get("ext") is not None:
                 k_ext = kw["ext"][2].shape[-2] * 64
-            recs.append((s, e, 2.0 * a.shape[0] * n * (a.shape[1] + k_ext), (a.shape[0], n, a.shape[1] + k_ext)))
+            recs.append((s, e, 2.0 * a.shape[0] * n * (a.shape[1] + k_ext), (a.shape[0], n, a.shape[1] + k_ext),
+                         kw.get("act") in ("swiglu64", "gelu_keep")))
             return out
         ops.gemm = traced
         import omni_avsr_b200.autograd_ops as ag
@@ -217,8 +218,14 @@ def run_ours(args):
             torch.cuda.synchronize()
         finally:
             ops.gemm = orig
+        # the dominant kernel = the plain-epilogue tcgen05 GEMM; the launches whose epilogue also runs SwiGLU / GELU and
+        # writes a second output (gemm_bf16_tn_2cta<5,1|2>) are reported next to it: their time contains that extra work
+        fused = [r for r in recs if r[4]]
+        recs = [r[:4] for r in recs if not r[4]]
         tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
         tot_fl = sum(f for _, _, f, _ in recs)
+        fused_ms = sum(s.elapsed_time(e) for s, e, _, _, _ in fused)
+        fused_fl = sum(f for _, _, f, _, _ in fused)
         if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
             by_shape = {}
             for s_, e_, f_, shp in recs:
@@ -237,6 +244,10 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 3), "traffic": NCU_TRAFFIC_BYTES,
                 "traffic_source": NCU_TRAFFIC_SOURCE,
                 "launches": len(recs), "gemm_ms_per_step": round(tot_ms, 2),
+                "fused_epilogue_gemms": {"launches": len(fused), "ms_per_step": round(fused_ms, 2),
+                                         "achieved_gemm_flops_only": round(fused_fl / max(fused_ms, 1e-9) / 1e9, 1),
+                                         "note": "SwiGLU (LLM gate_up) / GELU-keep (AV-HuBERT fc1) computed in the epilogue, "
+                                                 "second output written; replaces separate elementwise kernels"},
                 "how": "algorithmic 2*M*N*(K+K_ext) per launch / CUDA-event duration per launch, summed over one step"}
 
     # ---- greedy decode (second half of the BASELINE metric): elastic sweep over the 8 (task, rate) settings -------
