@@ -160,6 +160,51 @@ int omni_splice_prompt_bwd(const omni_splice_args* args, const void* const dout[
                            void* d_video_tok, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused Matryoshka path (north_star subsystem 1): compression -> projector MLP -> splice, ONE persistent launch.
+ * Replaces, for both modalities at once, the reference's op chain
+ *   transpose -> AvgPool1d(rate) -> transpose  or  the frame-stacking views   (modeling_OmniAVSR.py:544-546,562-568 audio,
+ *                                                                              :469-471,487-493 video)
+ *   Linear(K1 -> I) + ReLU + Linear(I -> H)                                   (:366 audio_proj, :353 video_proj)
+ *   cat(<audio>, tokens, </audio>) / cat(<video>, tokens, </video>)            (:347-368)
+ *   cat(bos, media, prompt, text) per task + the label tensors                 (:270-299, :373-387; infer :406-458)
+ * Kernel structure (csrc/pool_project_splice.cu): CTA pairs (tcgen05 cta_group::2) walk a static work list
+ * [GEMM-1 tiles | GEMM-2 tiles] of both modalities; four extra warps per CTA pool the encoder rows (TMA-staged r-row boxes,
+ * fp32 sum in window order, /rate, bf16: bit-exact with AvgPool1d) into `pooled`, then copy the marker / prompt / text
+ * embedding rows and write the labels.  GEMM-1 tiles wait on per-256-row-block "pooled" counters, GEMM-2 tiles on the
+ * "hidden" counters of GEMM-1; `pooled` and `hidden` stay in L2 between producer and consumer.  GEMM-2's epilogue
+ * (+bias, round to bf16) writes every projected token straight to its row in the own-task sequence and in the AVSR
+ * sequence -- the projected tokens never exist as a separate tensor unless `tok` is given.
+ * `splice` describes the destination exactly as for omni_splice_prompt; its audio_tok / video_tok pointers are ignored
+ * (presence = audio.x / video.x != NULL) and n_a / n_v must equal n_tok / rate of the modality.
+ * Limits: rate <= 256; D, I, H multiples of 8.  workspace: omni_pps_workspace_bytes() bytes of device memory (dependency
+ * counters; zeroed by the call itself).  mode = OMNI_COMPRESS_AVG / OMNI_COMPRESS_STACK (K1 = D / rate * D).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct omni_pps_modality {
+  const void* x;      /* [B, >= n_tok, D] encoder output, batch stride x_bs elements; NULL = modality absent */
+  int64_t x_bs;
+  int32_t n_tok, rate, D;
+  const void* w1;     /* [I, K1] */
+  const void* b1;     /* [I] */
+  const void* w2;     /* [H, I] */
+  const void* b2;     /* [H] */
+  void* pooled;       /* [B * (n_tok / rate), K1] compressed features (side output: backward, parity checks) */
+  void* hidden;       /* [B * (n_tok / rate), I]  relu(pooled . w1^T + b1) (side output) */
+  void* tok;          /* optional [B * (n_tok / rate), H] dense copy of the projected tokens, or NULL */
+} omni_pps_modality;
+
+typedef struct omni_pps_args {
+  omni_pps_modality audio, video;
+  omni_splice_args splice;
+  int32_t I;          /* projector intermediate width */
+  int32_t mode;       /* OMNI_COMPRESS_* */
+  void* workspace;
+  int64_t workspace_bytes;
+} omni_pps_args;
+
+int64_t omni_pps_workspace_bytes(const omni_pps_args* args);
+int omni_pool_project_splice(const omni_pps_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Flash-attention forward (tcgen05, head_dim 64 or 128) over one segment of the packed q|k|v rows:
  *   qkv [M, ld] bf16, every row = [q heads | k heads | v heads]; the segment is B clips x S tokens from row0.
  *   out [M, out_ld] bf16 (n_heads*head_dim columns written for the segment's rows); lse optional fp32 [n_heads, M].

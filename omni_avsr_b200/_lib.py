@@ -66,6 +66,23 @@ class SpliceArgs(C.Structure):
     ]
 
 
+class PpsModality(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_bs", C.c_int64),
+        ("n_tok", C.c_int32), ("rate", C.c_int32), ("D", C.c_int32),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("pooled", C.c_void_p), ("hidden", C.c_void_p), ("tok", C.c_void_p),
+    ]
+
+
+class PpsArgs(C.Structure):
+    _fields_ = [
+        ("audio", PpsModality), ("video", PpsModality), ("splice", SpliceArgs),
+        ("I", C.c_int32), ("mode", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 WGRAD_MAX_RANGES = 8
 
 
@@ -99,6 +116,8 @@ _sig("omni_matryoshka_compress_bwd",
 _sig("omni_splice_seq_len", [C.POINTER(SpliceArgs), C.c_int32], C.c_int32)
 _sig("omni_splice_prompt", [C.POINTER(SpliceArgs), C.c_void_p])
 _sig("omni_splice_prompt_bwd", [C.POINTER(SpliceArgs), C.c_void_p * 3, C.c_void_p, C.c_void_p, C.c_void_p])
+_sig("omni_pps_workspace_bytes", [C.POINTER(PpsArgs)], C.c_int64)
+_sig("omni_pool_project_splice", [C.POINTER(PpsArgs), C.c_void_p])
 
 
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -146,7 +165,7 @@ EXPORTS = [
     "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
     "omni_colsum_bf16", "omni_logmel_workspace_bytes", "omni_logmel", "omni_prelu_res", "omni_prelu_maxpool3x3s2",
     "omni_im2col_front3d", "omni_im2col_front2d", "omni_prelu_maxpool_front", "omni_attention_fwd", "omni_attention_bwd", "omni_decode_attention",
-    "omni_transpose_bf16", "omni_video_transform", "omni_audio_transform_workspace_bytes", "omni_audio_transform",
+    "omni_transpose_bf16", "omni_pps_workspace_bytes", "omni_pool_project_splice", "omni_video_transform", "omni_audio_transform_workspace_bytes", "omni_audio_transform",
 ]
 
 

@@ -119,6 +119,27 @@ def layernorm(x, w, b, eps):
     return LayerNormFn.apply(x, w, b, eps)
 
 
+class TrainableLayerNormFn(torch.autograd.Function):
+    """LayerNorm with a TRAINABLE affine (the projector's nn.LayerNorm(hidden), modeling_OmniAVSR.py:85,97,111): forward and
+    dx on the row kernels; dw = sum_rows(dy * xhat), db = sum_rows(dy) through the column-sum kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, w.detach(), b.detach(), eps, want_stats=True)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.layernorm_bwd(dy, x, w.detach(), mean, rstd) if ctx.needs_input_grad[0] else None
+        xhat = ((x.float() - mean[:, None]) * rstd[:, None])
+        dw = ops.colsum((dy.float() * xhat).to(torch.bfloat16))
+        db = ops.colsum(dy)
+        return dx, dw, db, None
+
+
 class LayerNormResidualFn(torch.autograd.Function):
     """LayerNorm twin of RMSNormResidualFn (AV-HuBERT pre-norm blocks)."""
 

@@ -1,0 +1,260 @@
+// Pieces of the tcgen05 GEMM shared by gemm_tcgen05.cu and pool_project_splice.cu: tile constants, the kernel
+// parameter block, and the epilogue helpers (bias -> rounding point -> activation -> residual -> store; the coalesced
+// 32x64 transposition tile of the CTA-pair kernels).
+#pragma once
+#include "common.cuh"
+#include "../../include/omni_avsr.h"
+
+namespace omni {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue
+constexpr int GEMM2_THREADS = 320; // CTA-pair kernel: warps 2..9 epilogue (two warps per TMEM lane quarter, 128 columns each)
+
+struct GemmKParams {
+  int M, N, K;
+  int num_k_blocks;
+  int n_tiles, m_tiles;
+  int n_ext;
+  const int* tile_group;
+  const int* b_row_table;
+  const int4* ext_table;  // {a2_col, b2_row, b2_col, unused}; b2_row < 0 => skip
+  const bf16* bias;
+  const bf16* residual;
+  void* out;
+  long long ldo, ldr;
+  int act;
+  int out_fp32;
+  float alpha;
+  bf16* out2;        // OMNI_ACT_SWIGLU64: [M, N/2]
+  long long ldo2;
+};
+
+// Residual values of one 32-column chunk, fetched one chunk AHEAD of the TMEM read so that the (strided, 64 bytes per
+// thread) loads are in flight while the previous chunk is converted and stored -- without this the epilogue is
+// latency-bound on short-K GEMMs (8 serialized ~1 us round trips per 128x256 tile).
+struct ResPrefetch {
+  uint4 r[4];
+  bool valid;
+};
+__device__ __forceinline__ void res_prefetch(const GemmKParams& p, int row, int col0, bool row_ok, ResPrefetch& o) {
+  o.valid = p.residual != nullptr && row_ok && (col0 + 32 <= p.N);
+  if (o.valid) {
+    const uint4* rp4 = reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.r[i] = ld_nc_u4(rp4 + i);
+  }
+}
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  // exact-erf GELU, x * Phi(x), with ONE special-function op: Phi(-|x|) = 0.5 * erfc(|x|/sqrt2) = 2^(q(z) - 1), where q is
+  // a degree-7 fit of log2(erfc(z)) on z = |x|/sqrt2 in [0, 4.5] (relative error of the GELU value <= 7e-6 -- 300x below
+  // bf16 resolution, also in the negative tail where Phi is tiny; the bf16-rounded result differs from the erff-based one
+  // in 0.03 % of inputs, by one ulp).  The Abramowitz-Stegun form used before needed an exp AND a reciprocal: with 256
+  // values per thread per tile the epilogue was MUFU-bound on the K = 1024 encoder GEMMs.
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.5f);
+  float q = -2.045480869e-05f;
+  q = fmaf(q, z, 4.882984795e-04f);
+  q = fmaf(q, z, -5.237891804e-03f);
+  q = fmaf(q, z, 3.395747021e-02f);
+  q = fmaf(q, z, -1.525140703e-01f);
+  q = fmaf(q, z, -9.170033932e-01f);
+  q = fmaf(q, z, -1.628095627e+00f);
+  q = fmaf(q, z, 3.904249297e-06f - 1.0f);
+  const float h = ex2_approx(q);                 // Phi(-|x|)
+  return x * (x < 0.f ? h : 1.0f - h);
+}
+
+// Epilogue of 32 accumulator columns of one row: alpha, bias, rounding point, activation, residual, store.
+__device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&v)[32], int row, int col0,
+                                                  const ResPrefetch* pre = nullptr) {
+  const bool full = (col0 + 32 <= p.N);
+  if (p.bias) {
+    if (full) {
+      const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 b = __ldg(bp + i);
+        float2 f;
+        f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+        f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+        f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+        f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __bfloat162float(p.bias[col0 + i]);
+    }
+  }
+  if (p.act != OMNI_ACT_NONE || p.residual) {
+    // reference rounding point: the linear's bf16 output feeds the activation / the residual add
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    if (p.act == OMNI_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (p.act == OMNI_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_fast(v[i])));
+    }
+  }
+  if (p.residual) {
+    const bf16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
+    if (full) {
+      const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 b = (pre && pre->valid) ? pre->r[i] : ld_nc_u4(rp4 + i);
+        float2 f;
+        f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+        f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+        f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+        f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __bfloat162float(rp[i]);
+    }
+  }
+  if (p.out_fp32) {
+    float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) op[i] = v[i];
+    }
+  } else {
+    bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
+        o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
+        o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
+        o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(op + 8 * i) = o;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) op[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+
+// ---- coalesced epilogue of the CTA-pair kernel ------------------------------------------------------------------
+// A thread owns one accumulator row (TMEM lane), so direct global accesses are 16 bytes per thread at the row pitch:
+// 32 different 128-byte lines per warp instruction, and the LSU retires about one line per clock -- on short-K GEMMs
+// (K = 1024: 8192 clk of MMA per 256x256 tile) the residual loads + output stores alone cost as much as the main loop.
+// Each epilogue warp therefore transposes 32 rows x 64 columns through a private padded shared-memory tile (pitch
+// 144 B: conflict-free for the 16-byte row writes and for the 8-lanes-per-row reads), so that global loads / stores are
+// full 128-byte row segments (4 lines per warp instruction).
+constexpr int EPI_PITCH = 144;
+constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
+
+struct ResTile {            // residual of a 32-row x 64-column block in the coalesced layout: lane -> (row l/8 + 4*pass, 16 B l%8)
+  uint4 r[8];
+};
+__device__ __forceinline__ void res_tile_prefetch(const GemmKParams& p, int row0, int col0, int lane, ResTile& o) {
+  const bf16* rp = p.residual + static_cast<long long>(row0 + (lane >> 3)) * p.ldr + col0 + (lane & 7) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const bool ok = (row0 + (lane >> 3) + 4 * pass) < p.M;
+    o.r[pass] = ok ? ld_nc_u4(rp + static_cast<long long>(4 * pass) * p.ldr) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// publish a prefetched residual block into the warp's transposition tile (frees its registers for the next prefetch)
+__device__ __forceinline__ void res_tile_publish(uint8_t* stage, int lane, const ResTile& res) {
+  uint8_t* co_ptr = stage + (lane >> 3) * EPI_PITCH + (lane & 7) * 16;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) *reinterpret_cast<uint4*>(co_ptr + 4 * pass * EPI_PITCH) = res.r[pass];
+  __syncwarp();
+}
+
+// 32 rows x 64 bf16 columns held one row per thread -> global memory as full 128-byte rows through the warp's padded
+// transposition tile.
+__device__ __forceinline__ void store_tile64(bf16* out, long long ldo, int M, uint8_t* stage, const float (&v)[64], int lane,
+                                             int row0, int col0) {
+  uint8_t* my_row = stage + lane * EPI_PITCH;
+  const uint8_t* co_ptr = stage + (lane >> 3) * EPI_PITCH + (lane & 7) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 o;
+    o.x = f2_to_bf2(v[8 * i + 0], v[8 * i + 1]);
+    o.y = f2_to_bf2(v[8 * i + 2], v[8 * i + 3]);
+    o.z = f2_to_bf2(v[8 * i + 4], v[8 * i + 5]);
+    o.w = f2_to_bf2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(my_row + 16 * i) = o;
+  }
+  __syncwarp();
+  bf16* op = out + static_cast<long long>(row0 + (lane >> 3)) * ldo + col0 + (lane & 7) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    if (row0 + (lane >> 3) + 4 * pass < M)
+      *reinterpret_cast<uint4*>(op + static_cast<long long>(4 * pass) * ldo) =
+          *reinterpret_cast<const uint4*>(co_ptr + 4 * pass * EPI_PITCH);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* stage, float (&v)[64], int lane, int row0,
+                                                int col0, bool res_staged) {
+  if (p.bias) {
+    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 b = __ldg(bp + i);
+      float2 f;
+      f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+      f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+      f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+      f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+    }
+  }
+  if (p.act != OMNI_ACT_NONE || p.residual) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    if (p.act == OMNI_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (p.act == OMNI_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_fast(v[i])));
+    }
+  }
+  uint8_t* my_row = stage + lane * EPI_PITCH;
+  uint8_t* co_ptr = stage + (lane >> 3) * EPI_PITCH + (lane & 7) * 16;
+  if (res_staged) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 b = *reinterpret_cast<const uint4*>(my_row + 16 * i);
+      float2 f;
+      f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+      f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+      f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+      f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+    }
+    __syncwarp();
+  }
+  store_tile64(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage, v, lane, row0, col0);
+}
+
+
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int m_fast, int& m_tile, int& n_tile) {
+  if (m_fast) {
+    n_tile = t / m_tiles;
+    m_tile = t - n_tile * m_tiles;
+  } else {
+    m_tile = t / n_tiles;
+    n_tile = t - m_tile * n_tiles;
+  }
+}
+
+}  // namespace omni

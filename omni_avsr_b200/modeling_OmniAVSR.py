@@ -68,9 +68,14 @@ class Projector(nn.Sequential):
         x2 = x.reshape(-1, shape[-1])
         h = ag.TrainableLinearFn.apply(x2, self[0].weight, self[0].bias, "relu")
         y = ag.TrainableLinearFn.apply(h, self[2].weight, self[2].bias, None)
-        if len(self) == 4:   # single-projector mode only (:102,:186); trainable affine -> library LN for now
-            y = torch.nn.functional.layer_norm(y, (self[3].d,), self[3].weight, self[3].bias, 1e-5)
+        if len(self) == 4:   # nn.LayerNorm(hidden) of the non-Matryoshka / single-projector recipes (:85,:97,:111)
+            y = ag.TrainableLayerNormFn.apply(y, self[3].weight, self[3].bias, 1e-5)
         return y.view(*shape[:-1], y.shape[-1])
+
+    @property
+    def fusable(self) -> bool:
+        """Linear + ReLU + Linear only: the whole projector runs inside omni_pool_project_splice."""
+        return len(self) == 3
 
     @staticmethod
     def param_count(in_dim, intermediate, hidden, layernorm):
@@ -105,13 +110,7 @@ class SpliceFn(torch.autograd.Function):
         xp = torch.empty((rows.M, H), device=layout.keep[2].device, dtype=torch.bfloat16)
         outs, labs, lab_t = [None] * 3, [None] * 3, []
         seg_of = {task: (B, S, off) for (task, B, S, off) in rows.segments}
-        cur = 0
-        for (task, B, S, off) in rows.segments:       # zero only the pad rows between the 128-aligned segments
-            if off > cur:
-                xp[cur:off].zero_()
-            cur = off + B * S
-        if cur < rows.M:
-            xp[cur:].zero_()
+        _pad_rows_zero(xp, rows)
         for t in range(3):
             if t in seg_of:
                 B, S, off = seg_of[t]
@@ -131,6 +130,79 @@ class SpliceFn(torch.autograd.Function):
             douts[t] = dxp[off: off + B * S]
         da, dv = ops.splice_prompt_bwd(ctx.layout, douts, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return da, dv, None, None, None
+
+
+def _pad_rows_zero(xp, rows):
+    cur = 0
+    for (task, B, S, off) in rows.segments:       # zero only the pad rows between the 128-aligned segments
+        if off > cur:
+            xp[cur:off].zero_()
+        cur = off + B * S
+    if cur < rows.M:
+        xp[cur:].zero_()
+
+
+class PoolProjectSpliceFn(torch.autograd.Function):
+    """Fused compression -> projector -> splice (ops.pool_project_splice, ONE launch) with the backward of the unfused
+    chain: splice_bwd -> Linear-2 (dgrad / wgrad / bias) -> ReLU mask -> Linear-1 (wgrad / bias, dgrad only where the
+    encoder trains) -> compression backward.  Tensor inputs: audio_enc, video_enc, then (w1, b1, w2, b2) per modality."""
+
+    @staticmethod
+    def forward(ctx, audio_enc, video_enc, w1a, b1a, w2a, b2a, w1v, b1v, w2v, b2v, meta):
+        layout, rows, n_tok_a, ra, n_tok_v, rv, mode, want_labels = meta
+        H = layout.H
+        xp = torch.empty((rows.M, H), device=layout.keep[2].device, dtype=torch.bfloat16)
+        _pad_rows_zero(xp, rows)
+        outs, labs = [None] * 3, [None] * 3
+        seg_of = {task: (B, S, off) for (task, B, S, off) in rows.segments}
+        for t in range(3):
+            if t in seg_of:
+                B, S, off = seg_of[t]
+                outs[t] = xp[off: off + B * S]
+                if want_labels:
+                    labs[t] = torch.empty((B, S), device=xp.device, dtype=torch.int64)
+        a_in = ops.PoolProjectInput(audio_enc.detach(), n_tok_a, ra, w1a.detach(), b1a.detach(), w2a.detach(), b2a.detach()) \
+            if audio_enc is not None else None
+        v_in = ops.PoolProjectInput(video_enc.detach(), n_tok_v, rv, w1v.detach(), b1v.detach(), w2v.detach(), b2v.detach()) \
+            if video_enc is not None else None
+        res = ops.pool_project_splice(layout, outs, labs, a_in, v_in, mode)
+        saved = []
+        for r, w1, w2 in ((res["audio"], w1a, w2a), (res["video"], w1v, w2v)):
+            saved += [r[0], r[1], w1, w2] if r is not None else [None, None, None, None]
+        ctx.save_for_backward(*saved)
+        ctx.layout, ctx.seg_of, ctx.meta = layout, seg_of, meta
+        ctx.enc_shapes = (None if audio_enc is None else audio_enc.shape[1], None if video_enc is None else video_enc.shape[1])
+        ctx.mark_non_differentiable(*[l for l in labs if l is not None])
+        return (xp, *[l if l is not None else torch.empty(0, device=xp.device, dtype=torch.int64) for l in labs])
+
+    @staticmethod
+    def backward(ctx, dxp, *_):
+        layout, rows, n_tok_a, ra, n_tok_v, rv, mode, _wl = ctx.meta
+        dxp = dxp.contiguous()
+        douts = [None] * 3
+        for t, (B, S, off) in ctx.seg_of.items():
+            douts[t] = dxp[off: off + B * S]
+        pa, ha, w1a, w2a, pv, hv, w1v, w2v = ctx.saved_tensors
+        da, dv = ops.splice_prompt_bwd(layout, douts, pa is not None, pv is not None)
+        grads = [None] * 10
+        for k, (dtok, pooled, hidden, w1, w2, n_tok, rate, t_full, need_enc) in enumerate((
+                (da, pa, ha, w1a, w2a, n_tok_a, ra, ctx.enc_shapes[0], ctx.needs_input_grad[0]),
+                (dv, pv, hv, w1v, w2v, n_tok_v, rv, ctx.enc_shapes[1], ctx.needs_input_grad[1]))):
+            if pooled is None:
+                continue
+            dy = dtok.view(-1, dtok.shape[-1])
+            dh = ops.gemm(dy, ops.transpose(w2.detach().contiguous()))
+            dh = dh * (hidden > 0)                                              # ReLU mask
+            g = 2 + 4 * k
+            grads[g + 2] = ops.gemm_wgrad(dy, hidden, mo=w2.shape[0], no=w2.shape[1])[0]
+            grads[g + 3] = ops.colsum(dy)
+            grads[g + 0] = ops.gemm_wgrad(dh, pooled, mo=w1.shape[0], no=w1.shape[1])[0]
+            grads[g + 1] = ops.colsum(dh)
+            if need_enc:
+                dpool = ops.gemm(dh, ops.transpose(w1.detach().contiguous()))
+                B = layout.B
+                grads[k] = ops.matryoshka_compress_bwd(dpool.view(B, -1, dpool.shape[-1]), n_tok, t_full, rate, mode)
+        return (*grads, None)
 
 
 class AVSR_LLMs(nn.Module):
@@ -160,6 +232,7 @@ class AVSR_LLMs(nn.Module):
         self.is_matryoshka = is_matryoshka
         self.is_single_matry_projector = is_single_matry_projector
         self.device_ = torch.device(device)
+        self.fused_projector = True      # compression + projector + splice in one launch whenever the projectors allow it
         if compression_mode not in ("stack", "avg-pooling"):
             raise ValueError(compression_mode)
         if PETF_LLM_name != "lora":
@@ -318,7 +391,96 @@ class AVSR_LLMs(nn.Module):
                                  pad_token_id=vocab["<pad>"], modality=modality,                # :313-317
                                  trim=not getattr(self, "decode_no_trim", False))
 
+    # ------------------------------------------------------------------------------------------------
+    def _projector_for(self, which, rate):
+        proj = self.audio_proj if which == "audio" else self.video_proj
+        mm = self.matry_map_audio if which == "audio" else self.matry_map_video
+        if isinstance(proj, nn.ModuleList):
+            proj = proj[mm[rate]]                      # KeyError for an unknown rate, as in the reference (:353,:366)
+        return proj
+
+    def _media(self, inputs, which, is_trainval, test_ratio):
+        """(encoder output [B, T, D], n_tok, rate, projector) of one modality -- the inputs of the fused
+        compression -> projector -> splice launch (rate 1 = no compression)."""
+        if which == "audio":
+            enc, n_tok = self._audio_encoder_output(inputs["audio"], max(inputs["lengths"]))
+            rates = self.downsample_ratio_audio
+            mm = self.matry_map_audio
+        else:
+            enc = self._video_encoder_output(inputs["video"])
+            n_tok = enc.shape[1]
+            rates = self.downsample_ratio_video
+            mm = self.matry_map_video
+        if self.is_matryoshka:
+            rate = self._pick_rate(rates, test_ratio, is_trainval)
+            if rate not in mm:
+                raise KeyError(rate)
+        else:
+            rate = rates
+        return enc.contiguous(), n_tok, rate, self._projector_for(which, rate)
+
+    def _fused_inputs(self, inputs, is_trainval, use_a, use_v, ra_test, rv_test):
+        a = self._media(inputs, "audio", is_trainval, ra_test) if use_a else None
+        v = self._media(inputs, "video", is_trainval, rv_test) if use_v else None
+        return a, v
+
     def prepare_inputs(self, inputs, is_trainval, test_ratio_matry_audio=None, test_ratio_matry_video=None):
+        use_a = True if is_trainval else self.modality in ("audio", "audiovisual")
+        use_v = True if is_trainval else self.modality in ("video", "audiovisual")
+        fused = self.fused_projector and all(
+            isinstance(p, Projector) and p.fusable
+            for p in ([*(self.audio_proj if isinstance(self.audio_proj, nn.ModuleList) else [self.audio_proj])] if use_a else []) +
+                     ([*(self.video_proj if isinstance(self.video_proj, nn.ModuleList) else [self.video_proj])] if use_v else []))
+        if fused:
+            return self._prepare_inputs_fused(inputs, is_trainval, use_a, use_v, test_ratio_matry_audio, test_ratio_matry_video)
+        return self._prepare_inputs_unfused(inputs, is_trainval, test_ratio_matry_audio, test_ratio_matry_video)
+
+    def _prepare_inputs_fused(self, inputs, is_trainval, use_a, use_v, ra_test, rv_test):
+        """ONE launch (omni_pool_project_splice): compression + projector MLP + marker / prompt / text splice + labels."""
+        a, v = self._fused_inputs(inputs, is_trainval, use_a, use_v, ra_test, rv_test)
+        tokens = inputs["tokens"]
+        B = tokens.shape[0]
+        mode = self.compression_mode
+        na = a[1] // a[2] if a is not None else None
+        nv = v[1] // v[2] if v is not None else None
+        for x in (a, v):
+            if x is not None and mode == "avg-pooling" and x[1] // x[2] == 0:
+                raise RuntimeError(f"Given input size: ({x[0].shape[2]}x1x{x[1]}). Calculated output size: "
+                                   f"({x[0].shape[2]}x1x0). Output size is too small")       # nn.AvgPool1d (:545)
+        prompts = [self.prompt_audio[0], self.prompt_video[0], self.prompt_audiovisual[0]]
+        embed = self.llm.model.embed_tokens.weight.data
+
+        def weights(x):
+            if x is None:
+                return (None,) * 4
+            p = x[3]
+            return p[0].weight, p[0].bias, p[2].weight, p[2].bias
+
+        if is_trainval:
+            labels = inputs.get("labels")
+            layout = ops.SpliceLayout(tokens=tokens.contiguous(), labels=None if labels is None else labels.contiguous(),
+                                      embed=embed, audio_tok=None, video_tok=None, prompts=prompts,
+                                      marker_ids=self._marker_ids, has_bos=self._has_bos, task_mask=7, n_audio=na, n_video=nv)
+            rows = PackedRows.get([(t, B, layout.seq_len[t]) for t in range(3)], embed.device)
+            meta = (layout, rows, a[1], a[2], v[1], v[2], mode, True)
+            xp, la, lv, lav = PoolProjectSpliceFn.apply(a[0], v[0], *weights(a), *weights(v), meta)
+            return {"packed": xp, "rows": rows, "labels": [la, lv, lav], "labels_audio": la, "labels_video": lv,
+                    "labels_audiovisual": lav, "selected_rates": (a[2], v[2])}
+        t = TASKS.index(self.modality)
+        tok1 = tokens[:, :1] if self._has_bos else tokens[:, :0]          # only e(BOS) is used (:419)
+        layout = ops.SpliceLayout(tokens=tok1.contiguous(), labels=None, embed=embed, audio_tok=None, video_tok=None,
+                                  prompts=prompts, marker_ids=self._marker_ids, has_bos=self._has_bos, task_mask=1 << t,
+                                  n_audio=na, n_video=nv)
+        out = [None] * 3
+        out[t] = torch.empty((B, layout.seq_len[t], self.hidden_size), device=tokens.device, dtype=torch.bfloat16)
+        with torch.no_grad():
+            mk = lambda x: None if x is None else ops.PoolProjectInput(x[0], x[1], x[2], *[w.data for w in weights(x)])
+            ops.pool_project_splice(layout, out, [None] * 3, mk(a), mk(v), mode)
+        return out[t]
+
+    def _prepare_inputs_unfused(self, inputs, is_trainval, test_ratio_matry_audio=None, test_ratio_matry_video=None):
+        """Separate launches (compress -> GEMM -> GEMM [-> LayerNorm] -> splice): projectors with a LayerNorm (the
+        non-Matryoshka and single-projector recipes, :85,:97,:111) and the parity tests of the individual kernels."""
         if is_trainval:
             if self.is_matryoshka:
                 audio_features, ra = self.encode_audio(inputs["audio"], max(inputs["lengths"]), is_trainval=is_trainval,
@@ -371,10 +533,20 @@ class AVSR_LLMs(nn.Module):
             return random.choice(rates)                                     # :474,:549 (python RNG)
         return test_ratio
 
-    def encode_video(self, videos, is_trainval=None, test_ratio_matry_video=None):
-        B = videos.shape[0]
+    def _video_encoder_output(self, videos):
         src = torch.reshape(videos, (-1, videos.shape[2], videos.shape[1], videos.shape[3], videos.shape[-1]))  # :463
         video_enc, _, _ = self.video_encoder.extract_finetune(source={"video": src, "audio": None})
+        return video_enc
+
+    def _audio_encoder_output(self, audio, max_len):
+        feats = self.audio_frontend(audio.squeeze(-1))                                  # :531-533 on the GPU
+        audio_enc = self.audio_encoder(feats).last_hidden_state                         # :534
+        ml = max_len if torch.is_tensor(max_len) else torch.tensor(max_len)
+        n_tok = max(int(ml.detach().cpu().to(torch.int64) / 16000 * 50), 25)            # :537 (float32 tensor arithmetic)
+        return audio_enc, min(n_tok, audio_enc.shape[1])
+
+    def encode_video(self, videos, is_trainval=None, test_ratio_matry_video=None):
+        video_enc = self._video_encoder_output(videos)
         n_tok = video_enc.shape[1]
         if self.is_matryoshka:
             rate = self._pick_rate(self.downsample_ratio_video, test_ratio_matry_video, is_trainval)
@@ -387,11 +559,7 @@ class AVSR_LLMs(nn.Module):
         return video_enc
 
     def encode_audio(self, audio, max_len, is_trainval=None, test_ratio_matry_audio=None):
-        feats = self.audio_frontend(audio.squeeze(-1))                                  # :531-533 on the GPU
-        audio_enc = self.audio_encoder(feats).last_hidden_state                         # :534
-        ml = max_len if torch.is_tensor(max_len) else torch.tensor(max_len)
-        n_tok = max(int(ml.detach().cpu().to(torch.int64) / 16000 * 50), 25)            # :537 (float32 tensor arithmetic)
-        n_tok = min(n_tok, audio_enc.shape[1])
+        audio_enc, n_tok = self._audio_encoder_output(audio, max_len)
         if self.is_matryoshka:
             rate = self._pick_rate(self.downsample_ratio_audio, test_ratio_matry_audio, is_trainval)
             if rate not in self.matry_map_audio:

@@ -9,7 +9,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, SpliceArgs, check, lib, ptr, require_cuda, stream_ptr
+from ._lib import GemmArgs, PpsArgs, SpliceArgs, check, lib, ptr, require_cuda, stream_ptr
 
 ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3, "gelu_keep": 4}
 SWIGLU_BLK = 64          # gate / up interleave of the OMNI_ACT_SWIGLU64 epilogue
@@ -156,8 +156,15 @@ class SpliceLayout:
     """Host-side description of one splice call (mirrors omni_splice_args)."""
 
     def __init__(self, *, tokens, labels, embed, audio_tok, video_tok, prompts: Sequence[torch.Tensor],
-                 marker_ids: Sequence[int], has_bos: bool, task_mask: int = 7):
+                 marker_ids: Sequence[int], has_bos: bool, task_mask: int = 7, n_audio: Optional[int] = None,
+                 n_video: Optional[int] = None):
+        """audio_tok / video_tok: projected tokens [B, n, H] (stand-alone splice).  For the fused path
+        (pool_project_splice) pass None for both and give the token counts per clip as n_audio / n_video (None = the
+        modality is absent): the tokens are then written by the projector epilogue, not read from a tensor."""
         require_cuda(tokens, labels, embed, audio_tok, video_tok, *prompts)
+        self.fused = audio_tok is None and video_tok is None and (n_audio is not None or n_video is not None)
+        self.has_audio = audio_tok is not None or n_audio is not None
+        self.has_video = video_tok is not None or n_video is not None
         self.keep = (tokens, labels, embed, audio_tok, video_tok, tuple(prompts))
         a = SpliceArgs()
         B, L = tokens.shape
@@ -181,19 +188,34 @@ class SpliceLayout:
                 a.prompt[t] = p.data_ptr()
                 a.prompt_len[t] = p.shape[-2]
         a.B, a.L, a.H = B, L, H
-        a.n_a = audio_tok.shape[1] if audio_tok is not None else 0
-        a.n_v = video_tok.shape[1] if video_tok is not None else 0
+        a.n_a = audio_tok.shape[1] if audio_tok is not None else int(n_audio or 0)
+        a.n_v = video_tok.shape[1] if video_tok is not None else int(n_video or 0)
         a.id_audio_sos, a.id_audio_eos, a.id_video_sos, a.id_video_eos = [int(i) for i in marker_ids]
         a.has_bos = 1 if has_bos else 0
         a.task_mask = task_mask
         a.vocab = embed.shape[0]
         self.args = a
         self.B, self.H = B, H
-        self.seq_len = [int(lib.omni_splice_seq_len(C.byref(a), t)) if (task_mask >> t) & 1 else 0 for t in range(3)]
+        bos = 1 if has_bos else 0
+        self.seq_len = [(bos + (a.n_a + 2 if self.has_audio and t in (0, 2) else 0) +
+                         (a.n_v + 2 if self.has_video and t in (1, 2) else 0) + a.prompt_len[t] + (L - bos))
+                        if (task_mask >> t) & 1 else 0 for t in range(3)]
+        if not self.fused:   # the library's own arithmetic must agree with the mirror above
+            for t in range(3):
+                if (task_mask >> t) & 1 and int(lib.omni_splice_seq_len(C.byref(a), t)) != self.seq_len[t]:
+                    raise RuntimeError("splice sequence length mismatch between the host mirror and the library")
 
 
 def splice_prompt(layout: SpliceLayout, outs: Sequence[Optional[torch.Tensor]],
                   out_labels: Sequence[Optional[torch.Tensor]], status: Optional[torch.Tensor] = None) -> None:
+    if layout.fused:
+        raise ValueError("this layout has no token tensors: use pool_project_splice")
+    _bind_splice_outputs(layout, outs, out_labels, status)
+    check(lib.omni_splice_prompt(C.byref(layout.args), stream_ptr()), "omni_splice_prompt")
+    _count()
+
+
+def _bind_splice_outputs(layout, outs, out_labels, status):
     a = layout.args
     for t in range(3):
         o, l = outs[t], out_labels[t]
@@ -208,8 +230,78 @@ def splice_prompt(layout: SpliceLayout, outs: Sequence[Optional[torch.Tensor]],
         a.out[t] = ptr(o)
         a.out_labels[t] = ptr(l)
     a.status = ptr(status)
-    check(lib.omni_splice_prompt(C.byref(a), stream_ptr()), "omni_splice_prompt")
+
+
+class PoolProjectInput:
+    """One modality of pool_project_splice: encoder output x [B, T, D] (only the first n_tok rows of a clip are read),
+    compression rate, projector weights Linear(K1 -> I) + ReLU + Linear(I -> H)."""
+
+    def __init__(self, x, n_tok: int, rate: int, w1, b1, w2, b2):
+        require_cuda(x, w1, b1, w2, b2)
+        if x.dtype != torch.bfloat16 or x.dim() != 3 or x.stride(2) != 1 or x.stride(1) != x.shape[2]:
+            raise ValueError("x must be bf16 [B, T, D] with contiguous rows")
+        if n_tok > x.shape[1]:
+            raise ValueError("n_tok exceeds T")
+        for t in (w1, b1, w2, b2):
+            if t.dtype != torch.bfloat16 or not t.is_contiguous():
+                raise ValueError("projector weights must be contiguous bf16")
+        self.x, self.n_tok, self.rate = x, int(n_tok), int(rate)
+        self.w1, self.b1, self.w2, self.b2 = w1, b1, w2, b2
+        self.n = self.n_tok // self.rate
+
+
+def pool_project_splice(layout: SpliceLayout, outs, out_labels, audio: Optional[PoolProjectInput],
+                        video: Optional[PoolProjectInput], mode: str = "avg-pooling", status=None, want_tok: bool = False):
+    """Fused compression -> projector MLP -> splice (omni_pool_project_splice): ONE persistent launch writes the three task
+    sequences (outs[t]: [B, S_t, H]) and their labels.  Returns per modality (pooled [B*n, K1], hidden [B*n, I],
+    tok [B*n, H] or None) -- the side outputs the backward needs."""
+    if not layout.fused:
+        raise ValueError("pool_project_splice needs a SpliceLayout built with n_audio / n_video (no token tensors)")
+    m = COMPRESS[mode]
+    _bind_splice_outputs(layout, outs, out_labels, status)
+    g = PpsArgs()
+    g.splice = layout.args
+    keep, res = [], {}
+    I = None
+    dev = layout.keep[2].device
+    for name, inp, n_lay in (("audio", audio, layout.args.n_a if layout.has_audio else None),
+                             ("video", video, layout.args.n_v if layout.has_video else None)):
+        if (inp is None) != (n_lay is None):
+            raise ValueError(f"{name}: the layout and the inputs disagree about the presence of the modality")
+        if inp is None:
+            res[name] = None
+            continue
+        B, T, D = inp.x.shape
+        if B != layout.B or inp.n != n_lay:
+            raise ValueError(f"{name}: batch / token count mismatch with the layout")
+        if m == 0 and inp.n == 0:
+            raise RuntimeError(f"Given input size: ({D}x1x{inp.n_tok}). Calculated output size: ({D}x1x0). Output size is too small")
+        K1 = D if m == 0 else D * inp.rate
+        if inp.w1.shape[1] != K1 or inp.w2.shape[1] != inp.w1.shape[0] or inp.w2.shape[0] != layout.H:
+            raise ValueError(f"{name}: projector shapes do not match (K1={K1}, H={layout.H})")
+        if I is None:
+            I = inp.w1.shape[0]
+        elif I != inp.w1.shape[0]:
+            raise ValueError("both projectors must share the intermediate width")
+        M = B * inp.n
+        pooled = torch.empty((M, K1), device=dev, dtype=torch.bfloat16)
+        hidden = torch.empty((M, I), device=dev, dtype=torch.bfloat16)
+        tok = torch.empty((M, layout.H), device=dev, dtype=torch.bfloat16) if want_tok else None
+        mm = g.audio if name == "audio" else g.video
+        mm.x, mm.x_bs, mm.n_tok, mm.rate, mm.D = inp.x.data_ptr(), inp.x.stride(0), inp.n_tok, inp.rate, D
+        mm.w1, mm.b1, mm.w2, mm.b2 = inp.w1.data_ptr(), inp.b1.data_ptr(), inp.w2.data_ptr(), inp.b2.data_ptr()
+        mm.pooled, mm.hidden, mm.tok = pooled.data_ptr(), hidden.data_ptr(), ptr(tok)
+        res[name] = (pooled, hidden, tok)
+        keep.append(inp)
+    if I is None:
+        raise ValueError("pool_project_splice needs at least one modality")
+    g.I, g.mode = I, m
+    nbytes = int(lib.omni_pps_workspace_bytes(C.byref(g)))
+    ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+    g.workspace, g.workspace_bytes = ws.data_ptr(), nbytes
+    check(lib.omni_pool_project_splice(C.byref(g), stream_ptr()), "omni_pool_project_splice")
     _count()
+    return res
 
 
 def splice_prompt_bwd(layout: SpliceLayout, douts: Sequence[Optional[torch.Tensor]], want_audio: bool,
@@ -225,7 +317,14 @@ def splice_prompt_bwd(layout: SpliceLayout, douts: Sequence[Optional[torch.Tenso
     dev = layout.keep[2].device
     da = torch.empty((layout.B, a.n_a, layout.H), device=dev, dtype=torch.bfloat16) if want_audio else None
     dv = torch.empty((layout.B, a.n_v, layout.H), device=dev, dtype=torch.bfloat16) if want_video else None
-    check(lib.omni_splice_prompt_bwd(C.byref(a), d, ptr(da), ptr(dv), stream_ptr()), "omni_splice_prompt_bwd")
+    saved = (a.audio_tok, a.video_tok)
+    if layout.fused:      # the kernel only tests these pointers for presence (it reads dout, not the tokens)
+        a.audio_tok = layout.keep[2].data_ptr() if layout.has_audio else None
+        a.video_tok = layout.keep[2].data_ptr() if layout.has_video else None
+    try:
+        check(lib.omni_splice_prompt_bwd(C.byref(a), d, ptr(da), ptr(dv), stream_ptr()), "omni_splice_prompt_bwd")
+    finally:
+        a.audio_tok, a.video_tok = saved
     _count()
     return da, dv
 

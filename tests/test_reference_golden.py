@@ -306,6 +306,86 @@ def test_gpu_compress_splice_labels_bit_exact_vs_reference(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["llama_avg", "llama_stack", "qwen_avg"])
+def test_gpu_fused_pool_project_splice_vs_reference(name):
+    """The FUSED launch (omni_pool_project_splice: compression + projector MLP + splice + labels in one persistent kernel)
+    against what the reference's encode_audio / encode_video / prepare_inputs / forward produced from the same encoder
+    outputs and projector weights: compressed features, every marker / prompt / text row and every label bit-exact;
+    the projected media rows (a bf16 matmul on the CPU in the reference, tcgen05 with fp32 accumulation here) within
+    1e-2 of the value range."""
+    from omni_avsr_b200 import ops
+    c = GOLD["omni"][name]
+    is_qwen = "Qwen" in c["llm_name"]
+    n_tok = 62
+    w_llm = fixture_weights(c["named"]["llm"], c["seeds"]["llm"], c["checksum"]["llm"])
+    embed_w = w_llm["model.embed_tokens.weight"].cuda()
+    prompts = [embed_w[torch.tensor(c["prompts"][k], device="cuda")] for k in ("PA", "PV", "PAV")]
+    v = c["vocab"]
+    marker = (v["<audio>"], v["</audio>"], v["<video>"], v["</video>"])
+    tokens, labels = c["inputs"]["tokens"].cuda(), c["inputs"]["labels"].cuda()
+    wa = fixture_weights(c["named"]["pa"], c["seeds"]["pa"], c["checksum"]["pa"])
+    wv = fixture_weights(c["named"]["pv"], c["seeds"]["pv"], c["checksum"]["pv"])
+    B, H = tokens.shape[0], embed_w.shape[1]
+    xa, xv = c["audio_enc"].cuda(), c["video_enc"].cuda()
+    bos = 0 if is_qwen else 1
+
+    def proj(w, i):
+        return [w[f"{i}.{k}"].cuda().contiguous() for k in ("0.weight", "0.bias", "2.weight", "2.bias")]
+
+    for (ra, rv), tr in c["train"].items():
+        ia, iv = [4, 16].index(ra), [2, 5].index(rv)
+        na, nv = n_tok // ra, 23 // rv
+        lay = ops.SpliceLayout(tokens=tokens, labels=labels, embed=embed_w, audio_tok=None, video_tok=None, prompts=prompts,
+                               marker_ids=marker, has_bos=not is_qwen, n_audio=na, n_video=nv)
+        outs = [torch.empty(B, s, H, device="cuda", dtype=torch.bfloat16) for s in lay.seq_len]
+        outl = [torch.empty(B, s, device="cuda", dtype=torch.int64) for s in lay.seq_len]
+        status = torch.zeros(1, device="cuda", dtype=torch.int32)
+        res = ops.pool_project_splice(lay, outs, outl, ops.PoolProjectInput(xa, n_tok, ra, *proj(wa, ia)),
+                                      ops.PoolProjectInput(xv, 23, rv, *proj(wv, iv)), c["mode"], status=status)
+        assert status.item() == 0
+        assert bits_equal(res["audio"][0].cpu().view(B, na, -1), tr["audio_comp"])
+        assert bits_equal(res["video"][0].cpu().view(B, nv, -1), tr["video_comp"])
+        for i, call in enumerate(tr["llm_calls"]):
+            got, ref = outs[i].cpu(), call["inputs_embeds"]
+            assert got.shape == ref.shape
+            media = torch.zeros(ref.shape[1], dtype=torch.bool)
+            pos = bos
+            if i in (0, 2):
+                media[pos + 1: pos + 1 + na] = True
+                pos += na + 2
+            if i in (1, 2):
+                media[pos + 1: pos + 1 + nv] = True
+            assert bits_equal(got[:, ~media].contiguous(), ref[:, ~media].contiguous()), (name, ra, rv, TASKS[i])
+            assert rel_err(got[:, media], ref[:, media]) <= 1e-2, (name, ra, rv, TASKS[i])
+            assert torch.equal(outl[i].cpu(), call["labels"])
+    for i, t in enumerate(TASKS):
+        emb = c["infer"][t]["embeddings"]
+        na, nv = n_tok // 4, 23 // 2
+        use_a, use_v = t in ("audio", "audiovisual"), t in ("video", "audiovisual")
+        toks = torch.zeros(1, 0, dtype=torch.long) if is_qwen else torch.tensor([[1]])
+        lay = ops.SpliceLayout(tokens=toks.cuda(), labels=None, embed=embed_w, audio_tok=None, video_tok=None,
+                               prompts=prompts, marker_ids=marker, has_bos=not is_qwen, task_mask=1 << i,
+                               n_audio=na if use_a else None, n_video=nv if use_v else None)
+        outs = [None, None, None]
+        outs[i] = torch.empty(1, lay.seq_len[i], H, device="cuda", dtype=torch.bfloat16)
+        # the reference's inference example is clip 0 at rates (4, 2)
+        ops.pool_project_splice(lay, outs, [None] * 3,
+                                ops.PoolProjectInput(xa[:1].contiguous(), n_tok, 4, *proj(wa, 0)) if use_a else None,
+                                ops.PoolProjectInput(xv[:1].contiguous(), 23, 2, *proj(wv, 0)) if use_v else None, c["mode"])
+        got = outs[i].cpu()
+        assert got.shape == emb.shape
+        media = torch.zeros(emb.shape[1], dtype=torch.bool)
+        pos = bos
+        if use_a:
+            media[pos + 1: pos + 1 + na] = True
+            pos += na + 2
+        if use_v:
+            media[pos + 1: pos + 1 + nv] = True
+        assert bits_equal(got[:, ~media].contiguous(), emb[:, ~media].contiguous()), (name, t)
+        assert rel_err(got[:, media], emb[:, media]) <= 1e-2, (name, t)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["llama_avg", "qwen_avg"])
 def test_gpu_losses_and_decode_match_reference_model(name):
     """The three task losses the reference's AVSR_LLMs.forward returned (matry_weights applied) and the greedy ids of

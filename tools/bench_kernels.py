@@ -148,8 +148,80 @@ def bench_transforms():
           flush=True)
 
 
+def fused_setup(B, ra=4, rv=2, H=2048, I=2048, D=1024, L=48, V=128261, infer_task=None):
+    """Inputs of the compression -> projector -> splice stage at BASELINE config 2 geometry (16 s clips)."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xa = torch.randn(B, 1500, D, device="cuda", generator=g).bfloat16()
+    xv = torch.randn(B, 400, D, device="cuda", generator=g).bfloat16()
+
+    def proj(K1):
+        return [(torch.randn(I, K1, device="cuda", generator=g) / K1 ** 0.5).bfloat16(),
+                (torch.randn(I, device="cuda", generator=g) * 0.1).bfloat16(),
+                (torch.randn(H, I, device="cuda", generator=g) / I ** 0.5).bfloat16(),
+                (torch.randn(H, device="cuda", generator=g) * 0.1).bfloat16()]
+    pa, pv = proj(D), proj(D)
+    embed = torch.randn(V, H, device="cuda", generator=g).bfloat16()
+    tokens = torch.randint(0, V - 8, (B, L), device="cuda", generator=g)
+    prompts = [torch.randn(pl, H, device="cuda", generator=g).bfloat16() for pl in (6, 6, 8)]
+    marker = (V - 4, V - 3, V - 2, V - 1)
+    return dict(xa=xa, xv=xv, pa=pa, pv=pv, embed=embed, tokens=tokens, prompts=prompts, marker=marker, ra=ra, rv=rv,
+                na=800 // ra, nv=400 // rv, B=B, H=H, I=I, D=D, L=L)
+
+
+def fused_bytes_flops(c):
+    """Algorithmic bytes / flops of the stage: encoder rows read once, each projected token written twice (own
+    task + AVSR), marker / prompt / text rows read + written, labels, projector weights once; 2*n*(D*I + I*H) flops."""
+    B, H, I, D, L = c["B"], c["H"], c["I"], c["D"], c["L"]
+    na, nv, ra, rv = c["na"], c["nv"], c["ra"], c["rv"]
+    media = B * (na * ra + nv * rv) * D * 2 + 2 * B * (na + nv) * H * 2
+    S = [1 + na + 2 + 6 + L - 1, 1 + nv + 2 + 6 + L - 1, 1 + na + 2 + nv + 2 + 8 + L - 1]
+    other_rows = B * (sum(S) - 2 * (na + nv))
+    other = other_rows * H * 2 * 2 + B * sum(S) * 8
+    weights = 2 * (D * I + I + I * H + H) * 2
+    flops = 2.0 * B * (na + nv) * (D * I + I * H)
+    return media + other, weights, flops
+
+
+def bench_fused():
+    for B in (32, 64):
+        for ra, rv in ((4, 2), (16, 5)):
+            c = fused_setup(B, ra, rv)
+            lay_f = ops.SpliceLayout(tokens=c["tokens"], labels=c["tokens"], embed=c["embed"], audio_tok=None, video_tok=None,
+                                     prompts=c["prompts"], marker_ids=c["marker"], has_bos=True, n_audio=c["na"],
+                                     n_video=c["nv"])
+            outs = [torch.empty(B, s, c["H"], device="cuda", dtype=torch.bfloat16) for s in lay_f.seq_len]
+            outl = [torch.empty(B, s, device="cuda", dtype=torch.int64) for s in lay_f.seq_len]
+            a_in = ops.PoolProjectInput(c["xa"], 800, ra, *c["pa"])
+            v_in = ops.PoolProjectInput(c["xv"], 400, rv, *c["pv"])
+            med, best = timeit(lambda: ops.pool_project_splice(lay_f, outs, outl, a_in, v_in, "avg-pooling"))
+
+            def unfused():
+                ca = ops.matryoshka_compress(c["xa"], 800, ra, "avg-pooling")
+                cv = ops.matryoshka_compress(c["xv"], 400, rv, "avg-pooling")
+                ta = ops.gemm(ops.gemm(ca.view(-1, c["D"]), c["pa"][0], bias=c["pa"][1], act="relu"), c["pa"][2], bias=c["pa"][3])
+                tv = ops.gemm(ops.gemm(cv.view(-1, c["D"]), c["pv"][0], bias=c["pv"][1], act="relu"), c["pv"][2], bias=c["pv"][3])
+                lay = ops.SpliceLayout(tokens=c["tokens"], labels=c["tokens"], embed=c["embed"],
+                                       audio_tok=ta.view(B, c["na"], -1), video_tok=tv.view(B, c["nv"], -1),
+                                       prompts=c["prompts"], marker_ids=c["marker"], has_bos=True)
+                ops.splice_prompt(lay, outs, outl)
+            medu, bestu = timeit(unfused)
+            byts, wbytes, flops = fused_bytes_flops(c)
+            t_hbm = (byts + wbytes) / (PEAKS["hbm_gbs"] * 1e9)
+            t_tc = flops / (PEAKS["bf16_tflops"] * 1e12)
+            print(json.dumps({"kernel": "pool_project_splice (fused, 1 launch)", "B": B, "rates": [ra, rv],
+                              "ms": round(med, 4), "ms_best": round(best, 4), "unfused_7_launches_ms": round(medu, 4),
+                              "MB_per_utt": round(byts / B / 1e6, 3), "GFLOP_per_utt": round(flops / B / 1e9, 3),
+                              "tflops": round(flops / (med * 1e-3) / 1e12, 1),
+                              "frac_tensor_burst": round(flops / (med * 1e-3) / 1e12 / PEAKS["bf16_tflops"], 3),
+                              "GBs": round((byts + wbytes) / med / 1e6, 1),
+                              "bound_ms": round(1e3 * max(t_hbm, t_tc), 4),
+                              "frac_of_bound": round(1e3 * max(t_hbm, t_tc) / med, 3)}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "compress", "splice"]
+    if "fused" in which:
+        bench_fused()
     if "compress" in which:
         bench_compress()
     if "splice" in which:
