@@ -12,7 +12,8 @@
 // What B200 does offer is a 126 MB L2: `pooled` (13 MB per modality at B = 32) and `hidden` (26 MB) are written and read
 // back by other SMs microseconds later without touching HBM.  So the kernel is a persistent CTA-pair GEMM
 // (tcgen05.mma cta_group::2, 256x256 tiles, TMEM double-buffered accumulators, 4-stage TMA pipeline) that walks the
-// static work list  [audio GEMM-1 | video GEMM-1 | audio GEMM-2 | video GEMM-2]  in order, plus four "pool" warps per
+// static work list  [audio GEMM-1 | audio GEMM-2 | video GEMM-1 | video GEMM-2]  in order (the audio GEMMs run while the
+// pool warps are still compressing the video rows), plus four "pool" warps per
 // CTA that run concurrently with the tensor pipe:
 //   * pool warps: TMA-stage the r encoder rows of one output token (3-D tensor map over [B, T, D], box [r, 256]) into a
 //     private 3-slot ring, sum them in window order in fp32, divide by r, round to bf16 (the arithmetic of AvgPool1d, bit
@@ -25,6 +26,7 @@
 //   * epilogue warps (8): GEMM-1: +bias, round, ReLU -> `hidden`, then release the block counter.  GEMM-2: +bias, round,
 //     and each row goes straight to its TWO destinations in the packed LLM buffer (own-task sequence + AVSR sequence)
 //     through the warp's transposition tile, so every store instruction writes full 128-byte row segments.
+#include <stdlib.h>
 #include <string.h>
 #include "gemm_epilogue.cuh"
 #include "splice_common.cuh"
@@ -33,10 +35,12 @@ namespace omni {
 
 constexpr int PPS_STAGES = 4;
 constexpr int PPS_EPI_WARPS = 8;
-constexpr int PPS_POOL_WARPS = 4;
-constexpr int PPS_THREADS = (2 + PPS_EPI_WARPS + PPS_POOL_WARPS) * 32;   // 448
-constexpr int PPS_POOL_SLOTS = 3;
-constexpr int PPS_SLOT_BYTES = 4096;
+constexpr int PPS_POOL_WARPS = 6;        // warps 2, 3 and 12..15 (the epilogue warps 4..11 keep TMEM lane quarter = warp % 4)
+constexpr int PPS_THREADS = (2 + PPS_EPI_WARPS + PPS_POOL_WARPS) * 32;   // 512 = 128 registers per thread
+constexpr int PPS_RING_BYTES = 10240;    // TMA landing ring of one pool warp, cut into slots of one unit each
+constexpr int PPS_MAX_SLOTS = 4;         // slots per ring: 4 x 2560 B or 2 x 5120 B (power of two: index = count & (n - 1))
+constexpr int PPS_SLOT_BYTES = 4096;     // largest unit
+constexpr int PPS_CHUNK = 8;             // pool units per dependency release; divides the units of a full 256-row block
 constexpr int PPS_BN = 256;
 
 struct PpsSmem {
@@ -45,8 +49,8 @@ struct PpsSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
   static constexpr int EPI_OFFSET = PPS_STAGES * STAGE_BYTES;
   static constexpr int POOL_OFFSET = EPI_OFFSET + PPS_EPI_WARPS * EPI_WARP_BYTES;
-  static constexpr int BAR_OFFSET = POOL_OFFSET + PPS_POOL_WARPS * PPS_POOL_SLOTS * PPS_SLOT_BYTES;
-  static constexpr int N_BARS = 2 * PPS_STAGES + 4 + PPS_POOL_WARPS * PPS_POOL_SLOTS;
+  static constexpr int BAR_OFFSET = POOL_OFFSET + PPS_POOL_WARPS * PPS_RING_BYTES;
+  static constexpr int N_BARS = 2 * PPS_STAGES + 4 + PPS_POOL_WARPS * PPS_MAX_SLOTS;
   static constexpr int TOTAL = BAR_OFFSET + N_BARS * 8 + 16 + 1024;
 };
 static_assert(PpsSmem::TOTAL <= 232448, "shared memory budget");
@@ -64,7 +68,7 @@ struct PpsGemmDesc {
   const int* wait_cnt;       // [m_pairs] counters the A operand of a row block depends on
   int wait_per_row;          // > 0: target = rows_in_block * wait_per_row (pooled units);  0: target = wait_fixed
   int wait_fixed;
-  int* signal_cnt;           // [m_pairs] bumped once per epilogue warp per tile (GEMM-1) or null
+  int* signal_cnt;           // [m_pairs] bumped once per CTA per tile (GEMM-1) or null
 };
 
 struct PpsScatter {          // where projected token (clip b, index j) of a modality goes
@@ -77,6 +81,9 @@ struct PpsScatter {          // where projected token (clip b, index j) of a mod
 struct PpsPool {
   int M, n, r, D, K1;
   int cw;                    // columns per TMA box
+  int lane_cols;             // columns per lane: 8 (16-byte accesses) or 4 (8-byte accesses, cw <= 128 so all lanes work)
+  int pow2;                  // rate is a power of two: x / r == x * rcp exactly
+  float rcp, fr;
   int n_boxes_row;           // boxes per output row
   int boxes_per_unit;
   int units_per_row;
@@ -86,7 +93,7 @@ struct PpsPool {
 };
 
 struct PpsParams {
-  PpsGemmDesc g[4];          // audio GEMM-1, video GEMM-1, audio GEMM-2, video GEMM-2 (absent modality: M = 0)
+  PpsGemmDesc g[4];          // audio GEMM-1, audio GEMM-2, video GEMM-1, video GEMM-2 (absent modality: M = 0)
   PpsScatter sc[2];
   PpsPool pool[2];
   SpliceK splice;
@@ -94,6 +101,7 @@ struct PpsParams {
   int n_items;
   int mode;
   int H;
+  int slot_bytes, n_slots;   // geometry of a pool warp's TMA ring (one unit per slot), common to both modalities
 };
 
 struct PpsMaps {
@@ -122,12 +130,12 @@ __device__ __forceinline__ void wait_counter(const int* p, int target) {
   }
 }
 // all lanes' global stores of this warp -> visible to whoever acquires the counter (also to its TMA loads)
-__device__ __forceinline__ void release_counter(int* p, int lane) {
+__device__ __forceinline__ void release_counter(int* p, int lane, int count = 1) {
   __syncwarp();
   if (lane == 0) {
     __threadfence();
     fence_proxy_async_global();
-    atomicAdd(p, 1);
+    atomicAdd(p, count);
   }
 }
 
@@ -179,7 +187,7 @@ pool_project_splice_kernel(const __grid_constant__ PpsMaps maps, const __grid_co
   uint64_t* tmem_full_bar = empty_bar + PPS_STAGES;                          // [2], one set per CTA
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                              // [2], used in the leader only (count 16)
   uint64_t* pool_bar = tmem_empty_bar + 2;                                   // [pool warps][slots]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pool_bar + PPS_POOL_WARPS * PPS_POOL_SLOTS);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pool_bar + PPS_POOL_WARPS * PPS_MAX_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,7 +214,7 @@ pool_project_splice_kernel(const __grid_constant__ PpsMaps maps, const __grid_co
         mbar_init(&tmem_full_bar[s], 1);
         mbar_init(&tmem_empty_bar[s], 2 * PPS_EPI_WARPS);
       }
-      for (int s = 0; s < PPS_POOL_WARPS * PPS_POOL_SLOTS; ++s) mbar_init(&pool_bar[s], 1);
+      for (int s = 0; s < PPS_POOL_WARPS * PPS_MAX_SLOTS; ++s) mbar_init(&pool_bar[s], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -282,11 +290,11 @@ pool_project_splice_kernel(const __grid_constant__ PpsMaps maps, const __grid_co
         if (as == 0) aphase ^= 1;
       }
     }
-  } else if (warp < 2 + PPS_EPI_WARPS) {
+  } else if (warp >= 4 && warp < 4 + PPS_EPI_WARPS) {
     // ===== epilogue (both CTAs: each drains its own 128 TMEM lanes; warp w: lane quarter w % 4, column half (w-2)/4) =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    uint8_t* stage_tile = smem + S::EPI_OFFSET + (warp - 2) * EPI_WARP_BYTES;
+    const int half = (warp - 4) >> 2;
+    uint8_t* stage_tile = smem + S::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES;
     int as = 0;
     uint32_t aphase = 0;
     for (int it = cluster_id; it < P.n_items; it += num_clusters) {
@@ -388,85 +396,166 @@ pool_project_splice_kernel(const __grid_constant__ PpsMaps maps, const __grid_co
           }
         }
       }
-      if (g.signal_cnt) release_counter(g.signal_cnt + mp, lane);
+      if (g.signal_cnt) {
+        // all eight epilogue warps have stored their part of the hidden tile: one gpu-scope release per CTA and tile
+        asm volatile("bar.sync 1, %0;" ::"n"(PPS_EPI_WARPS * 32) : "memory");
+        if (warp == 4 && lane == 0) {
+          __threadfence();
+          fence_proxy_async_global();
+          atomicAdd(g.signal_cnt + mp, 1);
+        }
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
   } else {
     // ===== pool warps: Matryoshka compression, then the marker / prompt / text rows and the labels =====
-    const int pw_local = warp - (2 + PPS_EPI_WARPS);
+    const int pw_local = warp < 4 ? warp - 2 : warp - (2 + PPS_EPI_WARPS);
     const long long pw = static_cast<long long>(blockIdx.x) * PPS_POOL_WARPS + pw_local;
     const long long PW = static_cast<long long>(gridDim.x) * PPS_POOL_WARPS;
-    uint8_t* ring = smem + S::POOL_OFFSET + pw_local * PPS_POOL_SLOTS * PPS_SLOT_BYTES;
-    uint64_t* bars = pool_bar + pw_local * PPS_POOL_SLOTS;
+    uint8_t* ring = smem + S::POOL_OFFSET + pw_local * PPS_RING_BYTES;
+    uint64_t* bars = pool_bar + pw_local * PPS_MAX_SLOTS;
     const long long units_a = P.pool[0].units;
-    const long long units = units_a + P.pool[1].units;
 
-    // issue the TMA boxes of unit u into ring slot s (lane 0)
-    auto issue = [&](long long u, int s) {
-      const int mod = u >= units_a ? 1 : 0;
-      const PpsPool& pl = P.pool[mod];
-      const long long ul = u - (mod ? units_a : 0);
-      const int m = static_cast<int>(ul / pl.units_per_row);
-      const int uq = static_cast<int>(ul - static_cast<long long>(m) * pl.units_per_row);
-      const int b = m / pl.n;
-      const int j = m - b * pl.n;
-      const int box0 = uq * pl.boxes_per_unit;
+    // Work is handed out in CHUNKS of PPS_CHUNK consecutive units (a unit = one ring slot of TMA boxes = part of one output
+    // row); a chunk never straddles a 256-row block, and the block counter is released ONCE per chunk -- a gpu-scope fence
+    // per 4 KB unit capped the whole kernel at ~0.8 TB/s of encoder rows.
+    const long long ch_a = ceil_div_ll(units_a, PPS_CHUNK);
+    const long long ch_total = ch_a + ceil_div_ll(P.pool[1].units, PPS_CHUNK);
+    struct Cur {                 // position in this warp's unit sequence; (m, uq, b, j) advance incrementally: one set of
+      long long chunk;           // divisions per chunk, none per unit (lane 0 used to spend ~300 instructions per issue)
+      int idx, len, mod;
+      int m, uq, b, j;           // output row, unit within the row, clip, token within the clip
+    };
+    auto load_chunk = [&](Cur& c) {
+      c.idx = 0;
+      if (c.chunk >= ch_total) { c.len = 0; return; }
+      c.mod = c.chunk >= ch_a ? 1 : 0;
+      const PpsPool& pl = P.pool[c.mod];
+      const long long u0 = (c.chunk - (c.mod ? ch_a : 0)) * PPS_CHUNK;
+      const long long left = pl.units - u0;
+      c.len = left < PPS_CHUNK ? static_cast<int>(left) : PPS_CHUNK;
+      c.m = static_cast<int>(u0 / pl.units_per_row);
+      c.uq = static_cast<int>(u0 - static_cast<long long>(c.m) * pl.units_per_row);
+      c.b = c.m / pl.n;
+      c.j = c.m - c.b * pl.n;
+    };
+    auto advance = [&](Cur& c) {
+      if (++c.idx >= c.len) {
+        c.chunk += PW;
+        load_chunk(c);
+        return;
+      }
+      const PpsPool& pl = P.pool[c.mod];
+      if (++c.uq == pl.units_per_row) {
+        c.uq = 0;
+        ++c.m;
+        if (++c.j == pl.n) { c.j = 0; ++c.b; }
+      }
+    };
+    // issue the TMA boxes of the unit under the cursor into ring slot s (lane 0)
+    auto issue = [&](const Cur& c, int s) {
+      const PpsPool& pl = P.pool[c.mod];
+      const int box0 = c.uq * pl.boxes_per_unit;
       const int nb = min(pl.boxes_per_unit, pl.n_boxes_row - box0);
       const uint32_t box_bytes = static_cast<uint32_t>(pl.r) * pl.cw * 2;
       mbar_expect_tx(&bars[s], box_bytes * nb);
       for (int k = 0; k < nb; ++k)
-        tma_load_3d(&maps.x[mod], &bars[s], ring + s * PPS_SLOT_BYTES + k * box_bytes, (box0 + k) * pl.cw, j * pl.r, b);
+        tma_load_3d(&maps.x[c.mod], &bars[s], ring + s * P.slot_bytes + k * box_bytes, (box0 + k) * pl.cw, c.j * pl.r, c.b);
     };
 
-    // prologue: PPS_POOL_SLOTS - 1 units in flight
-    if (lane == 0) {
-      long long u = pw;
-      for (int s = 0; s < PPS_POOL_SLOTS - 1 && u < units; ++s, u += PW) issue(u, s);
+    Cur cc, ci;
+    cc.chunk = ci.chunk = pw;
+    load_chunk(cc);
+    load_chunk(ci);
+    int issued = 0, consumed = 0;
+    const int slot_mask = P.n_slots - 1;                               // n_slots is 2 or 4
+    const int slot_shift = P.n_slots == 4 ? 2 : 1;
+    for (int s = 0; s < slot_mask && ci.len > 0; ++s) {                // prologue: n_slots - 1 units in flight
+      if (lane == 0) issue(ci, issued & slot_mask);
+      ++issued;
+      advance(ci);
     }
-    int it = 0;
-    for (long long u = pw; u < units; u += PW, ++it) {
-      const int s = it % PPS_POOL_SLOTS;
-      {
-        // the slot of unit (it - 1) was fully consumed before the __syncwarp that ended the previous iteration
-        const long long un = u + (PPS_POOL_SLOTS - 1) * PW;
-        if (lane == 0 && un < units) issue(un, (it + PPS_POOL_SLOTS - 1) % PPS_POOL_SLOTS);
+    while (cc.len > 0) {
+      if (ci.len > 0) {
+        // this slot held the unit consumed in the previous iteration (fully read before its closing __syncwarp)
+        if (lane == 0) issue(ci, issued & slot_mask);
+        ++issued;
+        advance(ci);
       }
-      mbar_wait(&bars[s], static_cast<uint32_t>((it / PPS_POOL_SLOTS) & 1));
-      const int mod = u >= units_a ? 1 : 0;
-      const PpsPool& pl = P.pool[mod];
-      const long long ul = u - (mod ? units_a : 0);
-      const int m = static_cast<int>(ul / pl.units_per_row);
-      const int uq = static_cast<int>(ul - static_cast<long long>(m) * pl.units_per_row);
-      const int box0 = uq * pl.boxes_per_unit;
+      const int s = consumed & slot_mask;
+      mbar_wait(&bars[s], static_cast<uint32_t>((consumed >> slot_shift) & 1));
+      const PpsPool& pl = P.pool[cc.mod];
+      const int m = cc.m;
+      const int box0 = cc.uq * pl.boxes_per_unit;
       const int nb = min(pl.boxes_per_unit, pl.n_boxes_row - box0);
       const int r = pl.r;
       const int cw = pl.cw;
-      const uint8_t* slot = ring + s * PPS_SLOT_BYTES;
-      for (int k = 0; k < nb; ++k) {
-        const int col = (box0 + k) * cw + lane * 8;
-        if (lane * 8 < cw && col < pl.D) {
-          const uint8_t* src = slot + (k * r * cw + lane * 8) * 2;
-          if (P.mode == OMNI_COMPRESS_AVG) {
-            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const uint8_t* slot = ring + s * P.slot_bytes;
+      if (pl.lane_cols == 8) {
+        for (int k = 0; k < nb; ++k) {
+          const int col = (box0 + k) * cw + lane * 8;
+          if (lane * 8 < cw && col < pl.D) {
+            const uint8_t* src = slot + (k * r * cw + lane * 8) * 2;
+            if (P.mode == OMNI_COMPRESS_AVG) {
+              float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-            for (int i = 0; i < r; ++i) acc8(a, *reinterpret_cast<const uint4*>(src + i * cw * 2));   // window order
-            const float fr = static_cast<float>(r);
-            uint4 o;
-            o.x = f2_to_bf2(a[0] / fr, a[1] / fr);
-            o.y = f2_to_bf2(a[2] / fr, a[3] / fr);
-            o.z = f2_to_bf2(a[4] / fr, a[5] / fr);
-            o.w = f2_to_bf2(a[6] / fr, a[7] / fr);
-            *reinterpret_cast<uint4*>(pl.pooled + static_cast<long long>(m) * pl.K1 + col) = o;
-          } else {
-            bf16* dst = pl.pooled + static_cast<long long>(m) * pl.K1 + col;
+              for (int i = 0; i < r; ++i) acc8(a, *reinterpret_cast<const uint4*>(src + i * cw * 2));   // window order
+              if (pl.pow2) {                              // x / 2^k == x * 2^-k exactly: no IEEE division sequence
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] *= pl.rcp;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = a[i] / pl.fr;
+              }
+              uint4 o;
+              o.x = f2_to_bf2(a[0], a[1]);
+              o.y = f2_to_bf2(a[2], a[3]);
+              o.z = f2_to_bf2(a[4], a[5]);
+              o.w = f2_to_bf2(a[6], a[7]);
+              *reinterpret_cast<uint4*>(pl.pooled + static_cast<long long>(m) * pl.K1 + col) = o;
+            } else {
+              bf16* dst = pl.pooled + static_cast<long long>(m) * pl.K1 + col;
 #pragma unroll 4
-            for (int i = 0; i < r; ++i)
-              *reinterpret_cast<uint4*>(dst + static_cast<long long>(i) * pl.D) = *reinterpret_cast<const uint4*>(src + i * cw * 2);
+              for (int i = 0; i < r; ++i)
+                *reinterpret_cast<uint4*>(dst + static_cast<long long>(i) * pl.D) = *reinterpret_cast<const uint4*>(src + i * cw * 2);
+            }
+          }
+        }
+      } else {
+        // narrow boxes (large rates: r * cw * 2 bytes must fit a ring slot): 4 columns per lane keep all 32 lanes busy
+        for (int k = 0; k < nb; ++k) {
+          const int col = (box0 + k) * cw + lane * 4;
+          if (lane * 4 < cw && col < pl.D) {
+            const uint8_t* src = slot + (k * r * cw + lane * 4) * 2;
+            if (P.mode == OMNI_COMPRESS_AVG) {
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+              for (int i = 0; i < r; ++i) {
+                const uint2 u = *reinterpret_cast<const uint2*>(src + i * cw * 2);
+                float2 f;
+                f = bf2_to_f2(u.x); a0 += f.x; a1 += f.y;
+                f = bf2_to_f2(u.y); a2 += f.x; a3 += f.y;
+              }
+              if (pl.pow2) { a0 *= pl.rcp; a1 *= pl.rcp; a2 *= pl.rcp; a3 *= pl.rcp; }
+              else { a0 = a0 / pl.fr; a1 = a1 / pl.fr; a2 = a2 / pl.fr; a3 = a3 / pl.fr; }
+              uint2 o;
+              o.x = f2_to_bf2(a0, a1);
+              o.y = f2_to_bf2(a2, a3);
+              *reinterpret_cast<uint2*>(pl.pooled + static_cast<long long>(m) * pl.K1 + col) = o;
+            } else {
+              bf16* dst = pl.pooled + static_cast<long long>(m) * pl.K1 + col;
+#pragma unroll 4
+              for (int i = 0; i < r; ++i)
+                *reinterpret_cast<uint2*>(dst + static_cast<long long>(i) * pl.D) = *reinterpret_cast<const uint2*>(src + i * cw * 2);
+            }
           }
         }
       }
-      release_counter(pl.ready + (m >> 8), lane);     // (also the __syncwarp that frees this slot for the next TMA)
+      ++consumed;
+      __syncwarp();                                   // slot s may be refilled from here on
+      if (cc.idx == cc.len - 1) release_counter(pl.ready + (m >> 8), lane, cc.len);
+      advance(cc);
     }
 
     // marker / prompt / text embedding rows + labels (media rows are written by the GEMM-2 epilogue; only their label)
@@ -477,7 +566,7 @@ pool_project_splice_kernel(const __grid_constant__ PpsMaps maps, const __grid_co
       if (gr >= k.row_end[0]) { t = 1; base = k.row_end[0]; }
       if (gr >= k.row_end[1]) { t = 2; base = k.row_end[1]; }
       const long long rr = gr - base;
-      const int b = static_cast<int>(rr / k.S[t]);
+      const int b = static_cast<int>(static_cast<unsigned>(rr) / static_cast<unsigned>(k.S[t]));   // rows < 2^31 (checked)
       const int pos = static_cast<int>(rr - static_cast<long long>(b) * k.S[t]);
       const RowSrc src = splice_resolve(k, t, b, pos);
       if (lane == 0 && k.out_labels[t]) k.out_labels[t][rr] = src.label;
@@ -574,6 +663,7 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
   int rc = fill_splice(sp, &P.splice, present[0] ? 1 : 0, present[1] ? 1 : 0);
   if (rc) return rc;
   P.splice_rows = P.splice.row_end[2];
+  OMNI_CHECK_ARG(P.splice_rows < (1ll << 31));
   P.mode = a->mode;
   P.H = sp->H;
   const int H = sp->H;
@@ -586,9 +676,10 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   int items = 0;
-  for (int layer = 0; layer < 2; ++layer) {
-    for (int i = 0; i < 2; ++i) {
-      PpsGemmDesc& g = P.g[layer * 2 + i];
+  for (int i = 0; i < 2; ++i) {
+    for (int layer = 0; layer < 2; ++layer) {
+      const int gidx = 2 * i + layer;
+      PpsGemmDesc& g = P.g[gidx];
       g.item_begin = items;
       g.mod = i;
       if (!present[i]) continue;
@@ -614,9 +705,9 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
         g.ldo = a->I;
         g.wait_cnt = pooled_cnt[i];
         g.signal_cnt = hidden_cnt[i];
-        rc = omni_make_tmap_2d_bf16(&maps.a[i], m->pooled, (uint64_t)M, (uint64_t)K1, (uint64_t)K1, BM, BK, 1);
+        rc = omni_make_tmap_2d_bf16(&maps.a[gidx], m->pooled, (uint64_t)M, (uint64_t)K1, (uint64_t)K1, BM, BK, 1);
         if (rc) return rc;
-        rc = omni_make_tmap_2d_bf16(&maps.b[i], m->w1, (uint64_t)a->I, (uint64_t)K1, (uint64_t)K1, BM, BK, 1);
+        rc = omni_make_tmap_2d_bf16(&maps.b[gidx], m->w1, (uint64_t)a->I, (uint64_t)K1, (uint64_t)K1, BM, BK, 1);
         if (rc) return rc;
       } else {
         g.N = H;
@@ -627,11 +718,11 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
         g.ldo = H;
         g.wait_cnt = hidden_cnt[i];
         g.wait_per_row = 0;
-        g.wait_fixed = 2 * PPS_EPI_WARPS * ceil_div(a->I, PPS_BN);     // every epilogue warp of every GEMM-1 tile of the block
+        g.wait_fixed = 2 * ceil_div(a->I, PPS_BN);                     // both CTAs of every GEMM-1 tile of the block
         g.signal_cnt = nullptr;
-        rc = omni_make_tmap_2d_bf16(&maps.a[2 + i], m->hidden, (uint64_t)M, (uint64_t)a->I, (uint64_t)a->I, BM, BK, 1);
+        rc = omni_make_tmap_2d_bf16(&maps.a[gidx], m->hidden, (uint64_t)M, (uint64_t)a->I, (uint64_t)a->I, BM, BK, 1);
         if (rc) return rc;
-        rc = omni_make_tmap_2d_bf16(&maps.b[2 + i], m->w2, (uint64_t)H, (uint64_t)a->I, (uint64_t)a->I, BM, BK, 1);
+        rc = omni_make_tmap_2d_bf16(&maps.b[gidx], m->w2, (uint64_t)H, (uint64_t)a->I, (uint64_t)a->I, BM, BK, 1);
         if (rc) return rc;
       }
       g.n_tiles = ceil_div(g.N, PPS_BN);
@@ -642,10 +733,10 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
 
   // compression plan per modality
   for (int i = 0; i < 2; ++i) {
-    if (!present[i] || P.g[i].M == 0) continue;
+    if (!present[i] || P.g[2 * i].M == 0) continue;
     const omni_pps_modality* m = mods[i];
     PpsPool& pl = P.pool[i];
-    pl.M = P.g[i].M;
+    pl.M = P.g[2 * i].M;
     pl.n = m->n_tok / m->rate;
     pl.r = m->rate;
     pl.D = m->D;
@@ -654,15 +745,24 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
     while (cw > 8 && static_cast<long long>(m->rate) * cw * 2 > PPS_SLOT_BYTES) cw = (cw / 2 + 7) / 8 * 8;
     if (static_cast<long long>(m->rate) * cw * 2 > PPS_SLOT_BYTES) return OMNI_ERR_UNSUPPORTED;
     pl.cw = cw;
+    pl.lane_cols = (cw <= 128 && cw % 4 == 0 && m->D > 128) ? 4 : 8;
+    pl.pow2 = (m->rate & (m->rate - 1)) == 0 ? 1 : 0;
+    pl.fr = static_cast<float>(m->rate);
+    pl.rcp = 1.0f / pl.fr;
     pl.n_boxes_row = ceil_div(m->D, cw);
-    int bpu = PPS_SLOT_BYTES / (m->rate * cw * 2);
+    int bpu = 2048 / (m->rate * cw * 2);          // ~2 KB units: four ring slots per warp, enough bytes to amortise a unit
+    if (bpu < 1) bpu = 1;
     if (bpu > pl.n_boxes_row) bpu = pl.n_boxes_row;
+    {
+      const int unit_bytes = (bpu * m->rate * cw * 2 + 127) / 128 * 128;
+      if (unit_bytes > P.slot_bytes) P.slot_bytes = unit_bytes;
+    }
     pl.boxes_per_unit = bpu;
     pl.units_per_row = ceil_div(pl.n_boxes_row, bpu);
     pl.units = static_cast<long long>(pl.M) * pl.units_per_row;
     pl.pooled = reinterpret_cast<bf16*>(m->pooled);
     pl.ready = pooled_cnt[i];
-    P.g[i].wait_per_row = pl.units_per_row;
+    P.g[2 * i].wait_per_row = pl.units_per_row;
     rc = make_tmap_pool(&maps.x[i], m->x, (uint64_t)sp->B, (uint64_t)m->n_tok, (uint64_t)m->D, (uint64_t)m->x_bs,
                         (uint32_t)m->rate, (uint32_t)cw);
     if (rc) return rc;
@@ -678,6 +778,20 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
     sc.pos0[1] = hb + ((i == 1 && P.splice.has_a[2]) ? (P.splice.n_a + 2) : 0) + 1;
   }
 
+  {
+    // profiling switches (results are wrong with either): 1 = compression + row copies only, 2 = GEMMs only
+    static const char* dbg = getenv("OMNI_PPS_ONLY");
+    if (dbg && (dbg[0] == '1' || dbg[0] == '5')) P.n_items = items = 0;
+    if (dbg && dbg[0] == '5') P.splice_rows = 0;                   // 5: compression only
+    if (dbg && dbg[0] == '2') {
+      P.pool[0].units = P.pool[1].units = 0;
+      P.splice_rows = 0;
+      for (int i = 0; i < 4; ++i) { P.g[i].wait_per_row = 0; P.g[i].wait_fixed = 0; }
+    }
+  }
+  if (P.slot_bytes < 128) P.slot_bytes = 128;
+  P.n_slots = (PPS_RING_BYTES / P.slot_bytes) >= 4 ? 4 : 2;
+  if (P.n_slots * P.slot_bytes > PPS_RING_BYTES) return OMNI_ERR_UNSUPPORTED;
   if (cudaMemsetAsync(a->workspace, 0, static_cast<size_t>(cnt.total_ints) * 4, st) != cudaSuccess) return OMNI_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
@@ -689,7 +803,13 @@ extern "C" int omni_pool_project_splice(const omni_pps_args* a, void* stream) {
   const int sms = pps_sm_count();
   int clusters = sms / 2;
   // at least one CTA pair even when there is no GEMM work (pure splice); never more pairs than the SMs hold at once
-  const long long want = items > 0 ? items : 1;
+  long long want = items;
+  {
+    const long long pool_work = (P.pool[0].units + P.pool[1].units + PPS_CHUNK - 1) / PPS_CHUNK + P.splice_rows / 8;
+    const long long w2 = (pool_work + 2 * PPS_POOL_WARPS - 1) / (2 * PPS_POOL_WARPS);
+    if (w2 > want) want = w2;
+  }
+  if (want < 1) want = 1;
   if (want < clusters) clusters = static_cast<int>(want);
   if (clusters < 1) clusters = 1;
   pool_project_splice_kernel<<<2 * clusters, PPS_THREADS, PpsSmem::TOTAL, st>>>(maps, P);
