@@ -229,7 +229,7 @@ int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const void* out, 
  * packed q|k|v row, RoPE already applied) to k_cache / v_cache [B, n_kv_heads, max_len, head_dim] at position *len_idx
  * (device memory: the step is replayed from a CUDA graph) and attends over positions 0..*len_idx.  out [B, out_ld].
  * Replaces the cache update + SDPA of Llama_LoRA.py:284-300 / Qwen_LoRA.py:590-606 under HF generate.  GQA group sizes
- * 1/2/4/8 and head_dim 64/128; anything else returns OMNI_ERR_UNSUPPORTED. */
+ * 1..8 (every architecture of the reference's table) and head_dim 64/128; anything else returns OMNI_ERR_UNSUPPORTED. */
 int omni_decode_attention(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx, void* out,
                           int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
                           int32_t max_len, float scale, void* stream);

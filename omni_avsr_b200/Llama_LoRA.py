@@ -20,7 +20,6 @@ from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import autograd_ops as ag
@@ -138,6 +137,7 @@ class FlatParams:
         self.grad = torch.zeros(capacity, device=device, dtype=torch.bfloat16)
         self.used = 0
         self.names: List[Tuple[str, int, Tuple[int, ...]]] = []
+        self.params: List[nn.Parameter] = []
 
     def alloc(self, shape: Sequence[int], name: str = "") -> nn.Parameter:
         n = int(math.prod(shape))
@@ -148,8 +148,24 @@ class FlatParams:
         p = nn.Parameter(view, requires_grad=True)
         p.grad = self.grad[self.used: self.used + n].view(*shape)
         self.names.append((name, self.used, tuple(shape)))
+        self.params.append(p)
         self.used += n_al
         return p
+
+    def trainable_spans(self) -> List[Tuple[int, int]]:
+        """Maximal [start, end) element ranges of the flat buffer made of tensors with requires_grad=True (alignment padding
+        between two trainable neighbours included).  torch.optim.AdamW skips parameters without a gradient -- weight
+        decay included -- so the fused optimizer kernel must not touch the frozen ranges either."""
+        spans: List[Tuple[int, int]] = []
+        for (name, off, shape), p in zip(self.names, self.params):
+            if not p.requires_grad:
+                continue
+            n_al = (int(math.prod(shape)) + 7) // 8 * 8
+            if spans and spans[-1][1] == off:
+                spans[-1] = (spans[-1][0], off + n_al)
+            else:
+                spans.append((off, off + n_al))
+        return spans
 
     def flat(self):
         return self.data[: self.used], self.grad[: self.used]
@@ -541,7 +557,7 @@ class PackedSdpaFn(torch.autograd.Function):
 
     Forward: one launch per segment, straight from / into the packed rows, log-sum-exp kept for the backward.
     Backward: dQ | dK | dV written into ONE packed dqkv buffer (autograd's own slice gradients would materialise three
-    zero-filled [M, q+2kv] tensors per segment and add them up).  Other head dims fall to the library SDPA."""
+    zero-filled [M, q+2kv] tensors per segment and add them up).  There is no library fallback: other head dims raise."""
 
     @staticmethod
     def _views(qkv, B, S, off, nh, nkv, hd):
@@ -564,17 +580,10 @@ class PackedSdpaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, segments, nh, nkv, hd, causal):
         out = torch.empty((qkv.shape[0], nh * hd), device=qkv.device, dtype=torch.bfloat16)
-        ours = hd in (64, 128)
         lse = None
-        if ours:
-            if ctx.needs_input_grad[0]:
-                lse = torch.empty((nh, qkv.shape[0]), device=qkv.device, dtype=torch.float32)
-            ops.attention_fwd(qkv, out, segments, nh, nkv, hd, causal, lse=lse)
-        else:
-            for (_, B, S, off) in segments:
-                q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
-                o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
-                out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
+        if ctx.needs_input_grad[0]:
+            lse = torch.empty((nh, qkv.shape[0]), device=qkv.device, dtype=torch.float32)
+        ops.attention_fwd(qkv, out, segments, nh, nkv, hd, causal, lse=lse)      # raises for head dims other than 64 / 128
         PackedSdpaFn._zero_pad_rows(out, segments)
         if lse is not None:
             ctx.save_for_backward(qkv, out, lse)
@@ -588,47 +597,31 @@ class PackedSdpaFn(torch.autograd.Function):
         segments, nh, nkv, hd, causal = ctx.meta
         qkv = ctx.saved_tensors[0]
         dqkv = torch.empty_like(qkv)
-        if len(ctx.saved_tensors) == 3:
-            _, out, lse = ctx.saved_tensors
-            ops.attention_bwd(qkv, out, dout.contiguous(), lse, dqkv, segments, nh, nkv, hd, causal)
-        else:
-            for (_, B, S, off) in segments:
-                q, k, v = (t.detach().requires_grad_(True) for t in PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd))
-                with torch.enable_grad():
-                    o = F.scaled_dot_product_attention(q, k, v, is_causal=causal and S > 1, enable_gqa=nh != nkv)
-                do = dout[off: off + B * S].view(B, S, nh, hd).transpose(1, 2)
-                dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
-                gq, gk, gv = PackedSdpaFn._views(dqkv, B, S, off, nh, nkv, hd)
-                gq.copy_(dq)
-                gk.copy_(dk)
-                gv.copy_(dv)
+        _, out, lse = ctx.saved_tensors
+        ops.attention_bwd(qkv, out, dout.contiguous(), lse, dqkv, segments, nh, nkv, hd, causal)
         PackedSdpaFn._zero_pad_rows(dqkv, segments)
         return dqkv, None, None, None, None, None
 
 
 def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
-    """Causal GQA attention per segment of the packed rows (training / prefill without cache: PackedSdpaFn;
-    with a KV cache: SDPA against the cache, optionally under the graph-mode key mask)."""
+    """Causal GQA attention per segment of the packed rows.  Training / prefill: the tcgen05 flash kernel on the packed
+    buffer (the prefill also fills the static KV cache); decode step: the single-token kernel that appends K / V to the
+    cache and attends over it in one launch.  No library attention anywhere: unsupported geometries raise."""
     nh, nkv, hd = a.num_attention_heads, a.num_key_value_heads, a.head_dim
     if kv_cache is None:
         return PackedSdpaFn.apply(qkv, rows.segments, nh, nkv, hd, True)
     out = torch.empty((rows.M, a.q_dim), device=qkv.device, dtype=torch.bfloat16)
     for (task, B, S, off) in rows.segments:
-        if kv_cache.graph_mode and S == 1 and kv_cache.native_step:
-            # decode step: our single-token kernel appends K / V to the cache and attends over it in one launch
+        if S == 1 and kv_cache.graph_mode:
             ops.decode_attention(qkv[off: off + B], kv_cache.k[layer_idx], kv_cache.v[layer_idx], kv_cache.len_idx,
                                  out[off: off + B], B, nh, nkv, hd)
             continue
-        q, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
-        prefill = S > 1 and kv_cache.len == 0 and not kv_cache.graph_mode
-        k, v, mask = kv_cache.update(layer_idx, k, v)
-        if prefill and hd in (64, 128):
-            # prefill: keys == this segment's own rows -> our flash kernel on the packed buffer (cache filled above)
-            ops.attention_fwd(qkv, out, [(task, B, S, off)], nh, nkv, hd, True)
-            continue
-        causal = S > 1 and k.shape[2] == S and mask is None
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal, enable_gqa=True)
-        out[off: off + B * S].view(B, S, nh, hd).copy_(o.transpose(1, 2))
+        if kv_cache.len != 0 or kv_cache.graph_mode:
+            raise NotImplementedError("multi-token steps on top of a non-empty KV cache are not part of the Omni-AVSR decode "
+                                      "path (HF generate: one prefill, then single-token steps)")
+        _, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
+        kv_cache.fill(layer_idx, k, v)
+        ops.attention_fwd(qkv, out, [(task, B, S, off)], nh, nkv, hd, True)
     PackedSdpaFn._zero_pad_rows(out, rows.segments)
     return out
 
@@ -636,42 +629,32 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
 class KVCache:
     """Static per-layer KV cache [layers, B, kv_heads, max_len, head_dim].
 
-    Two write modes: eager (prefill / ungraphed steps: python-int offset `len`) and `graph_mode` (decode step captured
-    in a CUDA graph: the write index, the key mask and the RoPE positions live in device tensors that the graph itself
-    advances, and attention always spans max_len under the mask so every shape is static)."""
+    The prefill writes rows [0, S) (`fill`, python-int offset `len`); decode steps append through the single-token
+    attention kernel at the device-side index `len_idx`, so a step captured in a CUDA graph advances without the host."""
 
     def __init__(self, a: LLMArch, B: int, max_len: int, device):
+        if a.head_dim not in (64, 128) or (a.num_attention_heads // a.num_key_value_heads) not in ops.DECODE_ATTN_GROUPS:
+            raise NotImplementedError(f"decode attention: head_dim {a.head_dim} / GQA group "
+                                      f"{a.num_attention_heads // a.num_key_value_heads} has no kernel (no library fallback)")
         shape = (a.num_hidden_layers, B, a.num_key_value_heads, max_len, a.head_dim)
         self.k = torch.zeros(shape, device=device, dtype=torch.bfloat16)
         self.v = torch.zeros(shape, device=device, dtype=torch.bfloat16)
         self.len = 0
         self.max_len = max_len
-        self.graph_mode = False
+        self.graph_mode = False          # True: single-token steps (device-side write index)
         self.len_idx = torch.zeros(1, device=device, dtype=torch.int64)            # device copy of `len`
-        # single-token steps run on csrc/decode_attention.cu when the geometry is covered (every named architecture)
-        self.native_step = a.head_dim in (64, 128) and \
-            (a.num_attention_heads // a.num_key_value_heads) in ops.DECODE_ATTN_GROUPS
-        self.mask = torch.zeros((B, 1, 1, max_len), device=device, dtype=torch.bool)
 
-    def update(self, layer, k, v):
-        """Returns (k_all, v_all, attn_mask or None)."""
+    def fill(self, layer, k, v):
         S = k.shape[2]
-        if self.graph_mode:
-            self.k[layer].index_copy_(2, self.len_idx, k)
-            self.v[layer].index_copy_(2, self.len_idx, v)
-            return self.k[layer], self.v[layer], self.mask
         self.k[layer][:, :, self.len: self.len + S] = k
         self.v[layer][:, :, self.len: self.len + S] = v
-        return self.k[layer][:, :, : self.len + S], self.v[layer][:, :, : self.len + S], None
 
     def advance(self, S):
         self.len += S
 
     def sync_device_state(self):
-        """After the eager prefill: publish `len` to the device-side state used by the graphed decode step."""
+        """After the eager prefill: publish `len` to the device-side state used by the decode step."""
         self.len_idx.fill_(self.len)
-        self.mask.zero_()
-        self.mask[..., : self.len] = True
 
 
 class LlamaMLP(nn.Module):

@@ -67,9 +67,11 @@ def load_whisper_encoder(encoder, state_dict) -> Tuple[List[str], List[str]]:
     return missing, ignored
 
 
-def load_llm(llm, state_dict) -> Tuple[List[str], List[str]]:
+def load_llm(llm, state_dict, owner=None) -> Tuple[List[str], List[str]]:
     """HF `LlamaForCausalLM` / `Qwen2ForCausalLM` state dict -> our *_lora model.  The LoRA tensors are not in such a
-    file and stay as initialised (reported in `missing`)."""
+    file and stay as initialised (reported in `missing`).  `owner`: the AVSR_LLMs that holds `llm`; its prompt buffers
+    (embeddings of the task prompts, computed by the reference AFTER from_pretrained, modeling_OmniAVSR.py:218-221) are
+    re-embedded from the freshly loaded table."""
     sd = dict(state_dict)
     emb = sd.get("model.embed_tokens.weight")
     own_rows = llm.model.embed_tokens.weight.shape[0]
@@ -88,6 +90,8 @@ def load_llm(llm, state_dict) -> Tuple[List[str], List[str]]:
         raise ValueError("untied architecture but the file has no lm_head.weight")
     missing, ignored = _load(llm, sd)
     missing = [k for k in missing if k not in ("lm_head.weight", "model.embed_tokens.weight")]
+    if owner is not None and hasattr(owner, "refresh_prompts"):
+        owner.refresh_prompts()
     return missing, ignored
 
 

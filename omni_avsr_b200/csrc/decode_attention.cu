@@ -194,8 +194,11 @@ extern "C" int omni_decode_attention(const void* qkv, int64_t ld, void* k_cache,
 #define OMNI_DA(HD_, G_) \
   if (head_dim == HD_ && G == G_) \
     return launch_decode_attn<HD_, G_>(q, ld, kc, vc, li, o, out_ld, B, n_kv_heads, max_len, scale, st);
-  OMNI_DA(64, 1) OMNI_DA(64, 2) OMNI_DA(64, 4) OMNI_DA(64, 8)
-  OMNI_DA(128, 1) OMNI_DA(128, 2) OMNI_DA(128, 4) OMNI_DA(128, 8)
+  // every GQA group size of the reference's model table: 4 (Llama-3.2-1B / 3.1-8B), 3 (Llama-3.2-3B), 7 (Qwen2.5-0.5B / 7B),
+  // 6 (1.5B), 8 (3B), 5 (14B / 32B), + 1 / 2 for MHA-like test geometries
+  OMNI_DA(64, 1) OMNI_DA(64, 2) OMNI_DA(64, 3) OMNI_DA(64, 4) OMNI_DA(64, 5) OMNI_DA(64, 6) OMNI_DA(64, 7) OMNI_DA(64, 8)
+  OMNI_DA(128, 1) OMNI_DA(128, 2) OMNI_DA(128, 3) OMNI_DA(128, 4) OMNI_DA(128, 5) OMNI_DA(128, 6) OMNI_DA(128, 7)
+  OMNI_DA(128, 8)
 #undef OMNI_DA
   return OMNI_ERR_UNSUPPORTED;
 }

@@ -70,8 +70,6 @@ class GraphedGreedyStep:
         # forward of the chosen token
         x = ops.gather_rows(llm.model.embed_tokens.weight.data, nxt.contiguous())
         self.xpad[:B].copy_(x)
-        if not self.cache.native_step:                                     # (library-SDPA fallback only)
-            self.cache.mask.index_fill_(3, self.cache.len_idx, True)       # the new key is visible to its own query
         hid = llm.model.forward_packed(self.xpad, self.rows, self.cache)
         self.h_last.copy_(hid[:B])
         self.cache.len_idx.add_(1)
@@ -112,7 +110,7 @@ class GraphedGreedyStep:
             self.graph.replay()
 
     def _state(self):
-        return [self.unfinished, self.out, self.alive, self.step_idx, self.cache.len_idx, self.cache.mask, self.rows.pos,
+        return [self.unfinished, self.out, self.alive, self.step_idx, self.cache.len_idx, self.rows.pos,
                 self.h_last, self.cache.k, self.cache.v]
 
     def finish(self):

@@ -202,33 +202,62 @@ class ModelModule_LLM(torch.nn.Module):
     def zero_grad_flat(self):
         self.model.flat.grad[: self.model.flat.used].zero_()
 
+    def zero_grad(self, set_to_none: bool = False):
+        """nn.Module.zero_grad(set_to_none=True) would detach the `.grad` views from the flat gradient buffer (the optimizer
+        kernel would then read zeros forever); the gradients are zeroed in place instead."""
+        self.zero_grad_flat()
+
     def optimizer_step(self, lr: Optional[float] = None):
         if self._opt is None:
             self.configure_optimizers()
         o, flat = self._opt, self.model.flat
         p, g = flat.flat()
-        grad_scale = dp.allreduce_flat_grad(g)     # the single NCCL all-reduce of the step (sum; 1/W applied below)
+        red = getattr(self, "_reducer", None)
+        if red is not None:                        # started from the autograd hook on the LLM input (see training_step)
+            grad_scale = red.finish()
+            self._reducer = None
+        else:
+            grad_scale = dp.allreduce_flat_grad(g)     # the single NCCL all-reduce of the step (sum; 1/W applied below)
         o["step"] += 1
         o["sumsq"].zero_()
         ops.sumsq_(g, o["sumsq"])
         if lr is None:
             self.scheduler.step()
             lr = self.scheduler.lr()
-        ops.adamw_(p, g, o["m"], o["v"], lr=lr, beta1=0.9, beta2=0.98, eps=1e-8, weight_decay=self.args.weight_decay,
-                   step=o["step"], grad_scale=grad_scale, max_norm=float(getattr(self.args, "gradient_clip_val", 10.0)),
-                   sumsq=o["sumsq"])
+        # frozen tensors (requires_grad=False: e.g. the AV-HuBERT adapters of an audiovisual Llama-AVSR run) are left alone,
+        # weight decay included, as torch.optim.AdamW does for parameters without a gradient
+        for (a, b) in flat.trainable_spans():
+            ops.adamw_(p[a:b], g[a:b], o["m"][a:b], o["v"][a:b], lr=lr, beta1=0.9, beta2=0.98, eps=1e-8,
+                       weight_decay=self.args.weight_decay, step=o["step"], grad_scale=grad_scale,
+                       max_norm=float(getattr(self.args, "gradient_clip_val", 10.0)), sumsq=o["sumsq"])
         self.global_step += 1
 
     # ---- steps -------------------------------------------------------------------------------------------------
     def training_step(self, batch, batch_idx=0, rates=None):
         ra, rv = rates if rates is not None else (None, None)
+        # :171-173: loss *= W / sum(batch sizes).  The gather of the batch sizes is started here and waited for after the
+        # forward (one rank: the host constant 1 / B)
+        scale = dp.LossScale(batch["tokens"].shape[0], device=batch["tokens"].device)
+        if scale.w > 1:
+            # gradient all-reduce in two pieces: the LLM adapters' range goes out as soon as the gradient of the LLM input
+            # exists, under the backward of the projectors / AV-HuBERT encoder (see dp.GradReducer)
+            flat = self.model.flat
+            self._reducer = dp.GradReducer(flat.grad[: flat.used], self._llm_grad_offset())
+            self.model._llm_input_hook = self._reducer.hook
         audio_loss, video_loss, audiovisual_loss = self.model(batch, is_trainval=True, test_ratio_matry_audio=ra,
                                                               test_ratio_matry_video=rv)
+        self.model._llm_input_hook = None
         train_loss = (audio_loss + video_loss + audiovisual_loss) / 3                       # :162
         self.last_losses = (audio_loss.detach(), video_loss.detach(), audiovisual_loss.detach())
-        # :171-173: loss *= W / sum(batch sizes); equal per-rank batch sizes => 1/B
-        batch_size = batch["tokens"].shape[0]
-        return train_loss * dp.loss_scale(batch_size, device=train_loss.device)
+        return train_loss * scale.value()
+
+    def _llm_grad_offset(self) -> int:
+        """First element of the LLM adapters in the flat buffer (they are allocated last: [AV-HuBERT LoRA | projectors | LLM])."""
+        off = getattr(self, "_llm_off", None)
+        if off is None:
+            offs = [o for (name, o, _) in self.model.flat.names if name.startswith("layers.")]
+            off = self._llm_off = min(offs) if offs else self.model.flat.used
+        return off
 
     def train_step(self, batch, rates=None, lr=None):
         """zero_grad -> training_step -> backward -> all-reduce + clip + AdamW.  Returns the (detached) loss."""

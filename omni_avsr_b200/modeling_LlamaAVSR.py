@@ -72,6 +72,14 @@ class AVSR_LLMs(_OmniAVSR):
         return Projector(dim * r if stack else dim, inter, hidden, ln, self.flat, name), None
 
     # ------------------------------------------------------------------------------------------------
+    def _unfreeze_PETF(self, unfrozen_modules):
+        """modeling_LlamaAVSR.py:212-236: unlike Omni-AVSR, the AV-HuBERT adapters are unfrozen only when the model's
+        modality is "video"; in the audiovisual Llama-AVSR / MTSK recipes they stay frozen (down = 0: an identity)."""
+        super()._unfreeze_PETF(unfrozen_modules)
+        if hasattr(self, "video_encoder") and self.modality != "video":
+            for p in self.video_encoder.lora_parameters():
+                p.requires_grad_(False)
+
     def _prompt_embeddings(self):
         return self.llm.model.embed_tokens(self._prompt_ids)[0].detach()          # [P, H]  (:279)
 

@@ -291,9 +291,11 @@ class AVSR_LLMs(nn.Module):
 
         start = 0 if "Qwen" in self.llm_model else 1                       # :218
         emb = self.llm.model.embed_tokens
+        self._prompt_ids = {}
         for name, prompt in (("prompt_audio", prompt_audio), ("prompt_video", prompt_video),
                              ("prompt_audiovisual", prompt_audiovisual)):
             ids = self.tokenizer(prompt, return_tensors="pt").input_ids[:, start:-1].to(device)
+            self._prompt_ids[name] = ids
             self.register_buffer(name, emb(ids).detach().clone())        # [1, P, H] buffers (:219-221)
         self.prompt_audio_len = self.prompt_audio.shape[1]
         self.prompt_video_len = self.prompt_video.shape[1]
@@ -339,16 +341,43 @@ class AVSR_LLMs(nn.Module):
             for p in self.video_encoder.lora_parameters():
                 p.requires_grad_(avh_on)
 
+    # Parts of the reference's `video_encoder` (the full fairseq AVHubertModel: `remove_pretraining_modules` is never called,
+    # modeling_OmniAVSR.py:123-126) that the video-only `extract_finetune` path never touches.  A real `model_avg_N.pth`
+    # carries them; this mirror has no such modules, so they are dropped before the (strict) load.
+    _UNUSED_AVHUBERT = ("video_encoder.mask_emb", "video_encoder.label_embs_concat", "video_encoder.final_proj.",
+                        "video_encoder.feature_extractor_audio.", "video_encoder.target_glu.",
+                        "video_encoder.encoder.layers.", "video_encoder.feature_extractor_video.resnet.")
+
     def load_state_dict(self, state_dict, strict=True, assign=False):
         """Accepts the reference's bare AVSR_LLMs state dict (lightning_OmniAVSR.py:148-150); the packed / transposed
         copies used by the kernels are rebuilt lazily afterwards."""
-        out = super().load_state_dict(state_dict, strict=strict)
+        own = set(self.state_dict().keys())
+        sd = {}
+        for k, v in state_dict.items():
+            if k not in own and k.startswith(self._UNUSED_AVHUBERT[:5]):
+                continue                                   # pre-training heads / audio front-end of AV-HuBERT
+            if k not in own and k.endswith("num_batches_tracked"):
+                continue                                   # BatchNorm counters (the mirror runs eval-mode BN)
+            sd[k] = v
+        out = super().load_state_dict(sd, strict=strict)
+        self.refresh_prompts()
         for mod in self.modules():
             if hasattr(mod, "_wt"):
                 mod._wt = None
             if hasattr(mod, "_head_t"):
                 mod._head_t = None
         return out
+
+    def refresh_prompts(self):
+        """Re-embed the three task prompts from the CURRENT embedding table.  The reference computes the prompt buffers
+        after `from_pretrained` (:218-221); here weights arrive later (checkpoints.load_llm / load_state_dict), so the
+        buffers are recomputed whenever the table changes -- unless the state dict itself provided them."""
+        if not isinstance(self._prompt_ids, dict):
+            return                                          # Llama-AVSR embeds its prompt at call time (no buffers)
+        emb = self.llm.model.embed_tokens
+        with torch.no_grad():
+            for name, ids in self._prompt_ids.items():
+                getattr(self, name).copy_(emb(ids).detach())
 
     def trainable_parameter_count(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -374,6 +403,9 @@ class AVSR_LLMs(nn.Module):
             out = self.prepare_inputs(inputs, is_trainval, test_ratio_matry_audio=test_ratio_matry_audio,
                                       test_ratio_matry_video=test_ratio_matry_video)
             xp, rows, labels = out["packed"], out["rows"], out["labels"]
+            hook = getattr(self, "_llm_input_hook", None)
+            if hook is not None and xp.requires_grad:
+                xp.register_hook(hook)             # fires when every LLM layer has finished its backward (dp.GradReducer)
             hid = self.llm.model.forward_packed(xp, rows)
             w = self.matry_weights if self.matry_weights else (1.0, 1.0, 1.0)
             segs = [(B, S, off) for (_, B, S, off) in rows.segments]

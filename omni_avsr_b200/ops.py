@@ -723,7 +723,7 @@ def attention_bwd(qkv, out, dout, lse, dqkv, segments, n_heads: int, n_kv_heads:
     return dqkv
 
 
-DECODE_ATTN_GROUPS = (1, 2, 4, 8)
+DECODE_ATTN_GROUPS = (1, 2, 3, 4, 5, 6, 7, 8)
 
 
 def decode_attention(qkv, k_cache, v_cache, len_idx, out, B: int, n_heads: int, n_kv_heads: int, head_dim: int,

@@ -26,8 +26,9 @@ class AVSR_LLMs(nn.Module):
     def __init__(self, llm_cfg: ol.LLMConfig, lora_cfg, whisper_cfg: oe.WhisperCfg, avh_cfg: oe.AVHubertCfg,
                  intermediate_size, rates_audio, rates_video, compression_mode, prompts_ids, marker_ids, is_qwen,
                  matry_weights=None, is_task_specific=True, resnet_widths=(64, 128, 256, 512), modality="audiovisual",
-                 max_dec_tokens=32, eos_id=None, pad_id=None):
+                 max_dec_tokens=32, eos_id=None, pad_id=None, single_projector=False, projector_layernorm=False):
         super().__init__()
+        self.single_projector = single_projector
         self.compression_mode, self.is_qwen = compression_mode, is_qwen
         self.rates_audio, self.rates_video = list(rates_audio), list(rates_video)
         self.matry_weights, self.is_task_specific = matry_weights, is_task_specific
@@ -37,10 +38,17 @@ class AVSR_LLMs(nn.Module):
         self.video_encoder = oe.AVHubertVideo(avh_cfg, resnet_widths)
         H = llm_cfg.hidden_size
         stack = compression_mode == "stack"
-        self.audio_proj = nn.ModuleList([om.make_projector(whisper_cfg.d_model * (r if stack else 1), intermediate_size, H,
-                                                           False) for r in self.rates_audio])
-        self.video_proj = nn.ModuleList([om.make_projector(avh_cfg.embed_dim * (r if stack else 1), intermediate_size, H,
-                                                           False) for r in self.rates_video])
+        if single_projector:
+            # avg-pooling Matryoshka with ONE projector shared by every rate (:94-97, :101-102 audio; :178-186 video);
+            # nn.LayerNorm(hidden) at the end unless remove_layernorm_from_projector
+            assert not stack
+            self.audio_proj = om.make_projector(whisper_cfg.d_model, intermediate_size, H, projector_layernorm)
+            self.video_proj = om.make_projector(avh_cfg.embed_dim, intermediate_size, H, projector_layernorm)
+        else:
+            self.audio_proj = nn.ModuleList([om.make_projector(whisper_cfg.d_model * (r if stack else 1), intermediate_size,
+                                                               H, False) for r in self.rates_audio])
+            self.video_proj = nn.ModuleList([om.make_projector(avh_cfg.embed_dim * (r if stack else 1), intermediate_size,
+                                                               H, False) for r in self.rates_video])
         self.llm = ol.ForCausalLM_lora(llm_cfg, lora_cfg)
         self.prompts_ids = prompts_ids          # dict task -> LongTensor [1, P]
 
@@ -63,9 +71,11 @@ class AVSR_LLMs(nn.Module):
     def media_tokens(self, inputs, rate_a, rate_v, need_a=True, need_v=True):
         a = v = None
         if need_a:
-            a = self.audio_proj[self.rates_audio.index(rate_a)](self.encode_audio(inputs["audio"], max(inputs["lengths"]), rate_a))
+            pa = self.audio_proj if self.single_projector else self.audio_proj[self.rates_audio.index(rate_a)]   # :366
+            a = pa(self.encode_audio(inputs["audio"], max(inputs["lengths"]), rate_a))
         if need_v:
-            v = self.video_proj[self.rates_video.index(rate_v)](self.encode_video(inputs["video"], rate_v))
+            pv = self.video_proj if self.single_projector else self.video_proj[self.rates_video.index(rate_v)]   # :353
+            v = pv(self.encode_video(inputs["video"], rate_v))
         return a, v
 
     def forward(self, inputs, rate_a, rate_v):

@@ -38,7 +38,9 @@ def oracle_from_product(module, dtype=torch.bfloat16):
     rates_v = list(args.downsample_ratio_video) if args.is_matryoshka else [args.downsample_ratio_video]
     oracle = omod.AVSR_LLMs(llm_cfg, lora_cfg, whisper_cfg, avh_cfg, args.intermediate_size, rates_a, rates_v,
                             args.compression_mode, prompts_ids, marker, is_qwen, args.matry_weights,
-                            args.is_task_specific, va.resnet_widths, args.modality, args.max_dec_tokens, eos, pad)
+                            args.is_task_specific, va.resnet_widths, args.modality, args.max_dec_tokens, eos, pad,
+                            single_projector=bool(args.is_matryoshka and args.is_single_matry_projector),
+                            projector_layernorm=not args.no_layernorm_projector)
     sd = {k: t.detach().cpu() for k, t in m.state_dict().items()}
     missing, unexpected = oracle.load_state_dict(sd, strict=False)
     unexpected = [k for k in unexpected if not k.startswith("prompt_")]

@@ -3,7 +3,7 @@ import torch
 
 
 def small_module(llm="meta-llama/Llama-3.2-1B", task_specific=True, shared=True, compression="avg-pooling", seed=0,
-                 lora_std=0.05):
+                 lora_std=0.05, llm_over=None, **extra_args):
     from omni_avsr_b200 import lightning_OmniAVSR as pl_mod
     from omni_avsr_b200.encoders import AVHubertArch, WhisperArch
     torch.manual_seed(seed)
@@ -13,9 +13,11 @@ def small_module(llm="meta-llama/Llama-3.2-1B", task_specific=True, shared=True,
     if is_qwen:
         over = dict(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=8,
                     num_key_value_heads=1, head_dim=64)
+    if llm_over:
+        over.update(llm_over)
     args = pl_mod.make_args(llm_model=llm, rank=4 if not is_qwen else 8, alpha=2, intermediate_size=384,
                             is_task_specific=task_specific, use_shared_lora_task_specific=shared,
-                            compression_mode=compression, max_dec_tokens=8)
+                            compression_mode=compression, max_dec_tokens=8, **extra_args)
     mk = dict(llm_overrides=over, hidden_size_override=over["hidden_size"],
               audio_arch=WhisperArch(128, 2, 2, 256), video_arch=AVHubertArch(128, 256, 2, 2, 16, 4, (16, 32, 32, 64)))
     mod = pl_mod.ModelModule_LLM(args, model_kwargs=mk)

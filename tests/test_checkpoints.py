@@ -160,3 +160,70 @@ def test_lightning_checkpoint_round_trip_through_averaging(tmp_path):
     mod.model.load_state_dict({k: v.cuda() for k, v in avg.items()})                 # lightning_OmniAVSR.py:148-150
     for k in ("audio_proj.0.0.weight", "llm.model.layers.0.self_attn.lora_up_Q.audio.weight", "prompt_audio"):
         assert torch.equal(mod.model.state_dict()[k].cpu(), avg[k])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round-2 additions: real `model_avg_N.pth` files carry AV-HuBERT pre-training tensors, prompt buffers must
+# follow the embedding table, the fused optimizer must not touch frozen tensors
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_reference_state_dict_with_unused_avhubert_tensors_loads_strictly():
+    """The reference's `video_encoder` is the full fairseq AVHubertModel (remove_pretraining_modules is never called), so
+    its state dict has mask_emb / label_embs_concat / final_proj / feature_extractor_audio; a strict load must accept it."""
+    from tests._small import small_module
+    mod = small_module()
+    sd = {k: v.clone() for k, v in mod.model.state_dict().items()}
+    sd.update({"video_encoder.mask_emb": torch.zeros(128), "video_encoder.label_embs_concat": torch.zeros(10, 16),
+               "video_encoder.final_proj.weight": torch.zeros(16, 128), "video_encoder.final_proj.bias": torch.zeros(16),
+               "video_encoder.feature_extractor_audio.proj.weight": torch.zeros(128, 104),
+               "video_encoder.feature_extractor_audio.proj.bias": torch.zeros(128)})
+    res = mod.model.load_state_dict(sd)                      # strict=True
+    assert not res.missing_keys and not res.unexpected_keys
+    sd["llm.model.layers.0.bogus.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        mod.model.load_state_dict(sd)
+
+
+@pytest.mark.gpu
+def test_prompt_buffers_follow_the_embedding_table():
+    """The reference embeds the task prompts AFTER from_pretrained (modeling_OmniAVSR.py:218-221); loading base weights
+    into the mirror must refresh the prompt buffers, otherwise they keep the random-init rows."""
+    from omni_avsr_b200 import checkpoints
+    from tests._small import small_module
+    mod = small_module()
+    m = mod.model
+    g = torch.Generator().manual_seed(0)
+    new = (torch.randn(m.llm.model.embed_tokens.weight.shape, generator=g) * 0.02).bfloat16()
+    old_prompt = m.prompt_audio.clone()
+    checkpoints.load_llm(m.llm, {"model.embed_tokens.weight": new}, owner=m)
+    ids = m._prompt_ids["prompt_audio"].cpu()
+    assert torch.equal(m.prompt_audio.cpu(), new[ids])
+    assert not torch.equal(m.prompt_audio, old_prompt)
+    ids = m._prompt_ids["prompt_audiovisual"].cpu()
+    assert torch.equal(m.prompt_audiovisual.cpu(), new[ids])
+
+
+@pytest.mark.gpu
+def test_optimizer_leaves_frozen_tensors_alone_and_zero_grad_keeps_the_flat_views():
+    """torch.optim.AdamW skips parameters without a gradient (weight decay included); the fused kernel therefore runs
+    over the trainable spans of the flat buffer only.  zero_grad(set_to_none=True) must not detach the flat views."""
+    from omni_avsr_b200.synthetic import synthetic_batch, to_device
+    from tests._small import small_module
+    mod = small_module(seed=2)
+    m = mod.model
+    m._unfreeze_PETF(["peft_llm"])                           # AV-HuBERT adapters frozen
+    mod.args.weight_decay = 0.5
+    mod.configure_optimizers()
+    spans = m.flat.trainable_spans()
+    covered = sum(b - a for a, b in spans)
+    assert 0 < covered < m.flat.used
+    avh = [p.detach().clone() for p in m.video_encoder.lora_parameters()]
+    llm_before = m.llm.model.layers[0].self_attn.lora_up.detach().clone()
+    gpu = to_device(synthetic_batch(2, mod.tokenizer, seconds=2.0, text_len=12, seed=7), "cuda")
+    mod.zero_grad(set_to_none=True)
+    att = m.llm.model.layers[0].self_attn
+    assert att.lora_down.grad is not None and att.lora_down.grad.data_ptr() >= m.flat.grad.data_ptr()
+    mod.train_step(gpu, rates=(4, 2), lr=0.1)
+    for p, q in zip(m.video_encoder.lora_parameters(), avh):
+        assert torch.equal(p.detach(), q)                    # no drift under lr * wd = 0.05
+    assert not torch.equal(m.llm.model.layers[0].self_attn.lora_up.detach(), llm_before)

@@ -19,7 +19,17 @@ def _worker(rank, world, port, q):
     # each rank: mean over its utterances (what a per-rank mean loss produces), then reference scaling W / sum(B)
     scale = dp.loss_scale(local_b)
     flat = per_utt_grads[mine].sum(0) * scale
+    flat2 = flat.clone()
     factor = dp.allreduce_flat_grad(flat)
+    # the asynchronous forms used by ModelModule_LLM: gather started early, gradient buffer reduced in two pieces
+    ls = dp.LossScale(local_b)
+    assert abs(float(ls.value()) - float(scale)) < 1e-9
+    red = dp.GradReducer(flat2, split=10)
+    red.hook(None)                       # tail [10, 37) goes out first (autograd hook on the LLM input)
+    assert red.finish() == factor
+    assert torch.equal(flat, flat2)
+    red = dp.GradReducer(flat2.clone(), split=10)      # hook never fired: one reduction of the whole buffer
+    assert red.finish() == factor
     q.put((rank, mine, float(scale), (flat * factor).tolist()))
     dist.destroy_process_group()
 

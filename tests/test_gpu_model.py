@@ -226,3 +226,163 @@ def test_ragged_batch_like_collate_llm(pair):
     out = mod.model.prepare_inputs(gpu, True, test_ratio_matry_audio=4, test_ratio_matry_video=5)
     assert out["labels_audio"].shape[1] == 1 + (93 // 4 + 2) + mod.model.prompt_audio_len + 11
     assert (out["labels_audio"][2, -6:] == -100).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rows of SURVEY 8(a) that had no test in round 1: validation_step (a2), WER bookkeeping of test_step (a3), the
+# single-projector + LayerNorm recipe (a10), beam search with the near-tie rule, odd GQA group sizes in the decode step
+# ---------------------------------------------------------------------------------------------------------------
+def test_validation_step_fixed_rates(pair):
+    """lightning_OmniAVSR.py:178-192: validation = the train forward at the FIXED rates of the args, no batch scaling."""
+    mod, oracle = pair
+    cpu, gpu = _batch(mod, B=2, seed=21)
+    for ra, rv in ((16, 2), (4, 5)):
+        mod.args.downsample_ratio_test_matry_audio, mod.args.downsample_ratio_test_matry_video = ra, rv
+        got = mod.validation_step(gpu, 0)
+        with torch.no_grad():
+            parts = oracle(cpu, ra, rv)
+        want = sum(parts) / 3
+        assert not got.requires_grad
+        assert abs(got.item() - want.item()) <= 5e-2, (ra, rv, got.item(), want.item())
+        sel = mod.model.prepare_inputs(gpu, True, test_ratio_matry_audio=ra, test_ratio_matry_video=rv)["selected_rates"]
+        assert sel == (ra, rv)
+
+
+def test_wer_accumulation_with_gold_text(pair):
+    """test_step with `gold_text` (the B = 1 eval loop, lightning_OmniAVSR.py:194-219): word-level edit distance and
+    reference length are accumulated over utterances; on_test_epoch_start resets them."""
+    from omni_avsr_b200.lightning_OmniAVSR import compute_word_level_distance
+    mod, oracle = pair
+    cpu, gpu = _batch(mod, B=1, seed=5)
+    one = dict(gpu, tokens=gpu["tokens"][:, :1].contiguous())
+    mod.args.modality = "audio"
+    mod.args.downsample_ratio_test_matry_audio, mod.args.downsample_ratio_test_matry_video = 4, None
+    mod.on_test_epoch_start()
+    ids = mod.test_step(one)
+    hyp = mod.tokenizer.batch_decode(ids, skip_special_tokens=True)[0]
+    assert mod.total_length == 0 and mod.total_edit_distance == 0           # no gold text: nothing accumulated
+    gold_same, gold_diff = hyp, hyp + " extra words"
+    mod.test_step(dict(one, gold_text=gold_same))
+    assert (mod.total_edit_distance, mod.total_length) == (0, len(gold_same.split()))
+    mod.test_step(dict(one, gold_text=gold_diff))
+    assert mod.total_edit_distance == 2 == compute_word_level_distance(gold_diff, hyp)
+    assert mod.total_length == len(gold_same.split()) + len(gold_diff.split())
+    assert abs(mod.on_test_epoch_end() - 2 / mod.total_length) < 1e-12
+    mod.on_test_epoch_start()
+    assert mod.total_length == 0 and mod.total_edit_distance == 0
+    assert compute_word_level_distance("a b c", "A x c d") == 2             # lower-cased, substitution + insertion
+
+
+def test_single_matry_projector_with_layernorm():
+    """is_single_matry_projector (modeling_OmniAVSR.py:94-97,:178-186): ONE projector for every rate, ending in a trainable
+    nn.LayerNorm -- forward on the LayerNorm row kernel (not torch.layer_norm), losses and projector gradients vs the oracle."""
+    from oracle.modeling import training_step
+    from oracle.pairing import oracle_from_product
+    from omni_avsr_b200 import ops
+    mod = small_module(is_single_matry_projector=True, no_layernorm_projector=False, seed=3)
+    m = mod.model
+    assert len(m.audio_proj) == 4 and len(m.video_proj) == 4 and not m.audio_proj.fusable
+    with torch.no_grad():                       # non-trivial affine so that the LayerNorm parameters matter
+        m.audio_proj[3].weight.uniform_(0.5, 1.5)
+        m.audio_proj[3].bias.uniform_(-0.2, 0.2)
+    oracle = oracle_from_product(mod)
+    cpu, gpu = _batch(mod, seed=9)
+    for ra, rv in ((4, 2), (16, 5)):
+        oracle.zero_grad()
+        o_loss, o_parts = training_step(oracle, cpu, ra, rv)
+        o_loss.backward()
+        mod.zero_grad_flat()
+        calls = ops.LAUNCHES
+        loss = mod.training_step(gpu, 0, rates=(ra, rv))
+        loss.backward()
+        assert ops.LAUNCHES > calls
+        for a, b in zip(mod.last_losses, o_parts):
+            assert abs(a.item() - b.item()) <= 5e-2, (a.item(), b.item())
+        for got, want, name in ((m.audio_proj[3].weight.grad, oracle.audio_proj[3].weight.grad, "ln.weight"),
+                                (m.audio_proj[3].bias.grad, oracle.audio_proj[3].bias.grad, "ln.bias"),
+                                (m.video_proj[2].weight.grad, oracle.video_proj[2].weight.grad, "video.2.weight")):
+            assert _rel(got, want) <= 1e-1, (name, _rel(got, want))
+
+
+def _hyp_score(oracle, infer_cpu, b, task, ra, rv, ids):
+    """Oracle (teacher-forced) mean log-prob of a hypothesis for clip b (EOS kept, padding dropped)."""
+    from oracle import matryoshka as om
+    ids = [int(t) for t in ids]
+    if oracle.eos_id in ids:
+        ids = ids[: ids.index(oracle.eos_id) + 1]
+    ids = [t for t in ids if t != oracle.pad_id or t == oracle.eos_id]
+    one = {k: (v[b: b + 1] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == infer_cpu["tokens"].shape[0] else v)
+           for k, v in infer_cpu.items()}
+    one["lengths"] = infer_cpu["lengths"]          # the reference truncates by max(lengths) of the batch it saw
+    with torch.no_grad():
+        a, v = oracle.media_tokens(infer_cpu, ra, rv, task in ("audio", "audiovisual"), task in ("video", "audiovisual"))
+        a = None if a is None else a[b: b + 1]
+        v = None if v is None else v[b: b + 1]
+        emb = om.build_infer_sequence(oracle.llm.model.embed_tokens, infer_cpu["tokens"][b: b + 1], a, v,
+                                      oracle.prompts()[task], oracle.marker_ids, oracle.is_qwen)
+        S0 = emb.shape[1]
+        if len(ids) > 1:
+            emb = torch.cat([emb, oracle.llm.model.embed_tokens(torch.tensor(ids[:-1]))[None].to(emb.dtype)], dim=1)
+        logits = oracle.llm(inputs_embeds=emb, modality=task if oracle.is_task_specific else None).logits[0, S0 - 1:]
+        lp = torch.log_softmax(logits.float(), dim=-1)
+    return sum(lp[i, t].item() for i, t in enumerate(ids)) / max(len(ids), 1)
+
+
+def _beam_near_tie_ok(oracle, infer_cpu, task, ra, rv, K, got, want):
+    """Token-for-token, or -- when the hypotheses differ -- the product's hypothesis must be one the ORACLE scores within
+    2e-2 per token of its own best (the rule of tests/test_gpu_llm.py::test_beam_search_matches_oracle)."""
+    for b in range(want.shape[0]):
+        n = min(got.shape[1], want.shape[1])
+        if got.shape[1] == want.shape[1] and torch.equal(got[b, :n], want[b, :n]):
+            continue
+        s_got = _hyp_score(oracle, infer_cpu, b, task, ra, rv, got[b])
+        s_want = _hyp_score(oracle, infer_cpu, b, task, ra, rv, want[b])
+        assert abs(s_got - s_want) <= 2e-2, (b, got[b], want[b], s_got, s_want)
+
+
+def test_beam_search_transcripts_near_tie_rule(pair):
+    mod, oracle = pair
+    cpu, gpu = _batch(mod, B=2)
+    infer_cpu = dict(cpu, tokens=cpu["tokens"][:, :1])
+    infer_gpu = dict(gpu, tokens=gpu["tokens"][:, :1].contiguous())
+    want = oracle.decode(infer_cpu, "audiovisual", 4, 2, num_beams=4)
+    mod.args.modality = "audiovisual"
+    mod.args.downsample_ratio_test_matry_audio, mod.args.downsample_ratio_test_matry_video = 4, 2
+    mod.on_test_epoch_start()
+    mod.model.num_beams = 4
+    try:
+        got = mod.test_step(infer_gpu).cpu()
+    finally:
+        mod.model.num_beams = 1
+    _beam_near_tie_ok(oracle, infer_cpu, "audiovisual", 4, 2, 4, got, want)
+
+
+def test_decode_with_three_query_heads_per_kv_head():
+    """Llama-3.2-3B has 3 query heads per KV head (Qwen2.5-0.5B / 7B: 7, 1.5B: 6, 14B / 32B: 5): the single-token attention
+    kernel covers every group size 1..8, greedy AND beam search run on it (no library attention anywhere)."""
+    from oracle.pairing import oracle_from_product
+    mod = small_module(llm="meta-llama/Llama-3.2-3B",
+                       llm_over=dict(hidden_size=384, num_attention_heads=6, num_key_value_heads=2, head_dim=64,
+                                     intermediate_size=512), seed=4)
+    oracle = oracle_from_product(mod)
+    cpu, gpu = _batch(mod, B=2, seed=13)
+    infer_cpu = dict(cpu, tokens=cpu["tokens"][:, :1])
+    infer_gpu = dict(gpu, tokens=gpu["tokens"][:, :1].contiguous())
+    mod.args.modality = "audiovisual"
+    mod.args.downsample_ratio_test_matry_audio, mod.args.downsample_ratio_test_matry_video = 16, 5
+    mod.on_test_epoch_start()
+    want, margins = oracle.decode(infer_cpu, "audiovisual", 16, 5, return_margins=True)
+    got = mod.test_step(infer_gpu).cpu()
+    n = min(got.shape[1], want.shape[1])
+    for b in range(got.shape[0]):
+        for i in range(n):
+            if got[b, i] != want[b, i]:
+                assert margins[b, i] <= 2e-2, (b, i, margins[b, i])
+                break
+    wantb = oracle.decode(infer_cpu, "audiovisual", 16, 5, num_beams=3)
+    mod.model.num_beams = 3
+    try:
+        gotb = mod.test_step(infer_gpu).cpu()
+    finally:
+        mod.model.num_beams = 1
+    _beam_near_tie_ok(oracle, infer_cpu, "audiovisual", 16, 5, 3, gotb, wantb)
