@@ -75,9 +75,24 @@ typedef struct omni_gemm_args {
                               256-row boundaries), which lets the K-extended GEMM run on the CTA-pair kernel */
   void* out2;              /* OMNI_ACT_SWIGLU64: [M, N/2] bf16; OMNI_ACT_GELU_KEEP: [M, N] bf16; ld = ldo2; else NULL */
   int64_t ldo2;
+  void* workspace;         /* omni_gemm_skinny_bf16 only: split-K exchange buffer (256-byte aligned device memory, zero-filled
+                              once by the caller; the kernel leaves its counters at zero), or NULL = no split-K */
+  int64_t workspace_bytes; /* >= omni_gemm_skinny_workspace_bytes() */
 } omni_gemm_args;
 
 int omni_gemm_bf16(const omni_gemm_args* args, void* stream);
+
+/* Weight-streaming variant for the decode step (M <= 128 token rows; every nn.Linear of LlamaDecoderLayer_lora under HF
+ * generate, Llama_LoRA.py:580-655, one token per sequence): same argument block and the same results up to fp32
+ * summation order.  The weights are the M operand of the MMA (128 output features per CTA), K is split over a cluster of up
+ * to 8 co-resident CTAs whose partial sums are exchanged through `workspace` (L2-resident), so that ~all SMs stream weight bytes.
+ * Differences to omni_gemm_bf16: K % 64 == 0; bf16 output only; b_row_table is indexed per 64-feature block and
+ * ext_table per 128-feature tile (block_n must be 128 when given); OMNI_ACT_SWIGLU64 needs N % 128 == 0 and `out` may be
+ * NULL (only out2 = the activation is written); OMNI_ACT_GELU_KEEP is not available. */
+int omni_gemm_skinny_bf16(const omni_gemm_args* args, void* stream);
+/* Upper bound of the workspace any omni_gemm_skinny_bf16 call needs on the current device (fp32 partial tiles of at most
+ * SM-count CTAs x 128 tokens x 128 features + the per-tile counters). */
+int64_t omni_gemm_skinny_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Whisper log-mel front end on the device: audio [B, T] (fp32 or bf16, batch stride audio_bs) -> bf16 [B, 80, 3000].

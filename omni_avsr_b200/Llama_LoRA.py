@@ -291,7 +291,11 @@ class LoraPlan:
                         ext[g, nt, a * cb + c] = torch.tensor(
                             [(part * self.n_act + a) * rp + c * 64, base + self.slot_of(a, g) * width + nn0, c * 64, 0])
         self.ext_fwd = ext.contiguous().to(device)
-        self.ext_fwd_step = self.ext_fwd if bn == 64 else self._ext_table(64).to(device)   # decode step: 64-column tiles
+        # decode step (weight-streaming kernel, 128-feature tiles); None when q / k / v widths are not multiples of 128
+        self.ext_fwd_step = None
+        if self.q_cols % 128 == 0 and self.k_cols % 128 == 0 and self.v_cols % 128 == 0:
+            self.ext_fwd_step = self.ext_fwd if bn == 128 else self._ext_table(128).to(device)
+        self.ext_fwd_64 = self.ext_fwd if bn == 64 else self._ext_table(64).to(device)
         # backward phase 1': dT_part = s * dOut_part @ upT_part, upT_part [n_slots*rp, width]; tile -> (a, c)
         nt1b = self.n_act * cb
         browb = torch.zeros((3, nt1b), dtype=torch.int32)
@@ -548,6 +552,8 @@ class LlamaSdpaAttention_lora(nn.Module):
         else:
             ops.rope_(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim)
         attn = attention_packed(qkv, rows, a, kv_cache, self.layer_idx)
+        if ag.skinny_ok(attn, residual):
+            return ops.gemm(attn, self.o_proj.weight.data, residual=residual, skinny=True)      # decode step
         return ag.frozen_linear(attn, self.o_proj.weight.data, wt_o, residual=residual, block_n=256)
 
 
@@ -690,6 +696,12 @@ class LlamaMLP(nn.Module):
         if h.requires_grad and I % 64 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I):
             w_il, wt_il = self.interleaved()
             act = ag.GateUpSwigluFn.apply(h, w_il, wt_il)          # SwiGLU in the gate_up GEMM's epilogue
+        elif ag.skinny_ok(h, residual) and I % 64 == 0:
+            # decode step: weight-streaming kernel, SwiGLU in its epilogue (only the activation is written)
+            w_il, _ = self.interleaved()
+            act = torch.empty((h.shape[0], I), device=h.device, dtype=torch.bfloat16)
+            ops.gemm(h, w_il, act="swiglu64", out2=act, skinny=True)
+            return ops.gemm(act, self.down_proj.weight.data, residual=residual, skinny=True)
         else:
             gu = ag.frozen_linear(h, self.gate_up_weight, wt_gu, block_n=256)
             act = ag.swiglu(gu)

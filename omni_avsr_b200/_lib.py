@@ -49,6 +49,7 @@ class GemmArgs(C.Structure):
         ("n_ext", C.c_int32), ("block_n", C.c_int32), ("act", C.c_int32), ("out_fp32", C.c_int32),
         ("alpha", C.c_float), ("pair_aligned", C.c_int32),
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -109,6 +110,8 @@ def _sig(name, argtypes, restype=C.c_int):
 _sig("omni_abi_version", [])
 _sig("omni_device_cc", [])
 _sig("omni_gemm_bf16", [C.POINTER(GemmArgs), C.c_void_p])
+_sig("omni_gemm_skinny_bf16", [C.POINTER(GemmArgs), C.c_void_p])
+_sig("omni_gemm_skinny_workspace_bytes", [], C.c_int64)
 _sig("omni_matryoshka_compress",
      [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p])
 _sig("omni_matryoshka_compress_bwd",
@@ -158,7 +161,7 @@ _sig("omni_audio_transform", [_P, _P, _I64, _F, C.POINTER(C.c_int32), _I32, _P, 
 
 # every symbol include/omni_avsr.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
-    "omni_abi_version", "omni_device_cc", "omni_gemm_bf16", "omni_matryoshka_compress",
+    "omni_abi_version", "omni_device_cc", "omni_gemm_bf16", "omni_gemm_skinny_bf16", "omni_gemm_skinny_workspace_bytes", "omni_matryoshka_compress",
     "omni_matryoshka_compress_bwd", "omni_splice_seq_len", "omni_splice_prompt", "omni_splice_prompt_bwd",
     "omni_rmsnorm_fwd", "omni_rmsnorm_bwd", "omni_layernorm_fwd", "omni_layernorm_bwd", "omni_rope",
     "omni_swiglu_fwd", "omni_swiglu_bwd", "omni_swiglu_bwd_blocked", "omni_gelu_fwd", "omni_gelu_bwd", "omni_gather_rows", "omni_scatter_rows",

@@ -26,6 +26,12 @@ class FrozenLinearFn(torch.autograd.Function):
         return dx, None, None, None, (dy if ctx.has_res else None), None
 
 
+def skinny_ok(x, residual=None) -> bool:
+    """Decode-step shapes (<= 128 token rows, nothing to differentiate, K a multiple of 64): the weight-streaming kernel."""
+    return (x.shape[0] <= 128 and x.shape[1] % 64 == 0 and not x.requires_grad and not torch.is_grad_enabled()
+            and not (residual is not None and residual.requires_grad))
+
+
 def frozen_linear(x, W, WT, bias=None, residual=None, block_n=0):
     if not (x.requires_grad or (residual is not None and residual.requires_grad)):
         return ops.gemm(x, W, bias=bias, residual=residual, block_n=block_n)
@@ -288,11 +294,18 @@ class LoraLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W, WT, bias, down, up, rows, plan):
         tile_group = rows.tile_group
+        # (inside Function.forward grad mode is off and the inputs are detached: "nothing to differentiate" must come from ctx)
+        if not any(ctx.needs_input_grad) and h.shape[0] <= 128 and h.shape[1] % 64 == 0 and plan.ext_fwd_step is not None:
+            # decode step: both phases on the weight-streaming kernel (weights on the M side of the MMA, split-K clusters)
+            T = ops.gemm(h, down, n=plan.t_cols, alpha=plan.scaling, tile_group=tile_group, b_row_table=plan.brow_fwd,
+                         skinny=True)
+            out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd_step), block_n=128, skinny=True)
+            return out
         T = ops.gemm(h, down, n=plan.t_cols, alpha=plan.scaling, tile_group=tile_group, b_row_table=plan.brow_fwd,
                      block_n=64)
         if h.shape[0] <= 128 and not h.requires_grad:
-            # decode step (one tile of rows): 64-column tiles put 4x the CTAs on the weight stream (N = 3072: 48, not 12)
-            out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd_step), block_n=64)
+            # one tile of rows: 64-column tiles put 4x the CTAs on the weight stream (N = 3072: 48, not 12)
+            out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd_64), block_n=64)
         else:
             out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd), block_n=plan.block_n,
                            pair_aligned=getattr(rows, "pair_aligned", False))

@@ -24,16 +24,18 @@ from .Llama_LoRA import TILE, KVCache, PackedRows, pack_segments
 
 
 class _StepRows:
-    """PackedRows-like layout of the single-token step (B rows padded to one 128-row tile, static device tensors)."""
+    """PackedRows-like layout of the single-token step (B rows, static device tensors).  No padding to the 128-row tile:
+    every kernel of the step takes any row count, and the weight-streaming GEMM picks its token-tile width (64 / 128)
+    from it."""
 
     def __init__(self, B, device, max_pos):
-        self.M = (B + TILE - 1) // TILE * TILE
+        self.M = B
         self.segments = [(0, B, 1, 0)]
         self.valid_rows = B
         self.max_pos = max_pos
         self.runs = [(0, 0, self.M)]
         self.pair_aligned = True
-        self.tile_group = torch.zeros(self.M // TILE, dtype=torch.int32, device=device)
+        self.tile_group = torch.zeros((self.M + TILE - 1) // TILE, dtype=torch.int32, device=device)
         self.pos = torch.zeros(self.M, dtype=torch.int32, device=device)
 
 

@@ -34,11 +34,25 @@ def _bf16_2d(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+_SKINNY_WS = {}
+
+
+def _skinny_workspace(device) -> torch.Tensor:
+    """Split-K exchange buffer of the weight-streaming GEMM: one per device, zero-filled once (the kernel leaves its
+    counters at zero), reused by every launch -- launches on the same stream are ordered, which is how the decode step
+    runs (also under CUDA-graph replay: the pointer is stable)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _SKINNY_WS.get(key)
+    if ws is None:
+        ws = _SKINNY_WS[key] = torch.zeros(int(lib.omni_gemm_skinny_workspace_bytes()) + 256, device=device, dtype=torch.uint8)
+    return ws
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
          alpha: float = 1.0, n: Optional[int] = None, tile_group: Optional[torch.Tensor] = None,
          b_row_table: Optional[torch.Tensor] = None, ext: Optional[tuple] = None, block_n: int = 0,
-         pair_aligned: bool = False, out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         pair_aligned: bool = False, out2: Optional[torch.Tensor] = None, skinny: bool = False) -> torch.Tensor:
     """out[M,N] = epi(alpha * (a[M,K] @ b[rows,K]^T (+ K-extension)))  -- tcgen05 kernel.
 
     ext = (a2 [M, a2_cols], b2 [b2_rows, b2_cols], ext_table int32 [groups, n_tiles, n_ext, 4]).
@@ -46,6 +60,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     bf16(bf16(silu(gate)) * up); raises OmniKernelError(OMNI_ERR_UNSUPPORTED) when the shape is not one the CTA-pair
     kernel takes -- the caller then runs the unfused gemm + swiglu_fwd pair.
     act="gelu_keep": out = bf16(a @ b^T + bias) (the pre-activation the backward needs), out2 [M, N] = bf16(gelu(out)).
+    skinny=True (M <= 128, K % 64 == 0, bf16 out): the weight-streaming decode-step kernel (omni_gemm_skinny_bf16: weights on
+    the M side of the MMA, split-K over a cluster); b_row_table per 64-feature block, ext table per 128-feature tile
+    (block_n=128); act="swiglu64" writes only out2 (pass out=None).
     """
     require_cuda(a, b, bias, residual, out, tile_group, b_row_table)
     a = _bf16_2d(a, "a")
@@ -54,15 +71,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if b.shape[1] != K:
         raise ValueError(f"K mismatch: a {tuple(a.shape)} vs b {tuple(b.shape)}")
     N = int(n) if n is not None else b.shape[0]
-    if out is None:
+    skinny_swiglu = skinny and act == "swiglu64" and out is None
+    if skinny_swiglu:
+        out = out2                                   # placeholder for the shape checks below; only out2 is written
+    elif out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
-    if out.dim() != 2 or out.shape[0] != M or out.shape[1] != N or out.stride(1) != 1:
+    if skinny_swiglu:
+        pass
+    elif out.dim() != 2 or out.shape[0] != M or out.shape[1] != N or out.stride(1) != 1:
         raise ValueError("bad out tensor")
     if out.dtype not in (torch.bfloat16, torch.float32):
         raise TypeError("out must be bf16 or fp32")
     g = GemmArgs()
-    g.A, g.B, g.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
-    g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), out.stride(0)
+    g.A, g.B, g.out = a.data_ptr(), b.data_ptr(), (None if skinny_swiglu else out.data_ptr())
+    g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), (N if skinny_swiglu else out.stride(0))
     g.M, g.N, g.K = M, N, K
     g.b_rows = b.shape[0]
     if bias is not None:
@@ -110,6 +132,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.out2, g.ldo2 = out2.data_ptr(), out2.stride(0)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     g.alpha = float(alpha)
+    if skinny:
+        ws = _skinny_workspace(a.device)
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+        check(lib.omni_gemm_skinny_bf16(C.byref(g), stream_ptr()), "omni_gemm_skinny_bf16")
+        _count()
+        return out2 if skinny_swiglu else out
     check(lib.omni_gemm_bf16(C.byref(g), stream_ptr()), "omni_gemm_bf16")
     _count()
     return out

@@ -218,8 +218,25 @@ def bench_fused():
                               "frac_of_bound": round(1e3 * max(t_hbm, t_tc) / med, 3)}), flush=True)
 
 
+def bench_skinny():
+    """Decode-step GEMMs (64 token rows): weight-streaming kernel vs the general kernel, GB/s of weight bytes."""
+    import os
+    for M, N, K in ((64, 2048, 2048), (64, 2048, 8192), (64, 3072, 2048), (64, 16384, 2048), (64, 256, 2048), (15, 2048, 8192)):
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        med, best = timeit(lambda: ops.gemm(x, w, residual=res, skinny=True))
+        medo, _ = timeit(lambda: ops.gemm(x, w, residual=res, block_n=256))
+        print(json.dumps({"kernel": "gemm_skinny", "M": M, "N": N, "K": K, "split_env": os.environ.get("OMNI_SKINNY_SPLIT"),
+                          "us": round(med * 1e3, 2), "us_best": round(best * 1e3, 2), "GBs": round(N * K * 2 / med / 1e6, 1),
+                          "frac_hbm": round(N * K * 2 / med / 1e6 / PEAKS["hbm_gbs"], 3),
+                          "general_kernel_us": round(medo * 1e3, 2)}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "compress", "splice"]
+    if "skinny" in which:
+        bench_skinny()
     if "fused" in which:
         bench_fused()
     if "compress" in which:

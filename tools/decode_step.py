@@ -86,6 +86,14 @@ def main():
                 if ev.device_type == torch.autograd.DeviceType.CUDA:
                     agg[ev.name][0] += ev.device_time / 1e3
                     agg[ev.name][1] += 1
+            evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA),
+                         key=lambda ev: ev.time_range.start)
+            # the launches of one decoder layer in the middle of the second step, in order, with the gaps between them
+            per_step = len(evs) // n
+            seq = evs[per_step + per_step // 2: per_step + per_step // 2 + 14]
+            for a_, b_ in zip(seq, seq[1:] + [None]):
+                gap = (b_.time_range.start - a_.time_range.end) if b_ is not None else 0.0
+                print(f"   {a_.device_time:7.1f} us  (+{gap:5.1f} us gap)  {a_.name[:90]}")
             rows = sorted(((v[0], v[1], k) for k, v in agg.items()), reverse=True)
             total = sum(r[0] for r in rows)
             print(f"kernel time {total / n:.4f} ms/step, {sum(r[1] for r in rows) // n} launches/step")
