@@ -248,6 +248,14 @@ int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const void* out, 
 int omni_decode_attention(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx, void* out,
                           int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
                           int32_t max_len, float scale, void* stream);
+/* Same with the rotary embedding fused in: the packed row holds q|k|v BEFORE RoPE; the q heads and the new key are rotated
+ * at position *len_idx with the bf16 tables cos_t / sin_t [table_rows >= max_len, head_dim] (rounding points of omni_rope /
+ * apply_rotary_pos_emb, Llama_LoRA.py:277) before the key is appended and attended.  Saves the separate omni_rope launch of
+ * every layer in a decode step. */
+int omni_decode_attention_rope(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx, void* out,
+                               int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                               int32_t max_len, float scale, const void* cos_t, const void* sin_t, int32_t table_rows,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row kernels of the decoder / encoder blocks (all bf16 in/out, fp32 statistics).

@@ -544,14 +544,27 @@ class LlamaSdpaAttention_lora(nn.Module):
         """h [M, H] normed hidden rows -> residual + o_proj(attn)."""
         a = self.config
         wt_qkv, wt_o = self.transposed()
-        qkv = ag.LoraLinearFn.apply(h, self.qkv_weight, wt_qkv, self.qkv_bias, self.lora_down, self.lora_up,
-                                    rows, self.plan)
-        n_rot = self.num_heads + self.num_key_value_heads
-        if qkv.requires_grad:
-            qkv = ag.RopeFn.apply(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim, True)
+        if ag.skinny_ok(h) and self.plan.ext_fwd_step is not None:
+            # decode step: both LoRA phases on the weight-streaming kernel (no autograd node: nothing to differentiate)
+            p = self.plan
+            T = ops.gemm(h, self.lora_down.data, n=p.t_cols, alpha=p.scaling, tile_group=rows.tile_group,
+                         b_row_table=p.brow_fwd, skinny=True)
+            qkv = ops.gemm(h, self.qkv_weight, bias=self.qkv_bias, tile_group=rows.tile_group,
+                           ext=(T, self.lora_up.data, p.ext_fwd_step), block_n=128, skinny=True)
         else:
-            ops.rope_(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim)
-        attn = attention_packed(qkv, rows, a, kv_cache, self.layer_idx)
+            qkv = ag.LoraLinearFn.apply(h, self.qkv_weight, wt_qkv, self.qkv_bias, self.lora_down, self.lora_up,
+                                        rows, self.plan)
+        n_rot = self.num_heads + self.num_key_value_heads
+        step = kv_cache is not None and kv_cache.graph_mode and all(S == 1 for (_, _, S, _) in rows.segments)
+        if step:
+            # decode step: the rotary embedding is applied inside the single-token attention kernel (position = cache length)
+            attn = attention_packed(qkv, rows, a, kv_cache, self.layer_idx, rope=(cos_t, sin_t))
+        else:
+            if qkv.requires_grad:
+                qkv = ag.RopeFn.apply(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim, True)
+            else:
+                ops.rope_(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim)
+            attn = attention_packed(qkv, rows, a, kv_cache, self.layer_idx)
         if ag.skinny_ok(attn, residual):
             return ops.gemm(attn, self.o_proj.weight.data, residual=residual, skinny=True)      # decode step
         return ag.frozen_linear(attn, self.o_proj.weight.data, wt_o, residual=residual, block_n=256)
@@ -609,7 +622,7 @@ class PackedSdpaFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
-def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
+def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx, rope=None):
     """Causal GQA attention per segment of the packed rows.  Training / prefill: the tcgen05 flash kernel on the packed
     buffer (the prefill also fills the static KV cache); decode step: the single-token kernel that appends K / V to the
     cache and attends over it in one launch.  No library attention anywhere: unsupported geometries raise."""
@@ -620,15 +633,18 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx):
     for (task, B, S, off) in rows.segments:
         if S == 1 and kv_cache.graph_mode:
             ops.decode_attention(qkv[off: off + B], kv_cache.k[layer_idx], kv_cache.v[layer_idx], kv_cache.len_idx,
-                                 out[off: off + B], B, nh, nkv, hd)
+                                 out[off: off + B], B, nh, nkv, hd, rope=rope)
             continue
+        if rope is not None:
+            raise RuntimeError("fused RoPE is a decode-step feature")
         if kv_cache.len != 0 or kv_cache.graph_mode:
             raise NotImplementedError("multi-token steps on top of a non-empty KV cache are not part of the Omni-AVSR decode "
                                       "path (HF generate: one prefill, then single-token steps)")
         _, k, v = PackedSdpaFn._views(qkv, B, S, off, nh, nkv, hd)
         kv_cache.fill(layer_idx, k, v)
         ops.attention_fwd(qkv, out, [(task, B, S, off)], nh, nkv, hd, True)
-    PackedSdpaFn._zero_pad_rows(out, rows.segments)
+    if rows.valid_rows != rows.M:
+        PackedSdpaFn._zero_pad_rows(out, rows.segments)
     return out
 
 

@@ -294,13 +294,6 @@ class LoraLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W, WT, bias, down, up, rows, plan):
         tile_group = rows.tile_group
-        # (inside Function.forward grad mode is off and the inputs are detached: "nothing to differentiate" must come from ctx)
-        if not any(ctx.needs_input_grad) and h.shape[0] <= 128 and h.shape[1] % 64 == 0 and plan.ext_fwd_step is not None:
-            # decode step: both phases on the weight-streaming kernel (weights on the M side of the MMA, split-K clusters)
-            T = ops.gemm(h, down, n=plan.t_cols, alpha=plan.scaling, tile_group=tile_group, b_row_table=plan.brow_fwd,
-                         skinny=True)
-            out = ops.gemm(h, W, bias=bias, tile_group=tile_group, ext=(T, up, plan.ext_fwd_step), block_n=128, skinny=True)
-            return out
         T = ops.gemm(h, down, n=plan.t_cols, alpha=plan.scaling, tile_group=tile_group, b_row_table=plan.brow_fwd,
                      block_n=64)
         if h.shape[0] <= 128 and not h.requires_grad:

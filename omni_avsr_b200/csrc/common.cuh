@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <string.h>
 
 #define OMNI_OK 0
 #define OMNI_ERR_BAD_ARG (-1)
@@ -329,6 +330,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, i
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor in the
+// stream is still running; everything before pdl_wait() must touch only data no predecessor writes (weights, tables).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // math
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -342,6 +350,27 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace omni
+
+// host-side: launch with the programmatic-stream-serialization attribute (OMNI_NO_PDL=1 in the environment turns it off)
+#include <stdlib.h>
+#include <utility>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t omni_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args&&... args) {
+  static const bool off = getenv("OMNI_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // host-side: tensor-map encoder resolved at run time (no link-time libcuda dependency, so the library
 // loads on a CPU-only box for the symbol-export test).

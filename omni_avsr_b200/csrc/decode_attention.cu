@@ -24,11 +24,28 @@ __device__ __forceinline__ void unpack_u4(const uint4& u, float (&f)[8]) {
   t = bf2_to_f2(u.w); f[6] = t.x; f[7] = t.y;
 }
 
+__device__ __forceinline__ float rbf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// RoPE of 8 consecutive dims of one head held by a lane (partner dims +- HD/2 live in lane l ^ (LPK / 2)):
+//   out = bf16( bf16(x * cos) + bf16(rotate_half(x) * sin) )  -- the rounding points of apply_rotary_pos_emb in bf16
+// (transformers modeling_llama.py, called at Llama_LoRA.py:277), identical to omni_rope.
+template <int LPK>
+__device__ __forceinline__ void rope8(float (&x)[8], const float (&cs)[8], const float (&sn)[8], bool second_half) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float xp = __shfl_xor_sync(0xffffffffu, x[i], LPK / 2);
+    const float rot = second_half ? xp : -xp;
+    x[i] = rbf16(rbf16(x[i] * cs[i]) + rbf16(rot * sn[i]));
+  }
+}
+
 template <int HD, int G>
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict__ kc, bf16* __restrict__ vc,
                    const long long* __restrict__ len_idx, bf16* __restrict__ out, long long out_ld, int n_kv_heads,
-                   int max_len, float scale_log2) {
+                   int max_len, float scale_log2, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t) {
+  pdl_launch_dependents();
+  pdl_wait();                          // q|k|v row and the cache position come from predecessors
   constexpr int LPK = HD / 8;          // lanes per key row
   constexpr int KPW = 32 / LPK;        // key rows per warp instruction
   extern __shared__ float sm[];
@@ -45,14 +62,31 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict_
   const int n_keys = pos + 1;
 
   const bf16* row = qkv + static_cast<long long>(b) * ld;
+  // fused RoPE (cos_t != null): the new token's position is `pos`; q heads and the new key are rotated on the fly, so the
+  // separate in-place rotation of the packed q|k|v row (one more launch per layer and step) disappears
+  float cs[8], sn[8];
+  const bool rope = cos_t != nullptr;
+  const bool second_half = l >= LPK / 2;
+  if (rope) {
+    unpack_u4(__ldg(reinterpret_cast<const uint4*>(cos_t + static_cast<long long>(pos) * HD) + l), cs);
+    unpack_u4(__ldg(reinterpret_cast<const uint4*>(sin_t + static_cast<long long>(pos) * HD) + l), sn);
+  }
   float q[G][8];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     unpack_u4(*reinterpret_cast<const uint4*>(row + (kvh * G + g) * HD + l * 8), q[g]);
+    if (rope) rope8<LPK>(q[g], cs, sn, second_half);
 #pragma unroll
     for (int i = 0; i < 8; ++i) q[g][i] *= scale_log2;
   }
-  const uint4 k_new = *reinterpret_cast<const uint4*>(row + (n_heads + kvh) * HD + l * 8);
+  uint4 k_new = *reinterpret_cast<const uint4*>(row + (n_heads + kvh) * HD + l * 8);
+  if (rope) {
+    float kf[8];
+    unpack_u4(k_new, kf);
+    rope8<LPK>(kf, cs, sn, second_half);
+    k_new.x = f2_to_bf2(kf[0], kf[1]); k_new.y = f2_to_bf2(kf[2], kf[3]);
+    k_new.z = f2_to_bf2(kf[4], kf[5]); k_new.w = f2_to_bf2(kf[6], kf[7]);
+  }
   const uint4 v_new = *reinterpret_cast<const uint4*>(row + (n_heads + n_kv_heads + kvh) * HD + l * 8);
   bf16* krow = kc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
   bf16* vrow = vc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
@@ -68,7 +102,12 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict_
     for (int u = 0; u < DA_UNROLL; ++u) {
       const int p = p0 + u * DA_WARPS * KPW + sub;
       kk[u] = k_new;
-      if (p < n_keys && p != pos) kk[u] = ld_nc_u4(krow + static_cast<long long>(p) * HD + l * 8);
+      if (p < n_keys && p != pos) {
+        kk[u] = ld_nc_u4(krow + static_cast<long long>(p) * HD + l * 8);
+        // pull the matching V row towards L2 now: pass 2 (which can only start after the softmax) then runs out of L2, and
+        // the HBM streams of K and V overlap instead of being serialised by the two barriers in between
+        if ((l & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + static_cast<long long>(p) * HD + l * 8));
+      }
     }
 #pragma unroll
     for (int u = 0; u < DA_UNROLL; ++u) {
@@ -162,16 +201,17 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict_
 
 template <int HD, int G>
 static int launch_decode_attn(const bf16* qkv, long long ld, bf16* kc, bf16* vc, const long long* len_idx, bf16* out,
-                              long long out_ld, int B, int n_kv_heads, int max_len, float scale, cudaStream_t st) {
+                              long long out_ld, int B, int n_kv_heads, int max_len, float scale, cudaStream_t st,
+                              const bf16* cos_t, const bf16* sin_t) {
   auto kfn = decode_attn_kernel<HD, G>;
   const int smem = (G * max_len + DA_WARPS * G * HD + G) * 4;
   if (smem > 200 * 1024) return OMNI_ERR_UNSUPPORTED;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return OMNI_ERR_CUDA;
-  kfn<<<B * n_kv_heads, DA_THREADS, smem, st>>>(qkv, ld, kc, vc, len_idx, out, out_ld, n_kv_heads, max_len,
-                                                scale * 1.4426950408889634f);
-  OMNI_LAUNCH_CHECK();
+  if (omni_launch_pdl(kfn, dim3(B * n_kv_heads), dim3(DA_THREADS), smem, st, qkv, ld, kc, vc, len_idx, out, out_ld, n_kv_heads,
+                      max_len, scale * 1.4426950408889634f, cos_t, sin_t) != cudaSuccess)
+    return OMNI_ERR_CUDA;
   return OMNI_OK;
 }
 
@@ -180,7 +220,20 @@ static int launch_decode_attn(const bf16* qkv, long long ld, bf16* kc, bf16* vc,
 extern "C" int omni_decode_attention(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx,
                                      void* out, int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads,
                                      int32_t head_dim, int32_t max_len, float scale, void* stream) {
+  return omni_decode_attention_rope(qkv, ld, k_cache, v_cache, len_idx, out, out_ld, B, n_heads, n_kv_heads, head_dim, max_len,
+                                    scale, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int omni_decode_attention_rope(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx,
+                                          void* out, int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads,
+                                          int32_t head_dim, int32_t max_len, float scale, const void* cos_t,
+                                          const void* sin_t, int32_t table_rows, void* stream) {
   using namespace omni;
+  OMNI_CHECK_ARG((cos_t == nullptr) == (sin_t == nullptr));
+  if (cos_t) OMNI_CHECK_ARG(table_rows >= max_len && (reinterpret_cast<uintptr_t>(cos_t) & 15) == 0 &&
+                            (reinterpret_cast<uintptr_t>(sin_t) & 15) == 0);
+  const bf16* ct = reinterpret_cast<const bf16*>(cos_t);
+  const bf16* stb = reinterpret_cast<const bf16*>(sin_t);
   OMNI_CHECK_ARG(qkv && k_cache && v_cache && len_idx && out && B > 0 && n_heads > 0 && n_kv_heads > 0 && max_len > 0);
   OMNI_CHECK_ARG(n_heads % n_kv_heads == 0 && (ld % 8) == 0 && (out_ld % 8) == 0);
   OMNI_CHECK_ARG(ld >= static_cast<int64_t>(n_heads + 2 * n_kv_heads) * head_dim);
@@ -193,7 +246,7 @@ extern "C" int omni_decode_attention(const void* qkv, int64_t ld, void* k_cache,
   bf16* o = reinterpret_cast<bf16*>(out);
 #define OMNI_DA(HD_, G_) \
   if (head_dim == HD_ && G == G_) \
-    return launch_decode_attn<HD_, G_>(q, ld, kc, vc, li, o, out_ld, B, n_kv_heads, max_len, scale, st);
+    return launch_decode_attn<HD_, G_>(q, ld, kc, vc, li, o, out_ld, B, n_kv_heads, max_len, scale, st, ct, stb);
   // every GQA group size of the reference's model table: 4 (Llama-3.2-1B / 3.1-8B), 3 (Llama-3.2-3B), 7 (Qwen2.5-0.5B / 7B),
   // 6 (1.5B), 8 (3B), 5 (14B / 32B), + 1 / 2 for MHA-like test geometries
   OMNI_DA(64, 1) OMNI_DA(64, 2) OMNI_DA(64, 3) OMNI_DA(64, 4) OMNI_DA(64, 5) OMNI_DA(64, 6) OMNI_DA(64, 7) OMNI_DA(64, 8)

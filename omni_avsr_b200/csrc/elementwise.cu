@@ -64,6 +64,8 @@ template <int NPL>
 __global__ void __launch_bounds__(EW_THREADS, 1)
 rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                    float* __restrict__ rstd_out, long long rows, int H8, long long ldx, long long ldy, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // x is the predecessor's output (no-op without the launch attribute)
   const int lane = threadIdx.x & 31;
   const long long wg = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -497,9 +499,23 @@ extern "C" int omni_rmsnorm_fwd(const void* x, const void* w, void* y, float* rs
                                 int64_t ldy, float eps, void* stream) {
   OMNI_CHECK_ARG(x && w && y && rows >= 0 && H > 0 && (H % 8) == 0 && (ldx % 8) == 0 && (ldy % 8) == 0);
   if (rows == 0) return OMNI_OK;
-  OMNI_NPL_DISPATCH(rmsnorm_fwd_kernel, H / 8, rows_grid(rows), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H / 8, ldx, ldy, eps));
-  OMNI_LAUNCH_CHECK();
+  // launched with the programmatic-dependent-launch attribute: inside the decode step its launch overlaps the tail of
+  // the GEMM that produced x (the kernel waits for it before its first load)
+  const dim3 grid(rows_grid(rows)), block(EW_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int h8 = H / 8;
+  const long long rows_ll = rows, ldx_ll = ldx, ldy_ll = ldy;
+  cudaError_t e;
+  if (h8 == 128)
+    e = omni_launch_pdl(rmsnorm_fwd_kernel<4>, grid, block, 0, st, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows_ll, h8,
+                        ldx_ll, ldy_ll, eps);
+  else if (h8 == 256)
+    e = omni_launch_pdl(rmsnorm_fwd_kernel<8>, grid, block, 0, st, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows_ll, h8,
+                        ldx_ll, ldy_ll, eps);
+  else
+    e = omni_launch_pdl(rmsnorm_fwd_kernel<0>, grid, block, 0, st, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows_ll, h8,
+                        ldx_ll, ldy_ll, eps);
+  if (e != cudaSuccess) return OMNI_ERR_CUDA;
   return OMNI_OK;
 }
 

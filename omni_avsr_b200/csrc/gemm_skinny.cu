@@ -59,9 +59,15 @@ struct SkinnySmem {
   static constexpr int X_BYTES = NTOK * BK * 2;            // 8 / 16 KB
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
   static constexpr int TSL = ((NTOK + SPLIT - 1) / SPLIT + 3) / 4 * 4;   // tokens finished by one rank (multiple of 4)
-  static constexpr int T_OFFSET = STAGES * STAGE_BYTES;
+  // the [token][feature] transposition tile of the epilogue ALIASES the pipeline stages: it is written only after the
+  // accumulator barrier, i.e. when every MMA has consumed its stage and no TMA load is pending.  (Measured: shrinking the
+  // pipeline to 4 stages so that the CTAs of two consecutive GEMMs are co-resident -- the next GEMM's weight prefetch
+  // would then run under this GEMM's split-K exchange -- made the step 5 % SLOWER: 64 KB in flight per CTA no longer
+  // covers the HBM latency at ~40 GB/s per SM.  One CTA per SM with 8 stages it is.)
+  static constexpr int T_OFFSET = 0;
   static constexpr int T_BYTES = TSL * SK_TPITCH * 2;
-  static constexpr int BAR_OFFSET = (T_OFFSET + T_BYTES + 15) / 16 * 16;
+  static_assert(T_BYTES <= STAGES * STAGE_BYTES, "transposition tile must fit in the stage area");
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
@@ -79,6 +85,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   bf16* ttile = reinterpret_cast<bf16*>(smem + S::T_OFFSET);            // [TSL][SK_TPITCH]
 
+  pdl_launch_dependents();      // the next kernel of the step may start its own prologue / weight prefetch right away
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x / SPLIT;
@@ -130,7 +137,21 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < kb_mine; ++it) {
+      // programmatic dependent launch: the WEIGHT boxes of the first pipeline fill (up to STAGES x 16 KB per CTA) go out
+      // before the predecessor has finished -- weights are static -- and only the token rows wait for it
+      const int pre = kb_mine < STAGES ? kb_mine : STAGES;
+      for (int it = 0; it < pre; ++it) {
+        uint8_t* sW = smem + it * S::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[it], S::STAGE_BYTES);
+        tma_load_2d(&tmW, &full_bar[it], sW, (kb0 + it) * BK, row_a);
+        tma_load_2d(&tmW, &full_bar[it], sW + S::W_BYTES / 2, (kb0 + it) * BK, row_b);
+      }
+      pdl_wait();
+      for (int it = 0; it < pre; ++it)
+        tma_load_2d(&tmX, &full_bar[it], smem + it * S::STAGE_BYTES + S::W_BYTES, (kb0 + it) * BK, 0);
+      stage = pre == STAGES ? 0 : pre;
+      phase = pre == STAGES ? 1 : 0;
+      for (int it = pre; it < kb_mine; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sW = smem + stage * S::STAGE_BYTES;
         uint8_t* sX = sW + S::W_BYTES;
@@ -184,6 +205,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int f = q * 32 + lane;                 // feature row of this thread inside the tile (epilogue warps only)
   float v[TSL];
   if (warp >= 2) {
+    pdl_wait();                                // residual / workspace / output buffers belong to the predecessor until here
     if (total_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -359,8 +381,8 @@ static int launch_skinny(const CUtensorMap& tmW, const CUtensorMap& tmX, const C
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return OMNI_ERR_CUDA;
     attr_set = true;
   }
-  kfn<<<p.n_tiles * SPLIT, SK_THREADS, S::TOTAL, st>>>(tmW, tmX, tmW2, tmX2, p);
-  OMNI_LAUNCH_CHECK();
+  if (omni_launch_pdl(kfn, dim3(p.n_tiles * SPLIT), dim3(SK_THREADS), S::TOTAL, st, tmW, tmX, tmW2, tmX2, p) != cudaSuccess)
+    return OMNI_ERR_CUDA;
   return OMNI_OK;
 }
 
@@ -408,15 +430,18 @@ extern "C" int omni_gemm_skinny_bf16(const omni_gemm_args* a, void* stream) {
   // n_tiles * split <= SM count (one CTA per SM at this shared-memory footprint)
   const int kb = a->K / BK;
   const int sms = skinny_sm_count();
-  static const int choices[] = {8, 6, 4, 3, 2};
+  static const int choices[] = {8, 6, 5, 4, 3, 2};
+  // measured inside the decode graph: 144 CTAs (24 tiles x 6) ran 2x slower than 96 (x 4) -- near the SM count the last
+  // CTAs of the grid only become resident when the predecessor's stragglers have left, and their peers spin meanwhile
+  const int cta_cap = sms < 132 ? sms : 132;
   int split = 1;
   static const char* force = getenv("OMNI_SKINNY_SPLIT");
   if (force) {
     split = atoi(force);
-    if (split != 1 && (p.n_tiles * split > sms || split > kb)) split = 1;
+    if (split != 1 && (p.n_tiles * split > cta_cap || split > kb)) split = 1;
   } else if (a->workspace) {
     for (int c : choices) {
-      if (p.n_tiles * c <= sms && kb >= 2 * c) { split = c; break; }
+      if (p.n_tiles * c <= cta_cap && kb >= 2 * c) { split = c; break; }
     }
   }
   p.kb_total = kb;
@@ -452,15 +477,17 @@ extern "C" int omni_gemm_skinny_bf16(const omni_gemm_args* a, void* stream) {
       case 2: OMNI_SK(64, 2, 8)
       case 3: OMNI_SK(64, 3, 8)
       case 4: OMNI_SK(64, 4, 8)
+      case 5: OMNI_SK(64, 5, 8)
       case 6: OMNI_SK(64, 6, 8)
       case 8: OMNI_SK(64, 8, 8)
     }
   } else {
     switch (split) {
-      case 1: OMNI_SK(128, 1, 5)
+      case 1: OMNI_SK(128, 1, 6)
       case 2: OMNI_SK(128, 2, 6)
       case 3: OMNI_SK(128, 3, 6)
       case 4: OMNI_SK(128, 4, 6)
+      case 5: OMNI_SK(128, 5, 6)
       case 6: OMNI_SK(128, 6, 6)
       case 8: OMNI_SK(128, 8, 6)
     }

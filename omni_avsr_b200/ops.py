@@ -755,10 +755,12 @@ DECODE_ATTN_GROUPS = (1, 2, 3, 4, 5, 6, 7, 8)
 
 
 def decode_attention(qkv, k_cache, v_cache, len_idx, out, B: int, n_heads: int, n_kv_heads: int, head_dim: int,
-                     scale: Optional[float] = None):
+                     scale: Optional[float] = None, rope: Optional[tuple] = None):
     """Single-token attention over the static KV cache [B, n_kv_heads, max_len, head_dim] (one layer): appends the new
     token's K / V (from the packed q|k|v rows, RoPE applied) at position len_idx[0] (int64, device) and attends over
-    positions 0..len_idx[0].  out [>=B, n_heads*head_dim] bf16; rows >= B untouched."""
+    positions 0..len_idx[0].  out [>=B, n_heads*head_dim] bf16; rows >= B untouched.
+    rope = (cos_t, sin_t) bf16 [>= max_len, head_dim]: the packed rows hold q|k|v BEFORE the rotary embedding, which the
+    kernel applies to the q heads and the new key at position len_idx[0] (no separate rope_ launch)."""
     require_cuda(qkv, k_cache, v_cache, len_idx, out)
     qkv = _bf16_2d(qkv, "qkv")
     out = _bf16_2d(out, "out")
@@ -769,6 +771,18 @@ def decode_attention(qkv, k_cache, v_cache, len_idx, out, B: int, n_heads: int, 
         raise ValueError("k_cache / v_cache must be contiguous bf16 [B, n_kv_heads, max_len, head_dim]")
     if scale is None:
         scale = head_dim ** -0.5
+    if rope is not None:
+        cos_t, sin_t = rope
+        require_cuda(cos_t, sin_t)
+        if cos_t.dtype != torch.bfloat16 or cos_t.shape[-1] != head_dim or not cos_t.is_contiguous() or \
+                not sin_t.is_contiguous() or cos_t.shape != sin_t.shape or cos_t.shape[0] < k_cache.shape[2]:
+            raise ValueError("rope tables must be contiguous bf16 [>= max_len, head_dim]")
+        check(lib.omni_decode_attention_rope(qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
+                                             len_idx.data_ptr(), out.data_ptr(), out.stride(0), B, n_heads, n_kv_heads,
+                                             head_dim, k_cache.shape[2], float(scale), cos_t.data_ptr(), sin_t.data_ptr(),
+                                             cos_t.shape[0], stream_ptr()), "omni_decode_attention_rope")
+        _count()
+        return out
     check(lib.omni_decode_attention(qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
                                     len_idx.data_ptr(), out.data_ptr(), out.stride(0), B, n_heads, n_kv_heads, head_dim,
                                     k_cache.shape[2], float(scale), stream_ptr()), "omni_decode_attention")

@@ -140,3 +140,40 @@ def test_decode_attention_step(B, nh, nkv, hd, max_len, pos):
     err = (out[:B].float() - want).abs().max().item()
     assert err <= 1e-2 * max(1.0, want.abs().max().item()), err
     assert (out[B:] == 5.0).all()
+
+
+@pytest.mark.parametrize("B,nh,nkv,hd,max_len,pos", [(3, 32, 8, 64, 384, 300), (2, 16, 2, 128, 256, 255), (4, 6, 2, 64, 128, 0),
+                                                     (64, 32, 8, 64, 512, 445), (2, 14, 2, 64, 256, 77), (1, 12, 2, 128, 256, 9),
+                                                     (2, 40, 8, 128, 256, 100)])
+def test_decode_attention_fused_rope_equals_rope_then_attention(B, nh, nkv, hd, max_len, pos):
+    """omni_decode_attention_rope (rotary embedding of the q heads and of the new key inside the single-token kernel) must
+    give, bit for bit, the output AND the cache contents of the two-launch sequence omni_rope -> omni_decode_attention.
+    Covers the GQA group sizes 3 (Llama-3.2-3B), 5 (Qwen2.5-14B/32B), 6 (1.5B), 7 (0.5B/7B) next to 4 and 8."""
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(pos * 7 + nh)
+    kc = torch.randn(B, nkv, max_len, hd, device="cuda", generator=g).bfloat16()
+    vc = torch.randn(B, nkv, max_len, hd, device="cuda", generator=g).bfloat16()
+    qkv = (torch.randn(B, (nh + 2 * nkv) * hd, device="cuda", generator=g) * 1.2).bfloat16()
+    ang = torch.rand(max_len, hd // 2, device="cuda", generator=g) * 6.28
+    emb = torch.cat([ang, ang], dim=-1)
+    cos_t, sin_t = emb.cos().bfloat16().contiguous(), emb.sin().bfloat16().contiguous()
+    len_idx = torch.tensor([pos], device="cuda", dtype=torch.int64)
+    # two launches
+    kc1, vc1, q1 = kc.clone(), vc.clone(), qkv.clone()
+    ops.rope_(q1, cos_t, sin_t, torch.full((B,), pos, device="cuda", dtype=torch.int32), nh + nkv, hd)
+    out1 = torch.empty(B, nh * hd, device="cuda", dtype=torch.bfloat16)
+    ops.decode_attention(q1, kc1, vc1, len_idx, out1, B, nh, nkv, hd)
+    # fused
+    kc2, vc2 = kc.clone(), vc.clone()
+    out2 = torch.empty(B, nh * hd, device="cuda", dtype=torch.bfloat16)
+    ops.decode_attention(qkv, kc2, vc2, len_idx, out2, B, nh, nkv, hd, rope=(cos_t, sin_t))
+    assert torch.equal(kc1.view(torch.int16), kc2.view(torch.int16)) and torch.equal(vc1.view(torch.int16), vc2.view(torch.int16))
+    assert torch.equal(out1.view(torch.int16), out2.view(torch.int16))
+    # and against fp32 torch
+    q = q1[:, : nh * hd].float().view(B, nh, hd)
+    G = nh // nkv
+    K = kc1[:, :, : pos + 1].float().repeat_interleave(G, dim=1)
+    V = vc1[:, :, : pos + 1].float().repeat_interleave(G, dim=1)
+    s = torch.einsum("bhd,bhnd->bhn", q, K) / math.sqrt(hd)
+    want = torch.einsum("bhn,bhnd->bhd", torch.softmax(s, dim=-1), V).reshape(B, nh * hd)
+    assert (out2.float() - want).abs().max().item() <= 1e-2 * max(1.0, want.abs().max().item())
