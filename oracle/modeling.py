@@ -57,9 +57,10 @@ class AVSR_LLMs(nn.Module):
         return {k: e(v) for k, v in self.prompts_ids.items()}
 
     def encode_audio(self, audio, max_len, rate):
-        audios = audio.to(torch.float32)                                            # :531
+        audios = audio.to(torch.float32).cpu()                                      # :531-532 (.cpu().numpy())
         feats = oe.log_mel(audios.squeeze(-1))                                      # :533 (host feature extractor)
-        enc = self.audio_encoder(feats.to(audio.dtype))                             # :534
+        dev = next(self.audio_encoder.parameters()).device                          # :534 (.cuda() in the reference)
+        enc = self.audio_encoder(feats.to(device=dev, dtype=audio.dtype))
         enc = enc[:, 0: om.num_audio_tokens(max_len), :]                            # :537
         return om.compress(enc, rate, self.compression_mode)
 

@@ -386,3 +386,41 @@ def test_decode_with_three_query_heads_per_kv_head():
     finally:
         mod.model.num_beams = 1
     _beam_near_tie_ok(oracle, infer_cpu, "audiovisual", 16, 5, 3, gotb, wantb)
+
+
+def test_config2_geometry_losses_and_label_row_logits():
+    """Parity at BENCHMARK scale (BASELINE config 2): Whisper-medium + AV-HuBERT-Large + Llama-3.2-1B (24 + 24 + 16 layers,
+    H = 2048, V = 128261, r = 64, hybrid Omni-LoRA), one 16 s utterance, rates (4, 2) -- 972 packed LLM rows, S = 1500
+    Whisper tokens.  The CUDA path against the CPU oracle holding the SAME weights: three task losses <= 5e-2, logits of the
+    AVSR label rows max|a-b| <= 1e-2 * max|b| (north_star's tolerance), greedy tokens of a short decode under the margin rule."""
+    import bench
+    from types import SimpleNamespace
+    from oracle import matryoshka as om
+    from oracle.pairing import oracle_from_product
+    from omni_avsr_b200.synthetic import synthetic_batch, to_device
+    mod = bench.build_module(SimpleNamespace(workload="omni", llm=None), torch.device("cuda", 0))
+    oracle = oracle_from_product(mod)
+    cpu = synthetic_batch(1, mod.tokenizer, seconds=16.0, text_len=48, seed=99)
+    gpu = to_device(cpu, "cuda")
+    m = mod.model
+    with torch.no_grad():
+        want = oracle(cpu, 4, 2)
+        mod.training_step(gpu, 0, rates=(4, 2))
+        for a, b in zip(mod.last_losses, want):
+            assert abs(a.item() - b.item()) <= 5e-2, (a.item(), b.item())
+        # logits of the rows whose shifted label is not ignored, AVSR sequence
+        out = m.prepare_inputs(gpu, True, test_ratio_matry_audio=4, test_ratio_matry_video=2)
+        xp, rows, labels = out["packed"], out["rows"], out["labels"]
+        assert rows.valid_rows == 256 + 256 + 460
+        hid = m.llm.model.forward_packed(xp, rows)
+        (_, B, S, off) = rows.segments[2]
+        lab = labels[2]
+        keep = (lab[0, 1:] != -100).nonzero().flatten()
+        got = m.llm.logits_rows(hid[off + keep]).float().cpu()
+        a_tok, v_tok = oracle.media_tokens(cpu, 4, 2)
+        seqs, labs = om.build_train_sequences(oracle.llm.model.embed_tokens, cpu["tokens"], cpu["labels"], a_tok, v_tok,
+                                              oracle.prompts(), oracle.marker_ids, oracle.is_qwen)
+        assert torch.equal(labs["audiovisual"], lab.cpu())
+        ref = oracle.llm(inputs_embeds=seqs["audiovisual"], modality="audiovisual").logits[0, keep.cpu()].float()
+        assert got.shape == ref.shape == (47, 128261)
+        assert _rel(got, ref) <= 1e-2, _rel(got, ref)
