@@ -314,6 +314,7 @@ class Model_lora(nn.Module):  # Llama_LoRA.py:446-578
         if position_ids is None:                                  # :503-509
             position_ids = torch.arange(past, past + inputs_embeds.shape[1]).unsqueeze(0)
         cos, sin = rope_cos_sin(self.cfg, position_ids, inputs_embeds.dtype)   # :517
+        cos, sin = cos.to(inputs_embeds.device), sin.to(inputs_embeds.device)  # (tables built on the host; GPU-eager runs)
         h = inputs_embeds
         for layer in self.layers:
             h = layer(h, cos, sin, past_kv, modality)

@@ -54,7 +54,7 @@ class AVSR_LLMs(nn.Module):
 
     def prompts(self):
         e = self.llm.model.embed_tokens
-        return {k: e(v) for k, v in self.prompts_ids.items()}
+        return {k: e(v.to(e.weight.device)) for k, v in self.prompts_ids.items()}
 
     def encode_audio(self, audio, max_len, rate):
         audios = audio.to(torch.float32).cpu()                                      # :531-532 (.cpu().numpy())
