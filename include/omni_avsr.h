@@ -304,6 +304,23 @@ int omni_im2col_front3d(const void* video, void* out, int32_t B, int32_t T, int3
 int omni_im2col_front2d(const void* video, void* out2, int32_t B, int32_t T, int32_t H, int32_t W, void* stream);
 int omni_prelu_maxpool_front(const void* x, const void* slope, void* y, int32_t B, int32_t T, int32_t H, int32_t W,
                              int32_t C, void* stream);
+/* ResNet-18 trunk without library convolutions (resnet.py:35-74,77-129,156-164): activations are channels-last frames with a
+ * one-pixel ZERO RING, [N, H+2, W+2, C].  A 3x3 stride-1 convolution is ONE omni_gemm_bf16 call on an overlapping-row view
+ * of that buffer (row stride C; main K = the dy=-1 taps, K-extension blocks = the dy=0 / +1 taps; see csrc/resnet_trunk.cu).
+ *   omni_prelu_maxpool_front_ring: omni_prelu_maxpool_front writing the ring-padded layout (interior only; the caller keeps
+ *     the ring at zero);
+ *   omni_prelu_res_ring: omni_prelu_res on the interior pixels, zeros on the ring (the GEMM leaves garbage there);
+ *   omni_gather_s2_ring: GEMM operand rows of the strided convolutions for every position of the ring-padded OUTPUT grid,
+ *     taps = 9 (conv3x3 pad 1: out [N (Ho+2)(Wo+2), 9 C], tap-major) or 1 (1x1 downsample: [.., C]); stride 2 in the trunk,
+ *     stride 1 for channel counts the overlapping-row GEMM cannot take (3 C not a multiple of 64);
+ *   omni_avgpool_ring: AdaptiveAvgPool2d(1) over the interior -> [N, C]. */
+int omni_prelu_maxpool_front_ring(const void* x, const void* slope, void* y, int32_t B, int32_t T, int32_t H, int32_t W,
+                                  int32_t C, void* stream);
+int omni_prelu_res_ring(void* x, const void* residual, const void* slope, const void* bias, const void* res_bias, int64_t N,
+                        int32_t H, int32_t W, int32_t C, void* stream);
+int omni_gather_s2_ring(const void* x, void* out, int64_t N, int32_t H, int32_t W, int32_t C, int32_t taps, int32_t stride,
+                        void* stream);
+int omni_avgpool_ring(const void* x, void* out, int64_t N, int32_t H, int32_t W, int32_t C, void* stream);
 /* out[i,:] = table[idx[i],:] (embed_tokens of the decode step, label-row selection); status as in the splice. */
 int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
                      int64_t table_rows, int32_t* status, void* stream);

@@ -844,7 +844,7 @@ im2col_front2d_kernel(const bf16* __restrict__ video, bf16* __restrict__ out, in
 // x: conv output [B][H][W][Tp][C] (rows of the time-major GEMM), y: [B*T][Ho][Wo][C] channels-last
 __global__ void __launch_bounds__(EW_THREADS)
 prelu_maxpool_front_kernel(const bf16* __restrict__ x, const bf16* __restrict__ slope, bf16* __restrict__ y, int T, int Tp,
-                           int H, int W, int Ho, int Wo, int C8, long long total8) {
+                           int H, int W, int Ho, int Wo, int C8, long long total8, int ring) {
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(idx % C8);
@@ -874,7 +874,11 @@ prelu_maxpool_front_kernel(const bf16* __restrict__ x, const bf16* __restrict__ 
         }
       }
     }
-    st_na_u4(reinterpret_cast<uint4*>(y) + ((((b * T + t) * Ho + ho) * Wo + wo) * C8 + c), pack8(m));
+    // ring = 1: the frame is stored with a one-pixel border [Ho + 2, Wo + 2] that the caller keeps at zero (the layout
+    // the 3x3 convolutions of the trunk read as an overlapping-row GEMM operand, csrc/resnet_trunk.cu)
+    st_na_u4(reinterpret_cast<uint4*>(y) +
+                 ((((b * T + t) * (Ho + 2 * ring) + ho + ring) * (Wo + 2 * ring) + wo + ring) * C8 + c),
+             pack8(m));
   }
 }
 
@@ -901,7 +905,20 @@ extern "C" int omni_prelu_maxpool_front(const void* x, const void* slope, void* 
   long long blocks = ceil_div_ll(total8, EW_THREADS);
   if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
   prelu_maxpool_front_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)slope, (bf16*)y, T, T + 4, H, W, Ho, Wo, C / 8, total8);
+      (const bf16*)x, (const bf16*)slope, (bf16*)y, T, T + 4, H, W, Ho, Wo, C / 8, total8, 0);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_prelu_maxpool_front_ring(const void* x, const void* slope, void* y, int32_t B, int32_t T, int32_t H,
+                                             int32_t W, int32_t C, void* stream) {
+  OMNI_CHECK_ARG(x && slope && y && B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total8 = static_cast<long long>(B) * T * Ho * Wo * (C / 8);
+  long long blocks = ceil_div_ll(total8, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  prelu_maxpool_front_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)slope, (bf16*)y, T, T + 4, H, W, Ho, Wo, C / 8, total8, 1);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }

@@ -12,8 +12,8 @@
 Linear layers, LayerNorm, GELU and the LoRA-fused q|k|v projection run on our kernels (tcgen05 GEMM with bias /
 GELU / residual epilogues), the attention core is the tcgen05 flash kernel (forward and backward), the log-mel front end
 is our DFT kernel, the Whisper conv stem and the AV-HuBERT Conv3d front-end run on the GEMM.
-Still on library kernels in this round (TODO round 2): the ResNet-18 trunk and the grouped positional
-convolution (cuDNN).
+The ResNet-18 trunk runs on the same GEMM (3x3 stride-1 convolutions as overlapping-row views of ring-padded channels-last
+frames, csrc/resnet_trunk.cu), so does the grouped positional convolution: no cuDNN / library convolution on the path.
 Encoders run in eval mode (no dropout / layerdrop, BatchNorm running statistics): SURVEY §5.8 / §7.
 """
 from __future__ import annotations
@@ -24,7 +24,6 @@ from typing import Optional
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import autograd_ops as ag
@@ -293,7 +292,8 @@ class _Trunk(nn.Module):
 
 
 class _ResEncoder(nn.Module):
-    """Conv3d front-end + ResNet-18 trunk (library convolutions, channels-last, eval-mode BatchNorm)."""
+    """Conv3d front-end + ResNet-18 trunk (resnet.py:131-169), eval-mode BatchNorm folded into the filters; every
+    convolution is a tcgen05 GEMM (no library convolution)."""
 
     def __init__(self, widths):
         super().__init__()
@@ -324,40 +324,49 @@ class _ResEncoder(nn.Module):
                 ds = None
                 if blk.downsample is not None:
                     wd, bd = self._fold(blk.downsample[0].weight, blk.downsample[1])
-                    ds = (wd.contiguous(memory_format=torch.channels_last), bd, blk.downsample[0].stride)
-                f[(li, bi)] = (w1.contiguous(memory_format=torch.channels_last), b1, blk.conv1.stride,
-                               w2.contiguous(memory_format=torch.channels_last), b2, ds)
+                    ds = (wd.reshape(wd.shape[0], wd.shape[1]).contiguous(), bd)
+                # filter matrices of the overlapping-row GEMM: g output pixels per GEMM row so that every layer presents a
+                # 256-wide N to the CTA-pair kernel (64 channels: g = 4, 128: g = 2); the stride-2 convolutions read gathered
+                # tap-major rows
+                tap = lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+                grp = lambda w: max(1, min(4, 256 // w.shape[0])) if (w.shape[1] * 3) % 64 == 0 else 1
+                s1 = blk.conv1.stride[0]
+                g1, g2 = (grp(w1) if s1 == 1 else 1), grp(w2)
+                m1 = ops.conv3x3_group_weights(w1, g1) if s1 == 1 else tap(w1)
+                f[(li, bi)] = (m1, b1, s1, ops.conv3x3_group_weights(w2, g2), b2, ds, g1, g2)
         return f
 
     def forward(self, x):                       # [B, 1, T, 88, 88] -> [B*T, C]
         if self.training:
-            B = x.shape[0]
-            x = self.frontend3D(x)
-            T = x.shape[2]
-            x = x.transpose(1, 2).reshape(B * T, *x.shape[1:2], *x.shape[3:])
-            return self.trunk(x.contiguous(memory_format=torch.channels_last))
+            raise RuntimeError("the AV-HuBERT front-end runs with eval semantics (BatchNorm running statistics folded into "
+                               "the filters); AVHubertVideoEncoder.train() keeps it in eval mode")
         if getattr(self, "_wt", None) is None:
             self._wt = self._prepare()
         f = self._wt
         B, _, T, Hh, Ww = x.shape
         # Conv3d(1 -> C, (5,7,7), stride (1,2,2)) = time-major im2col of the 49 spatial taps + ONE tcgen05 GEMM whose five
         # K blocks (temporal taps) read five consecutive rows, against the BatchNorm-folded [C, 5*64] filter matrix; the
-        # pooling kernel turns the time-major GEMM output into the channels-last activation of the trunk.
+        # pooling kernel writes the ring-padded channels-last frames the trunk's convolution GEMMs read.
         w, b = f["front"]
-        y = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data)  # [B*T, C, 22, 22] NHWC
+        Hp, Wp = ((Hh + 6 - 7) // 2 + 1 + 2 - 3) // 2 + 1, ((Ww + 6 - 7) // 2 + 1 + 2 - 3) // 2 + 1
+        key = (B * T, Hp, Wp, w.shape[0])
+        if getattr(self, "_ring0", None) is None or self._ring0[0] != key:
+            # the ring of this buffer is zeroed once and never written again (the pooling kernel fills the interior only)
+            self._ring0 = (key, ops.RingFrames(B * T, Hp, Wp, w.shape[0], x.device, zero=True))
+        y = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data, ring_out=self._ring0[1])
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
-                w1, b1, s1, w2, b2, ds = f[(li, bi)]
+                w1, b1, s1, w2, b2, ds, g1, g2 = f[(li, bi)]
                 # the folded-BatchNorm shifts ride in the PReLU kernel (a conv bias would cost one more elementwise pass)
-                o = F.conv2d(y, w1, None, stride=s1, padding=1).contiguous(memory_format=torch.channels_last)
-                ops.prelu_res_(o, blk.relu1.weight.data, bias=b1)
-                o = F.conv2d(o, w2, None, stride=1, padding=1).contiguous(memory_format=torch.channels_last)
+                o = ops.conv3x3s1_ring(y, w1, g1) if s1 == 1 else ops.conv_s2_ring(y, w1, 9)
+                ops.prelu_res_ring_(o, blk.relu1.weight.data, bias=b1)
+                o = ops.conv3x3s1_ring(o, w2, g2)
                 if ds is None:
-                    y = ops.prelu_res_(o, blk.relu2.weight.data, y, bias=b2)
+                    y = ops.prelu_res_ring_(o, blk.relu2.weight.data, y, bias=b2)
                 else:
-                    res = F.conv2d(y, ds[0], None, stride=ds[2]).contiguous(memory_format=torch.channels_last)
-                    y = ops.prelu_res_(o, blk.relu2.weight.data, res, bias=b2, res_bias=ds[1])
-        return y.mean(dim=(2, 3))
+                    res = ops.conv_s2_ring(y, ds[0], 1)
+                    y = ops.prelu_res_ring_(o, blk.relu2.weight.data, res, bias=b2, res_bias=ds[1])
+        return ops.avgpool_ring(y)
 
 
 class _VideoFeatureExtractor(nn.Module):

@@ -675,7 +675,7 @@ def conv3d_front(video, wmat, bias):
     return out.view(B * T, Ho, Wo, Cc).permute(0, 3, 1, 2)
 
 
-def front3d_prelu_maxpool(video, wmat5, bias, slope):
+def front3d_prelu_maxpool(video, wmat5, bias, slope, ring_out: Optional["RingFrames"] = None):
     """AV-HuBERT front-end Conv3d(1, C, (5,7,7), (1,2,2), (2,3,3)) (+ folded BatchNorm bias) + PReLU + MaxPool3d((1,3,3),
     (1,2,2), (0,1,1)) on video [B, T, H, W] bf16.  wmat5 [C, 320]: column dt*64 + ky*7 + kx (49 taps + 15 zero columns
     per temporal tap).  Time-major im2col of the 49 spatial taps, one tcgen05 GEMM whose five K blocks read five
@@ -690,7 +690,12 @@ def front3d_prelu_maxpool(video, wmat5, bias, slope):
     Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
     Cc = wmat5.shape[0]
     Tp = T + 4
-    y = torch.empty((B * T, Cc, Hp, Wp), device=video.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    if ring_out is not None:
+        if (ring_out.N, ring_out.H, ring_out.W, ring_out.C) != (B * T, Hp, Wp, Cc):
+            raise ValueError("ring_out geometry mismatch")
+        y = None
+    else:
+        y = torch.empty((B * T, Cc, Hp, Wp), device=video.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
     per_clip = Ho * Wo * Tp
     clips = max(1, (16 << 20) // per_clip)          # <= ~16M rows (2 GB of taps + 2 GB of conv output) in flight
     nb_max = min(B, clips)
@@ -704,10 +709,147 @@ def front3d_prelu_maxpool(video, wmat5, bias, slope):
         _count()
         a = cols.as_strided((nb * per_clip, 320), (64, 1))
         gemm(a, wmat5, bias=bias, out=conv[: nb * per_clip], block_n=64 if Cc <= 64 else 128)
-        check(lib.omni_prelu_maxpool_front(conv.data_ptr(), slope.data_ptr(), y[b0 * T:].data_ptr(), nb, T, Ho, Wo, Cc,
-                                           stream_ptr()), "omni_prelu_maxpool_front")
+        if ring_out is not None:
+            dst = ring_out.rows[b0 * T * ring_out.P:]
+            check(lib.omni_prelu_maxpool_front_ring(conv.data_ptr(), slope.data_ptr(), dst.data_ptr(), nb, T, Ho, Wo, Cc,
+                                                    stream_ptr()), "omni_prelu_maxpool_front_ring")
+        else:
+            check(lib.omni_prelu_maxpool_front(conv.data_ptr(), slope.data_ptr(), y[b0 * T:].data_ptr(), nb, T, Ho, Wo, Cc,
+                                               stream_ptr()), "omni_prelu_maxpool_front")
         _count()
-    return y
+    return ring_out if ring_out is not None else y
+
+
+# ---------------------------------------------------------------------------------------------------
+# ResNet-18 trunk on the tcgen05 GEMM: ring-padded channels-last frames (csrc/resnet_trunk.cu)
+# ---------------------------------------------------------------------------------------------------
+class RingFrames:
+    """N channels-last frames [H + 2, W + 2, C] with a one-pixel zero ring, flattened to rows of C channels.  The storage
+    has (W + 3) * C spare elements before and after the rows: the overlapping-row GEMM view of a 3x3 convolution starts one
+    padded line + one pixel before row 0 and ends as much after the last row (those reads only feed ring outputs)."""
+
+    def __init__(self, N, H, W, C, device, zero=False):
+        self.N, self.H, self.W, self.C = int(N), int(H), int(W), int(C)
+        self.P = (H + 2) * (W + 2)
+        self.M = self.N * self.P
+        self.margin = (W + 3) * C
+        n = 2 * self.margin + self.M * C + 8 * C          # (+ 8 pixels: grouped GEMM rows may run past the last frame)
+        self.buf = (torch.zeros if zero else torch.empty)(n, device=device, dtype=torch.bfloat16)
+        self.rows = self.buf[self.margin: self.margin + self.M * C].view(self.M, C)
+        if not zero:
+            # the spare elements must be FINITE: the pixel-grouped convolution multiplies them by zero filter blocks
+            self.buf[: self.margin].zero_()
+            self.buf[self.margin + self.M * C:].zero_()
+
+    _pool = {}
+
+    @classmethod
+    def get(cls, N, H, W, C, device):
+        """Activation buffer from a small per-geometry ring of persistent buffers (six per geometry: a BasicBlock keeps at
+        most four alive -- input, conv1 output, conv2 output, downsample output -- and its successor two more), so that the
+        trunk allocates nothing and zero-fills nothing per step.  Only for the frozen, no-grad trunk."""
+        key = (int(N), int(H), int(W), int(C), str(device))
+        ent = cls._pool.get(key)
+        if ent is None:
+            if len(cls._pool) > 64:
+                cls._pool.clear()
+            ent = cls._pool[key] = [[cls(N, H, W, C, device) for _ in range(6)], 0]
+        ent[1] = (ent[1] + 1) % 6
+        return ent[0][ent[1]]
+
+
+_CONV_TABLES = {}
+
+
+def _conv3x3_table(W, C, g, n_out, bn, device):
+    """K-extension table of the overlapping-row 3x3 convolution with g output pixels per GEMM row: segments dy = 0, +1 at
+    columns (W + 2) C, 2 (W + 2) C of the view, against columns (g + 2) C, 2 (g + 2) C of the filter matrix, in 64-column
+    blocks, per N tile."""
+    key = (W, C, g, n_out, bn, str(device))
+    t = _CONV_TABLES.get(key)
+    if t is None:
+        nt = (n_out + bn - 1) // bn
+        seg = (g + 2) * C
+        blocks = seg // 64
+        tab = torch.empty((1, nt, 2 * blocks, 4), dtype=torch.int32)
+        for i in range(nt):
+            j = 0
+            for s in (1, 2):
+                for b in range(blocks):
+                    tab[0, i, j] = torch.tensor([s * (W + 2) * C + 64 * b, i * bn, s * seg + 64 * b, 0])
+                    j += 1
+        t = _CONV_TABLES[key] = tab.contiguous().to(device)
+    return t
+
+
+def conv3x3_group_weights(w: torch.Tensor, g: int) -> torch.Tensor:
+    """[C_out, C_in, 3, 3] filters -> the filter matrix of the overlapping-row GEMM that computes g horizontally consecutive
+    output pixels per row: [g * C_out, 3 * (g + 2) * C_in], row p * C_out + co, column dy * (g + 2) C_in + q * C_in + ci holds
+    w[co, ci, dy, q - p] (zero where q - p is outside the 3-tap window).  g = 1 is the plain tap-major matrix.  Grouping
+    trades (g + 2) / 3 x the flops for a g x wider N: 64- and 128-channel layers reach the 256-wide CTA-pair GEMM tiles."""
+    Co, Ci = w.shape[0], w.shape[1]
+    out = torch.zeros((g, Co, 3, g + 2, Ci), device=w.device, dtype=w.dtype)
+    for p in range(g):
+        out[p, :, :, p: p + 3, :] = w.permute(0, 2, 3, 1)          # [Co, ky, kx, Ci] at pixel offsets p .. p + 2
+    return out.reshape(g * Co, 3 * (g + 2) * Ci).contiguous()
+
+
+def conv3x3s1_ring(x: RingFrames, wmat: torch.Tensor, group: int = 1) -> RingFrames:
+    """3x3 / stride 1 / pad 1 convolution of ring-padded frames as ONE tcgen05 GEMM launch.  wmat = conv3x3_group_weights(w,
+    group): [group * C_out, 3 * (group + 2) * C_in].  The ring rows of the result are garbage: follow with prelu_res_ring_."""
+    require_cuda(wmat)
+    C, g = x.C, group
+    Co = wmat.shape[0] // g
+    seg = (g + 2) * C
+    if wmat.dtype != torch.bfloat16 or wmat.shape[1] != 3 * seg or not wmat.is_contiguous() or g > 8:
+        raise ValueError("wmat must be contiguous bf16 [group * C_out, 3 * (group + 2) * C_in]")
+    if seg % 64:
+        if g != 1:
+            raise ValueError("grouped convolution needs (group + 2) * C_in to be a multiple of 64")
+        return conv_s2_ring(x, wmat, 9, stride=1)      # narrow test architectures: gather + plain GEMM
+    N = g * Co
+    bn = 64 if N <= 64 else (128 if N <= 128 else 256)
+    Mg = (x.M + g - 1) // g
+    a_main = torch.as_strided(x.buf, (Mg, seg), (g * C, 1), 0)
+    a_ext = torch.as_strided(x.buf, (Mg, (2 * (x.W + 2) + g + 2) * C), (g * C, 1), 0)
+    out = RingFrames.get(x.N, x.H, x.W, Co, x.buf.device)
+    out_rows = torch.as_strided(out.buf, (Mg, N), (N, 1), out.margin)
+    gemm(a_main, wmat[:, :seg], ext=(a_ext, wmat, _conv3x3_table(x.W, C, g, N, bn, x.buf.device)), out=out_rows, block_n=bn,
+         pair_aligned=True)
+    return out
+
+
+def conv_s2_ring(x: RingFrames, wmat: torch.Tensor, taps: int, stride: int = 2) -> RingFrames:
+    """Strided convolution (taps = 9: 3x3 pad 1; taps = 1: the 1x1 downsample) of ring-padded frames: gather kernel ->
+    plain GEMM.  The output grid is ring-padded too (ring rows: GEMM of zero rows = 0 before the bias)."""
+    require_cuda(wmat)
+    Ho, Wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
+    out = RingFrames.get(x.N, Ho, Wo, wmat.shape[0], x.buf.device)
+    cols = torch.empty((out.M, taps * x.C), device=x.buf.device, dtype=torch.bfloat16)
+    check(lib.omni_gather_s2_ring(x.rows.data_ptr(), cols.data_ptr(), x.N, x.H, x.W, x.C, taps, stride, stream_ptr()),
+          "omni_gather_s2_ring")
+    _count()
+    Co = wmat.shape[0]
+    gemm(cols, wmat, out=out.rows, block_n=64 if Co <= 64 else (128 if Co <= 128 else 256))
+    return out
+
+
+def prelu_res_ring_(x: RingFrames, slope, residual: Optional[RingFrames] = None, bias=None, res_bias=None) -> RingFrames:
+    """x <- PReLU((x + bias) (+ residual + res_bias)) on the interior, zeros on the ring (in place)."""
+    require_cuda(slope, bias, res_bias)
+    if residual is not None and (residual.M, residual.C) != (x.M, x.C):
+        raise ValueError("residual shape mismatch")
+    check(lib.omni_prelu_res_ring(x.rows.data_ptr(), None if residual is None else residual.rows.data_ptr(), slope.data_ptr(),
+                                  ptr(bias), ptr(res_bias), x.N, x.H, x.W, x.C, stream_ptr()), "omni_prelu_res_ring")
+    _count()
+    return x
+
+
+def avgpool_ring(x: RingFrames) -> torch.Tensor:
+    out = torch.empty((x.N, x.C), device=x.buf.device, dtype=torch.bfloat16)
+    check(lib.omni_avgpool_ring(x.rows.data_ptr(), out.data_ptr(), x.N, x.H, x.W, x.C, stream_ptr()), "omni_avgpool_ring")
+    _count()
+    return out
 
 
 def attention_fwd(qkv, out, segments, n_heads: int, n_kv_heads: int, head_dim: int, causal: bool, lse=None,

@@ -281,3 +281,76 @@ def test_transpose_bit_exact(shape):
     got = ops.transpose(x)
     want = x.transpose(-1, -2).contiguous()
     assert got.shape == want.shape and torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ResNet-18 trunk convolutions on the tcgen05 GEMM (ring-padded channels-last frames, csrc/resnet_trunk.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _ring_from_nchw(x):
+    from omni_avsr_b200 import ops
+    N, C, H, W = x.shape
+    r = ops.RingFrames(N, H, W, C, x.device, zero=True)
+    r.rows.view(N, H + 2, W + 2, C)[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    return r
+
+
+def _nchw_from_ring(r):
+    return r.rows.view(r.N, r.H + 2, r.W + 2, r.C)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("N,H,W,Ci,Co", [(5, 22, 22, 64, 64), (3, 11, 11, 128, 128), (2, 6, 6, 256, 256), (3, 3, 3, 512, 512),
+                                         (2, 7, 5, 64, 128), (4, 6, 6, 16, 32)])
+def test_conv3x3_stride1_as_overlapping_row_gemm(N, H, W, Ci, Co):
+    """3x3 / stride 1 / pad 1 convolution = one GEMM on the overlapping-row view of the ring-padded frames (main K = dy -1
+    taps, K-extension blocks = dy 0 / +1 taps) vs torch conv2d in fp32; max|a-b| <= 1e-2 * max|b|.  (16 -> 32: the gather
+    path of narrow test architectures.)"""
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N + H + Ci)
+    x = torch.randn(N, Ci, H, W, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (3 * Ci ** 0.5)).bfloat16()
+    want = torch.nn.functional.conv2d(x.float(), w.float(), padding=1)
+    for g in (1, 2, 4):                      # g output pixels per GEMM row (wider N for the 64- / 128-channel layers)
+        if g > 1 and ((g + 2) * Ci) % 64:
+            continue
+        wmat = ops.conv3x3_group_weights(w, g)
+        if g == 1:
+            assert torch.equal(wmat, w.permute(0, 2, 3, 1).reshape(Co, 9 * Ci))
+        out = ops.conv3x3s1_ring(_ring_from_nchw(x), wmat, g)
+        got = _nchw_from_ring(out).float()
+        assert (got - want).abs().max().item() <= 1e-2 * want.abs().max().item(), g
+
+
+@pytest.mark.parametrize("N,H,W,Ci,Co", [(3, 22, 22, 64, 128), (2, 11, 11, 128, 256), (2, 6, 6, 256, 512), (3, 5, 8, 16, 32)])
+def test_stride2_convs_prelu_ring_and_avgpool(N, H, W, Ci, Co):
+    """The stride-2 3x3 convolution and the 1x1 stride-2 downsample (gather + GEMM on the ring-padded output grid), the
+    PReLU / residual / folded-BN-shift kernel with ring re-zeroing and the final average pool, composed as one BasicBlock
+    with a downsample branch (resnet.py:35-74), vs the same ops in fp32 torch."""
+    from omni_avsr_b200 import ops
+    F = torch.nn.functional
+    g = torch.Generator(device="cuda").manual_seed(H * 31 + Ci)
+    x = torch.randn(N, Ci, H, W, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (3 * Ci ** 0.5)).bfloat16()
+    w2 = (torch.randn(Co, Co, 3, 3, device="cuda", generator=g) / (3 * Co ** 0.5)).bfloat16()
+    wd = (torch.randn(Co, Ci, 1, 1, device="cuda", generator=g) / Ci ** 0.5).bfloat16()
+    b1, b2, bd = [(torch.randn(Co, device="cuda", generator=g) * 0.1).bfloat16() for _ in range(3)]
+    s1, s2 = [(torch.rand(Co, device="cuda", generator=g) * 0.5).bfloat16() for _ in range(2)]
+    tap = lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+    y = _ring_from_nchw(x)
+    o = ops.conv_s2_ring(y, tap(w1), 9)
+    ops.prelu_res_ring_(o, s1, bias=b1)
+    ring = o.rows.view(N, o.H + 2, o.W + 2, Co)
+    assert (ring[:, 0] == 0).all() and (ring[:, -1] == 0).all() and (ring[:, :, 0] == 0).all() and (ring[:, :, -1] == 0).all()
+    o2 = ops.conv3x3s1_ring(o, ops.conv3x3_group_weights(w2, 1))
+    res = ops.conv_s2_ring(y, wd.reshape(Co, Ci).contiguous(), 1)
+    out = ops.prelu_res_ring_(o2, s2, res, bias=b2, res_bias=bd)
+    pooled = ops.avgpool_ring(out)
+    xf = x.float()
+    t = F.conv2d(xf, w1.float(), stride=2, padding=1) + b1.float().view(1, -1, 1, 1)
+    t = F.prelu(t.bfloat16().float(), s1.float()).bfloat16().float()
+    t = F.conv2d(t, w2.float(), padding=1).bfloat16().float() + b2.float().view(1, -1, 1, 1)
+    r = F.conv2d(xf, wd.float(), stride=2).bfloat16().float() + bd.float().view(1, -1, 1, 1)
+    want = F.prelu((t.bfloat16().float() + r.bfloat16().float()).bfloat16().float(), s2.float())
+    got = _nchw_from_ring(out).float()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+    assert (pooled.float() - want.mean(dim=(2, 3))).abs().max().item() <= 2e-2 * want.mean(dim=(2, 3)).abs().max().item()
