@@ -36,6 +36,12 @@ extern "C" {
  * bf16(A.B^T + bias), `out2` [M, N] (ld = ldo2) = bf16(gelu(out)) with the same erf formula as OMNI_ACT_GELU.  CTA-pair
  * kernel only; OMNI_ERR_UNSUPPORTED otherwise. */
 #define OMNI_ACT_GELU_KEEP 4
+/* ResNet BasicBlock epilogue of the ring-padded convolution GEMMs (resnet.py:35-74; csrc/resnet_trunk.cu): the GEMM row is
+ * `ring_group` consecutive pixels x `ring_c` channels (N = ring_group * ring_c).  Per element, with the rounding points of
+ * the unfused sequence conv -> omni_prelu_res_ring:  f = bf16(bf16(acc) + bias[ch]);  if residual: f = bf16(f +
+ * bf16(residual + res_bias[ch]));  f = PReLU(f, slope[ch]);  pixels on the one-pixel ring of their [ring_h + 2, ring_w + 2]
+ * frame are stored as 0.  bias / slope / res_bias are [ring_c].  CTA-pair kernel only; OMNI_ERR_UNSUPPORTED otherwise. */
+#define OMNI_ACT_PRELU_RING 5
 
 #define OMNI_COMPRESS_AVG 0   /* nn.AvgPool1d(r)  : modeling_OmniAVSR.py:544-546 (audio), :469-471 (video) */
 #define OMNI_COMPRESS_STACK 1 /* frame stacking   : modeling_OmniAVSR.py:562-568 (audio), :487-493 (video) */
@@ -75,6 +81,9 @@ typedef struct omni_gemm_args {
                               256-row boundaries), which lets the K-extended GEMM run on the CTA-pair kernel */
   void* out2;              /* OMNI_ACT_SWIGLU64: [M, N/2] bf16; OMNI_ACT_GELU_KEEP: [M, N] bf16; ld = ldo2; else NULL */
   int64_t ldo2;
+  const void* slope;       /* OMNI_ACT_PRELU_RING: per-channel PReLU slope [ring_c] */
+  const void* res_bias;    /* OMNI_ACT_PRELU_RING: folded-BatchNorm shift of the residual branch [ring_c] or NULL */
+  int32_t ring_h, ring_w, ring_group, ring_c;
   void* workspace;         /* omni_gemm_skinny_bf16 only: split-K exchange buffer (256-byte aligned device memory, zero-filled
                               once by the caller; the kernel leaves its counters at zero), or NULL = no split-K */
   int64_t workspace_bytes; /* >= omni_gemm_skinny_workspace_bytes() */

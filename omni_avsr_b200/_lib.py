@@ -49,6 +49,8 @@ class GemmArgs(C.Structure):
         ("n_ext", C.c_int32), ("block_n", C.c_int32), ("act", C.c_int32), ("out_fp32", C.c_int32),
         ("alpha", C.c_float), ("pair_aligned", C.c_int32),
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
+        ("slope", C.c_void_p), ("res_bias", C.c_void_p),
+        ("ring_h", C.c_int32), ("ring_w", C.c_int32), ("ring_group", C.c_int32), ("ring_c", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 

@@ -30,6 +30,10 @@ struct GemmKParams {
   float alpha;
   bf16* out2;        // OMNI_ACT_SWIGLU64: [M, N/2]
   long long ldo2;
+  // OMNI_ACT_PRELU_RING (ResNet BasicBlock epilogue on ring-padded frames)
+  const bf16* slope;
+  const bf16* res_bias;
+  int ring_hp, ring_wp, ring_g, ring_c;
 };
 
 // Residual values of one 32-column chunk, fetched one chunk AHEAD of the TMEM read so that the (strided, 64 bytes per
@@ -246,6 +250,63 @@ __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* s
   store_tile64(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage, v, lane, row0, col0);
 }
 
+
+// OMNI_ACT_PRELU_RING on a 32-row x 64-column block held one row per thread: f = bf16(bf16(acc) + bias); with a residual
+// (staged in the warp's transposition tile) f = bf16(f + bf16(res + res_bias)); PReLU; ring pixels -> 0 (same arithmetic and
+// rounding points as prelu_res_ring_kernel applied to the GEMM's bf16 output).
+__device__ __forceinline__ void epilogue_tile64_prelu_ring(const GemmKParams& p, uint8_t* stage, float (&v)[64], int lane,
+                                                           int row0, int col0, bool res_staged) {
+  const int ch0 = col0 % p.ring_c;                        // 64-column blocks never straddle a pixel (ring_c % 64 == 0)
+  const long long pix = static_cast<long long>(row0 + lane) * p.ring_g + col0 / p.ring_c;
+  const int px = static_cast<int>(pix % p.ring_wp);
+  const int py = static_cast<int>((pix / p.ring_wp) % p.ring_hp);
+  const bool ring = px == 0 || py == 0 || px == p.ring_wp - 1 || py == p.ring_hp - 1;
+  uint8_t* my_row = stage + lane * EPI_PITCH;
+  const uint4* bp = reinterpret_cast<const uint4*>(p.bias + ch0);
+  const uint4* sp = reinterpret_cast<const uint4*>(p.slope + ch0);
+  const uint4* rbp = p.res_bias ? reinterpret_cast<const uint4*>(p.res_bias + ch0) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 b = __ldg(bp + i);
+    const uint4 s = __ldg(sp + i);
+    const uint32_t bs[4] = {b.x, b.y, b.z, b.w};
+    const uint32_t ss[4] = {s.x, s.y, s.z, s.w};
+    uint32_t rs[4] = {0u, 0u, 0u, 0u}, rbs[4] = {0u, 0u, 0u, 0u};
+    if (res_staged) {
+      const uint4 r = *reinterpret_cast<const uint4*>(my_row + 16 * i);
+      rs[0] = r.x; rs[1] = r.y; rs[2] = r.z; rs[3] = r.w;
+      if (rbp) {
+        const uint4 rb = __ldg(rbp + i);
+        rbs[0] = rb.x; rbs[1] = rb.y; rbs[2] = rb.z; rbs[3] = rb.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 bf = bf2_to_f2(bs[j]);
+      const float2 sf = bf2_to_f2(ss[j]);
+      float f0 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * j]));
+      float f1 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * j + 1]));
+      f0 = __bfloat162float(__float2bfloat16_rn(f0 + bf.x));
+      f1 = __bfloat162float(__float2bfloat16_rn(f1 + bf.y));
+      if (res_staged) {
+        float2 rf = bf2_to_f2(rs[j]);
+        if (rbp) {
+          const float2 rbf2 = bf2_to_f2(rbs[j]);
+          rf.x = __bfloat162float(__float2bfloat16_rn(rf.x + rbf2.x));
+          rf.y = __bfloat162float(__float2bfloat16_rn(rf.y + rbf2.y));
+        }
+        f0 = __bfloat162float(__float2bfloat16_rn(f0 + rf.x));
+        f1 = __bfloat162float(__float2bfloat16_rn(f1 + rf.y));
+      }
+      f0 = f0 > 0.f ? f0 : f0 * sf.x;
+      f1 = f1 > 0.f ? f1 : f1 * sf.y;
+      v[8 * i + 2 * j] = ring ? 0.f : f0;
+      v[8 * i + 2 * j + 1] = ring ? 0.f : f1;
+    }
+  }
+  if (res_staged) __syncwarp();
+  store_tile64(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage, v, lane, row0, col0);
+}
 
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int m_fast, int& m_tile, int& n_tile) {
   if (m_fast) {

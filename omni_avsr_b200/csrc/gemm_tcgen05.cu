@@ -896,7 +896,11 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             res_tile_publish(stage_tile, lane, rt);
             if (c2 == 0) res_tile_prefetch(p, row0, n0 + 64, lane, rt);   // lands while block 0 is converted and stored
           }
-          epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);     // rounds v to bf16 when act != NONE
+          if constexpr (EPI == 3) {
+            epilogue_tile64_prelu_ring(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);
+          } else {
+            epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);     // rounds v to bf16 when act != NONE
+          }
           if constexpr (EPI == 2) {
             // v holds the rounded pre-activation that was just stored: second output = gelu of it
 #pragma unroll
@@ -995,6 +999,9 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
   p.ldo = a->ldo; p.ldr = a->ldr;
   p.act = a->act; p.out_fp32 = a->out_fp32; p.alpha = a->alpha;
   p.out2 = reinterpret_cast<bf16*>(a->out2); p.ldo2 = a->ldo2;
+  p.slope = reinterpret_cast<const bf16*>(a->slope);
+  p.res_bias = reinterpret_cast<const bf16*>(a->res_bias);
+  p.ring_hp = a->ring_h + 2; p.ring_wp = a->ring_w + 2; p.ring_g = a->ring_group; p.ring_c = a->ring_c;
 
   if constexpr (BN == 64) {
     // decode step: one tile of rows, few N tiles -> split K over a 4-CTA cluster so that enough SMs pull on HBM
@@ -1034,14 +1041,16 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     static const bool no_2cta = (getenv("OMNI_GEMM_NO_2CTA") != nullptr);
     const bool pair_ok = !no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) && p.m_tiles >= 2 &&
                          tiles >= sms / 2;
-    if ((a->act == OMNI_ACT_SWIGLU64 || a->act == OMNI_ACT_GELU_KEEP) && !pair_ok) return OMNI_ERR_UNSUPPORTED;
+    if ((a->act == OMNI_ACT_SWIGLU64 || a->act == OMNI_ACT_GELU_KEEP || a->act == OMNI_ACT_PRELU_RING) && !pair_ok)
+      return OMNI_ERR_UNSUPPORTED;
     if (pair_ok) {
       // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
       constexpr int ST2 = 5;     // 5 x 32 KB operand stages + 36 KB of epilogue transposition tiles
       using S2 = GemmSmem2<ST2>;
-      const int epi = a->act == OMNI_ACT_SWIGLU64 ? 1 : a->act == OMNI_ACT_GELU_KEEP ? 2 : 0;
-      auto k2 = epi == 1 ? gemm_bf16_tn_2cta<ST2, 1> : epi == 2 ? gemm_bf16_tn_2cta<ST2, 2> : gemm_bf16_tn_2cta<ST2, 0>;
-      static bool attr_set_2[3] = {false, false, false};
+      const int epi = a->act == OMNI_ACT_SWIGLU64 ? 1 : a->act == OMNI_ACT_GELU_KEEP ? 2 : a->act == OMNI_ACT_PRELU_RING ? 3 : 0;
+      auto k2 = epi == 1 ? gemm_bf16_tn_2cta<ST2, 1> : epi == 2 ? gemm_bf16_tn_2cta<ST2, 2>
+                : epi == 3 ? gemm_bf16_tn_2cta<ST2, 3> : gemm_bf16_tn_2cta<ST2, 0>;
+      static bool attr_set_2[4] = {false, false, false, false};
       if (!attr_set_2[epi]) {
         if (cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL) != cudaSuccess)
           return OMNI_ERR_CUDA;
@@ -1131,6 +1140,13 @@ extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
     OMNI_CHECK_ARG(a->out2 && (a->ldo2 % 8) == 0 && a->ldo2 >= a->N && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);
     if (a->block_n != 256 || (a->N % 256) != 0 || a->out_fp32 || a->residual || a->ext_table || a->b_row_table)
       return OMNI_ERR_UNSUPPORTED;
+  }
+  if (a->act == OMNI_ACT_PRELU_RING) {
+    OMNI_CHECK_ARG(a->slope && a->bias && a->ring_h > 0 && a->ring_w > 0 && a->ring_group > 0 && a->ring_c > 0);
+    OMNI_CHECK_ARG((a->ring_c % 64) == 0 && a->ring_group * a->ring_c == a->N);
+    OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->slope) & 15) == 0 &&
+                   (!a->res_bias || (reinterpret_cast<uintptr_t>(a->res_bias) & 15) == 0));
+    if (a->block_n != 256 || (a->N % 128) != 0 || a->out_fp32 || a->b_row_table) return OMNI_ERR_UNSUPPORTED;
   }
   if (a->act == OMNI_ACT_SWIGLU64) {
     OMNI_CHECK_ARG(a->out2 && (a->ldo2 % 8) == 0 && a->ldo2 >= a->N / 2 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);

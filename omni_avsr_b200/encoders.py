@@ -358,14 +358,18 @@ class _ResEncoder(nn.Module):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
                 w1, b1, s1, w2, b2, ds, g1, g2 = f[(li, bi)]
                 # the folded-BatchNorm shifts ride in the PReLU kernel (a conv bias would cost one more elementwise pass)
-                o = ops.conv3x3s1_ring(y, w1, g1) if s1 == 1 else ops.conv_s2_ring(y, w1, 9)
-                ops.prelu_res_ring_(o, blk.relu1.weight.data, bias=b1)
-                o = ops.conv3x3s1_ring(o, w2, g2)
+                # (... or in the epilogue of the convolution GEMM itself: bias, residual add, PReLU and ring re-zeroing)
+                if s1 == 1:
+                    o = ops.conv3x3s1_ring(y, w1, g1, prelu=dict(slope=blk.relu1.weight.data, bias=b1))
+                else:
+                    o = ops.conv_s2_ring(y, w1, 9)
+                    ops.prelu_res_ring_(o, blk.relu1.weight.data, bias=b1)
                 if ds is None:
-                    y = ops.prelu_res_ring_(o, blk.relu2.weight.data, y, bias=b2)
+                    y = ops.conv3x3s1_ring(o, w2, g2, prelu=dict(slope=blk.relu2.weight.data, bias=b2, residual=y))
                 else:
                     res = ops.conv_s2_ring(y, ds[0], 1)
-                    y = ops.prelu_res_ring_(o, blk.relu2.weight.data, res, bias=b2, res_bias=ds[1])
+                    y = ops.conv3x3s1_ring(o, w2, g2, prelu=dict(slope=blk.relu2.weight.data, bias=b2, residual=res,
+                                                                  res_bias=ds[1]))
         return ops.avgpool_ring(y)
 
 

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, PpsArgs, SpliceArgs, check, lib, ptr, require_cuda, stream_ptr
 
-ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3, "gelu_keep": 4}
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3, "gelu_keep": 4, "prelu_ring": 5}
 SWIGLU_BLK = 64          # gate / up interleave of the OMNI_ACT_SWIGLU64 epilogue
 COMPRESS = {"avg-pooling": 0, "avg": 0, "stack": 1}
 
@@ -52,7 +52,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
          alpha: float = 1.0, n: Optional[int] = None, tile_group: Optional[torch.Tensor] = None,
          b_row_table: Optional[torch.Tensor] = None, ext: Optional[tuple] = None, block_n: int = 0,
-         pair_aligned: bool = False, out2: Optional[torch.Tensor] = None, skinny: bool = False) -> torch.Tensor:
+         pair_aligned: bool = False, out2: Optional[torch.Tensor] = None, skinny: bool = False,
+         prelu_ring: Optional[tuple] = None) -> torch.Tensor:
     """out[M,N] = epi(alpha * (a[M,K] @ b[rows,K]^T (+ K-extension)))  -- tcgen05 kernel.
 
     ext = (a2 [M, a2_cols], b2 [b2_rows, b2_cols], ext_table int32 [groups, n_tiles, n_ext, 4]).
@@ -88,7 +89,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     g.M, g.N, g.K = M, N, K
     g.b_rows = b.shape[0]
     if bias is not None:
-        if bias.dtype != torch.bfloat16 or bias.numel() < N:
+        if bias.dtype != torch.bfloat16 or (bias.numel() < N and act != "prelu_ring"):
             raise ValueError("bias must be bf16 [N]")
         g.bias = bias.data_ptr()
     if residual is not None:
@@ -130,6 +131,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         if out2 is None or out2.dtype != torch.bfloat16 or out2.shape != (M, n2) or out2.stride(1) != 1:
             raise ValueError(f"{act} needs out2: bf16 [M, {n2}]")
         g.out2, g.ldo2 = out2.data_ptr(), out2.stride(0)
+    if act == "prelu_ring":
+        # ResNet BasicBlock epilogue on ring-padded frames: (slope [C], res_bias [C] or None, H, W, pixels per row, C)
+        slope, res_bias, rh, rw, rg, rc = prelu_ring
+        require_cuda(slope, res_bias)
+        g.slope, g.res_bias = slope.data_ptr(), ptr(res_bias)
+        g.ring_h, g.ring_w, g.ring_group, g.ring_c = int(rh), int(rw), int(rg), int(rc)
     g.out_fp32 = 1 if out.dtype == torch.float32 else 0
     g.alpha = float(alpha)
     if skinny:
@@ -794,9 +801,12 @@ def conv3x3_group_weights(w: torch.Tensor, g: int) -> torch.Tensor:
     return out.reshape(g * Co, 3 * (g + 2) * Ci).contiguous()
 
 
-def conv3x3s1_ring(x: RingFrames, wmat: torch.Tensor, group: int = 1) -> RingFrames:
+def conv3x3s1_ring(x: RingFrames, wmat: torch.Tensor, group: int = 1, prelu: Optional[dict] = None) -> RingFrames:
     """3x3 / stride 1 / pad 1 convolution of ring-padded frames as ONE tcgen05 GEMM launch.  wmat = conv3x3_group_weights(w,
-    group): [group * C_out, 3 * (group + 2) * C_in].  The ring rows of the result are garbage: follow with prelu_res_ring_."""
+    group): [group * C_out, 3 * (group + 2) * C_in].  Without `prelu` the ring rows of the result are garbage: follow with
+    prelu_res_ring_.  prelu = dict(slope, bias, residual=None, res_bias=None): the BasicBlock tail (folded-BN shift,
+    residual add, PReLU, ring re-zeroing) runs in the GEMM epilogue when the shape is on the CTA-pair kernel, otherwise in
+    the separate kernel -- same bits either way."""
     require_cuda(wmat)
     C, g = x.C, group
     Co = wmat.shape[0] // g
@@ -806,7 +816,10 @@ def conv3x3s1_ring(x: RingFrames, wmat: torch.Tensor, group: int = 1) -> RingFra
     if seg % 64:
         if g != 1:
             raise ValueError("grouped convolution needs (group + 2) * C_in to be a multiple of 64")
-        return conv_s2_ring(x, wmat, 9, stride=1)      # narrow test architectures: gather + plain GEMM
+        out = conv_s2_ring(x, wmat, 9, stride=1)       # narrow test architectures: gather + plain GEMM
+        if prelu is not None:
+            prelu_res_ring_(out, prelu["slope"], prelu.get("residual"), bias=prelu["bias"], res_bias=prelu.get("res_bias"))
+        return out
     N = g * Co
     bn = 64 if N <= 64 else (128 if N <= 128 else 256)
     Mg = (x.M + g - 1) // g
@@ -814,8 +827,21 @@ def conv3x3s1_ring(x: RingFrames, wmat: torch.Tensor, group: int = 1) -> RingFra
     a_ext = torch.as_strided(x.buf, (Mg, (2 * (x.W + 2) + g + 2) * C), (g * C, 1), 0)
     out = RingFrames.get(x.N, x.H, x.W, Co, x.buf.device)
     out_rows = torch.as_strided(out.buf, (Mg, N), (N, 1), out.margin)
-    gemm(a_main, wmat[:, :seg], ext=(a_ext, wmat, _conv3x3_table(x.W, C, g, N, bn, x.buf.device)), out=out_rows, block_n=bn,
-         pair_aligned=True)
+    ext = (a_ext, wmat, _conv3x3_table(x.W, C, g, N, bn, x.buf.device))
+    if prelu is not None and bn == 256 and N % 128 == 0 and Co % 64 == 0 and Mg > 128 and ((Mg + 127) // 128) * ((N + 255) // 256) >= 74:
+        res = prelu.get("residual")
+        res_rows = None if res is None else torch.as_strided(res.buf, (Mg, N), (N, 1), res.margin)
+        try:
+            gemm(a_main, wmat[:, :seg], ext=ext, out=out_rows, block_n=bn, pair_aligned=True, act="prelu_ring",
+                 bias=prelu["bias"], residual=res_rows,
+                 prelu_ring=(prelu["slope"], prelu.get("res_bias"), x.H, x.W, g, Co))
+            return out
+        except _lib.OmniKernelError as e:
+            if "unsupported" not in str(e):
+                raise
+    gemm(a_main, wmat[:, :seg], ext=ext, out=out_rows, block_n=bn, pair_aligned=True)
+    if prelu is not None:
+        prelu_res_ring_(out, prelu["slope"], prelu.get("residual"), bias=prelu["bias"], res_bias=prelu.get("res_bias"))
     return out
 
 

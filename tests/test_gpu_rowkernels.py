@@ -320,6 +320,29 @@ def test_conv3x3_stride1_as_overlapping_row_gemm(N, H, W, Ci, Co):
         assert (got - want).abs().max().item() <= 1e-2 * want.abs().max().item(), g
 
 
+@pytest.mark.parametrize("N,H,W,C,g", [(80, 22, 22, 64, 4), (120, 11, 11, 128, 2), (300, 6, 6, 256, 1), (900, 3, 3, 512, 1)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv_gemm_fused_prelu_ring_epilogue_is_bit_identical(N, H, W, C, g, with_res):
+    """The BasicBlock tail in the epilogue of the CTA-pair convolution GEMM (OMNI_ACT_PRELU_RING: folded-BN shift, residual +
+    its shift, PReLU, ring re-zeroing) == the unfused pair conv GEMM -> prelu_res_ring kernel, bit for bit."""
+    from omni_avsr_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(N, C, H, W, device="cuda", generator=gen).bfloat16()
+    w = (torch.randn(C, C, 3, 3, device="cuda", generator=gen) / (3 * C ** 0.5)).bfloat16()
+    bias, rb = [(torch.randn(C, device="cuda", generator=gen) * 0.2).bfloat16() for _ in range(2)]
+    slope = (torch.rand(C, device="cuda", generator=gen) * 0.5).bfloat16()
+    res = _ring_from_nchw(torch.randn(N, C, H, W, device="cuda", generator=gen).bfloat16()) if with_res else None
+    wmat = ops.conv3x3_group_weights(w, g)
+    xin = _ring_from_nchw(x)
+    launches = ops.LAUNCHES
+    fused = ops.conv3x3s1_ring(xin, wmat, g, prelu=dict(slope=slope, bias=bias, residual=res, res_bias=rb if with_res else None))
+    assert ops.LAUNCHES - launches == 1                      # one launch: the epilogue variant was taken
+    fused_rows = fused.rows.clone()
+    plain = ops.conv3x3s1_ring(xin, wmat, g)
+    ops.prelu_res_ring_(plain, slope, res, bias=bias, res_bias=rb if with_res else None)
+    assert torch.equal(fused_rows.view(torch.int16), plain.rows.view(torch.int16))
+
+
 @pytest.mark.parametrize("N,H,W,Ci,Co", [(3, 22, 22, 64, 128), (2, 11, 11, 128, 256), (2, 6, 6, 256, 512), (3, 5, 8, 16, 32)])
 def test_stride2_convs_prelu_ring_and_avgpool(N, H, W, Ci, Co):
     """The stride-2 3x3 convolution and the 1x1 stride-2 downsample (gather + GEMM on the ring-padded output grid), the
