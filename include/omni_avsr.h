@@ -69,7 +69,7 @@ typedef struct omni_gemm_args {
   const int32_t* b_row_table; /* [groups * n_tiles] B row per (group, n_tile) or NULL */
   const int32_t* ext_table;   /* [groups * n_tiles * n_ext][4] = {a2_col, b2_row, b2_col, 0}; b2_row<0: skip */
   int64_t lda, ldb, lda2, ldb2, ldo, ldr;
-  int32_t M, N, K;
+  int32_t M, N, K;         /* K = 0 with an ext_table: the reduction is the K-extension list alone (CTA-pair kernel) */
   int32_t b_rows;          /* rows of B visible to the tensor map (>= N; more when grouped) */
   int32_t a2_cols, b2_rows, b2_cols;
   int32_t n_ext;           /* extension slots per (group, n_tile) */
@@ -330,6 +330,14 @@ int omni_prelu_res_ring(void* x, const void* residual, const void* slope, const 
 int omni_gather_s2_ring(const void* x, void* out, int64_t N, int32_t H, int32_t W, int32_t C, int32_t taps, int32_t stride,
                         void* stream);
 int omni_avgpool_ring(const void* x, void* out, int64_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* Table-driven convolution of the small late-stage grids (layers 2-4 of the trunk, resnet.py:108-110): the GEMM row is ONE
+ * FRAME (plain channels-last [N, P_alloc, C], no ring), an N tile is the channels of one output pixel (or of 256 / C_out
+ * consecutive output pixels), and the whole reduction is the K-extension list of that tile -- omni_gemm_bf16 with K = 0
+ * (A / B may be NULL) and one {column of the input pixel, 0, column of the filter-pattern block} entry per 64 input
+ * channels of every contributing input pixel; taps that fall on the zero padding are simply absent.  OMNI_ACT_PRELU_RING
+ * with ring_h = ring_w = 0 is the same BasicBlock epilogue without ring zeroing.  omni_avgpool_frames: mean over the first
+ * P pixels of every frame -> [N, C] (AdaptiveAvgPool2d(1), resnet.py:163). */
+int omni_avgpool_frames(const void* x, void* out, int64_t N, int32_t P, int32_t P_alloc, int32_t C, void* stream);
 /* out[i,:] = table[idx[i],:] (embed_tokens of the decode step, label-row selection); status as in the splice. */
 int omni_gather_rows(const void* table, const int64_t* idx, void* out, int64_t n, int32_t H, int64_t ld_table,
                      int64_t table_rows, int32_t* status, void* stream);

@@ -24,30 +24,37 @@ constexpr int AB_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 compute
 struct AttnBwdParams {
   bf16* dqkv;            // [M, dqkv_ld] packed gradient rows, same column layout as qkv
   long long dqkv_ld;
-  const float* lse;      // [n_heads, M] natural-log-sum-exp of the scaled scores (forward kernel)
-  const float* delta;    // [n_heads, M] rowsum(dO o O)
+  const float* stats;    // [n_heads][B][n_qs][2][64]: per 64-query step, lse * log2(e) (+inf for the queries past S, which makes
+                         // their P = exp2(s - inf) = 0 without any test) then rowsum(dO o O); written by attn_delta_kernel
   long long M;
-  int row0, S, n_heads, n_kv_heads, causal;
+  int row0, S, n_heads, n_kv_heads, causal, B, n_qs;
   float scale, scale_log2;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// delta pre-pass: one warp per row, HD/8 lanes per head (16-byte loads), fp32 sum.
+// statistics pre-pass: one warp per (clip, padded query position), HD/8 lanes per head (16-byte loads), fp32 sum.
+// Writes the per-step statistics blocks the two kernels read: stats[h][clip][pos / 64][0][pos % 64] = lse * log2(e),
+// [1][pos % 64] = delta = rowsum(dO o O); positions in [S, 64 n_qs) get (+inf, 0).  The blocks are 512 bytes, 512-byte
+// aligned: the dK/dV kernel fetches one per step with a single bulk copy next to its Q / dO tiles.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ dout, long long do_ld, const bf16* __restrict__ out, long long o_ld,
-                  float* __restrict__ delta, long long M, int row0, int rows, int n_heads, int hd) {
+                  const float* __restrict__ lse, float* __restrict__ stats, long long M, int row0, int B, int S, int n_qs,
+                  int n_heads, int hd) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= rows) return;
-  const long long row = static_cast<long long>(row0) + w;
+  const int s_pad = n_qs * 64;
+  if (w >= B * s_pad) return;
+  const int clip = w / s_pad, pos = w - clip * s_pad;
+  const bool valid = pos < S;
+  const long long row = static_cast<long long>(row0) + static_cast<long long>(clip) * S + pos;
   const int lph = hd >> 3;                 // lanes per head
   const int hpp = 32 / lph;                // heads per pass
   const int sub = lane / lph, l = lane % lph;
   for (int h0 = 0; h0 < n_heads; h0 += hpp) {
     const int h = h0 + sub;
     float acc = 0.f;
-    if (h < n_heads) {
+    if (h < n_heads && valid) {
       const uint4 a = ld_nc_u4(dout + row * do_ld + h * hd + l * 8);
       const uint4 b = ld_nc_u4(out + row * o_ld + h * hd + l * 8);
       const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -59,7 +66,11 @@ attn_delta_kernel(const bf16* __restrict__ dout, long long do_ld, const bf16* __
       }
     }
     for (int o = lph >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (h < n_heads && l == 0) delta[static_cast<long long>(h) * M + row] = acc;
+    if (h < n_heads && l == 0) {
+      float* blk = stats + ((static_cast<long long>(h) * B + clip) * n_qs + (pos >> 6)) * 128 + (pos & 63);
+      blk[0] = valid ? lse[static_cast<long long>(h) * M + row] * 1.4426950408889634f : INFINITY;
+      blk[64] = acc;
+    }
   }
 }
 
@@ -234,9 +245,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const long long row = static_cast<long long>(clip_row0) + qpos;
     const bool row_ok = qpos < p.S;
-    const float lse2 = row_ok ? p.lse[static_cast<long long>(head) * p.M + row] * 1.4426950408889634f : 0.f;
-    const float dl = row_ok ? p.delta[static_cast<long long>(head) * p.M + row] : 0.f;
-    const int kmax = row_ok ? (p.causal ? qpos : (p.S - 1)) : -1;
+    // lse2 = +inf for the rows past the clip: their P (and dS) come out as exactly 0 on the compare-free path
+    const float* sblk = p.stats + ((static_cast<long long>(head) * p.B + clip) * p.n_qs + (qpos >> 6)) * 128 + (qpos & 63);
+    const float lse2 = row_ok ? sblk[0] : INFINITY;
+    const float dl = row_ok ? sblk[64] : 0.f;
+    const int kmax = p.causal ? min(qpos, p.S - 1) : (p.S - 1);      // last visible key position
     const float sc = p.scale_log2;
     uint8_t* sDS = smem + SM::OFF_DS;
     for (int j = 0; j < n_kv; ++j) {
@@ -254,23 +267,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sd_read);     // S / dP are in registers: the next step's score MMAs may overwrite TMEM
-        if (full) {
+        if (!full) {       // boundary step: masked scores become -inf once (exp2 -> 0), the pass below stays branch-free
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), sc, -lse2));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sc, -lse2));
-            w[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(d[i]) - dl), p1 * (__uint_as_float(d[i + 1]) - dl));
-          }
-        } else {
+          for (int i = 0; i < 32; ++i)
+            if (k0 + c * 32 + i > kmax) s[i] = 0xff800000u;
+        }
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float g0 = 0.f, g1 = 0.f;
-            if (k0 + c * 32 + i <= kmax)
-              g0 = ex2_approx(fmaf(__uint_as_float(s[i]), sc, -lse2)) * (__uint_as_float(d[i]) - dl);
-            if (k0 + c * 32 + i + 1 <= kmax)
-              g1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sc, -lse2)) * (__uint_as_float(d[i + 1]) - dl);
-            w[i >> 1] = f2_to_bf2(g0, g1);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), sc, -lse2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sc, -lse2));
+          w[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(d[i]) - dl), p1 * (__uint_as_float(d[i + 1]) - dl));
         }
         if (j > 0) mbar_wait(ds_free, (j - 1) & 1);      // the previous step's dQ MMAs are done with the dS tile
         store_operand_chunk(sDS, r, c, w);

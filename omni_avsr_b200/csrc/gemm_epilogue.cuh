@@ -260,7 +260,8 @@ __device__ __forceinline__ void epilogue_tile64_prelu_ring(const GemmKParams& p,
   const long long pix = static_cast<long long>(row0 + lane) * p.ring_g + col0 / p.ring_c;
   const int px = static_cast<int>(pix % p.ring_wp);
   const int py = static_cast<int>((pix / p.ring_wp) % p.ring_hp);
-  const bool ring = px == 0 || py == 0 || px == p.ring_wp - 1 || py == p.ring_hp - 1;
+  // ring_h == 0 (ring_hp == 2): plain frames without a ring (ops.conv_frames), nothing is zeroed
+  const bool ring = p.ring_hp > 2 && (px == 0 || py == 0 || px == p.ring_wp - 1 || py == p.ring_hp - 1);
   uint8_t* my_row = stage + lane * EPI_PITCH;
   const uint4* bp = reinterpret_cast<const uint4*>(p.bias + ch0);
   const uint4* sp = reinterpret_cast<const uint4*>(p.slope + ch0);

@@ -971,10 +971,14 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES>;
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
-  rc = omni_make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM, BK, 1);
-  if (rc) return rc;
-  rc = omni_make_tmap_2d_bf16(&tmB, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, BN, BK, 1);
-  if (rc) return rc;
+  // K == 0: the whole reduction is the K-extension list (table-driven convolution, ops.conv_frames); CTA-pair kernel only
+  const bool ext_only = a->K == 0;
+  if (!ext_only) {
+    rc = omni_make_tmap_2d_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM, BK, 1);
+    if (rc) return rc;
+    rc = omni_make_tmap_2d_bf16(&tmB, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, BN, BK, 1);
+    if (rc) return rc;
+  }
   if (a->ext_table) {
     rc = omni_make_tmap_2d_bf16(&tmA2, a->A2, (uint64_t)a->M, (uint64_t)a->a2_cols, (uint64_t)a->lda2, BM, BK, 1);
     if (rc) return rc;
@@ -983,6 +987,10 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
   } else {
     tmA2 = tmA;
     tmB2 = tmB;
+  }
+  if (ext_only) {
+    tmA = tmA2;
+    tmB = tmB2;
   }
   GemmKParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -1023,6 +1031,7 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     }
   }
   static const bool use_v1 = (getenv("OMNI_GEMM_V1") != nullptr);   // debugging switch: one tile per CTA
+  if (use_v1 && ext_only) return OMNI_ERR_UNSUPPORTED;
   if (!use_v1) {
     using SP = GemmSmemP<BN, STAGES>;
     auto kp = gemm_bf16_tn_persistent<BN, STAGES>;
@@ -1039,9 +1048,9 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     const long long a_bytes = static_cast<long long>(a->M) * a->K * 2;
     const int m_fast = (!a->b_row_table && !a->ext_table && p.m_tiles < p.n_tiles && a_bytes <= (40ll << 20)) ? 1 : 0;
     static const bool no_2cta = (getenv("OMNI_GEMM_NO_2CTA") != nullptr);
-    const bool pair_ok = !no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) && p.m_tiles >= 2 &&
-                         tiles >= sms / 2;
-    if ((a->act == OMNI_ACT_SWIGLU64 || a->act == OMNI_ACT_GELU_KEEP || a->act == OMNI_ACT_PRELU_RING) && !pair_ok)
+    const bool pair_ok = !no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) &&
+                         ((p.m_tiles >= 2 && tiles >= sms / 2) || ext_only);
+    if ((a->act == OMNI_ACT_SWIGLU64 || a->act == OMNI_ACT_GELU_KEEP || a->act == OMNI_ACT_PRELU_RING || ext_only) && !pair_ok)
       return OMNI_ERR_UNSUPPORTED;
     if (pair_ok) {
       // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
@@ -1057,8 +1066,10 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
         attr_set_2[epi] = true;
       }
       CUtensorMap tmBh, tmB2h2;
-      rc = omni_make_tmap_2d_bf16(&tmBh, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, 128, BK, 1);
-      if (rc) return rc;
+      if (!ext_only) {
+        rc = omni_make_tmap_2d_bf16(&tmBh, a->B, (uint64_t)a->b_rows, (uint64_t)a->K, (uint64_t)a->ldb, 128, BK, 1);
+        if (rc) return rc;
+      }
       if (a->ext_table) {
         rc = omni_make_tmap_2d_bf16(&tmB2h2, a->B2, (uint64_t)a->b2_rows, (uint64_t)a->b2_cols, (uint64_t)a->ldb2, 128,
                                     BK, 1);
@@ -1066,10 +1077,11 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
       } else {
         tmB2h2 = tmBh;
       }
+      if (ext_only) tmBh = tmB2h2;
       const int pairs = ((p.m_tiles + 1) / 2) * ceil_div(a->N, 256);
       int clusters = sms / 2;
       if (pairs < clusters) clusters = pairs;
-      const int m_fast2 = (((p.m_tiles + 1) / 2) < ceil_div(a->N, 256) && a_bytes <= (40ll << 20)) ? 1 : 0;
+      const int m_fast2 = (!ext_only && ((p.m_tiles + 1) / 2) < ceil_div(a->N, 256) && a_bytes <= (40ll << 20)) ? 1 : 0;
       k2<<<2 * clusters, GEMM2_THREADS, S2::TOTAL, stream>>>(tmA, tmBh, tmA2, tmB2h2, p, m_fast2);
       OMNI_LAUNCH_CHECK();
       return OMNI_OK;
@@ -1123,8 +1135,8 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
 extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
   using namespace omni;
   OMNI_CHECK_ARG(a != nullptr);
-  OMNI_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0);
-  OMNI_CHECK_ARG(a->A && a->B && a->out);
+  OMNI_CHECK_ARG(a->M > 0 && a->N > 0 && (a->K > 0 || (a->K == 0 && a->ext_table)));
+  OMNI_CHECK_ARG((a->K == 0 || (a->A && a->B)) && a->out);
   OMNI_CHECK_ARG((a->lda % 8) == 0 && (a->ldb % 8) == 0);
   OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
   OMNI_CHECK_ARG(a->ldo >= a->N);
@@ -1142,7 +1154,7 @@ extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
       return OMNI_ERR_UNSUPPORTED;
   }
   if (a->act == OMNI_ACT_PRELU_RING) {
-    OMNI_CHECK_ARG(a->slope && a->bias && a->ring_h > 0 && a->ring_w > 0 && a->ring_group > 0 && a->ring_c > 0);
+    OMNI_CHECK_ARG(a->slope && a->bias && a->ring_h >= 0 && a->ring_w >= 0 && a->ring_group > 0 && a->ring_c > 0);
     OMNI_CHECK_ARG((a->ring_c % 64) == 0 && a->ring_group * a->ring_c == a->N);
     OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->slope) & 15) == 0 &&
                    (!a->res_bias || (reinterpret_cast<uintptr_t>(a->res_bias) & 15) == 0));

@@ -130,6 +130,27 @@ avgpool_ring_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, i
   }
 }
 
+// mean over the P pixels of plain channels-last frames [N, P_alloc, C] (ops.FrameRows): same arithmetic as above
+__global__ void __launch_bounds__(RT_THREADS)
+avgpool_frames_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int P, int P_alloc, int C8, long long total8) {
+  const float inv = 1.0f / static_cast<float>(P);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    const long long n = idx / C8;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < P; ++q) {
+      float f[8];
+      rt_unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(x) + (n * P_alloc + q) * C8 + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] *= inv;
+    reinterpret_cast<uint4*>(out)[idx] = rt_pack8(a);
+  }
+}
+
 static int rt_grid(long long total) {
   long long blocks = ceil_div_ll(total, RT_THREADS);
   if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
@@ -171,6 +192,17 @@ extern "C" int omni_avgpool_ring(const void* x, void* out, int64_t N, int32_t H,
   if (N == 0) return OMNI_OK;
   const long long total8 = N * (C / 8);
   avgpool_ring_kernel<<<rt_grid(total8), RT_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, H, W, C / 8, total8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_avgpool_frames(const void* x, void* out, int64_t N, int32_t P, int32_t P_alloc, int32_t C, void* stream) {
+  using namespace omni;
+  OMNI_CHECK_ARG(x && out && N >= 0 && P > 0 && P_alloc >= P && C > 0 && (C % 8) == 0);
+  if (N == 0) return OMNI_OK;
+  const long long total8 = N * (C / 8);
+  avgpool_frames_kernel<<<rt_grid(total8), RT_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, P, P_alloc, C / 8,
+                                                                                total8);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }

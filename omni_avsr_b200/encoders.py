@@ -310,7 +310,36 @@ class _ResEncoder(nn.Module):
         b = (bn.bias.float() - bn.running_mean.float() * scale).to(torch.bfloat16)
         return w, b
 
+    def _frames_ok(self, li):
+        """Layer li (and every later one) can run as table-driven frame-row GEMMs: 64-multiple input channels, output channels
+        that tile the 256-wide CTA-pair N."""
+        if li < 2:
+            return False
+        ok = lambda c: c % 64 == 0 and ((c < 256 and 256 % c == 0) or c % 256 == 0)
+        widths = [getattr(self.trunk, f"layer{i}")[0].conv1.out_channels for i in range(1, 5)]
+        return all(ok(widths[i - 1]) for i in range(li, 5)) and widths[li - 2] % 64 == 0 and widths[li - 1] >= 128
+
+    def _frames_block(self, key, y, ent, blk):
+        """One BasicBlock on the table-driven path (resnet.py:35-74); y: RingFrames (first block after the ring layers) or
+        FrameRows."""
+        _, w1, b1, s1, w2, b2, ds = ent
+        ring = isinstance(y, ops.RingFrames)
+        ck = (key, y.H, y.W, ring)
+        specs = self._frame_specs.get(ck)
+        if specs is None:
+            c1 = ops.ConvFramesSpec(w1, y.H, y.W, s1, ring)
+            c2 = ops.ConvFramesSpec(w2, c1.Hout, c1.Wout, 1, False)
+            cd = None if ds is None else ops.ConvFramesSpec(ds[0], y.H, y.W, s1, ring)
+            specs = self._frame_specs[ck] = (c1, c2, cd)
+        c1, c2, cd = specs
+        o = ops.conv_frames(y, c1, prelu=dict(slope=blk.relu1.weight.data, bias=b1))
+        if cd is None:
+            return ops.conv_frames(o, c2, prelu=dict(slope=blk.relu2.weight.data, bias=b2, residual=y))
+        res = ops.conv_frames(y, cd)
+        return ops.conv_frames(o, c2, prelu=dict(slope=blk.relu2.weight.data, bias=b2, residual=res, res_bias=ds[1]))
+
     def _prepare(self):
+        self._frame_specs = {}
         conv3, bn3 = self.frontend3D[0], self.frontend3D[1]
         w3, b3 = self._fold(conv3.weight, bn3)                         # [C, 1, 5, 7, 7]
         C = w3.shape[0]
@@ -328,6 +357,12 @@ class _ResEncoder(nn.Module):
                 # filter matrices of the overlapping-row GEMM: g output pixels per GEMM row so that every layer presents a
                 # 256-wide N to the CTA-pair kernel (64 channels: g = 4, 128: g = 2); the stride-2 convolutions read gathered
                 # tap-major rows
+                if self._frames_ok(li):
+                    # layers 2-4 (11x11, 6x6, 3x3 grids): table-driven convolutions whose GEMM rows are whole frames
+                    # (ops.conv_frames): no ring, no gather buffers, no flops on the zero padding.  Specs are built per
+                    # input geometry at the first forward.
+                    f[(li, bi)] = ("frames", w1, b1, blk.conv1.stride[0], w2, b2, None if ds is None else (wd, bd))
+                    continue
                 tap = lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
                 grp = lambda w: max(1, min(4, 256 // w.shape[0])) if (w.shape[1] * 3) % 64 == 0 else 1
                 s1 = blk.conv1.stride[0]
@@ -356,6 +391,9 @@ class _ResEncoder(nn.Module):
         y = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data, ring_out=self._ring0[1])
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
+                if f[(li, bi)][0] == "frames":
+                    y = self._frames_block((li, bi), y, f[(li, bi)], blk)
+                    continue
                 w1, b1, s1, w2, b2, ds, g1, g2 = f[(li, bi)]
                 # the folded-BatchNorm shifts ride in the PReLU kernel (a conv bias would cost one more elementwise pass)
                 # (... or in the epilogue of the convolution GEMM itself: bias, residual add, PReLU and ring re-zeroing)
@@ -370,7 +408,7 @@ class _ResEncoder(nn.Module):
                     res = ops.conv_s2_ring(y, ds[0], 1)
                     y = ops.conv3x3s1_ring(o, w2, g2, prelu=dict(slope=blk.relu2.weight.data, bias=b2, residual=res,
                                                                   res_bias=ds[1]))
-        return ops.avgpool_ring(y)
+        return ops.avgpool_frames(y) if isinstance(y, ops.FrameRows) else ops.avgpool_ring(y)
 
 
 class _VideoFeatureExtractor(nn.Module):

@@ -871,6 +871,126 @@ def prelu_res_ring_(x: RingFrames, slope, residual: Optional[RingFrames] = None,
     return x
 
 
+class FrameRows:
+    """N plain channels-last frames [H, W, C] WITHOUT a ring, one frame per GEMM row: buf [N, PA * C] with PA >= H W pixel
+    slots (the slots past H W pad the last N tile of the convolution that wrote them and are never read)."""
+
+    def __init__(self, N, H, W, C, PA, device):
+        self.N, self.H, self.W, self.C, self.PA = int(N), int(H), int(W), int(C), int(PA)
+        self.buf = torch.empty((self.N, self.PA * self.C), device=device, dtype=torch.bfloat16)
+
+    _pool = {}
+
+    @classmethod
+    def get(cls, N, H, W, C, PA, device):
+        """Same small ring of persistent buffers per geometry as RingFrames.get (frozen, no-grad trunk only)."""
+        key = (int(N), int(H), int(W), int(C), int(PA), str(device))
+        ent = cls._pool.get(key)
+        if ent is None:
+            if len(cls._pool) > 64:
+                cls._pool.clear()
+            ent = cls._pool[key] = [[cls(N, H, W, C, PA, device) for _ in range(6)], 0]
+        ent[1] = (ent[1] + 1) % 6
+        return ent[0][ent[1]]
+
+
+class ConvFramesSpec:
+    """Filter-pattern matrix + K-extension table of one table-driven convolution (conv_frames)."""
+
+    def __init__(self, w: torch.Tensor, Hin: int, Win: int, stride: int, in_ring: bool):
+        Co, Ci, k, k2 = w.shape
+        if k != k2 or k not in (1, 3) or Ci % 64 or not ((Co < 256 and 256 % Co == 0 and Co % 64 == 0) or Co % 256 == 0):
+            raise ValueError("conv_frames: 1x1 / 3x3 filters, C_in % 64 == 0, C_out in {64, 128} or a multiple of 256")
+        pad = 1 if k == 3 else 0
+        self.Hout, self.Wout = (Hin + 2 * pad - k) // stride + 1, (Win + 2 * pad - k) // stride + 1
+        self.Hin, self.Win, self.Ci, self.Co, self.in_ring = Hin, Win, Ci, Co, bool(in_ring)
+        g = self.g = max(1, 256 // Co)                       # output pixels per 256-wide N tile
+        cob = max(1, Co // 256)                              # N tiles per output pixel
+        P = self.Hout * self.Wout
+        n_groups = (P + g - 1) // g
+        self.PA = n_groups * g
+        self.N = self.PA * Co
+        wp = Win + 2 if in_ring else Win
+        self.in_cols = ((Hin + 2) * (Win + 2) if in_ring else None)          # pixel slots of a ring-padded input frame
+        patterns, tiles = {}, []
+        for t in range(n_groups):
+            contrib = {}
+            for sl in range(g):
+                pix = t * g + sl
+                if pix >= P:
+                    continue
+                oy, ox = divmod(pix, self.Wout)
+                for ky in range(k):
+                    for kx in range(k):
+                        iy, ix = oy * stride + ky - pad, ox * stride + kx - pad
+                        if 0 <= iy < Hin and 0 <= ix < Win:      # taps on the zero padding are simply absent
+                            pin = (iy + 1) * wp + ix + 1 if in_ring else iy * Win + ix
+                            contrib.setdefault(pin, [-1] * g)[sl] = ky * k + kx
+            tiles.append([(pin, patterns.setdefault(tuple(contrib[pin]), len(patterns))) for pin in sorted(contrib)])
+        kb = Ci // 64
+        self.n_ext = max(len(e) for e in tiles) * kb
+        tab = torch.zeros((1, n_groups * cob, self.n_ext, 4), dtype=torch.int32)
+        tab[..., 1] = -1
+        for t, ents in enumerate(tiles):
+            for cb in range(cob):
+                row = [(pin * Ci + 64 * b, cb * 256, pid * Ci + 64 * b, 0) for pin, pid in ents for b in range(kb)]
+                tab[0, t * cob + cb, : len(row)] = torch.tensor(row, dtype=torch.int32)
+        b2 = torch.zeros((g * Co, len(patterns) * Ci), device=w.device, dtype=torch.bfloat16)
+        for pat, pid in patterns.items():
+            for sl, tap in enumerate(pat):
+                if tap >= 0:
+                    b2[sl * Co: (sl + 1) * Co, pid * Ci: (pid + 1) * Ci] = w[:, :, tap // k, tap % k]
+        self.b2 = b2.contiguous()
+        self.table = tab.contiguous().to(w.device)
+        self.macs_per_frame = sum(len(e) for e in tiles) * cob * 256 * Ci    # executed (zero pattern blocks included)
+
+
+def conv_frames(x, spec: ConvFramesSpec, prelu: Optional[dict] = None) -> FrameRows:
+    """Convolution of the small late-stage grids as ONE tcgen05 GEMM launch whose rows are whole frames: the reduction of an
+    N tile (the channels of one output pixel, or of 256 / C_out consecutive ones) is the K-extension list of that tile, one
+    64-channel block per contributing input pixel.  No ring, no im2col / gather buffer, no flops on the zero padding.
+    x: RingFrames (spec.in_ring) or FrameRows.  prelu as in conv3x3s1_ring (residual: FrameRows of the output geometry)."""
+    if isinstance(x, RingFrames):
+        if not spec.in_ring or (x.H, x.W, x.C) != (spec.Hin, spec.Win, spec.Ci):
+            raise ValueError("conv_frames: input geometry does not match the spec")
+        a2 = x.rows.view(x.N, x.P * x.C)
+    else:
+        if spec.in_ring or (x.H, x.W, x.C) != (spec.Hin, spec.Win, spec.Ci):
+            raise ValueError("conv_frames: input geometry does not match the spec")
+        a2 = x.buf
+    out = FrameRows.get(x.N, spec.Hout, spec.Wout, spec.Co, spec.PA, a2.device)
+    g = GemmArgs()
+    g.out, g.ldo = out.buf.data_ptr(), out.buf.stride(0)
+    g.M, g.N, g.K = x.N, spec.N, 0
+    g.A2, g.B2, g.ext_table = a2.data_ptr(), spec.b2.data_ptr(), spec.table.data_ptr()
+    g.lda2, g.ldb2 = a2.stride(0), spec.b2.stride(0)
+    g.a2_cols, g.b2_rows, g.b2_cols = a2.shape[1], spec.b2.shape[0], spec.b2.shape[1]
+    g.n_ext = spec.n_ext
+    g.block_n, g.pair_aligned, g.alpha = 256, 1, 1.0
+    g.act = ACT[None]
+    if prelu is not None:
+        res = prelu.get("residual")
+        require_cuda(prelu["slope"], prelu["bias"], prelu.get("res_bias"))
+        if res is not None:
+            if (res.N, res.PA, res.C) != (out.N, out.PA, out.C):
+                raise ValueError("conv_frames: residual geometry mismatch")
+            g.residual, g.ldr = res.buf.data_ptr(), res.buf.stride(0)
+        g.act = ACT["prelu_ring"]
+        g.bias, g.slope, g.res_bias = prelu["bias"].data_ptr(), prelu["slope"].data_ptr(), ptr(prelu.get("res_bias"))
+        g.ring_h, g.ring_w, g.ring_group, g.ring_c = 0, 0, spec.PA, spec.Co
+    check(lib.omni_gemm_bf16(C.byref(g), stream_ptr()), "omni_gemm_bf16 (conv_frames)")
+    _count()
+    return out
+
+
+def avgpool_frames(x: FrameRows) -> torch.Tensor:
+    out = torch.empty((x.N, x.C), device=x.buf.device, dtype=torch.bfloat16)
+    check(lib.omni_avgpool_frames(x.buf.data_ptr(), out.data_ptr(), x.N, x.H * x.W, x.PA, x.C, stream_ptr()),
+          "omni_avgpool_frames")
+    _count()
+    return out
+
+
 def avgpool_ring(x: RingFrames) -> torch.Tensor:
     out = torch.empty((x.N, x.C), device=x.buf.device, dtype=torch.bfloat16)
     check(lib.omni_avgpool_ring(x.rows.data_ptr(), out.data_ptr(), x.N, x.H, x.W, x.C, stream_ptr()), "omni_avgpool_ring")

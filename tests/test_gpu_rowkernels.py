@@ -377,3 +377,53 @@ def test_stride2_convs_prelu_ring_and_avgpool(N, H, W, Ci, Co):
     assert got.shape == want.shape
     assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
     assert (pooled.float() - want.mean(dim=(2, 3))).abs().max().item() <= 2e-2 * want.mean(dim=(2, 3)).abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Table-driven convolutions of the late trunk stages (ops.conv_frames: GEMM row = one frame, K-extension list per output pixel)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,H,W,Ci,Co", [(300, 22, 22, 64, 128), (260, 11, 11, 128, 256), (700, 6, 6, 256, 512), (40, 11, 11, 128, 256),
+                                         (130, 7, 5, 64, 128)])
+def test_conv_frames_basic_blocks_and_avgpool(N, H, W, Ci, Co):
+    """Two BasicBlocks (resnet.py:35-74) on the table-driven path: [3x3 stride-2 conv + PReLU, 1x1 stride-2 downsample, 3x3
+    conv + residual + PReLU] reading ring-padded frames, then [3x3, 3x3 + identity residual] on plain frame rows, then the
+    average pool -- vs the same ops in fp32 torch with the product's bf16 rounding points."""
+    from omni_avsr_b200 import ops
+    F = torch.nn.functional
+    g = torch.Generator(device="cuda").manual_seed(H * 31 + Ci)
+    x = torch.randn(N, Ci, H, W, device="cuda", generator=g).bfloat16()
+    mk = lambda co, ci, k: (torch.randn(co, ci, k, k, device="cuda", generator=g) / (k * ci ** 0.5)).bfloat16()
+    w1, w2, wd, w3, w4 = mk(Co, Ci, 3), mk(Co, Co, 3), mk(Co, Ci, 1), mk(Co, Co, 3), mk(Co, Co, 3)
+    b1, b2, bd, b3, b4 = [(torch.randn(Co, device="cuda", generator=g) * 0.1).bfloat16() for _ in range(5)]
+    s1, s2, s3, s4 = [(torch.rand(Co, device="cuda", generator=g) * 0.5).bfloat16() for _ in range(4)]
+    y = _ring_from_nchw(x)
+    c1 = ops.ConvFramesSpec(w1, H, W, 2, True)
+    cd = ops.ConvFramesSpec(wd, H, W, 2, True)
+    c2 = ops.ConvFramesSpec(w2, c1.Hout, c1.Wout, 1, False)
+    c3 = ops.ConvFramesSpec(w3, c1.Hout, c1.Wout, 1, False)
+    c4 = ops.ConvFramesSpec(w4, c1.Hout, c1.Wout, 1, False)
+    launches = ops.LAUNCHES
+    o = ops.conv_frames(y, c1, prelu=dict(slope=s1, bias=b1))
+    res = ops.conv_frames(y, cd)
+    blk1 = ops.conv_frames(o, c2, prelu=dict(slope=s2, bias=b2, residual=res, res_bias=bd))
+    o = ops.conv_frames(blk1, c3, prelu=dict(slope=s3, bias=b3))
+    blk2 = ops.conv_frames(o, c4, prelu=dict(slope=s4, bias=b4, residual=blk1))
+    pooled = ops.avgpool_frames(blk2)
+    assert ops.LAUNCHES - launches == 6                      # one launch per convolution + the pool
+
+    rb = lambda t: t.bfloat16().float()
+    bias = lambda b: b.float().view(1, -1, 1, 1)
+    xf = x.float()
+    t = F.prelu(rb(rb(F.conv2d(xf, w1.float(), stride=2, padding=1)) + bias(b1)), s1.float())
+    r = rb(rb(F.conv2d(xf, wd.float(), stride=2)) + bias(bd))
+    t = rb(rb(F.conv2d(rb(t), w2.float(), padding=1)) + bias(b2))
+    want1 = rb(F.prelu(rb(t + r), s2.float()))
+    t = rb(F.prelu(rb(rb(F.conv2d(want1, w3.float(), padding=1)) + bias(b3)), s3.float()))
+    t = rb(rb(F.conv2d(t, w4.float(), padding=1)) + bias(b4))
+    want2 = F.prelu(rb(t + want1), s4.float())
+
+    def nchw(fr):
+        return fr.buf.view(fr.N, fr.PA, fr.C)[:, : fr.H * fr.W].reshape(fr.N, fr.H, fr.W, fr.C).permute(0, 3, 1, 2).float()
+    assert (nchw(blk1) - want1).abs().max().item() <= 2e-2 * want1.abs().max().item()
+    assert (nchw(blk2) - want2).abs().max().item() <= 3e-2 * want2.abs().max().item()
+    assert (pooled.float() - want2.mean(dim=(2, 3))).abs().max().item() <= 3e-2 * want2.mean(dim=(2, 3)).abs().max().item()
