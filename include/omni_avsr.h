@@ -242,8 +242,11 @@ int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* out, int64_
 
 /* Flash-attention backward (tcgen05) of the same segment: dqkv [M, dqkv_ld] bf16 receives dQ | dK | dV in the column
  * layout of qkv (the segment's rows only; GQA group sums included).  out / lse are the forward results, dout the
- * gradient of out [M, dout_ld]; delta is caller-owned scratch, fp32 [n_heads, M].  Replaces what autograd derives for
+ * gradient of out [M, dout_ld]; delta is caller-owned scratch of omni_attention_bwd_scratch_floats(B, S, n_heads) fp32
+ * values, 16-byte aligned (the pre-pass writes per 64-query step the rows' lse * log2(e) and rowsum(dO o O) there, in
+ * 512-byte blocks the dK/dV kernel fetches with one bulk copy per step).  Replaces what autograd derives for
  * the SDPA calls listed above (Llama_LoRA.py:300, Qwen_LoRA.py:606, multihead_attention.py:619-654). */
+int64_t omni_attention_bwd_scratch_floats(int32_t B, int32_t S, int32_t n_heads);
 int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const void* out, int64_t out_ld, const void* dout,
                        int64_t dout_ld, const float* lse, float* delta, void* dqkv, int64_t dqkv_ld, int32_t row0,
                        int32_t B, int32_t S, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t causal,

@@ -325,7 +325,7 @@ struct BwdKVSmem {
   static constexpr int OFF_K = 0, OFF_V = TILE, OFF_QDO = 2 * TILE;     // 2 stages of (Q | dO)
   static constexpr int OFF_P = OFF_QDO + 4 * STEP;         // P^T [128 x 64] bf16
   static constexpr int OFF_DS = OFF_P + 16384;             // dS^T [128 x 64] bf16
-  static constexpr int OFF_STAT = OFF_DS + 16384;          // [2 buffers][lse2 | delta][64] fp32
+  static constexpr int OFF_STAT = OFF_DS + 16384;          // [2 stages][lse2 | delta][64] fp32 (bulk copy per step)
   static constexpr int BAR_OFFSET = OFF_STAT + 2 * 2 * AB_STEP * 4;
   static constexpr int ALIGN_SLACK = HD == 64 ? 768 : 1024;
   static constexpr int TOTAL = BAR_OFFSET + 128 + ALIGN_SLACK;
@@ -409,12 +409,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         const int st = it & 1;
         uint8_t* qd = smem + SM::OFF_QDO + st * 2 * SM::STEP;
         mbar_wait(q_empty + st, ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(q_full + st, 2 * SM::STEP);
+        mbar_expect_tx(q_full + st, 2 * SM::STEP + 512);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           tma_load_2d(&tm64, q_full + st, qd + b * 8192, head * HD + b * 64, clip_row0 + q0);
           tma_load_2d(&tmdo64, q_full + st, qd + SM::STEP + b * 8192, head * HD + b * 64, clip_row0 + q0);
         }
+        // the step's 64 (lse2, delta) pairs ride on the same barrier
+        bulk_load_1d(smem + SM::OFF_STAT + st * 512,
+                     p.stats + ((static_cast<long long>(head) * p.B + clip) * p.n_qs + (i0 + it % per_head)) * 128, 512,
+                     q_full + st);
       }
     }
   } else if (warp == 1) {
@@ -478,35 +482,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
     const float sc = p.scale_log2;
     uint8_t* sP = smem + SM::OFF_P;
     uint8_t* sDS = smem + SM::OFF_DS;
-    float* stat = reinterpret_cast<float*>(smem + SM::OFF_STAT);
-    // per-query statistics of a step: threads 0..63 fetch them one step ahead (the global-load latency hides under
-    // the previous step's arithmetic) and publish them through a double-buffered shared-memory row
-    // (head, step) of an iteration advance as counters: no integer division in the loop
-    auto fetch_stat = [&](int it, int head, int step, float& l2, float& dl) {
-      const int q0 = (i0 + step) * AB_STEP;
-      const bool ok = half == 0 && r < AB_STEP && it < n_it && q0 + r < p.S;
-      const long long idx = static_cast<long long>(head) * p.M + clip_row0 + q0 + r;
-      l2 = ok ? p.lse[idx] * 1.4426950408889634f : 0.f;
-      dl = ok ? p.delta[idx] : 0.f;
-    };
-    float nl2, ndl;
-    int cur_step = 0, nxt_head = kvh * G, nxt_step = 0;
-    fetch_stat(0, nxt_head, nxt_step, nl2, ndl);
+    const float* stat = reinterpret_cast<const float*>(smem + SM::OFF_STAT);
+    int step = 0;                                // 64-query step inside the current head (no integer division in the loop)
     for (int it = 0; it < n_it; ++it) {
       const uint32_t ph = it & 1;
-      cur_step = nxt_step;
-      const int q0 = (i0 + cur_step) * AB_STEP;
-      if (++nxt_step == per_head) { nxt_step = 0; ++nxt_head; }
-      float* st = stat + (it & 1) * 2 * AB_STEP;
-      if (half == 0 && r < AB_STEP) {
-        st[r] = nl2;
-        st[AB_STEP + r] = ndl;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      fetch_stat(it + 1, nxt_head, nxt_step, nl2, ndl);
+      const int q0 = (i0 + step) * AB_STEP;
+      if (++step == per_head) step = 0;
+      const float* st = stat + (it & 1) * 128;
+      mbar_wait(q_full + (it & 1), (it >> 1) & 1);         // the step's statistics block landed (TMA bulk copy)
       mbar_wait(s_full, ph);
       tc_fence_after();
-      const bool full = (qlo <= q0) && (q0 + AB_STEP - 1 < p.S);
+      // every query of the step sees this key (queries past S carry lse2 = +inf: P = 0 without a test)
+      const bool full = qlo <= q0;
       {
         const int c = half;
         uint32_t s[32], d[32], wp[16], wd[16];
@@ -516,26 +503,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sd_read);     // the next step's score MMAs may overwrite S^T / dP^T
+        if (!full) {       // diagonal step (or a key past S): masked scores become -inf once, the pass below is branch-free
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (q0 + c * 32 + i < qlo) s[i] = 0xff800000u;
+        }
         const float4* L4 = reinterpret_cast<const float4*>(st + c * 32);
         const float4* D4 = reinterpret_cast<const float4*>(st + AB_STEP + c * 32);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 l = L4[i4], dd = D4[i4];
-          const float ls[4] = {l.x, l.y, l.z, l.w}, ds[4] = {dd.x, dd.y, dd.z, dd.w};
-          float pv[4], gv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = i4 * 4 + e;
-            const int qc = q0 + c * 32 + i;
-            const bool ok = full || (qc >= qlo && qc < p.S);
-            const float pe = ok ? ex2_approx(fmaf(__uint_as_float(s[i]), sc, -ls[e])) : 0.f;
-            pv[e] = pe;
-            gv[e] = ok ? pe * (__uint_as_float(d[i]) - ds[e]) : 0.f;
-          }
-          wp[i4 * 2] = f2_to_bf2(pv[0], pv[1]);
-          wp[i4 * 2 + 1] = f2_to_bf2(pv[2], pv[3]);
-          wd[i4 * 2] = f2_to_bf2(gv[0], gv[1]);
-          wd[i4 * 2 + 1] = f2_to_bf2(gv[2], gv[3]);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4]), sc, -l.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4 + 1]), sc, -l.y));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4 + 2]), sc, -l.z));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4 + 3]), sc, -l.w));
+          wp[i4 * 2] = f2_to_bf2(p0, p1);
+          wp[i4 * 2 + 1] = f2_to_bf2(p2, p3);
+          wd[i4 * 2] = f2_to_bf2(p0 * (__uint_as_float(d[i4 * 4]) - dd.x), p1 * (__uint_as_float(d[i4 * 4 + 1]) - dd.y));
+          wd[i4 * 2 + 1] = f2_to_bf2(p2 * (__uint_as_float(d[i4 * 4 + 2]) - dd.z), p3 * (__uint_as_float(d[i4 * 4 + 3]) - dd.w));
         }
         if (it > 0) mbar_wait(pds_free, (it - 1) & 1);   // the previous step's dV / dK MMAs are done with the tiles
         store_operand_chunk(sP, r, c, wp);
@@ -603,6 +588,11 @@ static int launch_attn_bwd(const CUtensorMap& tm, const CUtensorMap& tm64, const
 
 }  // namespace omni
 
+extern "C" int64_t omni_attention_bwd_scratch_floats(int32_t B, int32_t S, int32_t n_heads) {
+  if (B <= 0 || S <= 0 || n_heads <= 0) return 0;
+  return static_cast<int64_t>(n_heads) * B * ((S + omni::AB_STEP - 1) / omni::AB_STEP) * 2 * omni::AB_STEP;
+}
+
 extern "C" int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const void* out, int64_t out_ld,
                                   const void* dout, int64_t dout_ld, const float* lse, float* delta, void* dqkv,
                                   int64_t dqkv_ld, int32_t row0, int32_t B, int32_t S, int32_t n_heads,
@@ -625,17 +615,19 @@ extern "C" int omni_attention_bwd(const void* qkv, int64_t M, int64_t ld, const 
   if (rc) return rc;
   rc = omni_make_tmap_2d_bf16(&tmdo64, dout, (uint64_t)M, (uint64_t)n_heads * head_dim, (uint64_t)dout_ld, AB_STEP, 64, 1);
   if (rc) return rc;
-  const int rows = B * S;
-  attn_delta_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(dout), dout_ld,
-                                                       reinterpret_cast<const bf16*>(out), out_ld, delta, M, row0, rows,
-                                                       n_heads, head_dim);
+  const int n_qs = ceil_div(S, AB_STEP);
+  const long long rows = static_cast<long long>(B) * n_qs * AB_STEP;
+  OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(delta) & 15) == 0 && rows / 8 < 0x7fffffffLL);
+  attn_delta_kernel<<<static_cast<unsigned>(ceil_div_ll(rows, 8)), 256, 0, st>>>(
+      reinterpret_cast<const bf16*>(dout), dout_ld, reinterpret_cast<const bf16*>(out), out_ld, lse, delta, M, row0, B, S,
+      n_qs, n_heads, head_dim);
   OMNI_LAUNCH_CHECK();
   AttnBwdParams p;
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
   p.dqkv_ld = dqkv_ld;
-  p.lse = lse;
-  p.delta = delta;
+  p.stats = delta;
   p.M = M;
+  p.B = B; p.n_qs = n_qs;
   p.row0 = row0; p.S = S; p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.causal = causal ? 1 : 0;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;

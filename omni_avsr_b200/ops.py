@@ -1029,7 +1029,9 @@ def attention_bwd(qkv, out, dout, lse, dqkv, segments, n_heads: int, n_kv_heads:
         raise ValueError("attention_bwd: lse must be contiguous fp32 [n_heads, M]")
     if scale is None:
         scale = head_dim ** -0.5
-    delta = torch.empty_like(lse)
+    # scratch of the statistics pre-pass: per segment [n_heads][B][ceil(S / 64)][2][64] fp32
+    need = max(int(lib.omni_attention_bwd_scratch_floats(B, S, n_heads)) for (_, B, S, _) in segments)
+    delta = torch.empty(need, device=lse.device, dtype=torch.float32)
     for (_, B, S, row0) in segments:
         check(lib.omni_attention_bwd(qkv.data_ptr(), qkv.shape[0], qkv.stride(0), out.data_ptr(), out.stride(0),
                                      dout.data_ptr(), dout.stride(0), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(),
