@@ -15,9 +15,12 @@ Eval-mode semantics (dropout / layerdrop off, BatchNorm running statistics) -- t
 parity runs use (SURVEY §7 "hard parts").
 
 Parity status: pinned against transformers (log-mel, Whisper encoder), the reference's own resnet.py (imported by
-path) and the reference's own fairseq MultiheadAttention.forward_lora (executed from /root/reference by
-tests/golden/make_reference_golden.py, checked in tests/test_reference_golden.py).  The fairseq TransformerEncoder
-wrapper (wav2vec2.py) cannot be imported here (omegaconf / hydra absent): restated from the cited lines, unpinned.
+path), the reference's own fairseq MultiheadAttention.forward_lora (tests/golden/make_reference_golden.py ->
+tests/test_reference_golden.py) and -- end to end -- the reference's own AVHubertModel.extract_finetune: hubert.py,
+wav2vec2.py (TransformerEncoder + TransformerSentenceEncoderLayer with apply_lora), resnet.py and multihead_attention.py
+are loaded by path from /root/reference and executed by tests/golden/make_avhubert_golden.py (only fairseq's registry /
+dataclass / task machinery is stubbed); tests/test_avhubert_golden.py checks AVHubertVideo below against that run
+(identical key layout, outputs equal to 1e-5) and the CUDA path against it within bf16 tolerance.
 """
 from __future__ import annotations
 
