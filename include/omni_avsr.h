@@ -42,6 +42,15 @@ extern "C" {
  * bf16(residual + res_bias[ch]));  f = PReLU(f, slope[ch]);  pixels on the one-pixel ring of their [ring_h + 2, ring_w + 2]
  * frame are stored as 0.  bias / slope / res_bias are [ring_c].  CTA-pair kernel only; OMNI_ERR_UNSUPPORTED otherwise. */
 #define OMNI_ACT_PRELU_RING 5
+/* Fused backward epilogues of the dgrad GEMMs that produce d(activation) (CTA-pair kernel only; OMNI_ERR_UNSUPPORTED
+ * otherwise; `residual` is NOT added, it carries the tensor saved by the forward):
+ *   OMNI_ACT_SWIGLU_BWD64: A = dY, B = W_down^T [I, H] -> d(act) [M, I = N] never reaches memory; residual = gate|up [M, 2I]
+ *     in the 64-column interleave of OMNI_ACT_SWIGLU64, out = d(gate|up) [M, 2I] (same layout, ldo >= 2N):
+ *     the arithmetic of omni_swiglu_bwd_blocked on the bf16-rounded d(act)  (LlamaMLP backward, Llama_LoRA.py MLP).
+ *   OMNI_ACT_GELU_BWD: residual = pre-activation [M, N], out = d(pre) = bf16(d(act)) * gelu'(pre)  (omni_gelu_bwd; the
+ *     AV-HuBERT fc2 -> fc1 backward under LoRA fine-tuning, wav2vec2.py:1003-1006). */
+#define OMNI_ACT_SWIGLU_BWD64 6
+#define OMNI_ACT_GELU_BWD 7
 
 #define OMNI_COMPRESS_AVG 0   /* nn.AvgPool1d(r)  : modeling_OmniAVSR.py:544-546 (audio), :469-471 (video) */
 #define OMNI_COMPRESS_STACK 1 /* frame stacking   : modeling_OmniAVSR.py:562-568 (audio), :487-493 (video) */

@@ -709,6 +709,11 @@ class LlamaMLP(nn.Module):
     def forward(self, h, residual):
         wt_gu, wt_d = self.transposed()
         I = self.gate_up_weight.shape[0] // 2
+        if h.requires_grad and I % 256 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I) \
+                and ag.pair_kernel_shape(h.shape[0], I):
+            # SwiGLU in the gate_up GEMM's epilogue, its backward in the epilogue of down_proj's dgrad GEMM
+            w_il, wt_il = self.interleaved()
+            return ag.MlpSwigluFn.apply(h, w_il, wt_il, self.down_proj.weight.data, wt_d, residual)
         if h.requires_grad and I % 64 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I):
             w_il, wt_il = self.interleaved()
             act = ag.GateUpSwigluFn.apply(h, w_il, wt_il)          # SwiGLU in the gate_up GEMM's epilogue

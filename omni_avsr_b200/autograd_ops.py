@@ -236,6 +236,57 @@ class GateUpSwigluFn(torch.autograd.Function):
         return ops.gemm(dgu, ctx.WT, block_n=256), None, None
 
 
+class MlpSwigluFn(torch.autograd.Function):
+    """y = residual + (silu(x Wg^T) * (x Wu^T)) W_down^T with FROZEN weights (LlamaMLP + the decoder layer's residual add,
+    Llama_LoRA.py decoder layer): forward = gate_up GEMM with the SwiGLU epilogue, down GEMM with the residual epilogue;
+    backward = TWO launches: the dgrad GEMM of down_proj with the SwiGLU-backward epilogue (d(act) never reaches memory, the
+    saved gate|up tile is read by the epilogue) and the dgrad GEMM of gate_up."""
+
+    @staticmethod
+    def forward(ctx, x, W_il, WT_il, W_down, WT_down, residual):
+        M, N = x.shape[0], W_il.shape[0]
+        gu = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+        act = torch.empty((M, N // 2), device=x.device, dtype=torch.bfloat16)
+        ops.gemm(x, W_il, out=gu, out2=act, act="swiglu64", block_n=256)
+        ctx.save_for_backward(gu)
+        ctx.WT, ctx.WTd, ctx.has_res = WT_il, WT_down, residual is not None
+        return ops.gemm(act, W_down, residual=residual, block_n=256)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (gu,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dgu = torch.empty_like(gu)
+        ops.gemm(dy, ctx.WTd, residual=gu, out=dgu, act="swiglu_bwd64")
+        dx = ops.gemm(dgu, ctx.WT, block_n=256) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, None, (dy if ctx.has_res else None)
+
+
+class FfnGeluFn(torch.autograd.Function):
+    """y = residual + gelu(x W1^T + b1) W2^T + b2 with FROZEN weights while something upstream trains (the AV-HuBERT FFN under
+    LoRA fine-tuning, wav2vec2.py:1001-1006): forward = fc1 GEMM writing pre-activation + activation, fc2 GEMM with the residual
+    epilogue; backward = the dgrad GEMM of fc2 with the GELU-backward epilogue + the dgrad GEMM of fc1."""
+
+    @staticmethod
+    def forward(ctx, x, W1, WT1, b1, W2, WT2, b2, residual):
+        M, N = x.shape[0], W1.shape[0]
+        pre = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+        act = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+        ops.gemm(x, W1, bias=b1, out=pre, out2=act, act="gelu_keep", block_n=256)
+        ctx.save_for_backward(pre)
+        ctx.WT1, ctx.WT2, ctx.has_res = WT1, WT2, residual is not None
+        return ops.gemm(act, W2, bias=b2, residual=residual, block_n=256)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (pre,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dpre = torch.empty_like(pre)
+        ops.gemm(dy, ctx.WT2, residual=pre, out=dpre, act="gelu_bwd")
+        dx = ops.gemm(dpre, ctx.WT1, block_n=256) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, None, None, None, (dy if ctx.has_res else None)
+
+
 def gate_up_swiglu_supported(M: int, N: int) -> bool:
     """Shapes the CTA-pair kernel takes for the fused epilogue (mirrors the dispatch in csrc/gemm_tcgen05.cu)."""
     return pair_kernel_shape(M, N)

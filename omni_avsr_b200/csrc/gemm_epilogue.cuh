@@ -251,6 +251,96 @@ __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* s
 }
 
 
+// 32 rows x 64 bf16 columns already packed (32 words per thread = one row) -> global memory, through the transposition tile
+// the warp's transposition tile (every thread has written its own 128-byte row) -> global memory as full 128-byte rows
+__device__ __forceinline__ void stage_to_global(bf16* out, long long ldo, int M, const uint8_t* stage, int lane, int row0,
+                                                int col0) {
+  const uint8_t* co_ptr = stage + (lane >> 3) * EPI_PITCH + (lane & 7) * 16;
+  __syncwarp();
+  bf16* op = out + static_cast<long long>(row0 + (lane >> 3)) * ldo + col0 + (lane & 7) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    if (row0 + (lane >> 3) + 4 * pass < M)
+      *reinterpret_cast<uint4*>(op + static_cast<long long>(4 * pass) * ldo) =
+          *reinterpret_cast<const uint4*>(co_ptr + 4 * pass * EPI_PITCH);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void store_tile64_packed(bf16* out, long long ldo, int M, uint8_t* stage, const uint32_t (&w)[32],
+                                                    int lane, int row0, int col0) {
+  uint8_t* my_row = stage + lane * EPI_PITCH;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<uint4*>(my_row + 16 * i) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  stage_to_global(out, ldo, M, stage, lane, row0, col0);
+}
+
+// a 32-row x 64-column bf16 block of `src` (row pitch ld) in the coalesced lane layout of ResTile
+__device__ __forceinline__ void tile_prefetch(const bf16* src, long long ld, int M, int row0, int col0, int lane, ResTile& o) {
+  const bf16* rp = src + static_cast<long long>(row0 + (lane >> 3)) * ld + col0 + (lane & 7) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const bool ok = (row0 + (lane >> 3) + 4 * pass) < M;
+    o.r[pass] = ok ? ld_nc_u4(rp + static_cast<long long>(4 * pass) * ld) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// publish a prefetched block and read back this thread's own row (64 bf16 = 32 packed words)
+__device__ __forceinline__ void tile_to_row(uint8_t* stage, int lane, const ResTile& t, uint32_t (&w)[32]) {
+  res_tile_publish(stage, lane, t);
+  const uint8_t* my_row = stage + lane * EPI_PITCH;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 b = *reinterpret_cast<const uint4*>(my_row + 16 * i);
+    w[4 * i] = b.x; w[4 * i + 1] = b.y; w[4 * i + 2] = b.z; w[4 * i + 3] = b.w;
+  }
+  __syncwarp();
+}
+
+// OMNI_ACT_SWIGLU_BWD64, 32 of a block's 64 intermediate channels (h = 0 / 1): r = the accumulator columns (fp32 bits), g / u
+// = the saved gate block of the row (packed bf16; the up block is read from the transposition tile) -> du words 16 h .. 16 h + 15
+// stay in registers, the d(gate) words go straight into the thread's row of the transposition tile.  Same arithmetic as swiglu_bwd_kernel on the GEMM's bf16-rounded
+// output, with the hardware reciprocal for the sigmoid (<= 1 ulp before the bf16 rounding).
+__device__ __forceinline__ void swiglu_bwd_half(const uint32_t (&r)[32], float alpha, const uint32_t (&g)[32], int h,
+                                                uint8_t* my_row, uint32_t (&du)[32]) {
+#pragma unroll
+  for (int i4 = 0; i4 < 4; ++i4) {
+    // the up block of the row sits in the thread's row of the transposition tile; each 16-byte piece is replaced in place
+    // by the d(gate) words of the same channels
+    const uint4 ub = *reinterpret_cast<const uint4*>(my_row + 64 * h + 16 * i4);
+    const uint32_t u[4] = {ub.x, ub.y, ub.z, ub.w};
+    uint32_t dgw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i4 * 4 + e, w = h * 16 + i;
+      const float2 gf = bf2_to_f2(g[w]), uf = bf2_to_f2(u[e]);
+      const float d0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[2 * i]) * alpha));
+      const float d1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[2 * i + 1]) * alpha));
+      const float s0 = __fdividef(1.0f, 1.0f + __expf(-gf.x));
+      const float s1 = __fdividef(1.0f, 1.0f + __expf(-gf.y));
+      du[w] = f2_to_bf2(d0 * (gf.x * s0), d1 * (gf.y * s1));
+      dgw[e] = f2_to_bf2(d0 * uf.x * (s0 * (1.0f + gf.x * (1.0f - s0))), d1 * uf.y * (s1 * (1.0f + gf.y * (1.0f - s1))));
+    }
+    *reinterpret_cast<uint4*>(my_row + 64 * h + 16 * i4) = make_uint4(dgw[0], dgw[1], dgw[2], dgw[3]);
+  }
+}
+
+// OMNI_ACT_GELU_BWD: v = d(act) (one row per thread, 64 columns), x = the saved pre-activation -> dx packed bf16 (same
+// arithmetic as gelu_bwd_kernel on the GEMM's bf16-rounded output)
+__device__ __forceinline__ void gelu_bwd_row64(const float (&v)[64], const uint32_t (&x)[32], uint32_t (&dx)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float2 xf = bf2_to_f2(x[i]);
+    const float d0 = __bfloat162float(__float2bfloat16_rn(v[2 * i]));
+    const float d1 = __bfloat162float(__float2bfloat16_rn(v[2 * i + 1]));
+    const float c0 = 0.5f * (1.0f + erff(xf.x * 0.70710678118654752440f));
+    const float c1 = 0.5f * (1.0f + erff(xf.y * 0.70710678118654752440f));
+    const float p0 = 0.39894228040143267794f * __expf(-0.5f * xf.x * xf.x);
+    const float p1 = 0.39894228040143267794f * __expf(-0.5f * xf.y * xf.y);
+    dx[i] = f2_to_bf2(d0 * (c0 + xf.x * p0), d1 * (c1 + xf.y * p1));
+  }
+}
+
 // OMNI_ACT_PRELU_RING on a 32-row x 64-column block held one row per thread: f = bf16(bf16(acc) + bias); with a residual
 // (staged in the warp's transposition tile) f = bf16(f + bf16(res + res_bias)); PReLU; ring pixels -> 0 (same arithmetic and
 // rounding points as prelu_res_ring_kernel applied to the GEMM's bf16 output).

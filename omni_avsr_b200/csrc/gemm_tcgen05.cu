@@ -865,14 +865,59 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = row < p.M;
       // fast path: bf16 output and both 64-column blocks inside N -> coalesced through the transposition tile
       const bool fast = !p.out_fp32 && (n0 + BN2 / 2 <= p.N);
-      const bool use_res = fast && p.residual != nullptr && row0 < p.M;
+      // EPI 4 / 5 read `residual` as the saved forward tensor of the fused backward, not as an addend
+      const bool use_res = EPI < 4 && fast && p.residual != nullptr && row0 < p.M;
       ResTile rt;
       if (use_res) res_tile_prefetch(p, row0, n0, lane, rt);       // in flight under the rest of this tile's main loop
+      ResTile rt2;
+      if constexpr (EPI == 4) {
+        // gate | up blocks of this thread's first 64 intermediate channels (interleaved layout: block b at columns 128 b)
+        if (fast && row0 < p.M) {
+          tile_prefetch(p.residual, p.ldr, p.M, row0, 2 * n0, lane, rt);
+          tile_prefetch(p.residual, p.ldr, p.M, row0, 2 * n0 + 64, lane, rt2);
+        }
+      }
+      if constexpr (EPI == 5) {
+        if (fast && row0 < p.M) tile_prefetch(p.residual, p.ldr, p.M, row0, n0, lane, rt);
+      }
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN2 + half * (BN2 / 2)) +
                                 (static_cast<uint32_t>(q * 32) << 16);
-      if (fast) {
+      if constexpr (EPI == 4) {
+        // fused SwiGLU backward (the dgrad GEMM of down_proj): this thread's d(act) row, 2 blocks of 64 intermediate channels,
+        // becomes the d(gate) | d(up) blocks of d(gate_up); the accumulator is read in 32-column pieces to stay in registers
+        const bool active = row0 < p.M;       // warp-uniform
+        uint8_t* my_row = stage_tile + lane * EPI_PITCH;
+        bf16* o = reinterpret_cast<bf16*>(p.out);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t g[32], du[32];
+          if (active) {
+            tile_to_row(stage_tile, lane, rt, g);
+            res_tile_publish(stage_tile, lane, rt2);      // the up block stays in the tile: consumed and overwritten in place
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(c2 * 64 + h * 32), r);
+            tmem_ld_wait();
+            if (c2 == 1 && h == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // leader's barrier
+            }
+            if (active) swiglu_bwd_half(r, alpha, g, h, my_row, du);
+          }
+          if (!active) continue;
+          if (c2 == 0) {     // next block's gate | up: in flight under this block's two tile stores
+            tile_prefetch(p.residual, p.ldr, p.M, row0, 2 * (n0 + 64), lane, rt);
+            tile_prefetch(p.residual, p.ldr, p.M, row0, 2 * (n0 + 64) + 64, lane, rt2);
+          }
+          stage_to_global(o, p.ldo, p.M, stage_tile, lane, row0, 2 * (n0 + c2 * 64));
+          store_tile64_packed(o, p.ldo, p.M, stage_tile, du, lane, row0, 2 * (n0 + c2 * 64) + 64);
+        }
+      } else if (fast) {
         uint32_t gate[EPI == 1 ? 32 : 1];     // the rounded gate block, packed bf16 pairs
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
@@ -891,6 +936,15 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int i = 0; i < 32; ++i) {
             v[i] = __uint_as_float(r0[i]) * alpha;
             v[32 + i] = __uint_as_float(r1[i]) * alpha;
+          }
+          if constexpr (EPI == 5) {
+            // fused GELU backward (the dgrad GEMM of fc2): d(act) block x gelu'(pre-activation block)
+            uint32_t x[32], dx[32];
+            tile_to_row(stage_tile, lane, rt, x);
+            if (c2 == 0) tile_prefetch(p.residual, p.ldr, p.M, row0, n0 + 64, lane, rt);
+            gelu_bwd_row64(v, x, dx);
+            store_tile64_packed(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage_tile, dx, lane, row0, n0 + c2 * 64);
+            continue;
           }
           if (use_res) {
             res_tile_publish(stage_tile, lane, rt);
@@ -1050,16 +1104,19 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
     static const bool no_2cta = (getenv("OMNI_GEMM_NO_2CTA") != nullptr);
     const bool pair_ok = !no_2cta && BN == 256 && !a->b_row_table && (!a->ext_table || a->pair_aligned) &&
                          ((p.m_tiles >= 2 && tiles >= sms / 2) || ext_only);
-    if ((a->act == OMNI_ACT_SWIGLU64 || a->act == OMNI_ACT_GELU_KEEP || a->act == OMNI_ACT_PRELU_RING || ext_only) && !pair_ok)
+    if ((a->act == OMNI_ACT_SWIGLU64 || a->act == OMNI_ACT_GELU_KEEP || a->act == OMNI_ACT_PRELU_RING ||
+         a->act == OMNI_ACT_SWIGLU_BWD64 || a->act == OMNI_ACT_GELU_BWD || ext_only) && !pair_ok)
       return OMNI_ERR_UNSUPPORTED;
     if (pair_ok) {
       // CTA pairs (tcgen05.mma.cta_group::2): 256 x 256 tile per pair, half the shared-memory traffic per MAC
       constexpr int ST2 = 5;     // 5 x 32 KB operand stages + 36 KB of epilogue transposition tiles
       using S2 = GemmSmem2<ST2>;
-      const int epi = a->act == OMNI_ACT_SWIGLU64 ? 1 : a->act == OMNI_ACT_GELU_KEEP ? 2 : a->act == OMNI_ACT_PRELU_RING ? 3 : 0;
+      const int epi = a->act == OMNI_ACT_SWIGLU64 ? 1 : a->act == OMNI_ACT_GELU_KEEP ? 2 : a->act == OMNI_ACT_PRELU_RING ? 3
+                      : a->act == OMNI_ACT_SWIGLU_BWD64 ? 4 : a->act == OMNI_ACT_GELU_BWD ? 5 : 0;
       auto k2 = epi == 1 ? gemm_bf16_tn_2cta<ST2, 1> : epi == 2 ? gemm_bf16_tn_2cta<ST2, 2>
-                : epi == 3 ? gemm_bf16_tn_2cta<ST2, 3> : gemm_bf16_tn_2cta<ST2, 0>;
-      static bool attr_set_2[4] = {false, false, false, false};
+                : epi == 3 ? gemm_bf16_tn_2cta<ST2, 3> : epi == 4 ? gemm_bf16_tn_2cta<ST2, 4>
+                : epi == 5 ? gemm_bf16_tn_2cta<ST2, 5> : gemm_bf16_tn_2cta<ST2, 0>;
+      static bool attr_set_2[6] = {false, false, false, false, false, false};
       if (!attr_set_2[epi]) {
         if (cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL) != cudaSuccess)
           return OMNI_ERR_CUDA;
@@ -1159,6 +1216,13 @@ extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
     OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->slope) & 15) == 0 &&
                    (!a->res_bias || (reinterpret_cast<uintptr_t>(a->res_bias) & 15) == 0));
     if (a->block_n != 256 || (a->N % 128) != 0 || a->out_fp32 || a->b_row_table) return OMNI_ERR_UNSUPPORTED;
+  }
+  if (a->act == OMNI_ACT_SWIGLU_BWD64 || a->act == OMNI_ACT_GELU_BWD) {
+    // `residual` = the saved forward tensor ([M, 2N] gate|up blocks, resp. [M, N] pre-activation); out = d of it
+    const int64_t width = a->act == OMNI_ACT_SWIGLU_BWD64 ? 2 * static_cast<int64_t>(a->N) : a->N;
+    OMNI_CHECK_ARG(a->residual && a->ldr >= width && a->ldo >= width);
+    if (a->block_n != 256 || (a->N % 256) != 0 || a->out_fp32 || a->bias || a->ext_table || a->b_row_table)
+      return OMNI_ERR_UNSUPPORTED;
   }
   if (a->act == OMNI_ACT_SWIGLU64) {
     OMNI_CHECK_ARG(a->out2 && (a->ldo2 % 8) == 0 && a->ldo2 >= a->N / 2 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);

@@ -11,7 +11,8 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, PpsArgs, SpliceArgs, check, lib, ptr, require_cuda, stream_ptr
 
-ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3, "gelu_keep": 4, "prelu_ring": 5}
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu64": 3, "gelu_keep": 4, "prelu_ring": 5, "swiglu_bwd64": 6,
+       "gelu_bwd": 7}
 SWIGLU_BLK = 64          # gate / up interleave of the OMNI_ACT_SWIGLU64 epilogue
 COMPRESS = {"avg-pooling": 0, "avg": 0, "stack": 1}
 
@@ -64,7 +65,36 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     skinny=True (M <= 128, K % 64 == 0, bf16 out): the weight-streaming decode-step kernel (omni_gemm_skinny_bf16: weights on
     the M side of the MMA, split-K over a cluster); b_row_table per 64-feature block, ext table per 128-feature tile
     (block_n=128); act="swiglu64" writes only out2 (pass out=None).
-    """
+    act="swiglu_bwd64" / "gelu_bwd" (fused backward epilogues, CTA-pair kernel only): a @ b^T is d(activation) and never
+    reaches memory; `residual` carries the tensor saved by the forward (gate|up blocks [M, 2N] / pre-activation [M, N]) and
+    `out` (required) receives its gradient ([M, 2N] / [M, N])."""
+    if act in ("swiglu_bwd64", "gelu_bwd"):
+        return _gemm_fused_bwd(a, b, residual, out, act)
+    return _gemm(a, b, bias=bias, act=act, residual=residual, out=out, out_dtype=out_dtype, alpha=alpha, n=n,
+                 tile_group=tile_group, b_row_table=b_row_table, ext=ext, block_n=block_n, pair_aligned=pair_aligned, out2=out2,
+                 skinny=skinny, prelu_ring=prelu_ring)
+
+
+def _gemm_fused_bwd(a, b, saved, out, act):
+    require_cuda(a, b, saved, out)
+    a, b, saved, out = _bf16_2d(a, "a"), _bf16_2d(b, "b"), _bf16_2d(saved, "residual"), _bf16_2d(out, "out")
+    M, K = a.shape
+    N = b.shape[0]
+    width = 2 * N if act == "swiglu_bwd64" else N
+    if b.shape[1] != K or saved.shape != (M, width) or out.shape != (M, width):
+        raise ValueError(f"{act}: a [M, K], b [N, K], residual / out [M, {width}]")
+    g = GemmArgs()
+    g.A, g.B, g.out, g.residual = a.data_ptr(), b.data_ptr(), out.data_ptr(), saved.data_ptr()
+    g.lda, g.ldb, g.ldo, g.ldr = a.stride(0), b.stride(0), out.stride(0), saved.stride(0)
+    g.M, g.N, g.K, g.b_rows = M, N, K, N
+    g.block_n, g.act, g.alpha = 256, ACT[act], 1.0
+    check(lib.omni_gemm_bf16(C.byref(g), stream_ptr()), f"omni_gemm_bf16 ({act})")
+    _count()
+    return out
+
+
+def _gemm(a, b, *, bias, act, residual, out, out_dtype, alpha, n, tile_group, b_row_table, ext, block_n, pair_aligned, out2,
+          skinny, prelu_ring):
     require_cuda(a, b, bias, residual, out, tile_group, b_row_table)
     a = _bf16_2d(a, "a")
     b = _bf16_2d(b, "b")

@@ -85,3 +85,76 @@ def test_gelu_keep_epilogue_matches_separate_kernels():
     act_f.backward(dact)
     dx = ops.gemm(ops.gelu_bwd(dact, pre), WT, block_n=256)
     assert _bits(xg.grad, dx)
+
+
+@pytest.mark.parametrize("M,H,I", [(9600, 256, 1024), (31232, 2048, 8192), (9473, 512, 1536)])
+def test_swiglu_backward_epilogue_matches_separate_kernels(M, H, I):
+    """OMNI_ACT_SWIGLU_BWD64: the dgrad GEMM of down_proj with the SwiGLU backward in its epilogue == dgrad GEMM ->
+    omni_swiglu_bwd_blocked.  Same bf16-rounded d(act), same formula; the epilogue's sigmoid uses the hardware reciprocal, so
+    single bf16 ulps may differ: at most 0.1 % of the elements, each within 2^-7 relative, everything else bit-identical.
+    Then the whole MLP (MlpSwigluFn) against the unfused autograd chain: dx within 1e-2, d(residual) bit-identical."""
+    from omni_avsr_b200 import autograd_ops as ag
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + 1)
+    dy = (torch.randn(M, H, device="cuda", generator=g) * 0.1).bfloat16()
+    Wd = (torch.randn(H, I, device="cuda", generator=g) * 0.05).bfloat16()          # down_proj.weight [H, I]
+    gu = torch.randn(M, 2 * I, device="cuda", generator=g).bfloat16()               # interleaved gate|up blocks
+    WTd = Wd.t().contiguous()
+    dact = ops.gemm(dy, WTd, block_n=256)
+    want = ops.swiglu_bwd(dact, gu, blk=ops.SWIGLU_BLK)
+    got = torch.empty_like(gu)
+    launches = ops.LAUNCHES
+    ops.gemm(dy, WTd, residual=gu, out=got, act="swiglu_bwd64")
+    assert ops.LAUNCHES - launches == 1
+    diff = got.view(torch.int16) != want.view(torch.int16)
+    assert diff.float().mean().item() <= 1e-3, diff.float().mean().item()
+    rel = ((got.float() - want.float()).abs() / want.float().abs().clamp_min(1e-6))[diff]
+    assert rel.numel() == 0 or rel.max().item() <= 2 ** -7, rel.max().item()
+
+    if I % 256 == 0 and ag.pair_kernel_shape(M, I):
+        x = (torch.randn(M, H, device="cuda", generator=g) * 0.5).bfloat16()
+        W = (torch.randn(2 * I, H, device="cuda", generator=g) * 0.05).bfloat16()
+        res = torch.randn(M, H, device="cuda", generator=g).bfloat16()
+        W_il = ag.interleave_gate_up(W)
+        WT_il = W_il.t().contiguous()
+        xa, ra = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        ya = ag.MlpSwigluFn.apply(xa, W_il, WT_il, Wd, WTd, ra)
+        xb, rb = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        yb = ag.frozen_linear(ag.GateUpSwigluFn.apply(xb, W_il, WT_il), Wd, WTd, residual=rb, block_n=256)
+        assert _bits(ya.detach(), yb.detach())
+        ya.backward(dy)
+        yb.backward(dy)
+        assert _bits(ra.grad, rb.grad)
+        assert ((xa.grad.float() - xb.grad.float()).abs().max() / xb.grad.float().abs().max()).item() <= 1e-2
+
+
+def test_gelu_backward_epilogue_matches_separate_kernels():
+    """OMNI_ACT_GELU_BWD: the dgrad GEMM of fc2 with the GELU backward in its epilogue == dgrad GEMM -> omni_gelu_bwd, bit for
+    bit (same erff / __expf formula on the same bf16-rounded d(act)); FfnGeluFn == the unfused autograd chain."""
+    from omni_avsr_b200 import autograd_ops as ag
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, E, Fd = 12800, 1024, 4096
+    dy = (torch.randn(M, E, device="cuda", generator=g) * 0.1).bfloat16()
+    W2 = (torch.randn(E, Fd, device="cuda", generator=g) * 0.03).bfloat16()         # fc2.weight [E, ffn]
+    pre = torch.randn(M, Fd, device="cuda", generator=g).bfloat16()
+    WT2 = W2.t().contiguous()
+    want = ops.gelu_bwd(ops.gemm(dy, WT2, block_n=256), pre)
+    got = torch.empty_like(pre)
+    ops.gemm(dy, WT2, residual=pre, out=got, act="gelu_bwd")
+    assert _bits(got, want)
+
+    x = (torch.randn(M, E, device="cuda", generator=g) * 0.5).bfloat16()
+    W1 = (torch.randn(Fd, E, device="cuda", generator=g) * 0.03).bfloat16()
+    b1 = (torch.randn(Fd, device="cuda", generator=g) * 0.1).bfloat16()
+    b2 = (torch.randn(E, device="cuda", generator=g) * 0.1).bfloat16()
+    res = torch.randn(M, E, device="cuda", generator=g).bfloat16()
+    WT1 = W1.t().contiguous()
+    xa, ra = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    ya = ag.FfnGeluFn.apply(xa, W1, WT1, b1, W2, WT2, b2, ra)
+    xb, rb = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    yb = ag.frozen_linear(ag.FrozenLinearGeluFn.apply(xb, W1, WT1, b1), W2, WT2, bias=b2, residual=rb, block_n=256)
+    assert _bits(ya.detach(), yb.detach())
+    ya.backward(dy)
+    yb.backward(dy)
+    assert _bits(ra.grad, rb.grad) and _bits(xa.grad, xb.grad)
