@@ -399,8 +399,20 @@ __device__ __forceinline__ void epilogue_tile64_prelu_ring(const GemmKParams& p,
   store_tile64(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage, v, lane, row0, col0);
 }
 
+// Tile order of the persistent kernels.  m_fast = 0: N fastest (an M tile's row of output tiles is contiguous in time);
+// 1: M fastest (small A, huge B: lm_head); >= 2: N fastest inside GROUPS of m_fast N tiles, all M tiles per group -- the
+// group's B panel (m_fast * BN * K * 2 bytes, sized to stay L2-resident under the output stream) is read from HBM once
+// instead of once per M wave.
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int m_fast, int& m_tile, int& n_tile) {
-  if (m_fast) {
+  if (m_fast >= 2) {
+    const int per_group = m_fast * m_tiles;
+    const int g = t / per_group;
+    const int r = t - g * per_group;
+    const int n0 = g * m_fast;
+    const int w = min(m_fast, n_tiles - n0);
+    m_tile = r / w;
+    n_tile = n0 + r - m_tile * w;
+  } else if (m_fast) {
     n_tile = t / m_tiles;
     m_tile = t - n_tile * m_tiles;
   } else {

@@ -1138,7 +1138,17 @@ static int launch_gemm(const omni_gemm_args* a, cudaStream_t stream) {
       const int pairs = ((p.m_tiles + 1) / 2) * ceil_div(a->N, 256);
       int clusters = sms / 2;
       if (pairs < clusters) clusters = pairs;
-      const int m_fast2 = (!ext_only && ((p.m_tiles + 1) / 2) < ceil_div(a->N, 256) && a_bytes <= (40ll << 20)) ? 1 : 0;
+      int m_fast2 = (!ext_only && ((p.m_tiles + 1) / 2) < ceil_div(a->N, 256) && a_bytes <= (40ll << 20)) ? 1 : 0;
+      // L2-friendly raster for a B operand that does not stay L2-resident under the output stream (gate_up: 67 MB of weights
+      // against 1 GB of output per launch): groups of N tiles whose B panel is <= 32 MB, all M tiles per group.  Costs one more
+      // pass over A per extra group, so only when A is not the bigger operand.
+      static const bool no_group = (getenv("OMNI_GEMM_NO_NGROUP") != nullptr);
+      const long long b_bytes = static_cast<long long>(a->N) * a->K * 2;
+      if (!no_group && !m_fast2 && !a->ext_table && !ext_only && b_bytes > (48ll << 20) && a_bytes <= 2 * b_bytes) {
+        const long long tile_bytes = 256ll * a->K * 2;
+        const int ng = static_cast<int>((32ll << 20) / tile_bytes);
+        if (ng >= 2 && ng < ceil_div(a->N, 256)) m_fast2 = ng;
+      }
       k2<<<2 * clusters, GEMM2_THREADS, S2::TOTAL, stream>>>(tmA, tmBh, tmA2, tmB2h2, p, m_fast2);
       OMNI_LAUNCH_CHECK();
       return OMNI_OK;
