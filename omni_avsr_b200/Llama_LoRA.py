@@ -723,6 +723,11 @@ class LlamaMLP(nn.Module):
             act = torch.empty((h.shape[0], I), device=h.device, dtype=torch.bfloat16)
             ops.gemm(h, w_il, act="swiglu64", out2=act, skinny=True)
             return ops.gemm(act, self.down_proj.weight.data, residual=residual, skinny=True)
+        elif not h.requires_grad and I % 64 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I):
+            # prefill / evaluation: SwiGLU in the gate_up GEMM's epilogue, the gate|up tile itself is never written
+            w_il, _ = self.interleaved()
+            act = torch.empty((h.shape[0], I), device=h.device, dtype=torch.bfloat16)
+            ops.gemm(h, w_il, act="swiglu64", out2=act, block_n=256)
         else:
             gu = ag.frozen_linear(h, self.gate_up_weight, wt_gu, block_n=256)
             act = ag.swiglu(gu)

@@ -209,7 +209,7 @@ __device__ __forceinline__ void store_tile64(bf16* out, long long ldo, int M, ui
 }
 
 __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* stage, float (&v)[64], int lane, int row0,
-                                                int col0, bool res_staged) {
+                                                int col0, bool res_staged, bool store = true) {
   if (p.bias) {
     const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
 #pragma unroll
@@ -247,7 +247,7 @@ __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* s
     }
     __syncwarp();
   }
-  store_tile64(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage, v, lane, row0, col0);
+  if (store) store_tile64(reinterpret_cast<bf16*>(p.out), p.ldo, p.M, stage, v, lane, row0, col0);
 }
 
 

@@ -953,7 +953,8 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if constexpr (EPI == 3) {
             epilogue_tile64_prelu_ring(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);
           } else {
-            epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res);     // rounds v to bf16 when act != NONE
+            // rounds v to bf16 when act != NONE; SwiGLU without a gate|up output (inference): only the activation is stored
+            epilogue_tile64(p, stage_tile, v, lane, row0, n0 + c2 * 64, use_res, EPI != 1 || p.out != nullptr);
           }
           if constexpr (EPI == 2) {
             // v holds the rounded pre-activation that was just stored: second output = gelu of it
@@ -1203,11 +1204,13 @@ extern "C" int omni_gemm_bf16(const omni_gemm_args* a, void* stream) {
   using namespace omni;
   OMNI_CHECK_ARG(a != nullptr);
   OMNI_CHECK_ARG(a->M > 0 && a->N > 0 && (a->K > 0 || (a->K == 0 && a->ext_table)));
-  OMNI_CHECK_ARG((a->K == 0 || (a->A && a->B)) && a->out);
+  OMNI_CHECK_ARG((a->K == 0 || (a->A && a->B)) && (a->out || (a->act == OMNI_ACT_SWIGLU64 && a->out2)));
   OMNI_CHECK_ARG((a->lda % 8) == 0 && (a->ldb % 8) == 0);
   OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
-  OMNI_CHECK_ARG(a->ldo >= a->N);
-  OMNI_CHECK_ARG((a->ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0);
+  if (a->out) {
+    OMNI_CHECK_ARG(a->ldo >= a->N);
+    OMNI_CHECK_ARG((a->ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0);
+  }
   if (a->residual) OMNI_CHECK_ARG((a->ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
   if (a->bias) OMNI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0);
   if (a->ext_table) {

@@ -64,7 +64,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     act="gelu_keep": out = bf16(a @ b^T + bias) (the pre-activation the backward needs), out2 [M, N] = bf16(gelu(out)).
     skinny=True (M <= 128, K % 64 == 0, bf16 out): the weight-streaming decode-step kernel (omni_gemm_skinny_bf16: weights on
     the M side of the MMA, split-K over a cluster); b_row_table per 64-feature block, ext table per 128-feature tile
-    (block_n=128); act="swiglu64" writes only out2 (pass out=None).
+    (block_n=128).  act="swiglu64" with out=None writes only out2 = the activation (both kernels).
     act="swiglu_bwd64" / "gelu_bwd" (fused backward epilogues, CTA-pair kernel only): a @ b^T is d(activation) and never
     reaches memory; `residual` carries the tensor saved by the forward (gate|up blocks [M, 2N] / pre-activation [M, N]) and
     `out` (required) receives its gradient ([M, 2N] / [M, N])."""
@@ -102,7 +102,7 @@ def _gemm(a, b, *, bias, act, residual, out, out_dtype, alpha, n, tile_group, b_
     if b.shape[1] != K:
         raise ValueError(f"K mismatch: a {tuple(a.shape)} vs b {tuple(b.shape)}")
     N = int(n) if n is not None else b.shape[0]
-    skinny_swiglu = skinny and act == "swiglu64" and out is None
+    skinny_swiglu = act == "swiglu64" and out is None      # only out2 = the activation is written (decode step, prefill)
     if skinny_swiglu:
         out = out2                                   # placeholder for the shape checks below; only out2 is written
     elif out is None:
@@ -177,7 +177,7 @@ def _gemm(a, b, *, bias, act, residual, out, out_dtype, alpha, n, tile_group, b_
         return out2 if skinny_swiglu else out
     check(lib.omni_gemm_bf16(C.byref(g), stream_ptr()), "omni_gemm_bf16")
     _count()
-    return out
+    return out2 if skinny_swiglu else out
 
 
 def matryoshka_compress(x: torch.Tensor, n_tok: int, rate: int, mode: str = "avg-pooling") -> torch.Tensor:

@@ -158,3 +158,19 @@ def test_gelu_backward_epilogue_matches_separate_kernels():
     ya.backward(dy)
     yb.backward(dy)
     assert _bits(ra.grad, rb.grad) and _bits(xa.grad, xb.grad)
+
+
+def test_swiglu_epilogue_without_gate_up_output():
+    """Inference form of OMNI_ACT_SWIGLU64 (out = NULL): only the activation is written, bit-identical to the training form."""
+    from omni_avsr_b200 import autograd_ops as ag
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, H, I = 9473, 512, 1536
+    x = (torch.randn(M, H, device="cuda", generator=g) * 0.5).bfloat16()
+    W_il = ag.interleave_gate_up((torch.randn(2 * I, H, device="cuda", generator=g) * 0.05).bfloat16())
+    gu = torch.empty(M, 2 * I, device="cuda", dtype=torch.bfloat16)
+    act = torch.empty(M, I, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, W_il, out=gu, out2=act, act="swiglu64", block_n=256)
+    act2 = torch.full((M, I), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ret = ops.gemm(x, W_il, out2=act2, act="swiglu64", block_n=256)
+    assert ret is act2 and _bits(act2, act)
