@@ -68,7 +68,8 @@ struct SkinnySmem {
   static constexpr int T_BYTES = TSL * SK_TPITCH * 2;
   static_assert(T_BYTES <= STAGES * STAGE_BYTES, "transposition tile must fit in the stage area");
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int EXT_OFFSET = BAR_OFFSET + ((2 * STAGES + 1) * 8 + 16 + 15) / 16 * 16;
+  static constexpr int TOTAL = EXT_OFFSET + 32 * 16 + 1024;
 };
 
 template <int NTOK, int SPLIT, int STAGES>
@@ -83,6 +84,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  int4* ext_smem = reinterpret_cast<int4*>(smem + S::EXT_OFFSET);       // [32] the tile's K-extension entries
   bf16* ttile = reinterpret_cast<bf16*>(smem + S::T_OFFSET);            // [TSL][SK_TPITCH]
 
   pdl_launch_dependents();      // the next kernel of the step may start its own prologue / weight prefetch right away
@@ -95,11 +97,16 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int n0 = n_tile * SK_FEATS;
   const int group = p.tile_group ? p.tile_group[0] : 0;
   const int4* ext = p.ext_table ? p.ext_table + static_cast<long long>(group * p.n_tiles + n_tile) * p.n_ext : nullptr;
-  int n_ext_valid = 0;
-  if (ext && rank == SPLIT - 1)
-    for (int j = 0; j < p.n_ext; ++j) n_ext_valid += ext[j].y >= 0 ? 1 : 0;
+  // K-extension list of the tile (static data: read before the predecessor finishes).  One PARALLEL load per warp -- lane j
+  // fetches entry j -- instead of a dependent global load per entry in the producer loop: on the last rank those ~0.7 us
+  // round trips sat in front of the split-K exchange every other rank of the tile waits in (qkv: 20 us -> see profiles/).
+  int4 ext_mine = make_int4(0, -1, 0, 0);
+  if (ext && rank == SPLIT - 1 && lane < p.n_ext) ext_mine = ext[lane];
+  const unsigned ext_mask = __ballot_sync(0xffffffffu, ext_mine.y >= 0);
+  const int n_ext_valid = __popc(ext_mask);
   const int total_iters = kb_mine + n_ext_valid;
 
+  if (warp == 0) ext_smem[lane] = ext_mine;      // visible to the producer lane after the __syncthreads below
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmX);
@@ -163,7 +170,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
       if (n_ext_valid) {
         for (int j = 0; j < p.n_ext; ++j) {
-          const int4 e = ext[j];
+          const int4 e = ext_smem[j];
           if (e.y < 0) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sW = smem + stage * S::STAGE_BYTES;
@@ -404,7 +411,7 @@ extern "C" int omni_gemm_skinny_bf16(const omni_gemm_args* a, void* stream) {
     if ((a->N % 128) != 0 || a->residual || a->bias || a->ext_table || a->b_row_table) return OMNI_ERR_UNSUPPORTED;
   }
   if (a->ext_table) {
-    OMNI_CHECK_ARG(a->A2 && a->B2 && a->n_ext > 0 && (a->lda2 % 8) == 0 && (a->ldb2 % 8) == 0);
+    OMNI_CHECK_ARG(a->A2 && a->B2 && a->n_ext > 0 && a->n_ext <= 32 && (a->lda2 % 8) == 0 && (a->ldb2 % 8) == 0);
     OMNI_CHECK_ARG(a->block_n == 128);           // the table is indexed with this kernel's 128-feature tiles
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -430,7 +437,10 @@ extern "C" int omni_gemm_skinny_bf16(const omni_gemm_args* a, void* stream) {
   // n_tiles * split <= SM count (one CTA per SM at this shared-memory footprint)
   const int kb = a->K / BK;
   const int sms = skinny_sm_count();
-  static const int choices[] = {8, 6, 5, 4, 3, 2};
+  // (5 and 3 are never chosen: measured in isolation on the qkv GEMM, 64 x 3072 x 2048, tools/skinny_probe.py: split 5 =
+  // 25.6 us, split 4 = 15.4 us, split 6 = 17.4 us, split 3 = 19.5 us -- the uneven K slices of the odd factors start off the
+  // 1 KB-aligned columns of the weight rows)
+  static const int choices[] = {8, 6, 4, 2};
   // measured inside the decode graph: 144 CTAs (24 tiles x 6) ran 2x slower than 96 (x 4) -- near the SM count the last
   // CTAs of the grid only become resident when the predecessor's stragglers have left, and their peers spin meanwhile
   const int cta_cap = sms < 132 ? sms : 132;
