@@ -437,10 +437,11 @@ extern "C" int omni_gemm_skinny_bf16(const omni_gemm_args* a, void* stream) {
   // n_tiles * split <= SM count (one CTA per SM at this shared-memory footprint)
   const int kb = a->K / BK;
   const int sms = skinny_sm_count();
-  // (5 and 3 are never chosen: measured in isolation on the qkv GEMM, 64 x 3072 x 2048, tools/skinny_probe.py: split 5 =
-  // 25.6 us, split 4 = 15.4 us, split 6 = 17.4 us, split 3 = 19.5 us -- the uneven K slices of the odd factors start off the
-  // 1 KB-aligned columns of the weight rows)
-  static const int choices[] = {8, 6, 4, 2};
+  // Powers of two only.  Measured in isolation (tools/skinny_probe.py, 64 tokens, L2 flushed, ~5 us of event overhead
+  // included): qkv 64 x 3072 x 2048 -- split 4: 15.4 us, 5: 25.6, 6: 17.4, 3: 19.5; o_proj 2048 x 2048 -- split 8: 13.3, 6: 23.6,
+  // 4: 13.3; Qwen2.5-3B qkv 2560 x 2048 -- split 4: 15.3, 6: 23.6.  The uneven K slices of 3 / 5 / 6 cost more than the extra
+  // CTAs bring.
+  static const int choices[] = {8, 4, 2};
   // measured inside the decode graph: 144 CTAs (24 tiles x 6) ran 2x slower than 96 (x 4) -- near the SM count the last
   // CTAs of the grid only become resident when the predecessor's stragglers have left, and their peers spin meanwhile
   const int cta_cap = sms < 132 ? sms : 132;

@@ -1,5 +1,7 @@
-"""Decode-step qkv GEMM (64 tokens, N=3072, K=2048) on the weight-streaming kernel, in isolation: with / without the LoRA
-K-extension, for the split-K factor given by OMNI_SKINNY_SPLIT (unset = the dispatcher's choice).  CUDA events, L2 flushed."""
+"""Weight-streaming GEMMs of the decode step (64 tokens) in isolation, for the split-K factor given by OMNI_SKINNY_SPLIT
+(unset = the dispatcher's choice): CUDA events, median of 15, L2 flushed between launches (the events add ~5 us of launch
+latency to every figure: compare columns, not absolute values).
+   python tools/skinny_probe.py [llama1b|qwen3b]"""
 import json
 import os
 import sys
@@ -10,18 +12,9 @@ sys.path.insert(0, __file__.rsplit("/tools/", 1)[0])
 from omni_avsr_b200 import ops  # noqa: E402
 
 g = torch.Generator(device="cuda").manual_seed(0)
-M, N, K = 64, 3072, 2048
-x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
-W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
-T = (torch.randn(M, 256, device="cuda", generator=g) * 0.5).bfloat16()
-up = (torch.randn(N, 256, device="cuda", generator=g) * 0.05).bfloat16()
-nt = N // 128
-tab = torch.full((1, nt, 4, 4), -1, dtype=torch.int32)
-for t in range(nt):
-    if t < 16 or t >= 20:          # q and v tiles carry two adapters (task + shared), one 64-column block each
-        tab[0, t, 0] = torch.tensor([0, t * 128, 0, 0])
-        tab[0, t, 1] = torch.tensor([64, t * 128, 64, 0])
-tab = tab.cuda()
+which = sys.argv[1] if len(sys.argv) > 1 else "llama1b"
+H, I, QKV = (2048, 8192, 3072) if which == "llama1b" else (2048, 11008, 2560)
+shapes = {"qkv": (QKV, H), "o_proj": (H, H), "down": (H, I), "lora_down": (256, H), "gate_up": (2 * I, H)}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
@@ -38,8 +31,13 @@ def timeit(fn, iters=15):
     return sorted(ts)[len(ts) // 2] * 1e3
 
 
-res = {"split": os.environ.get("OMNI_SKINNY_SPLIT", "auto")}
-res["plain_us"] = round(timeit(lambda: ops.gemm(x, W, skinny=True)), 2)
-res["ext_us"] = round(timeit(lambda: ops.gemm(x, W, ext=(T, up, tab), block_n=128, skinny=True)), 2)
-res["o_proj_us"] = round(timeit(lambda: ops.gemm(x, W[:2048], skinny=True)), 2)
+res = {"model": which, "split": os.environ.get("OMNI_SKINNY_SPLIT", "auto")}
+for name, (N, K) in shapes.items():
+    x = (torch.randn(64, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    if name == "gate_up":
+        act = torch.empty(64, N // 2, device="cuda", dtype=torch.bfloat16)
+        res[name] = round(timeit(lambda: ops.gemm(x, W, act="swiglu64", out2=act, skinny=True)), 1)
+    else:
+        res[name] = round(timeit(lambda: ops.gemm(x, W, skinny=True)), 1)
 print(json.dumps(res))
