@@ -16,6 +16,7 @@
 // Every tcgen05 / TMA instruction is issued from an `elect.sync` branch: with `if (lane == 0)` ptxas wraps each
 // UTCHMMA / UTCBAR / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (~100 cycles of issue latency per MMA, more
 // than the 32..64 cycles these small MMAs execute for).
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/omni_avsr.h"
 
@@ -341,6 +342,7 @@ attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p)
 // P.V(t-2) finished: group t&1's P tile is free and its O accumulator is stable.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int AT64_THREADS = 320;
+// AT64_POLY (template parameter of the kernel): 1 of every AT64_POLY exponentials runs on the FMA pipe (0: none)
 
 struct AttnSmem64 {
   static constexpr int Q_BYTES = AT_BQ * 64 * 2;           // 16 KB
@@ -354,6 +356,7 @@ struct AttnSmem64 {
   static constexpr int TOTAL = BAR_OFFSET + 12 * 8 + 16 + ALIGN_SLACK;
 };
 
+template <int AT64_POLY>
 __global__ void __launch_bounds__(AT64_THREADS, 2)
 attn_fwd64_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   constexpr int AT_HD = 64;
@@ -519,8 +522,10 @@ attn_fwd64_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));       // -inf -> 0
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+          // every AT64_POLY-th exponential runs on the FMA pipe (ex2_poly) instead of the MUFU
+          const float x0 = fmaf(__uint_as_float(v[i]), sc, neg_m), x1 = fmaf(__uint_as_float(v[i + 1]), sc, neg_m);
+          const float p0 = ex2_approx(x0);                                            // -inf -> 0
+          const float p1 = (AT64_POLY > 0 && ((i + 1) % AT64_POLY) == AT64_POLY - 1) ? ex2_poly(x1) : ex2_approx(x1);
           sa += p0;
           sb += p1;
           packed[i >> 1] = f2_to_bf2(p0, p1);
@@ -628,7 +633,13 @@ extern "C" int omni_attention_fwd(const void* qkv, int64_t M, int64_t ld, void* 
   dim3 grid(n_heads, B, ceil_div(S, AT_BQ));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) {
-    auto k64 = attn_fwd64_kernel;
+    // share of the exponentials computed on the FMA pipe: OMNI_AT64_POLY = 0 (none, default), 2 (1/2), 3 (1/6), 4 (1/4).
+    // Measured at Whisper's shape (B=16, S=1500, 16 x 64; profiles/README.md): 0.273 / 0.286 / 0.280 / 0.297 ms for
+    // 0 / 3 / 4 / 2 -- the kernel is bound by issue slots and latency (MUFU pipe at 58 %), so trading one MUFU op for
+    // eight FMA-pipe instructions loses; kept as a switch for the experiment's record.
+    static const int poly = getenv("OMNI_AT64_POLY") ? atoi(getenv("OMNI_AT64_POLY")) : 0;
+    auto k64 = poly == 0 ? attn_fwd64_kernel<0> : poly == 2 ? attn_fwd64_kernel<2> : poly == 3 ? attn_fwd64_kernel<3>
+                                                                                               : attn_fwd64_kernel<4>;
     static bool attr64 = false;
     if (!attr64) {
       if (cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem64::TOTAL) != cudaSuccess)

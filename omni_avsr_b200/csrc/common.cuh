@@ -351,6 +351,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (no MUFU): Cody-Waite split x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+// polynomial (max relative error 7.6e-5, 50x below bf16 resolution); 2^n by adding n to the exponent bits.  Valid for
+// -126 <= x < 128 after the clamp (x = -inf -> 2^-126 ~ 1e-38, which rounds to 0 in bf16 and vanishes in the row sums).
+// The attention kernels compute a fixed fraction of their exponentials this way: the softmax of head_dim-64 attention is
+// bound by the 16 ex2/clk/SM of the MUFU pipe (1 exponential per 256 tensor-core flop), the FMA pipe has slack.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: n lands in the low mantissa bits (two's complement)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05520550534129143f, 0.24261397123336792f);
+  p = fmaf(p, f, 0.6932547688484192f);
+  p = fmaf(p, f, 0.9999276995658875f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // x * sigmoid(x) with the hardware reciprocal (MUFU.RCP, <= 1 ulp): an IEEE division costs ~12 instructions plus a
 // slow-path subroutine per element, which made the SwiGLU epilogue of the gate_up GEMM longer than its main loop.
