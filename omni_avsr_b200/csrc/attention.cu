@@ -517,17 +517,18 @@ attn_fwd64_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         m = m_tile;
       }
       const float neg_m = (m == -INFINITY) ? 0.f : -m;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      auto emit = [&](uint32_t (&v)[32], int c, float& sa, float& sb) {
+      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+      const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
+      auto emit = [&](uint32_t (&v)[32], int c, float2& sab) {
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
+          // packed fp32 (FFMA2 / FADD2): one issue slot per pair of scores for the scaling and for the row sum;
           // every AT64_POLY-th exponential runs on the FMA pipe (ex2_poly) instead of the MUFU
-          const float x0 = fmaf(__uint_as_float(v[i]), sc, neg_m), x1 = fmaf(__uint_as_float(v[i + 1]), sc, neg_m);
-          const float p0 = ex2_approx(x0);                                            // -inf -> 0
-          const float p1 = (AT64_POLY > 0 && ((i + 1) % AT64_POLY) == AT64_POLY - 1) ? ex2_poly(x1) : ex2_approx(x1);
-          sa += p0;
-          sb += p1;
+          const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+          const float p0 = ex2_approx(x.x);                                           // -inf -> 0
+          const float p1 = (AT64_POLY > 0 && ((i + 1) % AT64_POLY) == AT64_POLY - 1) ? ex2_poly(x.y) : ex2_approx(x.y);
+          sab = fadd2(sab, make_float2(p0, p1));
           packed[i >> 1] = f2_to_bf2(p0, p1);
         }
         // 32 keys = 4 chunks of 16 bytes; chunk index inside the 128-byte row = c * 4 + t4, XOR-swizzled with the row
@@ -538,9 +539,9 @@ attn_fwd64_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
               make_uint4(packed[4 * t4], packed[4 * t4 + 1], packed[4 * t4 + 2], packed[4 * t4 + 3]);
         }
       };
-      emit(v0, 0, s0, s1);
-      emit(v1, 1, s2, s3);
-      l = l * alpha + ((s0 + s1) + (s2 + s3));
+      emit(v0, 0, s01);
+      emit(v1, 1, s23);
+      l = l * alpha + ((s01.x + s01.y) + (s23.x + s23.y));
       // O_g(TMEM) *= alpha for the rows of this warp, only when some row raised its maximum (never on the group's first
       // step: its first P.V overwrites O_g).  The group's previous P.V(t-2) has finished (s_full(t) was committed after it).
       if (t >= 2 && __any_sync(0xffffffffu, raise)) {

@@ -24,8 +24,8 @@ constexpr int AB_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 compute
 struct AttnBwdParams {
   bf16* dqkv;            // [M, dqkv_ld] packed gradient rows, same column layout as qkv
   long long dqkv_ld;
-  const float* stats;    // [n_heads][B][n_qs][2][64]: per 64-query step, lse * log2(e) (+inf for the queries past S, which makes
-                         // their P = exp2(s - inf) = 0 without any test) then rowsum(dO o O); written by attn_delta_kernel
+  const float* stats;    // [n_heads][B][n_qs][2][64]: per 64-query step, -lse * log2(e) (-inf for the queries past S, which makes
+                         // their P = exp2(s - inf) = 0 without any test) then -rowsum(dO o O); written by attn_delta_kernel
   long long M;
   int row0, S, n_heads, n_kv_heads, causal, B, n_qs;
   float scale, scale_log2;
@@ -33,8 +33,9 @@ struct AttnBwdParams {
 
 // ---------------------------------------------------------------------------------------------------------------
 // statistics pre-pass: one warp per (clip, padded query position), HD/8 lanes per head (16-byte loads), fp32 sum.
-// Writes the per-step statistics blocks the two kernels read: stats[h][clip][pos / 64][0][pos % 64] = lse * log2(e),
-// [1][pos % 64] = delta = rowsum(dO o O); positions in [S, 64 n_qs) get (+inf, 0).  The blocks are 512 bytes, 512-byte
+// Writes the per-step statistics blocks the two kernels read, NEGATED (they are the addends of packed FFMA2 / FADD2
+// instructions): stats[h][clip][pos / 64][0][pos % 64] = -lse * log2(e), [1][pos % 64] = -delta = -rowsum(dO o O);
+// positions in [S, 64 n_qs) get (-inf, 0).  The blocks are 512 bytes, 512-byte
 // aligned: the dK/dV kernel fetches one per step with a single bulk copy next to its Q / dO tiles.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -68,8 +69,8 @@ attn_delta_kernel(const bf16* __restrict__ dout, long long do_ld, const bf16* __
     for (int o = lph >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (h < n_heads && l == 0) {
       float* blk = stats + ((static_cast<long long>(h) * B + clip) * n_qs + (pos >> 6)) * 128 + (pos & 63);
-      blk[0] = valid ? lse[static_cast<long long>(h) * M + row] * 1.4426950408889634f : INFINITY;
-      blk[64] = acc;
+      blk[0] = valid ? -lse[static_cast<long long>(h) * M + row] * 1.4426950408889634f : -INFINITY;
+      blk[64] = -acc;
     }
   }
 }
@@ -245,10 +246,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const long long row = static_cast<long long>(clip_row0) + qpos;
     const bool row_ok = qpos < p.S;
-    // lse2 = +inf for the rows past the clip: their P (and dS) come out as exactly 0 on the compare-free path
+    // -lse2 = -inf for the rows past the clip: their P (and dS) come out as exactly 0 on the compare-free path
     const float* sblk = p.stats + ((static_cast<long long>(head) * p.B + clip) * p.n_qs + (qpos >> 6)) * 128 + (qpos & 63);
-    const float lse2 = row_ok ? sblk[0] : INFINITY;
-    const float dl = row_ok ? sblk[64] : 0.f;
+    const float nlse2 = row_ok ? sblk[0] : -INFINITY;      // -lse * log2(e)
+    const float ndl = row_ok ? sblk[64] : 0.f;             // -delta
     const int kmax = p.causal ? min(qpos, p.S - 1) : (p.S - 1);      // last visible key position
     const float sc = p.scale_log2;
     uint8_t* sDS = smem + SM::OFF_DS;
@@ -272,11 +273,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
           for (int i = 0; i < 32; ++i)
             if (k0 + c * 32 + i > kmax) s[i] = 0xff800000u;
         }
+        const float2 sc2 = make_float2(sc, sc), nl2 = make_float2(nlse2, nlse2), ndl2 = make_float2(ndl, ndl);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), sc, -lse2));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), sc, -lse2));
-          w[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(d[i]) - dl), p1 * (__uint_as_float(d[i + 1]) - dl));
+          // packed fp32 (FFMA2 / FADD2 / FMUL2): three issue slots per PAIR of elements around the two exponentials
+          const float2 x = ffma2(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nl2);
+          const float2 t = fadd2(make_float2(__uint_as_float(d[i]), __uint_as_float(d[i + 1])), ndl2);
+          const float2 g2 = fmul2(make_float2(ex2_approx(x.x), ex2_approx(x.y)), t);
+          w[i >> 1] = f2_to_bf2(g2.x, g2.y);
         }
         if (j > 0) mbar_wait(ds_free, (j - 1) & 1);      // the previous step's dQ MMAs are done with the dS tile
         store_operand_chunk(sDS, r, c, w);
@@ -492,7 +496,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
       mbar_wait(q_full + (it & 1), (it >> 1) & 1);         // the step's statistics block landed (TMA bulk copy)
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // every query of the step sees this key (queries past S carry lse2 = +inf: P = 0 without a test)
+      // every query of the step sees this key (queries past S carry -lse2 = -inf: P = 0 without a test)
       const bool full = qlo <= q0;
       {
         const int c = half;
@@ -508,19 +512,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
           for (int i = 0; i < 32; ++i)
             if (q0 + c * 32 + i < qlo) s[i] = 0xff800000u;
         }
+        const float2 sc2 = make_float2(sc, sc);
         const float4* L4 = reinterpret_cast<const float4*>(st + c * 32);
         const float4* D4 = reinterpret_cast<const float4*>(st + AB_STEP + c * 32);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 l = L4[i4], dd = D4[i4];
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4]), sc, -l.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4 + 1]), sc, -l.y));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4 + 2]), sc, -l.z));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(s[i4 * 4 + 3]), sc, -l.w));
+          // packed fp32 (FFMA2 / FADD2 / FMUL2): s * scale - lse2, dP - delta, P * (dP - delta) for two queries per issue slot
+          // (the statistics block holds -lse2 and -delta: plain addends)
+          const float2 xa = ffma2(make_float2(__uint_as_float(s[i4 * 4]), __uint_as_float(s[i4 * 4 + 1])), sc2, make_float2(l.x, l.y));
+          const float2 xb = ffma2(make_float2(__uint_as_float(s[i4 * 4 + 2]), __uint_as_float(s[i4 * 4 + 3])), sc2, make_float2(l.z, l.w));
+          const float p0 = ex2_approx(xa.x), p1 = ex2_approx(xa.y), p2 = ex2_approx(xb.x), p3 = ex2_approx(xb.y);
+          const float2 ta = fadd2(make_float2(__uint_as_float(d[i4 * 4]), __uint_as_float(d[i4 * 4 + 1])), make_float2(dd.x, dd.y));
+          const float2 tb = fadd2(make_float2(__uint_as_float(d[i4 * 4 + 2]), __uint_as_float(d[i4 * 4 + 3])), make_float2(dd.z, dd.w));
+          const float2 ga = fmul2(make_float2(p0, p1), ta), gb = fmul2(make_float2(p2, p3), tb);
           wp[i4 * 2] = f2_to_bf2(p0, p1);
           wp[i4 * 2 + 1] = f2_to_bf2(p2, p3);
-          wd[i4 * 2] = f2_to_bf2(p0 * (__uint_as_float(d[i4 * 4]) - dd.x), p1 * (__uint_as_float(d[i4 * 4 + 1]) - dd.y));
-          wd[i4 * 2 + 1] = f2_to_bf2(p2 * (__uint_as_float(d[i4 * 4 + 2]) - dd.z), p3 * (__uint_as_float(d[i4 * 4 + 3]) - dd.w));
+          wd[i4 * 2] = f2_to_bf2(ga.x, ga.y);
+          wd[i4 * 2 + 1] = f2_to_bf2(gb.x, gb.y);
         }
         if (it > 0) mbar_wait(pds_free, (it - 1) & 1);   // the previous step's dV / dK MMAs are done with the tiles
         store_operand_chunk(sP, r, c, wp);

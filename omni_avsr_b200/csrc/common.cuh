@@ -351,6 +351,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 arithmetic of sm_100 (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of a register pair).  The softmax /
+// dS arithmetic of the attention kernels is bound by issue slots, not by the MUFU pipe: halving its FFMA / FADD / FMUL count is
+// what moves them (the register pairs cost nothing: ptxas allocates the operands as aligned pairs).
+__device__ __forceinline__ unsigned long long pack_f2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f2(unsigned long long r) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pack_f2(a.x, a.y)), "l"(pack_f2(b.x, b.y)), "l"(pack_f2(c.x, c.y)));
+  return unpack_f2(rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pack_f2(a.x, a.y)), "l"(pack_f2(b.x, b.y)));
+  return unpack_f2(rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pack_f2(a.x, a.y)), "l"(pack_f2(b.x, b.y)));
+  return unpack_f2(rd);
+}
 // 2^x on the FMA pipe (no MUFU): Cody-Waite split x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
 // polynomial (max relative error 7.6e-5, 50x below bf16 resolution); 2^n by adding n to the exponent bits.  Valid for
 // -126 <= x < 128 after the clamp (x = -inf -> 2^-126 ~ 1e-38, which rounds to 0 in bf16 and vanishes in the row sums).
