@@ -38,13 +38,20 @@ WORKLOAD = ("Omni-AVSR AVSR train step: Whisper-medium + AV-HuBERT-Large + Llama
             "rates {2,5} (step k uses pair k mod 4), hybrid Omni-LoRA (task-specific + shared, r=64), bf16, 3 tasks/utterance")
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-# capture (three consecutive launches of gemm_bf16_tn_2cta inside a B=32 train step: 2893 / 1191 / 315 MB)
-NCU_TRAFFIC_BYTES = 1466.4e6
-NCU_TRAFFIC_SOURCE = ("profiles/gemm2cta_r1b_ncu_full_summary.csv: mean of 3 captured launches (B=32); tensor pipe active "
-                      "93-97 %, DRAM throughput 15-25 %; the largest (gate_up, M=31232 N=16384 K=2048) moves 2893 MB against "
-                      "1218 MB algorithmic: the weight panel is re-read from HBM because 74 CTA pairs sweep all 64 N tiles "
-                      "per M wave -- not the limiter at 25 % DRAM utilisation")
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
+    (profiles/gemm_traffic.json, written by tools/ncu_traffic.py from an ncu pass over one B=32 train step).  The capture is
+    tied to the source digest it was taken from: `stale` says whether the library running now is a different build."""
+    path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        t = json.load(open(path))
+        from omni_avsr_b200 import build as b
+        dig = b._digest(sorted(b.CSRC.glob("*.cu")) + sorted(b.CSRC.glob("*.cuh")) + sorted((b.ROOT / "include").glob("*.h")))
+        return t["plain"]["mean_bytes_per_launch"], {
+            "file": "profiles/gemm_traffic.json", "launches_captured": t["plain"]["launches"],
+            "stale": dig != t.get("source_digest"), "how": t.get("how")}
+    except Exception as e:          # no capture committed: say so instead of quoting a number from another build
+        return None, {"file": "profiles/gemm_traffic.json", "error": repr(e)}
 
 
 def load_peaks():
@@ -461,8 +468,8 @@ def run_ours(args):
         ach = tot_fl / (tot_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "omni::gemm_bf16_tn_{2cta,cluster,persistent} (tcgen05)", "achieved": round(ach, 1),
                 "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["_source"] + " (sustained: timed inside a long step)",
-                "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 3), "traffic": NCU_TRAFFIC_BYTES,
-                "traffic_source": NCU_TRAFFIC_SOURCE,
+                "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_tflops_sustained"], 3), "traffic": load_traffic()[0],
+                "traffic_source": load_traffic()[1],
                 "launches": len(recs), "gemm_ms_per_step": round(tot_ms, 2),
                 "fused_epilogue_gemms": {"launches": len(fused), "ms_per_step": round(fused_ms, 2),
                                          "achieved_gemm_flops_only": round(fused_fl / max(fused_ms, 1e-9) / 1e9, 1),
