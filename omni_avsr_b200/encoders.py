@@ -313,11 +313,9 @@ class _ResEncoder(nn.Module):
     def _frames_ok(self, li):
         """Layer li (and every later one) can run as table-driven frame-row GEMMs: 64-multiple input channels, output channels
         that tile the 256-wide CTA-pair N."""
-        if li < 2:
-            return False
         ok = lambda c: c % 64 == 0 and ((c < 256 and 256 % c == 0) or c % 256 == 0)
         widths = [getattr(self.trunk, f"layer{i}")[0].conv1.out_channels for i in range(1, 5)]
-        return all(ok(widths[i - 1]) for i in range(li, 5)) and widths[li - 2] % 64 == 0 and widths[li - 1] >= 128
+        return all(ok(widths[i - 1]) for i in range(li, 5)) and widths[max(li - 2, 0)] % 64 == 0 and widths[li - 1] >= 64
 
     def _frames_block(self, key, y, ent, blk):
         """One BasicBlock on the table-driven path (resnet.py:35-74); y: RingFrames (first block after the ring layers) or
@@ -358,7 +356,8 @@ class _ResEncoder(nn.Module):
                 # 256-wide N to the CTA-pair kernel (64 channels: g = 4, 128: g = 2); the stride-2 convolutions read gathered
                 # tap-major rows
                 if self._frames_ok(li):
-                    # layers 2-4 (11x11, 6x6, 3x3 grids): table-driven convolutions whose GEMM rows are whole frames
+                    # every layer whose widths tile the 256-wide N (all four at the real widths): table-driven convolutions
+                    # whose GEMM rows are whole frames
                     # (ops.conv_frames): no ring, no gather buffers, no flops on the zero padding.  Specs are built per
                     # input geometry at the first forward.
                     f[(li, bi)] = ("frames", w1, b1, blk.conv1.stride[0], w2, b2, None if ds is None else (wd, bd))
@@ -388,7 +387,12 @@ class _ResEncoder(nn.Module):
         if getattr(self, "_ring0", None) is None or self._ring0[0] != key:
             # the ring of this buffer is zeroed once and never written again (the pooling kernel fills the interior only)
             self._ring0 = (key, ops.RingFrames(B * T, Hp, Wp, w.shape[0], x.device, zero=True))
-        y = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data, ring_out=self._ring0[1])
+        if f[(1, 0)][0] == "frames":
+            # layer 1 on the table-driven path too: the pooling kernel writes plain channels-last frames [B T, Hp Wp C]
+            yp = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data)
+            y = ops.FrameRows.wrap(yp.permute(0, 2, 3, 1).reshape(B * T, Hp * Wp * w.shape[0]), Hp, Wp, w.shape[0])
+        else:
+            y = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data, ring_out=self._ring0[1])
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
                 if f[(li, bi)][0] == "frames":

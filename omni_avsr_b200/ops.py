@@ -909,6 +909,15 @@ class FrameRows:
         self.N, self.H, self.W, self.C, self.PA = int(N), int(H), int(W), int(C), int(PA)
         self.buf = torch.empty((self.N, self.PA * self.C), device=device, dtype=torch.bfloat16)
 
+    @classmethod
+    def wrap(cls, buf2d: torch.Tensor, H, W, C):
+        """View an existing contiguous [N, H W C] bf16 matrix as frames (PA = H W)."""
+        if buf2d.dim() != 2 or buf2d.shape[1] != H * W * C or not buf2d.is_contiguous() or buf2d.dtype != torch.bfloat16:
+            raise ValueError("wrap: contiguous bf16 [N, H * W * C]")
+        o = cls.__new__(cls)
+        o.N, o.H, o.W, o.C, o.PA, o.buf = buf2d.shape[0], int(H), int(W), int(C), int(H) * int(W), buf2d
+        return o
+
     _pool = {}
 
     @classmethod
