@@ -387,7 +387,7 @@ class _ResEncoder(nn.Module):
         if getattr(self, "_ring0", None) is None or self._ring0[0] != key:
             # the ring of this buffer is zeroed once and never written again (the pooling kernel fills the interior only)
             self._ring0 = (key, ops.RingFrames(B * T, Hp, Wp, w.shape[0], x.device, zero=True))
-        if f[(1, 0)][0] == "frames":
+        if isinstance(f[(1, 0)][0], str):
             # layer 1 on the table-driven path too: the pooling kernel writes plain channels-last frames [B T, Hp Wp C]
             yp = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data)
             y = ops.FrameRows.wrap(yp.permute(0, 2, 3, 1).reshape(B * T, Hp * Wp * w.shape[0]), Hp, Wp, w.shape[0])
@@ -395,7 +395,7 @@ class _ResEncoder(nn.Module):
             y = ops.front3d_prelu_maxpool(x[:, 0].contiguous(), w, b, self.frontend3D[2].weight.data, ring_out=self._ring0[1])
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self.trunk, f"layer{li}")):
-                if f[(li, bi)][0] == "frames":
+                if isinstance(f[(li, bi)][0], str):          # "frames": table-driven path
                     y = self._frames_block((li, bi), y, f[(li, bi)], blk)
                     continue
                 w1, b1, s1, w2, b2, ds, g1, g2 = f[(li, bi)]
