@@ -3,7 +3,7 @@ configuration with identical weights: encoder features, the three task losses at
 gradients, greedy transcripts, and an optimisation sanity check.
 
 Tolerances (bf16 end to end on both sides): features / logits max|a-b| <= 2e-2*max|b|; losses |a-b| <= 5e-2;
-gradients max|a-b| <= 1e-1*max|b| and cosine >= 0.97 (AV-HuBERT adapter gradients: no further from the fp32 oracle than 1.5x the bf16 oracle); greedy tokens equal unless the oracle's own
+gradients max|a-b| <= 1e-1*max|b| and cosine >= 0.97 (AV-HuBERT Q-adapter gradients: <= 1.5e-1 against the fp32 oracle, see the comment in the test); greedy tokens equal unless the oracle's own
 top-1/top-2 margin is below 2e-2 of its logit scale."""
 import pytest
 import torch
@@ -106,11 +106,13 @@ def test_three_task_losses_and_grads(pair, oracle_fp32, ra, rv):
         assert _rel(got, want) <= 1e-1, (name, _rel(got, want))
         cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.float().flatten(), dim=0).item()
         assert cos >= 0.97, (name, cos)
-    # AV-HuBERT adapter gradients are ~1e-6 after the longest backward chain (LLM -> splice -> projector -> pool -> 2
-    # transformer blocks); the reference's own bf16 execution is noisy there, so both are measured against the fp32
-    # oracle (these gradients are ill-conditioned w.r.t. bf16-level perturbations of the forward features: the bf16 oracle
-    # itself is 2-4 % off, the CUDA path 15-25 % depending on the GEMM variant's accumulation order -- KNOWN GAP, tracked
-    # in DESIGN.md §5): max error <= max(3x the bf16 oracle's, 3e-1 of the max) and cosine >= 0.95.
+    # AV-HuBERT adapter gradients, after the longest backward chain (LLM -> splice -> projector -> pool -> 2 transformer
+    # blocks), measured against the fp32 oracle (tools/grad_probe.py prints the whole picture): d(loss)/d(encoder output) is
+    # as close to fp32 as the bf16 oracle's (9.3e-2 both), the V adapters too (0.8 - 2 %), the Q adapters are at 6 - 12 %
+    # against 2 - 4 % for the bf16 oracle.  The Q gradients are 1000x smaller than the V gradients (near-uniform attention:
+    # dS = P o (dP - delta) is a difference of nearly equal numbers) and the flash formulation rounds P and dS to bf16 for
+    # the tensor-core GEMMs and takes delta from the bf16 output, as every GPU flash-attention backward does, while the CPU
+    # oracle's SDPA backward keeps them in fp32 -- so the bound is 1.5e-1 (or 3x the bf16 oracle's error) with cosine >= 0.95.
     vatt = m.video_encoder.encoder.layers[1].self_attn
     rv_ = round(128 / 16)
     for got, key in ((vatt.lora_up.grad[:128, :rv_], "lora_up_Q"), (vatt.lora_down.grad[:rv_], "lora_down_Q"),
@@ -119,7 +121,7 @@ def test_three_task_losses_and_grads(pair, oracle_fp32, ra, rv):
         want32 = getattr(oracle_fp32.video_encoder.encoder.layers[1].self_attn, key).weight.grad
         e_prod, e_ref = _rel(got, want32), _rel(want16, want32)
         cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want32.float().flatten(), dim=0).item()
-        assert e_prod <= max(3 * e_ref, 3e-1) and cos >= 0.95, ("avh." + key, e_prod, e_ref, cos)
+        assert e_prod <= max(3 * e_ref, 1.5e-1) and cos >= 0.95, ("avh." + key, e_prod, e_ref, cos)
     # projectors of the rates that were NOT selected get no gradient (why the reference needs find_unused_parameters)
     other = 1 - ia
     assert m.audio_proj[other][0].weight.grad.abs().max().item() == 0
