@@ -96,6 +96,15 @@ typedef struct omni_gemm_args {
   void* workspace;         /* omni_gemm_skinny_bf16 only: split-K exchange buffer (256-byte aligned device memory, zero-filled
                               once by the caller; the kernel leaves its counters at zero), or NULL = no split-K */
   int64_t workspace_bytes; /* >= omni_gemm_skinny_workspace_bytes() */
+  /* omni_gemm_skinny_bf16 with split-K only (N = the full row width, N % 8 == 0, act NONE): RMSNorm of the finished rows in
+   * the SAME launch.  The CTA that completes the last 128-feature tile of a token slice re-reads those rows from L2 and
+   * writes norm_out[t, :] = norm_weight * bf16(out[t, :] * rsqrt(mean(out[t, :]^2) + norm_eps)) -- the arithmetic (and the
+   * bits) of omni_rmsnorm_fwd.  Replaces the LlamaRMSNorm that follows o_proj / down_proj in a decode step
+   * (post_attention_layernorm, the next layer's input_layernorm, the final norm).  norm_out NULL = off. */
+  const void* norm_weight; /* [N] bf16 */
+  void* norm_out;          /* [M, N] bf16, ld = norm_ld */
+  int64_t norm_ld;
+  float norm_eps;
 } omni_gemm_args;
 
 int omni_gemm_bf16(const omni_gemm_args* args, void* stream);

@@ -16,6 +16,7 @@ There is no CPU path: every op below launches a kernel from libomni_avsr.so.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -540,8 +541,9 @@ class LlamaSdpaAttention_lora(nn.Module):
             self._wt = (self.qkv_weight.t().contiguous(), self.o_proj.weight.data.t().contiguous())
         return self._wt
 
-    def forward(self, h, rows: PackedRows, cos_t, sin_t, kv_cache=None, residual=None):
-        """h [M, H] normed hidden rows -> residual + o_proj(attn)."""
+    def forward(self, h, rows: PackedRows, cos_t, sin_t, kv_cache=None, residual=None, norm=None):
+        """h [M, H] normed hidden rows -> residual + o_proj(attn).  norm=(weight, eps) (decode step only): also returns the
+        RMSNorm of the result, computed in the o_proj launch."""
         a = self.config
         wt_qkv, wt_o = self.transposed()
         if ag.skinny_ok(h) and self.plan.ext_fwd_step is not None:
@@ -566,7 +568,8 @@ class LlamaSdpaAttention_lora(nn.Module):
                 ops.rope_(qkv, cos_t, sin_t, rows.pos, n_rot, self.head_dim)
             attn = attention_packed(qkv, rows, a, kv_cache, self.layer_idx)
         if ag.skinny_ok(attn, residual):
-            return ops.gemm(attn, self.o_proj.weight.data, residual=residual, skinny=True)      # decode step
+            return ops.gemm(attn, self.o_proj.weight.data, residual=residual, skinny=True, norm=norm)      # decode step
+        assert norm is None
         return ag.frozen_linear(attn, self.o_proj.weight.data, wt_o, residual=residual, block_n=256)
 
 
@@ -706,9 +709,18 @@ class LlamaMLP(nn.Module):
             self._il = (w, w.t().contiguous())
         return self._il
 
-    def forward(self, h, residual):
+    def forward(self, h, residual, norm=None):
+        """residual + down(silu(gate(h)) * up(h)).  norm=(weight, eps) (decode step only): also returns the RMSNorm of the
+        result, computed in the down_proj launch."""
         wt_gu, wt_d = self.transposed()
         I = self.gate_up_weight.shape[0] // 2
+        if ag.skinny_ok(h, residual) and I % 64 == 0:
+            # decode step: weight-streaming kernel, SwiGLU in its epilogue (only the activation is written)
+            w_il, _ = self.interleaved()
+            act = torch.empty((h.shape[0], I), device=h.device, dtype=torch.bfloat16)
+            ops.gemm(h, w_il, act="swiglu64", out2=act, skinny=True)
+            return ops.gemm(act, self.down_proj.weight.data, residual=residual, skinny=True, norm=norm)
+        assert norm is None, "the fused norm belongs to the decode step"
         if h.requires_grad and I % 256 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I) \
                 and ag.pair_kernel_shape(h.shape[0], I):
             # SwiGLU in the gate_up GEMM's epilogue, its backward in the epilogue of down_proj's dgrad GEMM
@@ -717,12 +729,6 @@ class LlamaMLP(nn.Module):
         if h.requires_grad and I % 64 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I):
             w_il, wt_il = self.interleaved()
             act = ag.GateUpSwigluFn.apply(h, w_il, wt_il)          # SwiGLU in the gate_up GEMM's epilogue
-        elif ag.skinny_ok(h, residual) and I % 64 == 0:
-            # decode step: weight-streaming kernel, SwiGLU in its epilogue (only the activation is written)
-            w_il, _ = self.interleaved()
-            act = torch.empty((h.shape[0], I), device=h.device, dtype=torch.bfloat16)
-            ops.gemm(h, w_il, act="swiglu64", out2=act, skinny=True)
-            return ops.gemm(act, self.down_proj.weight.data, residual=residual, skinny=True)
         elif not h.requires_grad and I % 64 == 0 and ag.gate_up_swiglu_supported(h.shape[0], 2 * I):
             # prefill / evaluation: SwiGLU in the gate_up GEMM's epilogue, the gate|up tile itself is never written
             w_il, _ = self.interleaved()
@@ -732,6 +738,9 @@ class LlamaMLP(nn.Module):
             gu = ag.frozen_linear(h, self.gate_up_weight, wt_gu, block_n=256)
             act = ag.swiglu(gu)
         return ag.frozen_linear(act, self.down_proj.weight.data, wt_d, residual=residual, block_n=256)
+
+
+_FUSED_STEP_NORM = bool(os.environ.get("OMNI_DECODE_FUSED_NORM"))
 
 
 class _NormWeight(nn.Module):
@@ -759,6 +768,13 @@ class LlamaDecoderLayer_lora(nn.Module):
         self.mlp = LlamaMLP(config, device)
         self.input_layernorm = _NormWeight(config.hidden_size, config.rms_norm_eps, device)
         self.post_attention_layernorm = _NormWeight(config.hidden_size, config.rms_norm_eps, device)
+
+    def forward_step(self, x, h, rows, cos_t, sin_t, kv_cache, next_norm):
+        """Decode step: x = residual stream, h = input_layernorm(x) (computed by the previous launch).  Both RMSNorms that
+        follow this layer's o_proj / down_proj run inside those GEMM launches; returns (x_out, next_norm(x_out))."""
+        post = (self.post_attention_layernorm.weight.data, self.post_attention_layernorm.variance_epsilon)
+        x, h = self.self_attn(h, rows, cos_t, sin_t, kv_cache, residual=x, norm=post)
+        return self.mlp(h, residual=x, norm=next_norm)
 
     def forward(self, x, rows, cos_t, sin_t, kv_cache=None):
         res, h = self.input_layernorm.with_residual(x)
@@ -798,6 +814,19 @@ class LlamaModel_lora(nn.Module):
 
     def forward_packed(self, x, rows: PackedRows, kv_cache=None):
         cos_t, sin_t = self.rope(rows.max_pos)
+        I = self.layers[0].mlp.gate_up_weight.shape[0] // 2
+        if (_FUSED_STEP_NORM and kv_cache is not None and kv_cache.graph_mode and ag.skinny_ok(x) and I % 64 == 0
+                and all(S == 1 for (_, _, S, _) in rows.segments) and self.layers[0].self_attn.plan.ext_fwd_step is not None):
+            # decode step with every RMSNorm but the first in the epilogue of the GEMM that produces its input (the CTA that
+            # completes a token slice normalises it; bit-identical).  OFF by default: measured SLOWER at B = 64 (Llama-1B
+            # 1.50 ms per step against 1.36, Qwen2.5-3B 4.24 against 3.85) -- the fence + arrival atomic of all 128 CTAs and
+            # the serial two-pass tail of the last one cost more than the 2.7 us norm kernel they remove under programmatic
+            # dependent launch.  OMNI_DECODE_FUSED_NORM=1 turns it on.
+            h = self.layers[0].input_layernorm(x)
+            for i, layer in enumerate(self.layers):
+                nxt = self.layers[i + 1].input_layernorm if i + 1 < len(self.layers) else self.norm
+                x, h = layer.forward_step(x, h, rows, cos_t, sin_t, kv_cache, (nxt.weight.data, nxt.variance_epsilon))
+            return h
         for layer in self.layers:
             x = layer(x, rows, cos_t, sin_t, kv_cache)
         return self.norm(x)

@@ -13,6 +13,7 @@ import torch
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libomni_avsr.so"
 
+OMNI_ERR_UNSUPPORTED = -4
 ERR = {-1: "bad argument", -2: "CUDA error", -3: "CUDA driver entry point unavailable", -4: "unsupported",
        -5: "workspace too small"}
 
@@ -52,6 +53,7 @@ class GemmArgs(C.Structure):
         ("slope", C.c_void_p), ("res_bias", C.c_void_p),
         ("ring_h", C.c_int32), ("ring_w", C.c_int32), ("ring_group", C.c_int32), ("ring_c", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("norm_weight", C.c_void_p), ("norm_out", C.c_void_p), ("norm_ld", C.c_int64), ("norm_eps", C.c_float),
     ]
 
 

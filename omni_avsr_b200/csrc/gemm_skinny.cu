@@ -51,6 +51,12 @@ struct SkinnyParams {
   float alpha;
   bf16* out2;               // SWIGLU64: [M, N / 2]
   long long ldo2;
+  // fused RMSNorm of the finished rows (split-K launches only): see omni_gemm_args.norm_out
+  const bf16* norm_w;
+  bf16* norm_out;
+  long long norm_ld;
+  float norm_eps;
+  int* norm_cnt;            // [SPLIT] arrivals per token slice, zero between launches (self-resetting)
 };
 
 template <int NTOK, int SPLIT, int STAGES>
@@ -358,6 +364,58 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           }
         }
       }
+      if constexpr (SPLIT > 1) {
+        if (p.norm_out) {
+          // Fused RMSNorm: this CTA has written features [n0, n0 + 128) of the token slice [rank * TSL, rank * TSL + TSL).  The
+          // CTA that completes the slice's LAST feature tile normalises its rows (re-read from L2, where every CTA's stores
+          // landed) -- one warp per row, chunks lane, lane + 32, ... and the butterfly sum of rmsnorm_fwd_kernel: same bits.
+          __shared__ int s_last;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            __threadfence();
+            const int old = atomicAdd(p.norm_cnt + rank, 1);
+            s_last = (old == p.n_tiles - 1) ? 1 : 0;
+            if (s_last) p.norm_cnt[rank] = 0;          // every CTA of the slice has arrived: ready for the next launch
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (s_last) {
+            __threadfence();
+            const int H8 = p.N >> 3;
+            for (int t = warp - 2; t < TSL; t += 4) {
+              const int tg = tok0 + t;
+              if (tg >= p.M) continue;
+              const uint4* xr = reinterpret_cast<const uint4*>(p.out + static_cast<long long>(tg) * p.ldo);
+              float ss = 0.f;
+              for (int c = lane; c < H8; c += 32) {
+                const uint4 u = __ldcg(xr + c);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = bf2_to_f2(w4[i]);
+                  ss += f.x * f.x;
+                  ss += f.y * f.y;
+                }
+              }
+              ss = warp_sum(ss);
+              const float rstd = rsqrtf(ss / static_cast<float>(H8 * 8) + p.norm_eps);
+              uint4* yr = reinterpret_cast<uint4*>(p.norm_out + static_cast<long long>(tg) * p.norm_ld);
+              for (int c = lane; c < H8; c += 32) {
+                const uint4 u = __ldcg(xr + c);
+                const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.norm_w) + c);
+                const uint32_t x4[4] = {u.x, u.y, u.z, u.w}, g4[4] = {g.x, g.y, g.z, g.w};
+                uint32_t o4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = bf2_to_f2(x4[i]), gw = bf2_to_f2(g4[i]);
+                  o4[i] = f2_to_bf2(gw.x * __bfloat162float(__float2bfloat16_rn(f.x * rstd)),
+                                    gw.y * __bfloat162float(__float2bfloat16_rn(f.y * rstd)));
+                }
+                yr[c] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+              }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -432,6 +490,14 @@ extern "C" int omni_gemm_skinny_bf16(const omni_gemm_args* a, void* stream) {
   p.ldo = a->ldo; p.ldr = a->ldr;
   p.act = a->act; p.alpha = a->alpha;
   p.out2 = reinterpret_cast<bf16*>(a->out2); p.ldo2 = a->ldo2;
+  p.norm_w = reinterpret_cast<const bf16*>(a->norm_weight);
+  p.norm_out = reinterpret_cast<bf16*>(a->norm_out);
+  p.norm_ld = a->norm_ld; p.norm_eps = a->norm_eps;
+  if (a->norm_out) {
+    OMNI_CHECK_ARG(a->norm_weight && a->out && (a->N % 8) == 0 && (a->norm_ld % 8) == 0 && a->norm_ld >= a->N &&
+                   (reinterpret_cast<uintptr_t>(a->norm_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->norm_weight) & 15) == 0);
+    if (a->act != OMNI_ACT_NONE || !a->workspace) return OMNI_ERR_UNSUPPORTED;
+  }
 
   // split K until ~all SMs stream weights; the ranks of a tile wait for each other, so the whole grid must be resident:
   // n_tiles * split <= SM count (one CTA per SM at this shared-memory footprint)
@@ -465,6 +531,11 @@ extern "C" int omni_gemm_skinny_bf16(const omni_gemm_args* a, void* stream) {
       return OMNI_ERR_WORKSPACE;
     p.ws_cnt = reinterpret_cast<int*>(a->workspace);                          // counters first (they stay zero between launches)
     p.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + cnt);
+    // the fused norm's per-slice arrival counters sit in the last 32 bytes of the counter region
+    if (a->norm_out && p.n_tiles * 8 > cnt - 32) return OMNI_ERR_UNSUPPORTED;
+    p.norm_cnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(a->workspace) + cnt - 32);
+  } else if (a->norm_out) {
+    return OMNI_ERR_UNSUPPORTED;               // no split-K: one CTA would have to normalise every row
   }
 
   CUtensorMap tmW, tmX, tmW2, tmX2;

@@ -54,7 +54,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          alpha: float = 1.0, n: Optional[int] = None, tile_group: Optional[torch.Tensor] = None,
          b_row_table: Optional[torch.Tensor] = None, ext: Optional[tuple] = None, block_n: int = 0,
          pair_aligned: bool = False, out2: Optional[torch.Tensor] = None, skinny: bool = False,
-         prelu_ring: Optional[tuple] = None) -> torch.Tensor:
+         prelu_ring: Optional[tuple] = None, norm: Optional[tuple] = None) -> torch.Tensor:
     """out[M,N] = epi(alpha * (a[M,K] @ b[rows,K]^T (+ K-extension)))  -- tcgen05 kernel.
 
     ext = (a2 [M, a2_cols], b2 [b2_rows, b2_cols], ext_table int32 [groups, n_tiles, n_ext, 4]).
@@ -65,6 +65,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     skinny=True (M <= 128, K % 64 == 0, bf16 out): the weight-streaming decode-step kernel (omni_gemm_skinny_bf16: weights on
     the M side of the MMA, split-K over a cluster); b_row_table per 64-feature block, ext table per 128-feature tile
     (block_n=128).  act="swiglu64" with out=None writes only out2 = the activation (both kernels).
+    norm=(weight [N], eps) with skinny=True: returns (out, rmsnorm(out)) -- the RMSNorm that follows o_proj / down_proj in a
+    decode step runs in the same launch (the CTA that completes a token slice normalises it; same bits as rmsnorm_fwd);
+    shapes the fused form does not take run the GEMM and the norm kernel.
     act="swiglu_bwd64" / "gelu_bwd" (fused backward epilogues, CTA-pair kernel only): a @ b^T is d(activation) and never
     reaches memory; `residual` carries the tensor saved by the forward (gate|up blocks [M, 2N] / pre-activation [M, N]) and
     `out` (required) receives its gradient ([M, 2N] / [M, N])."""
@@ -72,7 +75,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         return _gemm_fused_bwd(a, b, residual, out, act)
     return _gemm(a, b, bias=bias, act=act, residual=residual, out=out, out_dtype=out_dtype, alpha=alpha, n=n,
                  tile_group=tile_group, b_row_table=b_row_table, ext=ext, block_n=block_n, pair_aligned=pair_aligned, out2=out2,
-                 skinny=skinny, prelu_ring=prelu_ring)
+                 skinny=skinny, prelu_ring=prelu_ring, norm=norm)
 
 
 def _gemm_fused_bwd(a, b, saved, out, act):
@@ -94,7 +97,7 @@ def _gemm_fused_bwd(a, b, saved, out, act):
 
 
 def _gemm(a, b, *, bias, act, residual, out, out_dtype, alpha, n, tile_group, b_row_table, ext, block_n, pair_aligned, out2,
-          skinny, prelu_ring):
+          skinny, prelu_ring, norm=None):
     require_cuda(a, b, bias, residual, out, tile_group, b_row_table)
     a = _bf16_2d(a, "a")
     b = _bf16_2d(b, "b")
@@ -172,9 +175,25 @@ def _gemm(a, b, *, bias, act, residual, out, out_dtype, alpha, n, tile_group, b_
     if skinny:
         ws = _skinny_workspace(a.device)
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+        if norm is not None:
+            nw, eps = norm
+            require_cuda(nw)
+            h = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+            g.norm_weight, g.norm_out, g.norm_ld, g.norm_eps = nw.data_ptr(), h.data_ptr(), N, float(eps)
+            rc = lib.omni_gemm_skinny_bf16(C.byref(g), stream_ptr())
+            if rc == _lib.OMNI_ERR_UNSUPPORTED:          # no split-K for this shape: GEMM, then the norm kernel
+                g.norm_weight, g.norm_out = None, None
+                check(lib.omni_gemm_skinny_bf16(C.byref(g), stream_ptr()), "omni_gemm_skinny_bf16")
+                _count()
+                return out, rmsnorm_fwd(out, nw, eps)
+            check(rc, "omni_gemm_skinny_bf16 (+rmsnorm)")
+            _count()
+            return out, h
         check(lib.omni_gemm_skinny_bf16(C.byref(g), stream_ptr()), "omni_gemm_skinny_bf16")
         _count()
         return out2 if skinny_swiglu else out
+    if norm is not None:
+        raise ValueError("norm= is a decode-step (skinny=True) epilogue")
     check(lib.omni_gemm_bf16(C.byref(g), stream_ptr()), "omni_gemm_bf16")
     _count()
     return out2 if skinny_swiglu else out

@@ -121,3 +121,24 @@ def test_skinny_lora_k_extension_and_grouped_rows(task):
     T2 = ops.gemm(h, down, n=plan.t_cols, alpha=s, tile_group=tg, b_row_table=plan.brow_fwd, block_n=64)
     out2 = ops.gemm(h, W, bias=b, tile_group=tg, ext=(T2, up, plan.ext_fwd_64), block_n=64)
     assert _rel(T, T2) <= 8e-3 and _rel(out, out2) <= 8e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 2048, 2048), (64, 2048, 8192), (37, 2048, 2048), (128, 4096, 4096), (64, 16384, 2048)])
+def test_fused_rmsnorm_of_the_finished_rows_is_bit_identical(M, N, K):
+    """norm=(weight, eps): the RMSNorm that follows o_proj / down_proj in a decode step runs in the GEMM launch (the CTA that
+    completes a token slice normalises it) and equals omni_rmsnorm_fwd of the GEMM's output bit for bit; output and residual
+    add unchanged.  N = 16384 has no split-K: the wrapper runs GEMM + norm kernel.  Run twice: the arrival counters reset."""
+    from omni_avsr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    nw = (1.0 + 0.1 * torch.randn(N, device="cuda", generator=g)).bfloat16()
+    want = ops.gemm(x, W, residual=res, skinny=True)
+    want_h = ops.rmsnorm_fwd(want, nw, 1e-5)
+    for _ in range(2):
+        launches = ops.LAUNCHES
+        out, h = ops.gemm(x, W, residual=res, skinny=True, norm=(nw, 1e-5))
+        assert ops.LAUNCHES - launches == (1 if N <= 4096 else 2)
+        assert torch.equal(out.view(torch.int16), want.view(torch.int16))
+        assert torch.equal(h.view(torch.int16), want_h.view(torch.int16))
