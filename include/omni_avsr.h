@@ -383,6 +383,15 @@ int omni_ce_fwd(const void* logits, const int64_t* targets, float* loss, float* 
 int omni_ce_bwd(void* logits, const int64_t* targets, const float* lse, const float* scale, int64_t rows, int32_t V,
                 int64_t ld, int64_t ignore_index, void* stream);
 int omni_argmax(const void* logits, int64_t* out, int64_t rows, int32_t V, int64_t ld, void* stream);
+/* Token bookkeeping of one greedy decode step in ONE launch (HF `_sample` semantics of transformers 4.43.1, driven by
+ * modeling_OmniAVSR.py:313-322): tok = argmax(logits[b, :V]) (first maximal index), pad for finished sequences;
+ * out[step, b] = tok; unfinished[b] &= tok != eos; alive[step] = any unfinished (caller zeroes alive once per decode);
+ * x_next[b, :] = embed[tok, :] (the next forward's input row).  step / eos / pad are device scalars (CUDA-graph replay).
+ * omni_decode_advance: step_idx += 1, len_idx += 1, pos[0..n_pos) += 1 after the step's forward. */
+int omni_decode_pick(const void* logits, int32_t V, int64_t ld, int64_t* unfinished, const int64_t* eos, const int64_t* pad,
+                     const int64_t* step_idx, int64_t* out, int32_t B, int64_t* alive, const void* embed, int64_t ld_embed,
+                     void* x_next, int64_t ld_x, int32_t H, void* stream);
+int omni_decode_advance(int64_t* step_idx, int64_t* len_idx, int32_t* pos, int32_t n_pos, void* stream);
 int omni_sumsq(const void* g, int64_t n, float* acc, void* stream);
 int omni_adamw(void* p, const void* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int32_t step, float grad_scale, float max_norm, const float* sumsq, void* stream);

@@ -162,6 +162,8 @@ _sig("omni_attention_fwd", [_P, _I64, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32
 _sig("omni_attention_bwd", [_P, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32,
                             _I32, _F, _P])
 _sig("omni_attention_bwd_scratch_floats", [_I32, _I32, _I32], C.c_int64)
+_sig("omni_decode_pick", [_P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _I64, _P, _I64, _I32, _P])
+_sig("omni_decode_advance", [_P, _P, _P, _I32, _P])
 _sig("omni_decode_attention", [_P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P])
 _sig("omni_decode_attention_rope", [_P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _I32, _P])
 _sig("omni_logmel_workspace_bytes", [_I32], C.c_int64)
@@ -176,7 +178,7 @@ EXPORTS = [
     "omni_matryoshka_compress_bwd", "omni_splice_seq_len", "omni_splice_prompt", "omni_splice_prompt_bwd",
     "omni_rmsnorm_fwd", "omni_rmsnorm_bwd", "omni_layernorm_fwd", "omni_layernorm_bwd", "omni_rope",
     "omni_swiglu_fwd", "omni_swiglu_bwd", "omni_swiglu_bwd_blocked", "omni_gelu_fwd", "omni_gelu_bwd", "omni_gather_rows", "omni_scatter_rows",
-    "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
+    "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_decode_pick", "omni_decode_advance", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
     "omni_colsum_bf16", "omni_logmel_workspace_bytes", "omni_logmel", "omni_prelu_res", "omni_prelu_maxpool3x3s2",
     "omni_im2col_front3d", "omni_im2col_front2d", "omni_prelu_maxpool_front", "omni_prelu_maxpool_front_ring", "omni_prelu_res_ring", "omni_gather_s2_ring", "omni_avgpool_ring", "omni_avgpool_frames", "omni_attention_fwd", "omni_attention_bwd", "omni_attention_bwd_scratch_floats", "omni_decode_attention", "omni_decode_attention_rope",
     "omni_transpose_bf16", "omni_pps_workspace_bytes", "omni_pool_project_splice", "omni_video_transform", "omni_audio_transform_workspace_bytes", "omni_audio_transform",

@@ -140,6 +140,82 @@ argmax_kernel(const bf16* __restrict__ logits, int64_t* __restrict__ out, int V,
   }
 }
 
+// One launch for the token bookkeeping of a greedy decode step (HF `_sample` semantics, transformers 4.43.1, as driven by
+// modeling_OmniAVSR.py:313-322): argmax of the row (16-byte loads; first maximal index, as torch.argmax), pad for finished
+// sequences, the output slot of this step, the unfinished flag (EOS), "any sequence still running", and the embedding row of
+// the chosen token written straight into the next forward's input.  Replaces argmax + ~12 elementwise / index ATen kernels.
+__global__ void __launch_bounds__(CE_THREADS)
+decode_pick_kernel(const bf16* __restrict__ logits, int V, long long ld, long long* __restrict__ unfinished,
+                   const long long* __restrict__ eos, const long long* __restrict__ pad, const long long* __restrict__ step_idx,
+                   long long* __restrict__ out, int B, long long* __restrict__ alive, const bf16* __restrict__ embed,
+                   long long ld_embed, bf16* __restrict__ x_next, long long ld_x, int H8) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  __shared__ long long s_tok;
+  const int b = blockIdx.x;
+  const bf16* row = logits + static_cast<long long>(b) * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  auto take = [&](float f, int v) {
+    if (f > best || (f == best && v < bi)) { best = f; bi = v; }
+  };
+  const int V8 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (V >> 3) : 0;      // 16-byte chunks when the row is aligned
+  for (int c = threadIdx.x; c < V8; c += CE_THREADS) {
+    const uint4 u = ld_nc_u4(reinterpret_cast<const uint4*>(row) + c);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = bf2_to_f2(w[i]);
+      take(f.x, c * 8 + 2 * i);
+      take(f.y, c * 8 + 2 * i + 1);
+    }
+  }
+  for (int v = V8 * 8 + threadIdx.x; v < V; v += CE_THREADS) take(__bfloat162float(row[v]), v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float f2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (f2 > best || (f2 == best && i2 < bi)) { best = f2; bi = i2; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < CE_THREADS / 32 ? sv[lane] : -INFINITY;
+    bi = lane < CE_THREADS / 32 ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float f2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (f2 > best || (f2 == best && i2 < bi)) { best = f2; bi = i2; }
+    }
+    if (lane == 0) {
+      const long long step = *step_idx;
+      const long long u = unfinished[b];
+      const long long tok = u ? static_cast<long long>(bi) : *pad;       // next = argmax * unfinished + pad * (1 - unfinished)
+      out[step * B + b] = tok;
+      const long long u2 = (u && tok != *eos) ? 1 : 0;
+      unfinished[b] = u2;
+      if (u2) atomicMax(reinterpret_cast<unsigned long long*>(alive + step), 1ull);
+      s_tok = tok;
+    }
+  }
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(embed + s_tok * ld_embed);
+  uint4* dst = reinterpret_cast<uint4*>(x_next + static_cast<long long>(b) * ld_x);
+  for (int c = threadIdx.x; c < H8; c += CE_THREADS) dst[c] = __ldg(src + c);
+}
+
+// step_idx += 1, len_idx += 1, pos[i] += 1: the device-side counters of the captured decode step, after its forward
+__global__ void decode_advance_kernel(long long* step_idx, long long* len_idx, int* pos, int n_pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pos) pos[i] += 1;
+  if (i == 0) {
+    *step_idx += 1;
+    *len_idx += 1;
+  }
+}
+
 // sum of squares of a bf16 buffer into *acc (fp32, atomically) -- global grad norm
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const bf16* __restrict__ g, long long n8, long long n, float* __restrict__ acc) {
@@ -228,6 +304,27 @@ extern "C" int omni_argmax(const void* logits, int64_t* out, int64_t rows, int32
   OMNI_CHECK_ARG(logits && out && rows >= 0 && V > 0 && ld >= V);
   if (rows == 0) return OMNI_OK;
   argmax_kernel<<<(unsigned)rows, CE_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)logits, out, V, ld);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_decode_pick(const void* logits, int32_t V, int64_t ld, int64_t* unfinished, const int64_t* eos,
+                                const int64_t* pad, const int64_t* step_idx, int64_t* out, int32_t B, int64_t* alive,
+                                const void* embed, int64_t ld_embed, void* x_next, int64_t ld_x, int32_t H, void* stream) {
+  OMNI_CHECK_ARG(logits && unfinished && eos && pad && step_idx && out && alive && embed && x_next && B > 0 && V > 0 && ld >= V);
+  OMNI_CHECK_ARG(H > 0 && (H % 8) == 0 && (ld_embed % 8) == 0 && (ld_x % 8) == 0 &&
+                 (reinterpret_cast<uintptr_t>(embed) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_next) & 15) == 0);
+  decode_pick_kernel<<<(unsigned)B, CE_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)logits, V, ld, (long long*)unfinished, (const long long*)eos, (const long long*)pad,
+      (const long long*)step_idx, (long long*)out, B, (long long*)alive, (const bf16*)embed, ld_embed, (bf16*)x_next, ld_x, H / 8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_decode_advance(int64_t* step_idx, int64_t* len_idx, int32_t* pos, int32_t n_pos, void* stream) {
+  OMNI_CHECK_ARG(step_idx && len_idx && pos && n_pos >= 0);
+  decode_advance_kernel<<<(n_pos + 255) / 256 + (n_pos == 0), 256, 0, (cudaStream_t)stream>>>(
+      (long long*)step_idx, (long long*)len_idx, pos, n_pos);
   OMNI_LAUNCH_CHECK();
   return OMNI_OK;
 }

@@ -63,19 +63,13 @@ class GraphedGreedyStep:
         """pick token from h_last -> bookkeeping -> (embed -> layers) -> new h_last, advance device state."""
         llm, B = self.llm, self.B
         logits = llm.logits_rows(self.h_last)
-        nxt = ops.argmax_rows(logits)
-        nxt = nxt * self.unfinished + self.pad * (1 - self.unfinished)
-        self.out.index_copy_(0, self.step_idx, nxt.unsqueeze(0))
-        self.unfinished.mul_((nxt != self.eos).long())
-        self.alive.index_copy_(0, self.step_idx, self.unfinished.max().unsqueeze(0))
-        self.step_idx.add_(1)
+        # argmax + pad-after-EOS + output slot + unfinished / alive flags + embedding row of the chosen token: one launch
+        ops.decode_pick(logits, llm.config.vocab_size, self.unfinished, self.eos, self.pad, self.step_idx, self.out,
+                        self.alive, llm.model.embed_tokens.weight.data, self.xpad)
         # forward of the chosen token
-        x = ops.gather_rows(llm.model.embed_tokens.weight.data, nxt.contiguous())
-        self.xpad[:B].copy_(x)
         hid = llm.model.forward_packed(self.xpad, self.rows, self.cache)
         self.h_last.copy_(hid[:B])
-        self.cache.len_idx.add_(1)
-        self.rows.pos.add_(1)
+        ops.decode_advance(self.step_idx, self.cache.len_idx, self.rows.pos)
 
     def start(self, task, prefill_len, h_last, eos, pad):
         self.rows.tile_group.fill_(task)

@@ -569,6 +569,33 @@ def ce_bwd_(logits, targets, lse, scale, ignore_index: int = -100):
     return logits
 
 
+def decode_pick(logits, V: int, unfinished, eos, pad, step_idx, out, alive, embed, x_next):
+    """Token bookkeeping of one greedy decode step in one launch (see omni_decode_pick): argmax, pad-after-EOS, output slot,
+    unfinished / alive flags, embedding row of the chosen token into x_next[:B]."""
+    require_cuda(logits, unfinished, eos, pad, step_idx, out, alive, embed, x_next)
+    B = unfinished.shape[0]
+    for t in (unfinished, eos, pad, step_idx, out, alive):
+        if t.dtype != torch.int64 or not t.is_contiguous():
+            raise TypeError("decode_pick: int64 contiguous state tensors")
+    if logits.dtype != torch.bfloat16 or embed.dtype != torch.bfloat16 or x_next.dtype != torch.bfloat16:
+        raise TypeError("decode_pick: bf16 logits / embed / x_next")
+    if logits.shape[0] != B or x_next.shape[0] < B or out.shape[1] != B or embed.shape[1] != x_next.shape[1]:
+        raise ValueError("decode_pick: shape mismatch")
+    check(lib.omni_decode_pick(logits.data_ptr(), V, logits.stride(0), unfinished.data_ptr(), eos.data_ptr(), pad.data_ptr(),
+                               step_idx.data_ptr(), out.data_ptr(), B, alive.data_ptr(), embed.data_ptr(), embed.stride(0),
+                               x_next.data_ptr(), x_next.stride(0), embed.shape[1], stream_ptr()), "omni_decode_pick")
+    _count()
+
+
+def decode_advance(step_idx, len_idx, pos):
+    require_cuda(step_idx, len_idx, pos)
+    if step_idx.dtype != torch.int64 or len_idx.dtype != torch.int64 or pos.dtype != torch.int32:
+        raise TypeError("decode_advance: int64 counters, int32 positions")
+    check(lib.omni_decode_advance(step_idx.data_ptr(), len_idx.data_ptr(), pos.data_ptr(), pos.numel(), stream_ptr()),
+          "omni_decode_advance")
+    _count()
+
+
 def argmax_rows(logits):
     require_cuda(logits)
     R, V = logits.shape
