@@ -5,8 +5,7 @@
 // Reference semantics (third-party transformers==4.43.1 classes used by Omni_AVSR/Llama_LoRA.py:12, Qwen_LoRA.py:7):
 //   LlamaRMSNorm / Qwen2RMSNorm, apply_rotary_pos_emb (Llama_LoRA.py:277), LlamaMLP (SwiGLU),
 //   fairseq LayerNorm + gelu (av_hubert/fairseq/fairseq/modules/{layer_norm,gelu}.py), WhisperEncoderLayer LN/GELU.
-#include "common.cuh"
-#include "../../include/omni_avsr.h"
+#include "gemm_epilogue.cuh"      // gelu_fast / gelu_grad_fast (shared with the GEMM epilogues: same bits)
 
 namespace omni {
 
@@ -388,11 +387,7 @@ gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* _
     unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(x) + idx), f);
     unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(dy) + idx), d);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float cdf = 0.5f * (1.0f + erff(f[i] * 0.70710678118654752440f));
-      const float pdf = 0.39894228040143267794f * __expf(-0.5f * f[i] * f[i]);
-      f[i] = d[i] * (cdf + f[i] * pdf);
-    }
+    for (int i = 0; i < 8; ++i) f[i] = d[i] * gelu_grad_fast(f[i]);
     st_na_u4(reinterpret_cast<uint4*>(dx) + idx, pack8(f));
   }
 }

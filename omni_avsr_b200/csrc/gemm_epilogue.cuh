@@ -71,6 +71,25 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * (x < 0.f ? h : 1.0f - h);
 }
 
+// d gelu(x) / dx = Phi(x) + x * phi(x) with the same one-MUFU Phi as gelu_fast (plus one ex2 for the density): ~20 instructions
+// against ~45 for erff + __expf -- the stand-alone backward kernel was compute-bound at 2x its HBM time.  Relative error of
+// Phi <= 7e-6 (see gelu_fast), of phi the ex2.approx error (2^-22).
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.5f);
+  float q = -2.045480869e-05f;
+  q = fmaf(q, z, 4.882984795e-04f);
+  q = fmaf(q, z, -5.237891804e-03f);
+  q = fmaf(q, z, 3.395747021e-02f);
+  q = fmaf(q, z, -1.525140703e-01f);
+  q = fmaf(q, z, -9.170033932e-01f);
+  q = fmaf(q, z, -1.628095627e+00f);
+  q = fmaf(q, z, 3.904249297e-06f - 1.0f);
+  const float h = ex2_approx(q);                                   // Phi(-|x|)
+  const float cdf = x < 0.f ? h : 1.0f - h;
+  const float pdf = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x * x);     // exp(-x^2 / 2) / sqrt(2 pi)
+  return fmaf(x, pdf, cdf);
+}
+
 // Epilogue of 32 accumulator columns of one row: alpha, bias, rounding point, activation, residual, store.
 __device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&v)[32], int row, int col0,
                                                   const ResPrefetch* pre = nullptr) {
@@ -333,11 +352,7 @@ __device__ __forceinline__ void gelu_bwd_row64(const float (&v)[64], const uint3
     const float2 xf = bf2_to_f2(x[i]);
     const float d0 = __bfloat162float(__float2bfloat16_rn(v[2 * i]));
     const float d1 = __bfloat162float(__float2bfloat16_rn(v[2 * i + 1]));
-    const float c0 = 0.5f * (1.0f + erff(xf.x * 0.70710678118654752440f));
-    const float c1 = 0.5f * (1.0f + erff(xf.y * 0.70710678118654752440f));
-    const float p0 = 0.39894228040143267794f * __expf(-0.5f * xf.x * xf.x);
-    const float p1 = 0.39894228040143267794f * __expf(-0.5f * xf.y * xf.y);
-    dx[i] = f2_to_bf2(d0 * (c0 + xf.x * p0), d1 * (c1 + xf.y * p1));
+    dx[i] = f2_to_bf2(d0 * gelu_grad_fast(xf.x), d1 * gelu_grad_fast(xf.y));
   }
 }
 
