@@ -71,6 +71,26 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * (x < 0.f ? h : 1.0f - h);
 }
 
+// gelu_fast on two values with packed fp32 arithmetic (FMUL2 / FFMA2): the same operations per lane, hence the same bits, at
+// ~9.5 instead of ~15 issue slots per element -- the GELU epilogues of the K = 1024 encoder GEMMs are issue-bound (two
+// epilogue warps per sub-partition against a 4096-clk main loop).
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  float2 z = fmul2(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  z.x = fminf(z.x, 4.5f);
+  z.y = fminf(z.y, 4.5f);
+  auto c2 = [](float c) { return make_float2(c, c); };
+  float2 q = c2(-2.045480869e-05f);
+  q = ffma2(q, z, c2(4.882984795e-04f));
+  q = ffma2(q, z, c2(-5.237891804e-03f));
+  q = ffma2(q, z, c2(3.395747021e-02f));
+  q = ffma2(q, z, c2(-1.525140703e-01f));
+  q = ffma2(q, z, c2(-9.170033932e-01f));
+  q = ffma2(q, z, c2(-1.628095627e+00f));
+  q = ffma2(q, z, c2(3.904249297e-06f - 1.0f));
+  const float h0 = ex2_approx(q.x), h1 = ex2_approx(q.y);
+  return fmul2(x, make_float2(x.x < 0.f ? h0 : 1.0f - h0, x.y < 0.f ? h1 : 1.0f - h1));
+}
+
 // d gelu(x) / dx = Phi(x) + x * phi(x) with the same one-MUFU Phi as gelu_fast (plus one ex2 for the density): ~20 instructions
 // against ~45 for erff + __expf -- the stand-alone backward kernel was compute-bound at 2x its HBM time.  Relative error of
 // Phi <= 7e-6 (see gelu_fast), of phi the ex2.approx error (2^-22).
@@ -234,22 +254,33 @@ __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* s
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 b = __ldg(bp + i);
-      float2 f;
-      f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-      f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-      f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-      f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                 // packed fp32 adds (FADD2): same sums, half the issue slots
+        const float2 r = fadd2(make_float2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]), bf2_to_f2(bw[j]));
+        v[8 * i + 2 * j] = r.x;
+        v[8 * i + 2 * j + 1] = r.y;
+      }
     }
   }
   if (p.act != OMNI_ACT_NONE || p.residual) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    for (int i = 0; i < 64; i += 2) {               // one packed conversion per pair (same round-to-nearest-even)
+      const float2 f = bf2_to_f2(f2_to_bf2(v[i], v[i + 1]));
+      v[i] = f.x;
+      v[i + 1] = f.y;
+    }
     if (p.act == OMNI_ACT_RELU) {
 #pragma unroll
       for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
     } else if (p.act == OMNI_ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_fast(v[i])));
+      for (int i = 0; i < 64; i += 2) {
+        const float2 g = gelu_fast2(make_float2(v[i], v[i + 1]));
+        const float2 f = bf2_to_f2(f2_to_bf2(g.x, g.y));
+        v[i] = f.x;
+        v[i + 1] = f.y;
+      }
     }
   }
   uint8_t* my_row = stage + lane * EPI_PITCH;
@@ -258,11 +289,13 @@ __device__ __forceinline__ void epilogue_tile64(const GemmKParams& p, uint8_t* s
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 b = *reinterpret_cast<const uint4*>(my_row + 16 * i);
-      float2 f;
-      f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-      f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-      f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-      f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 r = fadd2(make_float2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]), bf2_to_f2(bw[j]));
+        v[8 * i + 2 * j] = r.x;
+        v[8 * i + 2 * j + 1] = r.y;
+      }
     }
     __syncwarp();
   }

@@ -959,7 +959,11 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if constexpr (EPI == 2) {
             // v holds the rounded pre-activation that was just stored: second output = gelu of it
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = gelu_fast(v[i]);
+            for (int i = 0; i < 64; i += 2) {
+              const float2 g = gelu_fast2(make_float2(v[i], v[i + 1]));
+              v[i] = g.x;
+              v[i + 1] = g.y;
+            }
             store_tile64(p.out2, p.ldo2, p.M, stage_tile, v, lane, row0, n0 + c2 * 64);
           }
           if constexpr (EPI == 1) {
