@@ -397,6 +397,19 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // x * sigmoid(x) with the hardware reciprocal (MUFU.RCP, <= 1 ulp): an IEEE division costs ~12 instructions plus a
 // slow-path subroutine per element, which made the SwiGLU epilogue of the gate_up GEMM longer than its main loop.
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ uint32_t f2_to_bf2_pair(float2 v) { return f2_to_bf2(v.x, v.y); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid of two values: packed scaling / add around the two exponentials and the two hardware reciprocals (the operations
+// of 1 / (1 + __expf(-x)) per lane: __expf(-x) = ex2(-x * log2 e), __fdividef(1, y) = rcp.approx(y))
+__device__ __forceinline__ float2 sigmoid2(float2 x) {
+  const float2 t = fmul2(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = fadd2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
+  return make_float2(rcp_approx(e.x), rcp_approx(e.y));
+}
 
 }  // namespace omni
 

@@ -355,6 +355,7 @@ __device__ __forceinline__ void tile_to_row(uint8_t* stage, int lane, const ResT
 // output, with the hardware reciprocal for the sigmoid (<= 1 ulp before the bf16 rounding).
 __device__ __forceinline__ void swiglu_bwd_half(const uint32_t (&r)[32], float alpha, const uint32_t (&g)[32], int h,
                                                 uint8_t* my_row, uint32_t (&du)[32]) {
+  const float2 al2 = make_float2(alpha, alpha), one2 = make_float2(1.0f, 1.0f), m1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
   for (int i4 = 0; i4 < 4; ++i4) {
     // the up block of the row sits in the thread's row of the transposition tile; each 16-byte piece is replaced in place
@@ -364,14 +365,14 @@ __device__ __forceinline__ void swiglu_bwd_half(const uint32_t (&r)[32], float a
     uint32_t dgw[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+      // two channels per step, packed fp32 (FMUL2 / FFMA2): the epilogue is issue-bound, this halves its arithmetic slots
       const int i = i4 * 4 + e, w = h * 16 + i;
       const float2 gf = bf2_to_f2(g[w]), uf = bf2_to_f2(u[e]);
-      const float d0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[2 * i]) * alpha));
-      const float d1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[2 * i + 1]) * alpha));
-      const float s0 = __fdividef(1.0f, 1.0f + __expf(-gf.x));
-      const float s1 = __fdividef(1.0f, 1.0f + __expf(-gf.y));
-      du[w] = f2_to_bf2(d0 * (gf.x * s0), d1 * (gf.y * s1));
-      dgw[e] = f2_to_bf2(d0 * uf.x * (s0 * (1.0f + gf.x * (1.0f - s0))), d1 * uf.y * (s1 * (1.0f + gf.y * (1.0f - s1))));
+      const float2 d = bf2_to_f2(f2_to_bf2_pair(fmul2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), al2)));
+      const float2 s = sigmoid2(gf);
+      du[w] = f2_to_bf2_pair(fmul2(d, fmul2(gf, s)));                                        // d * silu(g)
+      const float2 t = fmul2(s, ffma2(gf, ffma2(s, m1, one2), one2));                        // s * (1 + g * (1 - s))
+      dgw[e] = f2_to_bf2_pair(fmul2(fmul2(d, uf), t));                                       // d * u * silu'(g)
     }
     *reinterpret_cast<uint4*>(my_row + 64 * h + 16 * i4) = make_uint4(dgw[0], dgw[1], dgw[2], dgw[3]);
   }

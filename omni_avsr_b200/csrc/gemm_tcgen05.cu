@@ -974,9 +974,13 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
+                // bf16(silu(gate)) * up on pairs, packed fp32 arithmetic (silu = g * sigmoid(g): the multiplication by the
+                // reciprocal that __fdividef(g, 1 + e) performs)
                 const float2 g = bf2_to_f2(gate[i]);
-                v[2 * i] = __bfloat162float(__float2bfloat16_rn(silu(g.x))) * v[2 * i];
-                v[2 * i + 1] = __bfloat162float(__float2bfloat16_rn(silu(g.y))) * v[2 * i + 1];
+                const float2 sl = bf2_to_f2(f2_to_bf2_pair(fmul2(g, sigmoid2(g))));
+                const float2 r = fmul2(sl, make_float2(v[2 * i], v[2 * i + 1]));
+                v[2 * i] = r.x;
+                v[2 * i + 1] = r.y;
               }
               store_tile64(p.out2, p.ldo2, p.M, stage_tile, v, lane, row0, n0 >> 1);
             }
