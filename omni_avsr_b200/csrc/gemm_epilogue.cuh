@@ -119,12 +119,14 @@ __device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&
       const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint4 b = __ldg(bp + i);
-        float2 f;
-        f = bf2_to_f2(b.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-        f = bf2_to_f2(b.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-        f = bf2_to_f2(b.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-        f = bf2_to_f2(b.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+        const uint4 b = __ldg(bp + i);
+        const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {               // packed fp32 adds (FADD2)
+          const float2 r = fadd2(make_float2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]), bf2_to_f2(bw[j]));
+          v[8 * i + 2 * j] = r.x;
+          v[8 * i + 2 * j + 1] = r.y;
+        }
       }
     } else {
       for (int i = 0; i < 32; ++i)
@@ -134,13 +136,22 @@ __device__ __forceinline__ void epilogue_store_32(const GemmKParams& p, float (&
   if (p.act != OMNI_ACT_NONE || p.residual) {
     // reference rounding point: the linear's bf16 output feeds the activation / the residual add
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    for (int i = 0; i < 32; i += 2) {
+      const float2 f = bf2_to_f2(f2_to_bf2(v[i], v[i + 1]));
+      v[i] = f.x;
+      v[i + 1] = f.y;
+    }
     if (p.act == OMNI_ACT_RELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
     } else if (p.act == OMNI_ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(gelu_fast(v[i])));
+      for (int i = 0; i < 32; i += 2) {
+        const float2 g = gelu_fast2(make_float2(v[i], v[i + 1]));
+        const float2 f = bf2_to_f2(f2_to_bf2(g.x, g.y));
+        v[i] = f.x;
+        v[i + 1] = f.y;
+      }
     }
   }
   if (p.residual) {
@@ -422,26 +433,19 @@ __device__ __forceinline__ void epilogue_tile64_prelu_ring(const GemmKParams& p,
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 bf = bf2_to_f2(bs[j]);
+      // two channels per step: packed fp32 adds / multiply and one packed bf16 conversion per rounding point
+      auto rb2 = [](float2 x) { return bf2_to_f2(f2_to_bf2_pair(x)); };
       const float2 sf = bf2_to_f2(ss[j]);
-      float f0 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * j]));
-      float f1 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * j + 1]));
-      f0 = __bfloat162float(__float2bfloat16_rn(f0 + bf.x));
-      f1 = __bfloat162float(__float2bfloat16_rn(f1 + bf.y));
+      float2 f = rb2(make_float2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]));
+      f = rb2(fadd2(f, bf2_to_f2(bs[j])));
       if (res_staged) {
         float2 rf = bf2_to_f2(rs[j]);
-        if (rbp) {
-          const float2 rbf2 = bf2_to_f2(rbs[j]);
-          rf.x = __bfloat162float(__float2bfloat16_rn(rf.x + rbf2.x));
-          rf.y = __bfloat162float(__float2bfloat16_rn(rf.y + rbf2.y));
-        }
-        f0 = __bfloat162float(__float2bfloat16_rn(f0 + rf.x));
-        f1 = __bfloat162float(__float2bfloat16_rn(f1 + rf.y));
+        if (rbp) rf = rb2(fadd2(rf, bf2_to_f2(rbs[j])));
+        f = rb2(fadd2(f, rf));
       }
-      f0 = f0 > 0.f ? f0 : f0 * sf.x;
-      f1 = f1 > 0.f ? f1 : f1 * sf.y;
-      v[8 * i + 2 * j] = ring ? 0.f : f0;
-      v[8 * i + 2 * j + 1] = ring ? 0.f : f1;
+      const float2 neg = fmul2(f, sf);
+      v[8 * i + 2 * j] = ring ? 0.f : (f.x > 0.f ? f.x : neg.x);
+      v[8 * i + 2 * j + 1] = ring ? 0.f : (f.y > 0.f ? f.y : neg.y);
     }
   }
   if (res_staged) __syncwarp();

@@ -932,10 +932,13 @@ gemm_bf16_tn_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (row0 >= p.M) continue;                                      // warp-uniform
           float v[64];
+          const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = __uint_as_float(r0[i]) * alpha;
-            v[32 + i] = __uint_as_float(r1[i]) * alpha;
+          for (int i = 0; i < 32; i += 2) {          // packed scaling (FMUL2)
+            const float2 a = fmul2(make_float2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1])), al2);
+            const float2 b = fmul2(make_float2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1])), al2);
+            v[i] = a.x; v[i + 1] = a.y;
+            v[32 + i] = b.x; v[32 + i + 1] = b.y;
           }
           if constexpr (EPI == 5) {
             // fused GELU backward (the dgrad GEMM of fc2): d(act) block x gelu'(pre-activation block)
