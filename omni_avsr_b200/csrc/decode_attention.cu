@@ -40,7 +40,7 @@ __device__ __forceinline__ void rope8(float (&x)[8], const float (&cs)[8], const
 }
 
 template <int HD, int G>
-__global__ void __launch_bounds__(DA_THREADS)
+__global__ void __launch_bounds__(DA_THREADS, 4)
 decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict__ kc, bf16* __restrict__ vc,
                    const long long* __restrict__ len_idx, bf16* __restrict__ out, long long out_ld, int n_kv_heads,
                    int max_len, float scale_log2, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t) {
@@ -112,13 +112,15 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict_
 #pragma unroll
     for (int u = 0; u < DA_UNROLL; ++u) {
       const int p = p0 + u * DA_WARPS * KPW + sub;
-      float kf[8];
-      unpack_u4(kk[u], kf);
+      // packed fp32 (FFMA2): the kernel is issue-bound (ncu: 53 % issue slots at 13 warps / SM), the dot products are its
+      // dominant instruction class -- two lanes of a register pair per slot
+      const float2 kf2[4] = {bf2_to_f2(kk[u].x), bf2_to_f2(kk[u].y), bf2_to_f2(kk[u].z), bf2_to_f2(kk[u].w)};
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        float s = 0.f;
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(q[g][i], kf[i], s);
+        for (int i = 0; i < 4; ++i) s2 = ffma2(make_float2(q[g][2 * i], q[g][2 * i + 1]), kf2[i], s2);
+        float s = s2.x + s2.y;
 #pragma unroll
         for (int o = LPK >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (p < n_keys && l == 0) sc[g * max_len + p] = s;
@@ -162,13 +164,17 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict_
     for (int u = 0; u < DA_UNROLL; ++u) {
       const int p = p0 + u * DA_WARPS * KPW + sub;
       if (p < n_keys) {
-        float vf[8];
-        unpack_u4(vv[u], vf);
+        const float2 vf2[4] = {bf2_to_f2(vv[u].x), bf2_to_f2(vv[u].y), bf2_to_f2(vv[u].z), bf2_to_f2(vv[u].w)};
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float pg = sc[g * max_len + p];
+          const float2 pg2 = make_float2(pg, pg);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[g][i] = fmaf(pg, vf[i], acc[g][i]);
+          for (int i = 0; i < 4; ++i) {
+            const float2 a = ffma2(pg2, vf2[i], make_float2(acc[g][2 * i], acc[g][2 * i + 1]));
+            acc[g][2 * i] = a.x;
+            acc[g][2 * i + 1] = a.y;
+          }
         }
       }
     }
