@@ -255,7 +255,9 @@ def test_front3d_prelu_maxpool_matches_torch(B, T):
     video = torch.randn(B, T, H, W, generator=g).bfloat16()
     w3 = (torch.randn(C, 1, 5, 7, 7, generator=g) * 0.1).bfloat16()
     bias = torch.randn(C, generator=g).bfloat16()
-    slope = (torch.rand(C, generator=g) * 0.5).bfloat16()
+    # slopes of every kind: the pooling kernel takes max / min over the window first and applies PReLU to the two extremes,
+    # which is exact for negative slopes (V-shaped PReLU) and slopes above 1 as well
+    slope = torch.cat([torch.rand(C // 2, generator=g) * 0.5, torch.rand(C - C // 2, generator=g) * 2.0 - 0.75]).bfloat16()
     conv = F.conv3d(video.float().unsqueeze(1), w3.float(), bias.float(), stride=(1, 2, 2), padding=(2, 3, 3))
     conv = conv.bfloat16().float()                                     # the GEMM epilogue rounds to bf16
     act = F.prelu(conv, slope.float())
