@@ -23,11 +23,15 @@ class OmniKernelError(RuntimeError):
 
 
 def _load() -> C.CDLL:
-    try:    # (re)build when the sources changed since the last build (no-op when the stamp matches)
+    # (re)build when the sources changed since the last build (no-op when the stamp matches).  A failed rebuild is fatal
+    # even when an older library is lying around: running kernels that do not correspond to the sources would make every
+    # measurement and parity claim about this tree meaningless (OMNI_ALLOW_STALE_LIB=1 overrides, for bisecting only).
+    import os
+    try:
         from .build import build
         build()
     except Exception:
-        if not LIB_PATH.exists():
+        if not (LIB_PATH.exists() and os.environ.get("OMNI_ALLOW_STALE_LIB") == "1"):
             raise
     if not LIB_PATH.exists():
         raise ImportError(f"{LIB_PATH} is missing: run `python -m omni_avsr_b200.build` (needs nvcc)")

@@ -205,18 +205,320 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant (default).  The FFMA kernel above is issue-bound (ncu: 53 % issue slots at 13 warps / SM, 22 us per
+// layer against 9 us of K / V traffic at B = 64): per key and query head it spends 4 FFMA2 + 3 shuffle / add pairs on an
+// 8-lane dot product.  Here both contractions run as warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) on fragments
+// built DIRECTLY from the 16-byte global loads, no shared-memory staging of K or V:
+//   pass 1  S^T[16 keys x 8 heads] += K[16 keys x 16 d] . Q^T[16 d x 8 heads]: the d index of a contraction may be permuted
+//           freely, so lane (r = lane / 4, c = lane % 4) loads chunk c + 4q (8 consecutive d) of key rows r and r + 8 and
+//           feeds the four registers of each uint4 as the (k = 2c, 2c + 1) / (k = 2c + 8, 2c + 9) halves of two MMAs; the
+//           Q fragment of head r is the same chunk of the query row.  Heads >= G are zero fragments.
+//   pass 2  O^T[16 d x 8 heads] += V^T[16 d x 16 keys] . P^T[16 keys x 8 heads]: lane (r, c) loads chunk r (+ 8h) of keys
+//           4c .. 4c + 3, two PRMTs per register pair interleave two keys of one d, P = exp2(s - max) is computed from the
+//           fp32 scores in shared memory on the fly (no separate softmax stage: the maximum comes out of pass 1's
+//           accumulators) and packed to bf16 like every tensor-core attention does.
+// One barrier between the passes, one before the cross-warp reduction of the outputs.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int DM_THREADS = 256;
+constexpr int DM_WARPS = DM_THREADS / 32;
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint4 ld_plain_u4(const void* p) {      // coherent load (rows this CTA wrote before a barrier)
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// RoPE of one 8-dim chunk given its partner chunk (+- HD/2); rounding points of omni_rope / rope8 above.
+__device__ __forceinline__ uint4 rope_chunk(const uint4& x, const uint4& xp, const uint4& cs, const uint4& sn,
+                                            bool second_half) {
+  float xf[8], pf[8], cf[8], sf[8];
+  unpack_u4(x, xf); unpack_u4(xp, pf); unpack_u4(cs, cf); unpack_u4(sn, sf);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float rot = second_half ? pf[i] : -pf[i];
+    xf[i] = rbf16(rbf16(xf[i] * cf[i]) + rbf16(rot * sf[i]));
+  }
+  uint4 o;
+  o.x = f2_to_bf2(xf[0], xf[1]); o.y = f2_to_bf2(xf[2], xf[3]);
+  o.z = f2_to_bf2(xf[4], xf[5]); o.w = f2_to_bf2(xf[6], xf[7]);
+  return o;
+}
+
+template <int HD, int G>
+__global__ void __launch_bounds__(DM_THREADS, (HD == 64 ? 4 : 2))
+decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict__ kc, bf16* __restrict__ vc,
+                       const long long* __restrict__ len_idx, bf16* __restrict__ out, long long out_ld, int n_kv_heads,
+                       int max_len, int sc_stride, float scale_log2, const bf16* __restrict__ cos_t,
+                       const bf16* __restrict__ sin_t) {
+  pdl_launch_dependents();
+  pdl_wait();                          // q|k|v row and the cache position come from predecessors
+  constexpr int NCH = HD / 8;          // 16-byte chunks per row
+  constexpr int NQ = HD / 32;          // chunks per lane in pass 1 (c + 4q)
+  constexpr int NH = HD / 64;          // chunks per lane in pass 2 (r + 8h)
+  constexpr int U1 = (HD == 64) ? 2 : 1;   // 16-key blocks in flight per warp (8 x 16-byte loads per lane either way)
+  constexpr int U2 = 1;
+  extern __shared__ float sm[];
+  float* sc = sm;                                   // [G][sc_stride] scaled scores (log2 units)
+  float* red = sm + G * sc_stride + 16;             // [DM_WARPS][G][HD] partial outputs
+  float* wmax = red + DM_WARPS * G * HD;            // [DM_WARPS][8]
+  float* wsum = wmax + DM_WARPS * 8;                // [DM_WARPS][8]
+
+  const int b = blockIdx.x / n_kv_heads, kvh = blockIdx.x - b * n_kv_heads;
+  const int n_heads = n_kv_heads * G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane >> 2, c = lane & 3;
+  const int pos = static_cast<int>(*len_idx);       // position of the new token == number of cached keys
+  if (pos >= max_len) return;                       // cache full: the host sized max_len = prefill + max_new_tokens
+  const int n_keys = pos + 1;
+  const int n_blocks = (n_keys + 15) >> 4;
+  const bool rope = cos_t != nullptr;
+
+  const bf16* row = qkv + static_cast<long long>(b) * ld;
+  bf16* krow = kc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
+  bf16* vrow = vc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
+
+  // ---- append the new token (RoPE on the key), read back below with coherent loads after the barrier ----
+  if (threadIdx.x < NCH) {
+    const int ch = threadIdx.x;
+    const bf16* ksrc = row + (n_heads + kvh) * HD;
+    uint4 x = *reinterpret_cast<const uint4*>(ksrc + ch * 8);
+    if (rope) {
+      const uint4 xp = *reinterpret_cast<const uint4*>(ksrc + ((ch + NCH / 2) % NCH) * 8);
+      const uint4 cs = __ldg(reinterpret_cast<const uint4*>(cos_t + static_cast<long long>(pos) * HD) + ch);
+      const uint4 sn = __ldg(reinterpret_cast<const uint4*>(sin_t + static_cast<long long>(pos) * HD) + ch);
+      x = rope_chunk(x, xp, cs, sn, ch >= NCH / 2);
+    }
+    *reinterpret_cast<uint4*>(krow + static_cast<long long>(pos) * HD + ch * 8) = x;
+  } else if (threadIdx.x < 2 * NCH) {
+    const int ch = threadIdx.x - NCH;
+    *reinterpret_cast<uint4*>(vrow + static_cast<long long>(pos) * HD + ch * 8) =
+        *reinterpret_cast<const uint4*>(row + (n_heads + n_kv_heads + kvh) * HD + ch * 8);
+  }
+
+  // ---- Q fragments of head r (zero for r >= G): chunks c + 4q ----
+  uint4 qf[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) qf[q] = make_uint4(0u, 0u, 0u, 0u);
+  if (r < G) {
+    const bf16* qsrc = row + (kvh * G + r) * HD;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) qf[q] = *reinterpret_cast<const uint4*>(qsrc + (c + 4 * q) * 8);
+    if (rope) {
+      uint4 rot[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int ch = c + 4 * q;
+        const uint4 cs = __ldg(reinterpret_cast<const uint4*>(cos_t + static_cast<long long>(pos) * HD) + ch);
+        const uint4 sn = __ldg(reinterpret_cast<const uint4*>(sin_t + static_cast<long long>(pos) * HD) + ch);
+        rot[q] = rope_chunk(qf[q], qf[(q + NQ / 2) % NQ], cs, sn, ch >= NCH / 2);
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) qf[q] = rot[q];
+    }
+  }
+  __syncthreads();                                   // the appended K / V row is visible to the whole CTA
+
+  // ---- pass 1: scores ----
+  float m0 = -INFINITY, m1 = -INFINITY;              // running maxima of heads 2c, 2c + 1 over this lane's keys
+  for (int blk0 = warp; blk0 < n_blocks; blk0 += U1 * DM_WARPS) {
+    uint4 ka[U1][NQ], kb[U1][NQ];
+#pragma unroll
+    for (int u = 0; u < U1; ++u) {
+      const int blk = blk0 + u * DM_WARPS;
+      const int pa = blk * 16 + r, pb = pa + 8;
+      const bool last = blk == n_blocks - 1;         // the block holding the row this CTA just wrote
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        ka[u][q] = make_uint4(0u, 0u, 0u, 0u);
+        kb[u][q] = make_uint4(0u, 0u, 0u, 0u);
+        const bf16* pka = krow + static_cast<long long>(pa) * HD + (c + 4 * q) * 8;
+        const bf16* pkb = krow + static_cast<long long>(pb) * HD + (c + 4 * q) * 8;
+        if (blk < n_blocks) {
+          if (last) {
+            if (pa < n_keys) ka[u][q] = ld_plain_u4(pka);
+            if (pb < n_keys) kb[u][q] = ld_plain_u4(pkb);
+          } else {
+            ka[u][q] = ld_nc_u4(pka);
+            kb[u][q] = ld_nc_u4(pkb);
+          }
+        }
+      }
+      // pull the matching V rows towards L2 now (pass 2 then runs out of L2; the HBM streams of K and V overlap)
+      if (blk < n_blocks && c < 2 * NH) {
+        const int pv = blk * 16 + r + 8 * (c / NH);
+        if (pv < n_keys)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + static_cast<long long>(pv) * HD + (c % NH) * 64));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U1; ++u) {
+      const int blk = blk0 + u * DM_WARPS;
+      if (blk < n_blocks) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          mma_16816(s, ka[u][q].x, kb[u][q].x, ka[u][q].y, kb[u][q].y, qf[q].x, qf[q].y);
+          mma_16816(s, ka[u][q].z, kb[u][q].z, ka[u][q].w, kb[u][q].w, qf[q].z, qf[q].w);
+        }
+        const int pa = blk * 16 + r, pb = pa + 8;
+        if (2 * c < G) {
+          float* s0 = sc + (2 * c) * sc_stride;
+          float* s1 = s0 + sc_stride;
+          const bool h1 = 2 * c + 1 < G;              // odd G: the group's last column pair has one head only
+          if (pa < n_keys) {
+            const float a0 = s[0] * scale_log2, a1 = s[1] * scale_log2;
+            s0[pa] = a0; m0 = fmaxf(m0, a0);
+            if (h1) { s1[pa] = a1; m1 = fmaxf(m1, a1); }
+          }
+          if (pb < n_keys) {
+            const float a2 = s[2] * scale_log2, a3 = s[3] * scale_log2;
+            s0[pb] = a2; m0 = fmaxf(m0, a2);
+            if (h1) { s1[pb] = a3; m1 = fmaxf(m1, a3); }
+          }
+        }
+      }
+    }
+  }
+  // maxima over the 8 key rows of the lane group (lanes with equal c), then per warp into shared memory
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  if (r == 0) {
+    wmax[warp * 8 + 2 * c] = m0;
+    wmax[warp * 8 + 2 * c + 1] = m1;
+  }
+  __syncthreads();
+
+  // ---- pass 2: O^T += V^T . P^T with P = exp2(s - max) formed on the fly ----
+  float mx = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < DM_WARPS; ++w) mx = fmaxf(mx, wmax[w * 8 + r]);   // head r (unused for r >= G)
+  float acc[NH][4][4];
+#pragma unroll
+  for (int h = 0; h < NH; ++h)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[h][j][i] = 0.f;
+  float psum = 0.f;
+  const float* srow = sc + (r < G ? r : 0) * sc_stride;
+  for (int blk0 = warp; blk0 < n_blocks; blk0 += U2 * DM_WARPS) {
+    uint4 vv[U2][NH][4];
+#pragma unroll
+    for (int u = 0; u < U2; ++u) {
+      const int blk = blk0 + u * DM_WARPS;
+      const bool last = blk == n_blocks - 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = blk * 16 + 4 * c + i;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          vv[u][h][i] = make_uint4(0u, 0u, 0u, 0u);
+          const bf16* pv = vrow + static_cast<long long>(p) * HD + (r + 8 * h) * 8;
+          if (blk < n_blocks && p < n_keys) vv[u][h][i] = last ? ld_plain_u4(pv) : ld_nc_u4(pv);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U2; ++u) {
+      const int blk = blk0 + u * DM_WARPS;
+      if (blk < n_blocks) {
+        const int p = blk * 16 + 4 * c;
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < G) {
+          const float4 s4 = *reinterpret_cast<const float4*>(srow + p);
+          if (p + 0 < n_keys) e[0] = ex2_approx(s4.x - mx);
+          if (p + 1 < n_keys) e[1] = ex2_approx(s4.y - mx);
+          if (p + 2 < n_keys) e[2] = ex2_approx(s4.z - mx);
+          if (p + 3 < n_keys) e[3] = ex2_approx(s4.w - mx);
+          psum += (e[0] + e[1]) + (e[2] + e[3]);
+        }
+        const uint32_t b0 = f2_to_bf2(e[0], e[1]), b1 = f2_to_bf2(e[2], e[3]);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const uint4 &v0 = vv[u][h][0], &v1 = vv[u][h][1], &v2 = vv[u][h][2], &v3 = vv[u][h][3];
+          mma_16816(acc[h][0], __byte_perm(v0.x, v1.x, 0x5410), __byte_perm(v0.x, v1.x, 0x7632),
+                    __byte_perm(v2.x, v3.x, 0x5410), __byte_perm(v2.x, v3.x, 0x7632), b0, b1);
+          mma_16816(acc[h][1], __byte_perm(v0.y, v1.y, 0x5410), __byte_perm(v0.y, v1.y, 0x7632),
+                    __byte_perm(v2.y, v3.y, 0x5410), __byte_perm(v2.y, v3.y, 0x7632), b0, b1);
+          mma_16816(acc[h][2], __byte_perm(v0.z, v1.z, 0x5410), __byte_perm(v0.z, v1.z, 0x7632),
+                    __byte_perm(v2.z, v3.z, 0x5410), __byte_perm(v2.z, v3.z, 0x7632), b0, b1);
+          mma_16816(acc[h][3], __byte_perm(v0.w, v1.w, 0x5410), __byte_perm(v0.w, v1.w, 0x7632),
+                    __byte_perm(v2.w, v3.w, 0x5410), __byte_perm(v2.w, v3.w, 0x7632), b0, b1);
+        }
+      }
+    }
+  }
+  // row sums: over the 4 key groups of a head (lanes r, c = 0..3), then per warp
+  psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+  psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+  if (c == 0) wsum[warp * 8 + r] = psum;
+  // accumulators: acc[h][j] = {O[d][head 2c], O[d][head 2c+1], O[d+1][head 2c], O[d+1][head 2c+1]}, d = 8 (r + 8h) + 2j
+  if (2 * c < G) {
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = 8 * (r + 8 * h) + 2 * j;
+        float* r0 = red + (warp * G + 2 * c) * HD + d;
+        *reinterpret_cast<float2*>(r0) = make_float2(acc[h][j][0], acc[h][j][2]);
+        if (2 * c + 1 < G) *reinterpret_cast<float2*>(r0 + HD) = make_float2(acc[h][j][1], acc[h][j][3]);
+      }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < G * HD; e += DM_THREADS) {
+    const int g = e / HD;
+    float a = 0.f, sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < DM_WARPS; ++w) {
+      a += red[w * G * HD + e];
+      sum += wsum[w * 8 + g];
+    }
+    out[static_cast<long long>(b) * out_ld + (kvh * G + g) * HD + (e - g * HD)] = __float2bfloat16_rn(a / sum);
+  }
+}
+
+static bool da_use_ffma() {
+  static const bool v = [] { const char* e = getenv("OMNI_DA_FFMA"); return e && e[0] == '1'; }();
+  return v;
+}
+
 template <int HD, int G>
 static int launch_decode_attn(const bf16* qkv, long long ld, bf16* kc, bf16* vc, const long long* len_idx, bf16* out,
                               long long out_ld, int B, int n_kv_heads, int max_len, float scale, cudaStream_t st,
                               const bf16* cos_t, const bf16* sin_t) {
-  auto kfn = decode_attn_kernel<HD, G>;
-  const int smem = (G * max_len + DA_WARPS * G * HD + G) * 4;
+  if (da_use_ffma()) {                 // measurement switch: the FFMA formulation (see the comment above the MMA kernel)
+    auto kfn = decode_attn_kernel<HD, G>;
+    const int smem = (G * max_len + DA_WARPS * G * HD + G) * 4;
+    if (smem > 200 * 1024) return OMNI_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    if (omni_launch_pdl(kfn, dim3(B * n_kv_heads), dim3(DA_THREADS), smem, st, qkv, ld, kc, vc, len_idx, out, out_ld,
+                        n_kv_heads, max_len, scale * 1.4426950408889634f, cos_t, sin_t) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    return OMNI_OK;
+  }
+  auto kfn = decode_attn_mma_kernel<HD, G>;
+  const int sc_stride = (max_len + 15) / 16 * 16 + 8;     // + 8: heads 2c / 2c + 1 of a store land in different banks
+  const int smem = (G * sc_stride + 16 + DM_WARPS * G * HD + 2 * DM_WARPS * 8) * 4;
   if (smem > 200 * 1024) return OMNI_ERR_UNSUPPORTED;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return OMNI_ERR_CUDA;
-  if (omni_launch_pdl(kfn, dim3(B * n_kv_heads), dim3(DA_THREADS), smem, st, qkv, ld, kc, vc, len_idx, out, out_ld, n_kv_heads,
-                      max_len, scale * 1.4426950408889634f, cos_t, sin_t) != cudaSuccess)
+  if (omni_launch_pdl(kfn, dim3(B * n_kv_heads), dim3(DM_THREADS), smem, st, qkv, ld, kc, vc, len_idx, out, out_ld,
+                      n_kv_heads, max_len, sc_stride, scale * 1.4426950408889634f, cos_t, sin_t) != cudaSuccess)
     return OMNI_ERR_CUDA;
   return OMNI_OK;
 }

@@ -676,6 +676,178 @@ prelu_maxpool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ slope,
     const int wo = static_cast<int>(t % Wo); t /= Wo;
     const int ho = static_cast<int>(t % Ho);
     const long long n = t / Ho;
+    float s[8], m[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(slope) + c), s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int h = 2 * ho - 1 + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int w = 2 * wo - 1 + dx;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ld_nc_u4(reinterpret_cast<const uint4*>(x) + ((n * H + h) * W + w) * C8 + c), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = rbf(f[i] > 0.f ? f[i] : f[i] * s[i]);
+          m[i] = fmaxf(m[i], v);
+        }
+      }
+    }
+    st_na_u4(reinterpret_cast<uint4*>(y) + idx, pack8(m));
+  }
+}
+
+}  // namespace omni
+
+extern "C" int omni_prelu_res(void* x, const void* residual, const void* slope, const void* bias, const void* res_bias,
+                              int64_t rows, int32_t C, void* stream) {
+  OMNI_CHECK_ARG(x && slope && rows >= 0 && C > 0 && (C % 8) == 0);
+  if (rows == 0) return OMNI_OK;
+  const long long total8 = rows * (C / 8);
+  long long blocks = ceil_div_ll(total8, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  prelu_res_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((bf16*)x, (const bf16*)residual,
+                                                                          (const bf16*)slope, (const bf16*)bias,
+                                                                          (const bf16*)res_bias, C / 8, total8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+extern "C" int omni_prelu_maxpool3x3s2(const void* x, const void* slope, void* y, int64_t N, int32_t H, int32_t W,
+                                       int32_t C, void* stream) {
+  OMNI_CHECK_ARG(x && slope && y && N >= 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0);
+  if (N == 0) return OMNI_OK;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total8 = N * Ho * Wo * (C / 8);
+  long long blocks = ceil_div_ll(total8, EW_THREADS);
+  if (blocks > kNumSMs * 16LL) blocks = kNumSMs * 16LL;
+  prelu_maxpool_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)slope, (bf16*)y,
+                                                                              H, W, Ho, Wo, C / 8, total8);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col of AV-HuBERT's video front-end convolution (resnet.py:137: Conv3d(1, 64, (5,7,7), stride (1,2,2), pad (2,3,3))).
+// video [B, T, H, W] bf16 (C_in = 1)  ->  A [B*T*Ho*Wo, 256] bf16, column k = (kt*7 + ky)*7 + kx (245 taps, 11 zero pads),
+// so that the convolution becomes one tcgen05 GEMM against the [64, 256] (BatchNorm-folded) filter matrix.
+// One thread = 8 consecutive taps of one output position (one 16-byte store).
+// ------------------------------------------------------------------------------------------------
+namespace omni {
+
+__global__ void __launch_bounds__(EW_THREADS)
+im2col_front3d_kernel(const bf16* __restrict__ video, bf16* __restrict__ out, int T, int H, int W, int Ho, int Wo,
+                      long long total_chunks) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_chunks;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kc = static_cast<int>(idx & 31);          // 32 chunks of 8 taps per output position
+    long long m = idx >> 5;
+    const int xo = static_cast<int>(m % Wo); m /= Wo;
+    const int yo = static_cast<int>(m % Ho); m /= Ho;
+    const int t = static_cast<int>(m % T);
+    const long long b = m / T;
+    const bf16* clip = video + b * static_cast<long long>(T) * H * W;
+    __align__(16) bf16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kc * 8 + i;
+      bf16 val = __float2bfloat16_rn(0.f);
+      if (k < 245) {
+        const int kt = k / 49;
+        const int r = k - kt * 49;
+        const int ky = r / 7;
+        const int kx = r - ky * 7;
+        const int tt = t + kt - 2, yy = 2 * yo + ky - 3, xx = 2 * xo + kx - 3;
+        if (tt >= 0 && tt < T && yy >= 0 && yy < H && xx >= 0 && xx < W)
+          val = clip[(static_cast<long long>(tt) * H + yy) * W + xx];
+      }
+      v[i] = val;
+    }
+    st_na_u4(reinterpret_cast<uint4*>(out) + idx, *reinterpret_cast<const uint4*>(v));
+  }
+}
+
+}  // namespace omni
+
+extern "C" int omni_im2col_front3d(const void* video, void* out, int32_t B, int32_t T, int32_t H, int32_t W,
+                                   void* stream) {
+  OMNI_CHECK_ARG(video && out && B > 0 && T > 0 && H > 0 && W > 0);
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long total = static_cast<long long>(B) * T * Ho * Wo * 32;
+  long long blocks = ceil_div_ll(total, EW_THREADS);
+  if (blocks > kNumSMs * 32LL) blocks = kNumSMs * 32LL;
+  im2col_front3d_kernel<<<(int)blocks, EW_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)video, (bf16*)out, T, H, W, Ho,
+                                                                               Wo, total);
+  OMNI_LAUNCH_CHECK();
+  return OMNI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Time-major variant of the front-end convolution (resnet.py:137), 4x less HBM traffic than the 245-tap im2col above:
+// only the 7x7 spatial taps are materialised, A2[b][yo][xo][tt][64] (49 taps + 15 zero columns, tt = t + 2 in a
+// zero-padded time axis of T + 4), so that the five temporal taps of an output position are five CONSECUTIVE rows:
+// the GEMM reads A2 through an overlapping-row view [rows, 320] with row stride 64 (TMA global stride 128 B) against the
+// [C, 5*64] filter matrix.  Output row (b, yo, xo, t) for t < T is the convolution at time t; the 4 trailing rows of
+// every (b, yo, xo) line are scratch.  omni_prelu_maxpool_front then applies PReLU + MaxPool(1,3,3)/(1,2,2) reading that
+// layout and writes the channels-last [B*T, Hp, Wp, C] activation of the ResNet trunk.
+// ------------------------------------------------------------------------------------------------
+namespace omni {
+
+__global__ void __launch_bounds__(EW_THREADS)
+im2col_front2d_kernel(const bf16* __restrict__ video, bf16* __restrict__ out, int T, int H, int W, int Ho, int Wo,
+                      long long total) {
+  const int Tp = T + 4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long m = idx;
+    const int xo = static_cast<int>(m % Wo); m /= Wo;       // lanes run along x: neighbouring lanes read neighbouring pixels
+    const int yo = static_cast<int>(m % Ho); m /= Ho;
+    const int tt = static_cast<int>(m % Tp);
+    const long long b = m / Tp;
+    const int t = tt - 2;
+    const bool t_ok = t >= 0 && t < T;
+    const bf16* frame = video + (b * T + (t_ok ? t : 0)) * static_cast<long long>(H) * W;
+    uint32_t w[32];
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+      unsigned short lo = 0, hi = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 2 * k2 + e;
+        if (k < 49) {
+          const int ky = k / 7, kx = k % 7;
+          const int yy = 2 * yo + ky - 3, xx = 2 * xo + kx - 3;
+          unsigned short v = 0;
+          if (t_ok && yy >= 0 && yy < H && xx >= 0 && xx < W)
+            v = __ldg(reinterpret_cast<const unsigned short*>(frame) + yy * W + xx);
+          if (e == 0) lo = v; else hi = v;
+        }
+      }
+      w[k2] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+    }
+    const long long row = ((b * Ho + yo) * Wo + xo) * Tp + tt;
+    uint4* dst = reinterpret_cast<uint4*>(out) + row * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
+}
+
+// x: conv output [B][H][W][Tp][C] (rows of the time-major GEMM), y: [B*T][Ho][Wo][C] channels-last
+__global__ void __launch_bounds__(EW_THREADS)
+prelu_maxpool_front_kernel(const bf16* __restrict__ x, const bf16* __restrict__ slope, bf16* __restrict__ y, int T, int Tp,
+                           int H, int W, int Ho, int Wo, int C8, long long total8, int ring) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    long long r = idx / C8;
+    const int t = static_cast<int>(r % T); r /= T;         // consecutive threads: channels, then time (contiguous reads)
+    const int wo = static_cast<int>(r % Wo); r /= Wo;
+    const int ho = static_cast<int>(r % Ho);
+    const long long b = r / Ho;
     // max-pool(PReLU(x)) = max(PReLU(max x), PReLU(min x)) for ANY slope (PReLU is monotone for slope >= 0 and V-shaped for
     // slope < 0: its maximum over a set sits at one of the two extremes; the bf16 rounding is monotone, so it commutes with
     // the maximum): the nine taps only cost packed bf16 max / min instructions (2 per 32-bit word), PReLU runs twice per
