@@ -286,6 +286,57 @@ int omni_decode_attention_rope(const void* qkv, int64_t ld, void* k_cache, void*
                                int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
                                int32_t max_len, float scale, const void* cos_t, const void* sin_t, int32_t table_rows,
                                void* stream);
+/* Beam-search variant (HF 4.43.1 `_beam_search` under eval_OmniAVSR.py:216-226, num_beams = K): the B rows are B/K
+ * utterances x K beams.  Instead of HF's `_reorder_cache` gather of the whole cache after every step, each physical cache row
+ * keeps what its own forwards appended and the kernel resolves the row per key position p:
+ *     p <  *prefill_len : row (b / K) * K               (the prompt is stored once per utterance)
+ *     p >= *prefill_len : beam_ind[par][b][p - *prefill_len],  par = (*len_idx - *prefill_len + 1) & 1
+ * beam_ind is the double-buffered table [2][B][ind_ld] (int32) maintained by omni_beam_select; the new token (position
+ * *len_idx) is appended to row b itself.  cos_t / sin_t may be NULL (RoPE already applied). */
+int omni_decode_attention_beam(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx, void* out,
+                               int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                               int32_t max_len, float scale, const void* cos_t, const void* sin_t, int32_t table_rows,
+                               const int32_t* beam_ind, int32_t ind_ld, const int64_t* prefill_len, int32_t K,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Beam-search ranking + scorer bookkeeping of one decode step, on the device (no host synchronisation per step).
+ * Replaces, inside HF transformers 4.43.1 `GenerationMixin._beam_search` (reached from modeling_OmniAVSR.py:313-322 with the
+ * evaluation default num_beams = 15 of eval_OmniAVSR.py:216-226): log_softmax + beam-score add + topk(2K) over [K*V], and
+ * `BeamSearchScorer.process` (length_penalty 1.0, early_stopping False).
+ *   omni_beam_topk_rows: per logits row (bf16 [rows, ld], V columns): fp32 log-softmax statistics and the row's n_cand best
+ *     tokens, cand_score[row][j] = (x - max - log(sum exp)) + beam_scores[row] in descending order, ties by lowest token id;
+ *     cand_tok = -1 / score = -inf past V candidates.
+ *   omni_beam_select: per utterance, merge the K candidate lists (ties by lowest k*V + tok), walk the n_cand = 2K best like
+ *     the scorer, and write the next step's state (see the struct).  All counters live in device memory so that the step can
+ *     be replayed from a CUDA graph; `step_idx` is advanced by omni_decode_advance after the step's forward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct omni_beam_select_args {
+  const float* cand_score;   /* [B*K, n_cand] from omni_beam_topk_rows */
+  const int32_t* cand_tok;   /* [B*K, n_cand] */
+  float* beam_scores;        /* [B*K] running sum of log-probs (in: read by omni_beam_topk_rows; out: the chosen beams') */
+  const int64_t* step_idx;   /* [1] tokens generated so far (cur_len - 1) */
+  const int64_t* eos;        /* [1] */
+  const int64_t* pad;        /* [1] */
+  int32_t* seqs;             /* [2][B*K, max_new] token history, buffer (step & 1) is read, the other written */
+  int32_t* ind;              /* [2][B*K, ind_ld] KV-cache row of every generated position (see omni_decode_attention_beam) */
+  int32_t* hyp_seq;          /* [B, K+1, max_new] finished hypotheses (slot storage) */
+  int32_t* hyp_len;          /* [B, K+1] */
+  double* hyp_score;         /* [B, K+1] sum_logprobs / length */
+  int32_t* hyp_order;        /* [B, K+1] slots in insertion order (first hyp_count entries are live); init 0..K */
+  int32_t* hyp_count;        /* [B] */
+  double* hyp_worst;         /* [B] init 1e9 */
+  int32_t* done;             /* [B] */
+  int32_t* n_done;           /* [1] number of finished utterances */
+  int32_t* status;           /* [1] set to 1 when fewer than K non-EOS candidates exist (HF raises ValueError there) */
+  const void* embed;         /* [vocab, H] bf16 embedding table, ld_embed */
+  void* x_next;              /* [B*K, H] bf16 input rows of the next forward, ld_x */
+  int64_t ld_embed, ld_x;
+  int32_t B, K, n_cand, V, max_new, ind_ld, H;
+} omni_beam_select_args;
+int omni_beam_topk_rows(const void* logits, int64_t ld, int32_t rows, int32_t V, const float* beam_scores, int32_t n_cand,
+                        float* cand_score, int32_t* cand_tok, void* stream);
+int omni_beam_select(const omni_beam_select_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row kernels of the decoder / encoder blocks (all bf16 in/out, fp32 statistics).

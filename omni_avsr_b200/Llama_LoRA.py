@@ -636,7 +636,7 @@ def attention_packed(qkv, rows: PackedRows, a: LLMArch, kv_cache, layer_idx, rop
     for (task, B, S, off) in rows.segments:
         if S == 1 and kv_cache.graph_mode:
             ops.decode_attention(qkv[off: off + B], kv_cache.k[layer_idx], kv_cache.v[layer_idx], kv_cache.len_idx,
-                                 out[off: off + B], B, nh, nkv, hd, rope=rope)
+                                 out[off: off + B], B, nh, nkv, hd, rope=rope, beam=kv_cache.beam)
             continue
         if rope is not None:
             raise RuntimeError("fused RoPE is a decode-step feature")
@@ -668,11 +668,16 @@ class KVCache:
         self.max_len = max_len
         self.graph_mode = False          # True: single-token steps (device-side write index)
         self.len_idx = torch.zeros(1, device=device, dtype=torch.int64)            # device copy of `len`
+        # beam search (decode.beam_generate): the prefill runs once per utterance and lands in every `row_stride`-th cache row;
+        # `beam` = (indirection table, prefill length on the device, K) resolves the cache row per key position in the
+        # single-token attention kernel (no cache gather per step)
+        self.row_stride = 1
+        self.beam = None
 
     def fill(self, layer, k, v):
         S = k.shape[2]
-        self.k[layer][:, :, self.len: self.len + S] = k
-        self.v[layer][:, :, self.len: self.len + S] = v
+        self.k[layer][:: self.row_stride, :, self.len: self.len + S] = k
+        self.v[layer][:: self.row_stride, :, self.len: self.len + S] = v
 
     def advance(self, S):
         self.len += S

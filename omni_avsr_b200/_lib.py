@@ -61,6 +61,22 @@ class GemmArgs(C.Structure):
     ]
 
 
+class BeamSelectArgs(C.Structure):
+    """omni_beam_select_args (include/omni_avsr.h)."""
+    _fields_ = [
+        ("cand_score", C.c_void_p), ("cand_tok", C.c_void_p), ("beam_scores", C.c_void_p),
+        ("step_idx", C.c_void_p), ("eos", C.c_void_p), ("pad", C.c_void_p),
+        ("seqs", C.c_void_p), ("ind", C.c_void_p),
+        ("hyp_seq", C.c_void_p), ("hyp_len", C.c_void_p), ("hyp_score", C.c_void_p), ("hyp_order", C.c_void_p),
+        ("hyp_count", C.c_void_p), ("hyp_worst", C.c_void_p),
+        ("done", C.c_void_p), ("n_done", C.c_void_p), ("status", C.c_void_p),
+        ("embed", C.c_void_p), ("x_next", C.c_void_p),
+        ("ld_embed", C.c_int64), ("ld_x", C.c_int64),
+        ("B", C.c_int32), ("K", C.c_int32), ("n_cand", C.c_int32), ("V", C.c_int32), ("max_new", C.c_int32),
+        ("ind_ld", C.c_int32), ("H", C.c_int32),
+    ]
+
+
 class SpliceArgs(C.Structure):
     _fields_ = [
         ("tokens", C.c_void_p), ("labels", C.c_void_p), ("embed", C.c_void_p),
@@ -170,6 +186,10 @@ _sig("omni_decode_pick", [_P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _I64
 _sig("omni_decode_advance", [_P, _P, _P, _I32, _P])
 _sig("omni_decode_attention", [_P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P])
 _sig("omni_decode_attention_rope", [_P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _I32, _P])
+_sig("omni_decode_attention_beam", [_P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _I32, _P, _I32,
+                                    _P, _I32, _P])
+_sig("omni_beam_topk_rows", [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P])
+_sig("omni_beam_select", [C.POINTER(BeamSelectArgs), _P])
 _sig("omni_logmel_workspace_bytes", [_I32], C.c_int64)
 _sig("omni_logmel", [_P, _I32, _I64, _I32, _I32, _P, _P, _P, _I64, _P])
 _sig("omni_video_transform", [_P, _I32, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_int32), _I32, _P, _I32, _P])
@@ -185,6 +205,7 @@ EXPORTS = [
     "omni_ce_fwd", "omni_ce_bwd", "omni_argmax", "omni_decode_pick", "omni_decode_advance", "omni_sumsq", "omni_adamw", "omni_gemm_wgrad_bf16",
     "omni_colsum_bf16", "omni_logmel_workspace_bytes", "omni_logmel", "omni_prelu_res", "omni_prelu_maxpool3x3s2",
     "omni_im2col_front3d", "omni_im2col_front2d", "omni_prelu_maxpool_front", "omni_prelu_maxpool_front_ring", "omni_prelu_res_ring", "omni_gather_s2_ring", "omni_avgpool_ring", "omni_avgpool_frames", "omni_attention_fwd", "omni_attention_bwd", "omni_attention_bwd_scratch_floats", "omni_decode_attention", "omni_decode_attention_rope",
+    "omni_decode_attention_beam", "omni_beam_topk_rows", "omni_beam_select",
     "omni_transpose_bf16", "omni_pps_workspace_bytes", "omni_pool_project_splice", "omni_video_transform", "omni_audio_transform_workspace_bytes", "omni_audio_transform",
 ]
 

@@ -253,12 +253,17 @@ __device__ __forceinline__ uint4 rope_chunk(const uint4& x, const uint4& xp, con
   return o;
 }
 
-template <int HD, int G>
+constexpr int DM_MAX_NEW = 128;      // generated positions a beam-search indirection row can describe
+
+// BEAM: the B rows are utterances x K beams and the cache row of a key position is looked up (see omni_decode_attention_beam
+// in the header: prompt rows once per utterance, generated positions through the indirection table of omni_beam_select).
+template <int HD, int G, bool BEAM>
 __global__ void __launch_bounds__(DM_THREADS, (HD == 64 ? 4 : 2))
 decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict__ kc, bf16* __restrict__ vc,
                        const long long* __restrict__ len_idx, bf16* __restrict__ out, long long out_ld, int n_kv_heads,
                        int max_len, int sc_stride, float scale_log2, const bf16* __restrict__ cos_t,
-                       const bf16* __restrict__ sin_t) {
+                       const bf16* __restrict__ sin_t, const int* __restrict__ beam_ind, int ind_ld, long long ind_plane,
+                       const long long* __restrict__ prefill_len, int beam_k) {
   pdl_launch_dependents();
   pdl_wait();                          // q|k|v row and the cache position come from predecessors
   constexpr int NCH = HD / 8;          // 16-byte chunks per row
@@ -283,8 +288,25 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restr
   const bool rope = cos_t != nullptr;
 
   const bf16* row = qkv + static_cast<long long>(b) * ld;
-  bf16* krow = kc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
-  bf16* vrow = vc + (static_cast<long long>(b) * n_kv_heads + kvh) * max_len * HD;
+  const long long row_elems = static_cast<long long>(max_len) * HD;
+  bf16* krow = kc + (static_cast<long long>(b) * n_kv_heads + kvh) * row_elems;
+  bf16* vrow = vc + (static_cast<long long>(b) * n_kv_heads + kvh) * row_elems;
+  __shared__ int s_ind[BEAM ? DM_MAX_NEW : 1];
+  int s0 = 0;
+  long long prompt_off = 0;            // element offset of (prompt row, kvh) relative to (row b, kvh)
+  if (BEAM) {
+    s0 = static_cast<int>(*prefill_len);
+    const int t_new = pos - s0;        // generated position of the new token
+    const int* ind = beam_ind + ((t_new + 1) & 1) * ind_plane + static_cast<long long>(b) * ind_ld;
+    for (int t = threadIdx.x; t < t_new && t < DM_MAX_NEW; t += DM_THREADS) s_ind[t] = ind[t];
+    prompt_off = (static_cast<long long>(b / beam_k * beam_k) - b) * n_kv_heads * row_elems;
+  }
+  // element offset (relative to this CTA's own cache row) of the cache row holding key position p
+  auto key_off = [&](int p) -> long long {
+    if (!BEAM || p >= pos) return 0;
+    if (p < s0) return prompt_off;
+    return (static_cast<long long>(s_ind[p - s0]) - b) * n_kv_heads * row_elems;
+  };
 
   // ---- append the new token (RoPE on the key), read back below with coherent loads after the barrier ----
   if (threadIdx.x < NCH) {
@@ -340,8 +362,8 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restr
       for (int q = 0; q < NQ; ++q) {
         ka[u][q] = make_uint4(0u, 0u, 0u, 0u);
         kb[u][q] = make_uint4(0u, 0u, 0u, 0u);
-        const bf16* pka = krow + static_cast<long long>(pa) * HD + (c + 4 * q) * 8;
-        const bf16* pkb = krow + static_cast<long long>(pb) * HD + (c + 4 * q) * 8;
+        const bf16* pka = krow + (pa < n_keys ? key_off(pa) : 0) + static_cast<long long>(pa) * HD + (c + 4 * q) * 8;
+        const bf16* pkb = krow + (pb < n_keys ? key_off(pb) : 0) + static_cast<long long>(pb) * HD + (c + 4 * q) * 8;
         if (blk < n_blocks) {
           if (last) {
             if (pa < n_keys) ka[u][q] = ld_plain_u4(pka);
@@ -356,7 +378,7 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restr
       if (blk < n_blocks && c < 2 * NH) {
         const int pv = blk * 16 + r + 8 * (c / NH);
         if (pv < n_keys)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + static_cast<long long>(pv) * HD + (c % NH) * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + key_off(pv) + static_cast<long long>(pv) * HD + (c % NH) * 64));
       }
     }
 #pragma unroll
@@ -425,8 +447,10 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restr
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           vv[u][h][i] = make_uint4(0u, 0u, 0u, 0u);
-          const bf16* pv = vrow + static_cast<long long>(p) * HD + (r + 8 * h) * 8;
-          if (blk < n_blocks && p < n_keys) vv[u][h][i] = last ? ld_plain_u4(pv) : ld_nc_u4(pv);
+          if (blk < n_blocks && p < n_keys) {
+            const bf16* pv = vrow + key_off(p) + static_cast<long long>(p) * HD + (r + 8 * h) * 8;
+            vv[u][h][i] = last ? ld_plain_u4(pv) : ld_nc_u4(pv);
+          }
         }
       }
     }
@@ -494,11 +518,19 @@ static bool da_use_ffma() {
   return v;
 }
 
+struct BeamView {
+  const int* ind = nullptr;
+  int ind_ld = 0;
+  long long ind_plane = 0;
+  const long long* prefill_len = nullptr;
+  int K = 1;
+};
+
 template <int HD, int G>
 static int launch_decode_attn(const bf16* qkv, long long ld, bf16* kc, bf16* vc, const long long* len_idx, bf16* out,
                               long long out_ld, int B, int n_kv_heads, int max_len, float scale, cudaStream_t st,
-                              const bf16* cos_t, const bf16* sin_t) {
-  if (da_use_ffma()) {                 // measurement switch: the FFMA formulation (see the comment above the MMA kernel)
+                              const bf16* cos_t, const bf16* sin_t, const BeamView& bv) {
+  if (da_use_ffma() && !bv.ind) {      // measurement switch: the FFMA formulation (see the comment above the MMA kernel)
     auto kfn = decode_attn_kernel<HD, G>;
     const int smem = (G * max_len + DA_WARPS * G * HD + G) * 4;
     if (smem > 200 * 1024) return OMNI_ERR_UNSUPPORTED;
@@ -510,17 +542,20 @@ static int launch_decode_attn(const bf16* qkv, long long ld, bf16* kc, bf16* vc,
       return OMNI_ERR_CUDA;
     return OMNI_OK;
   }
-  auto kfn = decode_attn_mma_kernel<HD, G>;
   const int sc_stride = (max_len + 15) / 16 * 16 + 8;     // + 8: heads 2c / 2c + 1 of a store land in different banks
   const int smem = (G * sc_stride + 16 + DM_WARPS * G * HD + 2 * DM_WARPS * 8) * 4;
   if (smem > 200 * 1024) return OMNI_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return OMNI_ERR_CUDA;
-  if (omni_launch_pdl(kfn, dim3(B * n_kv_heads), dim3(DM_THREADS), smem, st, qkv, ld, kc, vc, len_idx, out, out_ld,
-                      n_kv_heads, max_len, sc_stride, scale * 1.4426950408889634f, cos_t, sin_t) != cudaSuccess)
-    return OMNI_ERR_CUDA;
-  return OMNI_OK;
+  auto go = [&](auto kfn) -> int {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    if (omni_launch_pdl(kfn, dim3(B * n_kv_heads), dim3(DM_THREADS), smem, st, qkv, ld, kc, vc, len_idx, out, out_ld,
+                        n_kv_heads, max_len, sc_stride, scale * 1.4426950408889634f, cos_t, sin_t, bv.ind, bv.ind_ld,
+                        bv.ind_plane, bv.prefill_len, bv.K) != cudaSuccess)
+      return OMNI_ERR_CUDA;
+    return OMNI_OK;
+  };
+  return bv.ind ? go(decode_attn_mma_kernel<HD, G, true>) : go(decode_attn_mma_kernel<HD, G, false>);
 }
 
 }  // namespace omni
@@ -532,10 +567,10 @@ extern "C" int omni_decode_attention(const void* qkv, int64_t ld, void* k_cache,
                                     scale, nullptr, nullptr, 0, stream);
 }
 
-extern "C" int omni_decode_attention_rope(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx,
-                                          void* out, int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads,
-                                          int32_t head_dim, int32_t max_len, float scale, const void* cos_t,
-                                          const void* sin_t, int32_t table_rows, void* stream) {
+static int decode_attention_impl(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx,
+                                 void* out, int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads,
+                                 int32_t head_dim, int32_t max_len, float scale, const void* cos_t, const void* sin_t,
+                                 int32_t table_rows, const omni::BeamView& bv, void* stream) {
   using namespace omni;
   OMNI_CHECK_ARG((cos_t == nullptr) == (sin_t == nullptr));
   if (cos_t) OMNI_CHECK_ARG(table_rows >= max_len && (reinterpret_cast<uintptr_t>(cos_t) & 15) == 0 &&
@@ -554,7 +589,7 @@ extern "C" int omni_decode_attention_rope(const void* qkv, int64_t ld, void* k_c
   bf16* o = reinterpret_cast<bf16*>(out);
 #define OMNI_DA(HD_, G_) \
   if (head_dim == HD_ && G == G_) \
-    return launch_decode_attn<HD_, G_>(q, ld, kc, vc, li, o, out_ld, B, n_kv_heads, max_len, scale, st, ct, stb);
+    return launch_decode_attn<HD_, G_>(q, ld, kc, vc, li, o, out_ld, B, n_kv_heads, max_len, scale, st, ct, stb, bv);
   // every GQA group size of the reference's model table: 4 (Llama-3.2-1B / 3.1-8B), 3 (Llama-3.2-3B), 7 (Qwen2.5-0.5B / 7B),
   // 6 (1.5B), 8 (3B), 5 (14B / 32B), + 1 / 2 for MHA-like test geometries
   OMNI_DA(64, 1) OMNI_DA(64, 2) OMNI_DA(64, 3) OMNI_DA(64, 4) OMNI_DA(64, 5) OMNI_DA(64, 6) OMNI_DA(64, 7) OMNI_DA(64, 8)
@@ -562,4 +597,28 @@ extern "C" int omni_decode_attention_rope(const void* qkv, int64_t ld, void* k_c
   OMNI_DA(128, 8)
 #undef OMNI_DA
   return OMNI_ERR_UNSUPPORTED;
+}
+
+extern "C" int omni_decode_attention_rope(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx,
+                                          void* out, int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads,
+                                          int32_t head_dim, int32_t max_len, float scale, const void* cos_t,
+                                          const void* sin_t, int32_t table_rows, void* stream) {
+  return decode_attention_impl(qkv, ld, k_cache, v_cache, len_idx, out, out_ld, B, n_heads, n_kv_heads, head_dim, max_len,
+                               scale, cos_t, sin_t, table_rows, omni::BeamView(), stream);
+}
+
+extern "C" int omni_decode_attention_beam(const void* qkv, int64_t ld, void* k_cache, void* v_cache, const int64_t* len_idx,
+                                          void* out, int64_t out_ld, int32_t B, int32_t n_heads, int32_t n_kv_heads,
+                                          int32_t head_dim, int32_t max_len, float scale, const void* cos_t,
+                                          const void* sin_t, int32_t table_rows, const int32_t* beam_ind, int32_t ind_ld,
+                                          const int64_t* prefill_len, int32_t K, void* stream) {
+  OMNI_CHECK_ARG(beam_ind && prefill_len && K > 0 && B % K == 0 && ind_ld > 0 && ind_ld <= omni::DM_MAX_NEW);
+  omni::BeamView bv;
+  bv.ind = beam_ind;
+  bv.ind_ld = ind_ld;
+  bv.ind_plane = static_cast<long long>(B) * ind_ld;
+  bv.prefill_len = reinterpret_cast<const long long*>(prefill_len);
+  bv.K = K;
+  return decode_attention_impl(qkv, ld, k_cache, v_cache, len_idx, out, out_ld, B, n_heads, n_kv_heads, head_dim, max_len,
+                               scale, cos_t, sin_t, table_rows, bv, stream);
 }

@@ -163,13 +163,17 @@ def greedy_generate(llm, inputs_embeds, max_new_tokens, eos_token_id, pad_token_
 # ---------------------------------------------------------------------------------------------------------------
 # Beam search (the evaluation default of the reference: eval_OmniAVSR.py:216-226 -> num_beams = 15, max 32 new tokens;
 # HF transformers==4.43.1 `_beam_search` + `BeamSearchScorer` semantics with length_penalty 1.0, early_stopping False).
-# Device side: the B*K beam rows run through the same packed single-token step as greedy decode (split-K GEMMs, the
-# single-token attention kernel, lm_head GEMM); the candidate ranking (fp32 log-softmax + running beam score, top-2K
-# over K*V) stays on the device; only the 2K candidates per utterance cross to the host, where the hypothesis
-# bookkeeping of the scorer runs (it is inherently sequential and tiny).
+# Everything of a step runs on the device inside ONE CUDA graph: lm_head GEMM -> omni_beam_topk_rows (fp32 log-softmax +
+# running beam score, the 2K best tokens of every beam row) -> omni_beam_select (merge per utterance, the scorer's walk over
+# the 2K best candidates, finished-hypothesis heap, `done`, token history, embedding rows of the chosen tokens, KV-cache
+# indirection) -> the packed single-token forward of the B*K rows -> counter advance.  Differences from HF's execution
+# that do not change the result: the prompt is prefilled once per utterance (HF expands it to B*K identical rows), the
+# KV cache is never gathered by beam index (the attention kernel follows an indirection table instead), and the host
+# looks at the number of finished utterances every 8 steps only.
 # ---------------------------------------------------------------------------------------------------------------
 class _Hyps:
-    """Finished hypotheses of one utterance (at most K, ranked by sum_logprobs / length)."""
+    """Finished hypotheses of one utterance (at most K, ranked by sum_logprobs / length); host mirror of the device heap
+    (csrc/beam_search.cu: hyp_add), used to close the open beams after the last step."""
 
     def __init__(self, K):
         self.K, self.items, self.worst = K, [], 1e9
@@ -185,98 +189,183 @@ class _Hyps:
             else:
                 self.worst = min(score, self.worst)
 
-    def done(self, best_running, cur_len):
-        return len(self.items) >= self.K and self.worst >= best_running / cur_len
+
+BEAM_MAX_NEW = 128          # DM_MAX_NEW of csrc/decode_attention.cu (indirection row held in shared memory)
+BEAM_MAX_K = 32             # BS_MAX_K of csrc/beam_search.cu
+
+
+class BeamState:
+    """Device-side state of one beam search (the fields of omni_beam_select_args, include/omni_avsr.h)."""
+
+    def __init__(self, B, K, V, max_new, device):
+        BK = B * K
+        self.B, self.K, self.V, self.max_new = B, K, V, max_new
+
+        def z(shape, dtype):
+            return torch.zeros(shape, dtype=dtype, device=device)
+        self.cand_score = z((BK, 2 * K), torch.float32)
+        self.cand_tok = z((BK, 2 * K), torch.int32)
+        self.beam_scores = z(BK, torch.float32)
+        self.step_idx = z(1, torch.int64)
+        self.eos, self.pad, self.prefill_len = z(1, torch.int64), z(1, torch.int64), z(1, torch.int64)
+        self.seqs = z((2, BK, max_new), torch.int32)
+        self.ind = z((2, BK, max_new), torch.int32)
+        self.hyp_seq = z((B, K + 1, max_new), torch.int32)
+        self.hyp_len = z((B, K + 1), torch.int32)
+        self.hyp_score = z((B, K + 1), torch.float64)
+        self.hyp_order = z((B, K + 1), torch.int32)
+        self.hyp_count = z(B, torch.int32)
+        self.hyp_worst = z(B, torch.float64)
+        self.done, self.n_done, self.status = z(B, torch.int32), z(1, torch.int32), z(1, torch.int32)
+        self._order0 = torch.arange(K + 1, dtype=torch.int32, device=device).repeat(B, 1).contiguous()
+        first = torch.full((B, K), -1e9, dtype=torch.float32, device=device)
+        first[:, 0] = 0.0                    # HF: only the first beam of an utterance is live before the first step
+        self._scores0 = first.view(-1).contiguous()
+
+    def reset(self, eos, pad, prefill_len):
+        self.beam_scores.copy_(self._scores0)
+        self.hyp_order.copy_(self._order0)
+        self.hyp_worst.fill_(1e9)
+        for t in (self.step_idx, self.seqs, self.ind, self.hyp_count, self.done, self.n_done, self.status):
+            t.zero_()
+        self.eos.fill_(eos)
+        self.pad.fill_(pad)
+        self.prefill_len.fill_(prefill_len)
+
+    def tensors(self):
+        return [self.beam_scores, self.step_idx, self.seqs, self.ind, self.hyp_seq, self.hyp_len, self.hyp_score,
+                self.hyp_order, self.hyp_count, self.hyp_worst, self.done, self.n_done, self.status]
+
+
+class GraphedBeamStep:
+    """One beam-search step (ranking + scorer + forward of the B*K rows) captured in a CUDA graph."""
+
+    def __init__(self, llm, B, K, max_len, max_new, device):
+        a = llm.config
+        self.llm, self.B, self.K, self.max_len, self.max_new = llm, B, K, max_len, max_new
+        BK = B * K
+        self.cache = KVCache(a, BK, max_len, device)
+        self.cache.row_stride = K                      # the prefill of utterance u lands in cache row u * K
+        self.state = BeamState(B, K, a.vocab_size, max_new, device)
+        self.cache.beam = (self.state.ind, self.state.prefill_len, K)
+        self.rows = _StepRows(BK, device, max_len)
+        self.xpad = torch.zeros((BK, a.hidden_size), dtype=torch.bfloat16, device=device)
+        self.h_last = torch.zeros((BK, a.hidden_size), dtype=torch.bfloat16, device=device)
+        self.graph = None
+        llm.model.rope(max_len)
+
+    def _body(self):
+        llm, st = self.llm, self.state
+        logits = llm.logits_rows(self.h_last)                                    # [B*K, V] bf16 (lm_head GEMM)
+        ops.beam_topk_rows(logits, llm.config.vocab_size, st.beam_scores, st.cand_score, st.cand_tok)
+        ops.beam_select(st, llm.model.embed_tokens.weight.data, self.xpad)
+        hid = llm.model.forward_packed(self.xpad, self.rows, self.cache)
+        self.h_last.copy_(hid[: self.B * self.K])
+        ops.decode_advance(st.step_idx, self.cache.len_idx, self.rows.pos)
+
+    def start(self, task, prefill_len, h_last, eos, pad):
+        self.rows.tile_group.fill_(task)
+        self.rows.pos.fill_(prefill_len)
+        self.cache.len = prefill_len
+        self.cache.sync_device_state()
+        self.cache.graph_mode = True
+        self.state.reset(eos, pad, prefill_len)
+        self.h_last.copy_(h_last)
+
+    def _mutable(self):
+        return self.state.tensors() + [self.cache.len_idx, self.rows.pos, self.h_last, self.xpad]
+
+    def run(self, steps, use_graph=True):
+        """Runs up to `steps` ranking steps; returns how many were executed (== steps unless every utterance finished)."""
+        if use_graph and self.graph is None:
+            snap = [t.clone() for t in self._mutable()]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()                           # allocator / lazy-init warm-up outside the capture
+            torch.cuda.current_stream().wait_stream(s)
+            for t, v in zip(self._mutable(), snap):
+                t.copy_(v)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+            for t, v in zip(self._mutable(), snap):
+                t.copy_(v)
+        n = 0
+        while n < steps:
+            if use_graph:
+                self.graph.replay()
+            else:
+                self._body()
+            n += 1
+            if n % 8 == 0 and n < steps and int(self.state.n_done.item()) == self.B:
+                break                                  # HF leaves the loop as soon as every utterance is done
+        return n
+
+    def finish(self):
+        self.cache.graph_mode = False
+
+
+def _get_beam_step(llm, B, K, max_len, max_new, device):
+    cache = getattr(llm, "_graphed_beam_steps", None)
+    if cache is None:
+        cache = llm._graphed_beam_steps = {}
+    key = (B, K, max_len, max_new)
+    if key not in cache:
+        if len(cache) >= 2:
+            cache.clear()
+        cache[key] = GraphedBeamStep(llm, B, K, max_len, max_new, device)
+    return cache[key]
 
 
 @torch.no_grad()
-def beam_generate(llm, inputs_embeds, max_new_tokens, num_beams, eos_token_id, pad_token_id, modality=None):
+def beam_generate(llm, inputs_embeds, max_new_tokens, num_beams, eos_token_id, pad_token_id, modality=None, use_graph=True):
     ops.require_cuda(inputs_embeds)
     B, S0, H = inputs_embeds.shape
     K = int(num_beams)
-    BK = B * K
+    if K > BEAM_MAX_K or max_new_tokens > BEAM_MAX_NEW:
+        raise NotImplementedError(f"beam search kernels: num_beams <= {BEAM_MAX_K}, max_new_tokens <= {BEAM_MAX_NEW}")
     dev = inputs_embeds.device
-    a = llm.config
     task = llm._task_of(modality)
     if pad_token_id is None:
         pad_token_id = eos_token_id
     max_len = (S0 + max_new_tokens + 127) // 128 * 128
-    cache = KVCache(a, BK, max_len, dev)
-    # prefill on the expanded prompt (HF expands inputs_embeds to B*K rows before the first forward)
-    rows = PackedRows.get([(task, BK, S0)], dev)
-    x = inputs_embeds.to(torch.bfloat16).repeat_interleave(K, dim=0)
-    hid = llm.model.forward_packed(pack_segments([x], rows), rows, cache)
-    cache.advance(S0)
-    last = (torch.arange(BK, device=dev, dtype=torch.int64) * S0 + (S0 - 1)).contiguous()
-    h_last = ops.gather_rows(hid, last)
-    # single-token step state (same layout as the graphed greedy step, run eagerly: the beam permutation changes per step)
-    srows = _StepRows(BK, dev, max_len)
-    srows.tile_group.fill_(task)
-    xpad = torch.zeros((srows.M, a.hidden_size), dtype=torch.bfloat16, device=dev)
-    llm.model.rope(max_len)
-    cache.graph_mode = True
-
-    beam_scores = torch.zeros((B, K), dtype=torch.float32, device=dev)
-    beam_scores[:, 1:] = -1e9
-    beam_scores = beam_scores.view(-1)
-    hyps = [_Hyps(K) for _ in range(B)]
-    finished = [False] * B
-    seqs = [[] for _ in range(BK)]          # token history per beam row (host)
-    V = a.vocab_size
-    cur_len = 0
-    while True:
-        logits = llm.logits_rows(h_last)                                        # [BK, V] bf16 (lm_head GEMM)
-        logp = torch.log_softmax(logits.float(), dim=-1) + beam_scores[:, None]
-        top_s, top_i = torch.topk(logp.view(B, K * V), 2 * K, dim=1, largest=True, sorted=True)
-        top_s, top_i = top_s.tolist(), top_i.tolist()                           # the step's only host sync
-        cur_len += 1
-        new_scores, new_tokens, new_rows = [], [], []
-        for b in range(B):
-            if finished[b]:
-                new_scores += [0.0] * K
-                new_tokens += [pad_token_id] * K
-                new_rows += [0] * K
-                continue
-            taken = 0
-            for rank in range(2 * K):
-                tok, row, sc = top_i[b][rank] % V, b * K + top_i[b][rank] // V, top_s[b][rank]
-                if tok == eos_token_id:
-                    if rank < K:
-                        hyps[b].add(list(seqs[row]), sc, cur_len)
-                    continue
-                new_scores.append(sc)
-                new_tokens.append(tok)
-                new_rows.append(row)
-                taken += 1
-                if taken == K:
-                    break
-            if taken < K:
-                raise ValueError(f"At most {K} tokens can be equal to `eos_token_id: {eos_token_id}`.")
-            finished[b] = hyps[b].done(max(top_s[b]), cur_len)
-        seqs = [seqs[r] + [t] for r, t in zip(new_rows, new_tokens)]
-        beam_scores = torch.tensor(new_scores, dtype=torch.float32, device=dev)
-        if all(finished) or cur_len >= max_new_tokens:
-            break
-        # next step: reorder the cache rows by beam, embed the chosen tokens, one packed single-token forward
-        idx = torch.tensor(new_rows, dtype=torch.int64, device=dev)
-        n = cache.len
-        cache.k[:, :, :, :n] = cache.k[:, :, :, :n].index_select(1, idx)
-        cache.v[:, :, :, :n] = cache.v[:, :, :, :n].index_select(1, idx)
-        tok = torch.tensor(new_tokens, dtype=torch.int64, device=dev)
-        xpad[:BK].copy_(ops.gather_rows(llm.model.embed_tokens.weight.data, tok))
-        cache.sync_device_state()
-        srows.pos.fill_(cache.len)
-        hid = llm.model.forward_packed(xpad, srows, cache)
-        cache.advance(1)
-        h_last = hid[:BK].contiguous()
+    step = _get_beam_step(llm, B, K, max_len, max_new_tokens, dev)
+    cache = step.cache
     cache.graph_mode = False
-    # finalize: open beams become hypotheses, best one per utterance, EOS appended if it fits, right-padded
-    final = beam_scores.tolist()
+    cache.len = 0
+    # prefill once per utterance (HF expands inputs_embeds to B*K identical rows before the first forward)
+    rows = PackedRows.get([(task, B, S0)], dev)
+    hid = llm.model.forward_packed(pack_segments([inputs_embeds.to(torch.bfloat16)], rows), rows, cache)
+    cache.advance(S0)
+    last = (torch.arange(B, device=dev, dtype=torch.int64) * S0 + (S0 - 1)).contiguous()
+    h_last = ops.gather_rows(hid, last).repeat_interleave(K, dim=0)
+    step.start(task, S0, h_last, eos_token_id, pad_token_id)
+    cur_len = step.run(max_new_tokens, use_graph=use_graph and not os.environ.get("OMNI_DECODE_NO_GRAPH"))
+    step.finish()
+
+    # finalize on the host (one read-back per decode): open beams become hypotheses, best one per utterance, EOS appended if
+    # it fits, right-padded
+    st = step.state
+    if int(st.status.item()) != 0:
+        raise ValueError(f"At most {K} tokens can be equal to `eos_token_id: {eos_token_id}`.")
+    hyp_seq, hyp_len, hyp_score = st.hyp_seq.tolist(), st.hyp_len.tolist(), st.hyp_score.tolist()
+    hyp_order, hyp_count, hyp_worst = st.hyp_order.tolist(), st.hyp_count.tolist(), st.hyp_worst.tolist()
+    done = st.done.tolist()
+    seqs = st.seqs[cur_len & 1].tolist()               # step s writes buffer (s + 1) & 1
+    final = st.beam_scores.tolist()
+    best = []
     for b in range(B):
-        if not finished[b]:
+        h = _Hyps(K)
+        h.worst = hyp_worst[b]
+        for i in range(hyp_count[b]):
+            slot = hyp_order[b][i]
+            h.items.append((hyp_score[b][slot], hyp_seq[b][slot][: hyp_len[b][slot]]))
+        if not done[b]:
             for k in range(K):
-                hyps[b].add(list(seqs[b * K + k]), final[b * K + k], cur_len)
-    best = [sorted(h.items, key=lambda t: t[0])[-1][1] for h in hyps]
+                h.add(seqs[b * K + k][:cur_len], final[b * K + k], cur_len)
+        best.append(sorted(h.items, key=lambda t: t[0])[-1][1])
     lengths = [len(h) for h in best]
     sent_max = min(max(lengths) + 1, max_new_tokens)
     out = torch.full((B, sent_max), pad_token_id, dtype=torch.int64)

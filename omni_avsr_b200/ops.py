@@ -596,6 +596,36 @@ def decode_advance(step_idx, len_idx, pos):
     _count()
 
 
+def beam_topk_rows(logits, V: int, beam_scores, cand_score, cand_tok):
+    """Per logits row: fp32 log-softmax + running beam score of the row's n_cand best tokens, sorted (omni_beam_topk_rows)."""
+    require_cuda(logits, beam_scores, cand_score, cand_tok)
+    rows, n_cand = cand_score.shape
+    if logits.dtype != torch.bfloat16 or logits.stride(1) != 1 or beam_scores.dtype != torch.float32 or \
+            cand_score.dtype != torch.float32 or cand_tok.dtype != torch.int32 or not cand_score.is_contiguous() or \
+            not cand_tok.is_contiguous() or cand_tok.shape != cand_score.shape or logits.shape[0] != rows or \
+            beam_scores.numel() != rows:
+        raise ValueError("beam_topk_rows: bf16 logits [rows, >= V], fp32 scores [rows], fp32 / int32 candidates [rows, n_cand]")
+    check(lib.omni_beam_topk_rows(logits.data_ptr(), logits.stride(0), rows, V, beam_scores.data_ptr(), n_cand,
+                                  cand_score.data_ptr(), cand_tok.data_ptr(), stream_ptr()), "omni_beam_topk_rows")
+    _count()
+
+
+def beam_select(st, embed, x_next):
+    """BeamSearchScorer.process of one step on the device (omni_beam_select).  `st` is a decode.BeamState."""
+    from ._lib import BeamSelectArgs
+    require_cuda(embed, x_next)
+    a = BeamSelectArgs()
+    for name in ("cand_score", "cand_tok", "beam_scores", "step_idx", "eos", "pad", "seqs", "ind", "hyp_seq", "hyp_len",
+                 "hyp_score", "hyp_order", "hyp_count", "hyp_worst", "done", "n_done", "status"):
+        setattr(a, name, getattr(st, name).data_ptr())
+    a.embed, a.x_next = embed.data_ptr(), x_next.data_ptr()
+    a.ld_embed, a.ld_x = embed.stride(0), x_next.stride(0)
+    a.B, a.K, a.n_cand, a.V, a.max_new, a.ind_ld, a.H = st.B, st.K, 2 * st.K, st.V, st.max_new, st.ind.shape[2], embed.shape[1]
+    import ctypes
+    check(lib.omni_beam_select(ctypes.byref(a), stream_ptr()), "omni_beam_select")
+    _count()
+
+
 def argmax_rows(logits):
     require_cuda(logits)
     R, V = logits.shape
@@ -1130,12 +1160,14 @@ DECODE_ATTN_GROUPS = (1, 2, 3, 4, 5, 6, 7, 8)
 
 
 def decode_attention(qkv, k_cache, v_cache, len_idx, out, B: int, n_heads: int, n_kv_heads: int, head_dim: int,
-                     scale: Optional[float] = None, rope: Optional[tuple] = None):
+                     scale: Optional[float] = None, rope: Optional[tuple] = None, beam: Optional[tuple] = None):
     """Single-token attention over the static KV cache [B, n_kv_heads, max_len, head_dim] (one layer): appends the new
     token's K / V (from the packed q|k|v rows, RoPE applied) at position len_idx[0] (int64, device) and attends over
     positions 0..len_idx[0].  out [>=B, n_heads*head_dim] bf16; rows >= B untouched.
     rope = (cos_t, sin_t) bf16 [>= max_len, head_dim]: the packed rows hold q|k|v BEFORE the rotary embedding, which the
-    kernel applies to the q heads and the new key at position len_idx[0] (no separate rope_ launch)."""
+    kernel applies to the q heads and the new key at position len_idx[0] (no separate rope_ launch).
+    beam = (ind, prefill_len, K): beam-search rows (B = utterances x K); `ind` int32 [2, B, ind_ld] is the KV-cache
+    indirection table written by beam_select, `prefill_len` an int64 device scalar (see omni_decode_attention_beam)."""
     require_cuda(qkv, k_cache, v_cache, len_idx, out)
     qkv = _bf16_2d(qkv, "qkv")
     out = _bf16_2d(out, "out")
@@ -1152,6 +1184,21 @@ def decode_attention(qkv, k_cache, v_cache, len_idx, out, B: int, n_heads: int, 
         if cos_t.dtype != torch.bfloat16 or cos_t.shape[-1] != head_dim or not cos_t.is_contiguous() or \
                 not sin_t.is_contiguous() or cos_t.shape != sin_t.shape or cos_t.shape[0] < k_cache.shape[2]:
             raise ValueError("rope tables must be contiguous bf16 [>= max_len, head_dim]")
+    if beam is not None:
+        ind, prefill_len, K = beam
+        require_cuda(ind, prefill_len)
+        if ind.dtype != torch.int32 or not ind.is_contiguous() or ind.dim() != 3 or ind.shape[0] != 2 or ind.shape[1] != B \
+                or prefill_len.dtype != torch.int64 or B % K:
+            raise ValueError("beam = (int32 ind [2, B, ind_ld], int64 prefill_len [1], K) with B a multiple of K")
+        cp, sp, tr = (rope[0].data_ptr(), rope[1].data_ptr(), rope[0].shape[0]) if rope is not None else (None, None, 0)
+        check(lib.omni_decode_attention_beam(qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
+                                             len_idx.data_ptr(), out.data_ptr(), out.stride(0), B, n_heads, n_kv_heads,
+                                             head_dim, k_cache.shape[2], float(scale), cp, sp, tr, ind.data_ptr(),
+                                             ind.shape[2], prefill_len.data_ptr(), int(K), stream_ptr()),
+              "omni_decode_attention_beam")
+        _count()
+        return out
+    if rope is not None:
         check(lib.omni_decode_attention_rope(qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
                                              len_idx.data_ptr(), out.data_ptr(), out.stride(0), B, n_heads, n_kv_heads,
                                              head_dim, k_cache.shape[2], float(scale), cos_t.data_ptr(), sin_t.data_ptr(),
