@@ -256,14 +256,17 @@ def measure_train(mod, B, device, rank, world, barrier, steps, warmup, seed=1234
     host = synthetic_batch(B, mod.tokenizer, seconds=16.0, text_len=48, seed=seed + rank, pin=True)
     res = to_device(host, device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    if micro and micro < B and world == 1:
+    if micro and micro < B:
         parts = [{k: (v[i: i + micro].contiguous() if torch.is_tensor(v) else v) for k, v in res.items()}
                  for i in range(0, B, micro)]
 
         def one_step(k):
             mod.zero_grad_flat()
-            for p_ in parts:
-                (mod.training_step(p_, 0, RATE_GRID[k % 4]) * (p_["tokens"].shape[0] / B)).backward()
+            for i, p_ in enumerate(parts):
+                mod.no_sync = i < len(parts) - 1          # gradients accumulate locally; the last micro-batch reduces
+                # loss * W / sum(B) divides the mean loss by the batch size: weight (b / B) ** 2 reproduces the one-batch step
+                (mod.training_step(p_, 0, RATE_GRID[k % 4]) * (p_["tokens"].shape[0] / B) ** 2).backward()
+            mod.no_sync = False
             mod.optimizer_step(1e-4)
     else:
         def one_step(k):
@@ -340,60 +343,56 @@ def measure_ragged(mod, device, rank, world, barrier, max_frames=12800, n_utts=3
 
 
 def extra_configs(args, device, rank, world, barrier):
-    """BASELINE configs 3 / 4 / 5 and the strong-scaling point as extra objects of the ONE JSON line (bounded: a few steps
-    each).  None of them is the judged headline; each names its configuration."""
+    """BASELINE configs 3 / 4 / 5, the strong-scaling point and the ragged (bucketed) workload as extra objects of the ONE
+    JSON line (bounded: a few steps each).  None of them is the judged headline; each names its configuration."""
+    import gc
     out = {}
 
-    def free(m):
-        del m
-        import gc
-        gc.collect()
-        torch.cuda.empty_cache()
-    try:    # SURVEY 8(f) rank 3: variable-length utterances through the reference's frame-budget bucketing
-        m = build_module(args, device)
-        out["ragged_bucketed_train"] = measure_ragged(m, device, rank, world, barrier)
-        free(m)
-    except Exception as ex:      # noqa: BLE001
-        out["ragged_bucketed_train"] = {"error": repr(ex)[:300]}
-        torch.cuda.empty_cache()
-    try:    # config 3: joint 3-task training, TASK-SPECIFIC LoRA (no shared adapter), data parallel at this N
-        m = build_module(args, device, task_specific=True, shared=False)
+    def run(name, build_kw, fn):
+        """Build a module, measure, and drop the module (with its CUDA graphs and caches) before the next configuration."""
+        m = None
+        torch.cuda.reset_peak_memory_stats()
+        before = torch.cuda.memory_allocated()
+        try:
+            m = build_module(args, device, **build_kw)
+            out[name] = fn(m)
+        except Exception as ex:      # noqa: BLE001  (reported in the line, never fatal for the headline)
+            out[name] = {"error": repr(ex)[:300]}
+        finally:
+            m = None
+            gc.collect()
+            torch.cuda.empty_cache()
+            out[name]["hbm_gb"] = {"peak": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                                   "live_before": round(before / 2 ** 30, 1),
+                                   "live_after": round(torch.cuda.memory_allocated() / 2 ** 30, 1)}
+
+    # SURVEY 8(f) rank 3: variable-length utterances through the reference's frame-budget bucketing
+    run("ragged_bucketed_train", {}, lambda m: measure_ragged(m, device, rank, world, barrier))
+
+    def config3(m):     # joint 3-task training, TASK-SPECIFIC LoRA (no shared adapter), data parallel at this N
         v, ms = measure_train(m, args.batch, device, rank, world, barrier, steps=4, warmup=1)
-        out["config3_task_specific_lora"] = {"value": round(v, 2), "unit": "utterances/s", "ms_per_step": round(ms, 2),
-                                             "per_gpu_batch": args.batch, "n_gpus": world, "scaling": "weak",
-                                             "lora": "task-specific (IS_TASK_SPECIFIC, no shared adapter), Llama-3.2-1B"}
-        free(m)
-    except Exception as ex:      # noqa: BLE001
-        out["config3_task_specific_lora"] = {"error": repr(ex)[:200]}
-    try:    # strong scaling: global batch fixed at 256 utterances
-        gb = 256
-        per = gb // world
-        m = build_module(args, device)
+        return {"value": round(v, 2), "unit": "utterances/s", "ms_per_step": round(ms, 2), "per_gpu_batch": args.batch,
+                "n_gpus": world, "scaling": "weak", "lora": "task-specific (IS_TASK_SPECIFIC, no shared adapter), Llama-3.2-1B"}
+    run("config3_task_specific_lora", dict(task_specific=True, shared=False), config3)
+
+    def strong(m):      # strong scaling: global batch fixed at 256 utterances
+        per = 256 // world
         v, ms = measure_train(m, per, device, rank, world, barrier, steps=3, warmup=0, micro=64)
-        out["strong_scaling_global_batch_256"] = {"value": round(v, 2), "unit": "utterances/s", "ms_per_step": round(ms, 2),
-                                                  "per_gpu_batch": per, "n_gpus": world, "scaling": "strong",
-                                                  "note": "one optimizer step per 256 utterances; at N=1 the 256 utterances run as "
-                                                          "4 micro-batches of 64 accumulating into the flat gradient buffer"}
-        free(m)
-    except Exception as ex:      # noqa: BLE001
-        out["strong_scaling_global_batch_256"] = {"error": repr(ex)[:200]}
-        torch.cuda.empty_cache()
-    try:    # config 4: elastic greedy decode sweep, batch 64, Qwen2.5-3B backbone
-        m = build_module(args, device, llm="Qwen/Qwen2.5-3B")
-        out["config4_qwen25_3b_decode_B64"] = measure_decode(m, 64, device, rank, world, barrier, "Qwen/Qwen2.5-3B")
-        free(m)
-    except Exception as ex:      # noqa: BLE001
-        out["config4_qwen25_3b_decode_B64"] = {"error": repr(ex)[:200]}
-        torch.cuda.empty_cache()
-    try:    # config 5: Llama-3.1-8B backbone, hybrid Omni-LoRA, full rate grid
-        m = build_module(args, device, llm="meta-llama/Meta-Llama-3.1-8B")
+        return {"value": round(v, 2), "unit": "utterances/s", "ms_per_step": round(ms, 2), "per_gpu_batch": per,
+                "n_gpus": world, "scaling": "strong",
+                "note": "one optimizer step per 256 utterances; per-GPU batches above 64 run as micro-batches of 64 accumulating "
+                        "into the flat gradient buffer (one all-reduce per optimizer step)"}
+    run("strong_scaling_global_batch_256", {}, strong)
+
+    # config 4: elastic greedy decode sweep, batch 64, Qwen2.5-3B backbone
+    run("config4_qwen25_3b_decode_B64", dict(llm="Qwen/Qwen2.5-3B"),
+        lambda m: measure_decode(m, 64, device, rank, world, barrier, "Qwen/Qwen2.5-3B"))
+
+    def config5(m):     # Llama-3.1-8B backbone, hybrid Omni-LoRA, full rate grid
         v, ms = measure_train(m, 16, device, rank, world, barrier, steps=4, warmup=0)
-        out["config5_llama31_8b_train"] = {"value": round(v, 2), "unit": "utterances/s", "ms_per_step": round(ms, 2),
-                                           "per_gpu_batch": 16, "n_gpus": world, "scaling": "weak"}
-        free(m)
-    except Exception as ex:      # noqa: BLE001
-        out["config5_llama31_8b_train"] = {"error": repr(ex)[:200]}
-        torch.cuda.empty_cache()
+        return {"value": round(v, 2), "unit": "utterances/s", "ms_per_step": round(ms, 2), "per_gpu_batch": 16,
+                "n_gpus": world, "scaling": "weak"}
+    run("config5_llama31_8b_train", dict(llm="meta-llama/Meta-Llama-3.1-8B"), config5)
     return out
 
 

@@ -238,7 +238,9 @@ class ModelModule_LLM(torch.nn.Module):
         # :171-173: loss *= W / sum(batch sizes).  The gather of the batch sizes is started here and waited for after the
         # forward (one rank: the host constant 1 / B)
         scale = dp.LossScale(batch["tokens"].shape[0], device=batch["tokens"].device)
-        if scale.w > 1:
+        if scale.w > 1 and not getattr(self, "no_sync", False):
+            # (no_sync = True: a micro-batch of a gradient-accumulation step -- Lightning's accumulate_grad_batches under DDP --
+            # whose gradients only accumulate in the flat buffer; the last micro-batch runs with no_sync = False)
             # gradient all-reduce in two pieces: the LLM adapters' range goes out as soon as the gradient of the LLM input
             # exists, under the backward of the projectors / AV-HuBERT encoder (see dp.GradReducer)
             flat = self.model.flat

@@ -864,7 +864,9 @@ class RingFrames:
         key = (int(N), int(H), int(W), int(C), str(device))
         ent = cls._pool.get(key)
         if ent is None:
-            if len(cls._pool) > 64:
+            # one batch geometry at a time: a different frame count (variable-length batches, train / eval alternation)
+            # drops the previous geometry's buffers instead of keeping six buffers per layer for every length ever seen
+            if len(cls._pool) > 64 or any(k[0] != key[0] for k in cls._pool):
                 cls._pool.clear()
             ent = cls._pool[key] = [[cls(N, H, W, C, device) for _ in range(6)], 0]
         ent[1] = (ent[1] + 1) % 6
@@ -1002,7 +1004,7 @@ class FrameRows:
         key = (int(N), int(H), int(W), int(C), int(PA), str(device))
         ent = cls._pool.get(key)
         if ent is None:
-            if len(cls._pool) > 64:
+            if len(cls._pool) > 64 or any(k[0] != key[0] for k in cls._pool):     # one batch geometry at a time (see RingFrames)
                 cls._pool.clear()
             ent = cls._pool[key] = [[cls(N, H, W, C, PA, device) for _ in range(6)], 0]
         ent[1] = (ent[1] + 1) % 6

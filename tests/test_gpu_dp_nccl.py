@@ -44,10 +44,26 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world)
     mine = list(range(rank, 4, world))
     g2, loss2 = step(_slice(cpu, mine))
+    # gradient accumulation under data parallelism (Lightning accumulate_grad_batches): the rank's two utterances as two
+    # micro-batches, the first with no_sync (no collective, gradients accumulate in the flat buffer), ONE reduction after the
+    # second -- the same gradient as the one-batch step
+    mod.zero_grad_flat()
+    for i, u in enumerate(mine):
+        mod.no_sync = i < len(mine) - 1
+        # the reference's rule divides the MEAN loss by the batch size (loss * W / sum B): a micro-batch of b of the rank's
+        # B utterances therefore carries the weight (b / B) ** 2
+        (mod.training_step(to_device(_slice(cpu, [u]), "cuda"), 0, rates=(4, 2)) * (1.0 / len(mine)) ** 2).backward()
+        assert (getattr(mod, "_reducer", None) is None) == mod.no_sync
+    mod.no_sync = False
+    factor = mod._reducer.finish()
+    mod._reducer = None
+    torch.cuda.synchronize()
+    g3 = mod.model.flat.grad[:used].float().clone() * factor
     if rank == 0:
         want = single * world
         err = (g2 - want).abs().max().item() / want.abs().max().item()
-        q.put((err, float(want.abs().max()), loss2))
+        err_acc = (g3 - want).abs().max().item() / want.abs().max().item()
+        q.put((max(err, err_acc), float(want.abs().max()), loss2))
     dist.barrier()
     dist.destroy_process_group()
 
