@@ -265,7 +265,6 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restr
                        const bf16* __restrict__ sin_t, const int* __restrict__ beam_ind, int ind_ld, long long ind_plane,
                        const long long* __restrict__ prefill_len, int beam_k) {
   pdl_launch_dependents();
-  pdl_wait();                          // q|k|v row and the cache position come from predecessors
   constexpr int NCH = HD / 8;          // 16-byte chunks per row
   constexpr int NQ = HD / 32;          // chunks per lane in pass 1 (c + 4q)
   constexpr int NH = HD / 64;          // chunks per lane in pass 2 (r + 8h)
@@ -291,6 +290,21 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restr
   const long long row_elems = static_cast<long long>(max_len) * HD;
   bf16* krow = kc + (static_cast<long long>(b) * n_kv_heads + kvh) * row_elems;
   bf16* vrow = vc + (static_cast<long long>(b) * n_kv_heads + kvh) * row_elems;
+  // Everything above and the cached rows [0, pos) were written by EARLIER steps (the position counter by the previous step's
+  // omni_decode_advance, the rows by this layer's launches of the previous steps): under programmatic dependent launch they
+  // are complete while the producer of the q|k|v row (the immediate predecessor) is still running, so this CTA pulls its K
+  // and V rows towards L2 before griddepcontrol.wait -- the HBM stream of the cache overlaps the q|k|v GEMM instead of
+  // starting after this kernel's own prologue.  (BEAM: the prompt part, which is all but <= max_new positions.)
+  {
+    const int n_old = BEAM ? min(pos, static_cast<int>(*prefill_len)) : pos;
+    const long long poff = BEAM ? (static_cast<long long>(b / beam_k * beam_k) - b) * n_kv_heads * row_elems : 0;
+    const int n_lines = (n_old * HD * 2) >> 7;                   // 128-byte lines of one row range
+    for (int i = threadIdx.x; i < n_lines; i += DM_THREADS) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(krow + poff + i * 64));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + poff + i * 64));
+    }
+  }
+  pdl_wait();                          // the q|k|v row comes from the predecessor
   __shared__ int s_ind[BEAM ? DM_MAX_NEW : 1];
   int s0 = 0;
   long long prompt_off = 0;            // element offset of (prompt row, kvh) relative to (row b, kvh)
@@ -374,8 +388,8 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restr
           }
         }
       }
-      // pull the matching V rows towards L2 now (pass 2 then runs out of L2; the HBM streams of K and V overlap)
-      if (blk < n_blocks && c < 2 * NH) {
+      // BEAM: the generated positions live in other beams' rows and were not covered by the prefetch above
+      if (BEAM && blk < n_blocks && c < 2 * NH) {
         const int pv = blk * 16 + r + 8 * (c / NH);
         if (pv < n_keys)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + key_off(pv) + static_cast<long long>(pv) * HD + (c % NH) * 64));
