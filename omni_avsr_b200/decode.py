@@ -328,6 +328,8 @@ def beam_generate(llm, inputs_embeds, max_new_tokens, num_beams, eos_token_id, p
         raise NotImplementedError(f"beam search kernels: num_beams <= {BEAM_MAX_K}, max_new_tokens <= {BEAM_MAX_NEW}")
     dev = inputs_embeds.device
     task = llm._task_of(modality)
+    if eos_token_id is None:
+        raise ValueError("beam search needs an eos_token_id (HF BeamSearchScorer closes hypotheses on it)")
     if pad_token_id is None:
         pad_token_id = eos_token_id
     max_len = (S0 + max_new_tokens + 127) // 128 * 128
