@@ -60,7 +60,6 @@ __global__ void __launch_bounds__(BT_THREADS)
 beam_topk_rows_kernel(const bf16* __restrict__ logits, long long ld, int V, const float* __restrict__ beam_scores, int n_cand,
                       float* __restrict__ cand_score, int* __restrict__ cand_tok) {
   __shared__ float s_m[32], s_s[32];
-  __shared__ uint32_t s_tmax[BT_THREADS];
   __shared__ unsigned long long s_cand[BT_CAP];
   __shared__ unsigned long long s_red[32];
   __shared__ int s_count;
@@ -75,23 +74,31 @@ beam_topk_rows_kernel(const bf16* __restrict__ logits, long long ld, int V, cons
   // ---- pass 1: online max / sum-exp per thread, per-thread maximal key ----
   float m = -INFINITY, s = 0.f;
   uint32_t tk = 0;
-  for (int i = tid; i < nvec; i += BT_THREADS) {
-    const uint4 u = ld_nc_u4(reinterpret_cast<const uint4*>(x) + i);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float f[8];
+  constexpr int UN = 4;                 // 16-byte loads in flight per thread (the row passes are latency-bound otherwise)
+  for (int i0 = tid; i0 < nvec; i0 += UN * BT_THREADS) {
+    uint4 uu[UN];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = bf2_to_f2(w[j]);
-      f[2 * j] = t.x; f[2 * j + 1] = t.y;
-      const uint32_t k0 = bf16_key(w[j] & 0xffffu), k1 = bf16_key(w[j] >> 16);
-      tk = max(tk, max(k0, k1));
+    for (int k = 0; k < UN; ++k)
+      if (i0 + k * BT_THREADS < nvec) uu[k] = ld_nc_u4(reinterpret_cast<const uint4*>(x) + i0 + k * BT_THREADS);
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      if (i0 + k * BT_THREADS >= nvec) break;
+      const uint32_t w[4] = {uu[k].x, uu[k].y, uu[k].z, uu[k].w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = bf2_to_f2(w[j]);
+        f[2 * j] = t.x; f[2 * j + 1] = t.y;
+        const uint32_t k0 = bf16_key(w[j] & 0xffffu), k1 = bf16_key(w[j] >> 16);
+        tk = max(tk, max(k0, k1));
+      }
+      float cm = f[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) cm = fmaxf(cm, f[j]);
+      if (cm > m) { s *= __expf(m - cm); m = cm; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += __expf(f[j] - m);
     }
-    float cm = f[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) cm = fmaxf(cm, f[j]);
-    if (cm > m) { s *= __expf(m - cm); m = cm; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += __expf(f[j] - m);
   }
   for (int i = (nvec << 3) + tid; i < V; i += BT_THREADS) {            // tail (V not a multiple of 8)
     const uint32_t bits = xb[i];
@@ -105,7 +112,6 @@ beam_topk_rows_kernel(const bf16* __restrict__ logits, long long ld, int V, cons
     float wm = warp_max(m);
     float ws = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - wm));
     if ((tid & 31) == 0) { s_m[tid >> 5] = wm; s_s[tid >> 5] = ws; }
-    s_tmax[tid] = tk;
     if (tid == 0) s_count = 0;
     __syncthreads();
     if (tid < 32) {
@@ -115,15 +121,20 @@ beam_topk_rows_kernel(const bf16* __restrict__ logits, long long ld, int V, cons
       if (tid == 0) { s_stats[0] = bm; s_stats[1] = logf(bs); }
     }
   }
-  // the n_cand-th largest per-thread maximum is a lower bound of the row's n_cand-th largest element
+  // the n_cand-th largest per-thread maximum is a lower bound of the row's n_cand-th largest element: bitwise radix select
+  // over the 1024 16-bit keys (one __syncthreads_count per bit; a rank-by-counting loop over all pairs cost 26 us per row)
   {
-    const uint32_t mine = s_tmax[tid];
-    int cnt = 0;
-    for (int j = 0; j < BT_THREADS; ++j) {
-      const uint32_t o = s_tmax[j];
-      cnt += (o > mine) || (o == mine && j < tid);
+    const uint32_t mine = tk;
+    uint32_t prefix = 0;
+    int remaining = min(n_cand, BT_THREADS);
+#pragma unroll 1
+    for (int bit = 15; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      const int c = __syncthreads_count((mine >> bit) == (cand >> bit));      // keys with this prefix and the bit set
+      if (c >= remaining) prefix = cand;
+      else remaining -= c;
     }
-    if (cnt == min(n_cand, BT_THREADS) - 1) s_L = mine;
+    if (tid == 0) s_L = prefix;
   }
   __syncthreads();
   const uint32_t L = s_L;
@@ -131,15 +142,23 @@ beam_topk_rows_kernel(const bf16* __restrict__ logits, long long ld, int V, cons
   const float bscore = beam_scores[row];
 
   // ---- pass 2: collect every element >= L ----
-  for (int i = tid; i < nvec; i += BT_THREADS) {
-    const uint4 u = ld_nc_u4(reinterpret_cast<const uint4*>(x) + i);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int i0 = tid; i0 < nvec; i0 += UN * BT_THREADS) {
+    uint4 uu[UN];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t k = bf16_key((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
-      if (k >= L) {
-        const int p = atomicAdd(&s_count, 1);
-        if (p < BT_CAP) s_cand[p] = comp_of(k, static_cast<uint32_t>(i * 8 + j));
+    for (int k = 0; k < UN; ++k)
+      if (i0 + k * BT_THREADS < nvec) uu[k] = ld_nc_u4(reinterpret_cast<const uint4*>(x) + i0 + k * BT_THREADS);
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      const int i = i0 + k * BT_THREADS;
+      if (i >= nvec) break;
+      const uint32_t w[4] = {uu[k].x, uu[k].y, uu[k].z, uu[k].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t kk = bf16_key((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+        if (kk >= L) {
+          const int p = atomicAdd(&s_count, 1);
+          if (p < BT_CAP) s_cand[p] = comp_of(kk, static_cast<uint32_t>(i * 8 + j));
+        }
       }
     }
   }
@@ -310,18 +329,23 @@ beam_select_kernel(const BeamSelectK p) {
   }
   __syncthreads();
 
-  for (int j = 0; j < K; ++j) {
-    const int src = s_new_src[j], dst = b * K + j, tok = s_new_tok[j];
-    for (int t = tid; t <= step; t += BS_THREADS) {
-      seqs_out[static_cast<long long>(dst) * p.max_new + t] =
-          t < step ? seqs_in[static_cast<long long>(src) * p.max_new + t] : tok;
-      if (t < p.ind_ld)
-        ind_out[static_cast<long long>(dst) * p.ind_ld + t] = t < step ? ind_in[static_cast<long long>(src) * p.ind_ld + t] : dst;
-    }
-    const uint4* e = reinterpret_cast<const uint4*>(p.embed + static_cast<long long>(tok) * p.ld_embed);
-    uint4* xo = reinterpret_cast<uint4*>(p.x_next + static_cast<long long>(dst) * p.ld_x);
-    for (int h = tid; h < p.H8; h += BS_THREADS) xo[h] = __ldg(e + h);
-    if (tid == 0) p.beam_scores[dst] = s_new_score[j];
+  // all copies as flat loops over (beam, element): independent loads in flight instead of one round trip per beam
+  const int n_hist = K * (step + 1);
+  for (int idx = tid; idx < n_hist; idx += BS_THREADS) {
+    const int j = idx / (step + 1), t = idx - j * (step + 1);
+    const int src = s_new_src[j], dst = b * K + j;
+    seqs_out[static_cast<long long>(dst) * p.max_new + t] =
+        t < step ? seqs_in[static_cast<long long>(src) * p.max_new + t] : s_new_tok[j];
+    if (t < p.ind_ld)
+      ind_out[static_cast<long long>(dst) * p.ind_ld + t] = t < step ? ind_in[static_cast<long long>(src) * p.ind_ld + t] : dst;
+  }
+  if (tid < K) p.beam_scores[b * K + tid] = s_new_score[tid];
+  const int n_emb = K * p.H8;
+#pragma unroll 4
+  for (int idx = tid; idx < n_emb; idx += BS_THREADS) {
+    const int j = idx / p.H8, h = idx - j * p.H8;
+    const uint4* e = reinterpret_cast<const uint4*>(p.embed + static_cast<long long>(s_new_tok[j]) * p.ld_embed);
+    reinterpret_cast<uint4*>(p.x_next + static_cast<long long>(b * K + j) * p.ld_x)[h] = __ldg(e + h);
   }
 }
 
