@@ -188,7 +188,7 @@ class ModelModule_LLM(torch.nn.Module):
         self.global_step = 0
         self._opt = None
 
-    # ---- optimizer: fused all-reduce -> global-norm clip -> AdamW over the flat trainable buffer ---------------
+    # ---- optimizer: NCCL all-reduce of the flat gradient buffer, then ONE global-norm clip + AdamW kernel over the flat trainable buffer ---------------
     def configure_optimizers(self):
         flat = self.model.flat
         n = flat.used
